@@ -1,0 +1,235 @@
+/*
+ * quadsim.h -- C-ABI of the B200-native batched quadrotor-swarm simulator.
+ *
+ * This is the drop-in boundary for the reference's per-control-step hot path.  The reference
+ * (priban42/quad-swarm-rl-stable-baselines3) is pure Python, so "the FFI a maintainer would bind"
+ * is a ctypes binding (shown in INTEGRATION.md).  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference root):
+ *
+ *   qs_create / qs_destroy   QuadrotorEnvMulti.__init__            gym_art/quadrotor_multi/quadrotor_multi.py:27-228
+ *                            SubprocVecEnvCustom.__init__/close    swarm_rl/env_wrappers/subproc_vec_env_custom.py:112-139,190-201
+ *   qs_reset                 QuadrotorEnvMulti.reset               gym_art/quadrotor_multi/quadrotor_multi.py:440-519
+ *                            SubprocVecEnvCustom.reset             swarm_rl/env_wrappers/subproc_vec_env_custom.py:155-164
+ *   qs_step                  QuadrotorEnvMulti.step                gym_art/quadrotor_multi/quadrotor_multi.py:521-842
+ *                            SubprocVecEnvCustom.step_async/_wait  swarm_rl/env_wrappers/subproc_vec_env_custom.py:141-153
+ *                            (+ the worker auto-reset,             swarm_rl/env_wrappers/subproc_vec_env_custom.py:35-52)
+ *   qs_step_host / qs_reset_host   the same two calls with HOST buffers (what SB3's numpy rollout loop sees)
+ *   qs_get_state/qs_set_state      envs[i].dynamics.{pos,vel,rot,omega,...} attribute access
+ *                                  (gym_art/quadrotor_multi/quadrotor_dynamics.py:180-191)
+ *   qs_set_param             rew_coeff updates / set_capture_radius  quadrotor_multi.py:101-112, quadrotor_multi_rewards.py:210-211
+ *   qs_episode_stats         infos[i]['episode_extra_stats']       gym_art/quadrotor_multi/quadrotor_multi.py:739-831
+ *
+ * Conventions
+ *   - plain C types only; all device pointers are raw CUDA device addresses (e.g. torch tensor.data_ptr()).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Nothing in qs_step /
+ *     qs_reset allocates, synchronises or touches the host; the *_host variants copy through pinned staging
+ *     buffers owned by the handle and synchronise the stream before returning.
+ *   - every call returns 0 on success or a negative qs_status; qs_last_error() gives a message.
+ *   - a handle is bound to one device and is not thread-safe (reference analogue: one process per env).
+ *   - N = num_envs on this device, K = num_agents, D = qs_obs_dim(), A = qs_act_dim().
+ *     Agent-major flattening is the reference VecEnv's: row = env * K + agent
+ *     (swarm_rl/env_wrappers/subproc_vec_env_custom.py:145-147, 250-262).
+ */
+#ifndef QUADSIM_H_
+#define QUADSIM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_API_VERSION 1
+#define QS_MAX_AGENTS 32      /* drones per env handled by the warp-group kernels */
+#define QS_MAX_OBSTACLES 64
+
+typedef enum qs_status {
+    QS_OK = 0,
+    QS_ERR_BAD_CONFIG = -1,
+    QS_ERR_CUDA = -2,
+    QS_ERR_SHAPE = -3,
+    QS_ERR_NULL = -4,
+    QS_ERR_UNSUPPORTED = -5
+} qs_status;
+
+/* quads_mode values that run on the device (gym_art/quadrotor_multi/scenarios/) */
+enum { QS_SCENARIO_STATIC_SAME_GOAL = 0,      /* scenarios/static_same_goal.py */
+       QS_SCENARIO_O_MIX = 1,                 /* scenarios/mix.py with obstacles: o_random | o_static_same_goal per episode */
+       QS_SCENARIO_O_RANDOM = 2,              /* scenarios/obstacles/o_random.py */
+       QS_SCENARIO_O_STATIC_SAME_GOAL = 3 };  /* scenarios/obstacles/o_static_same_goal.py */
+
+/* obs_repr (gym_art/quadrotor_multi/quad_utils.py:30-38, get_state.py:226-292) */
+enum { QS_OBS_XYZ_VXYZ_R_OMEGA = 0, QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR = 1, QS_OBS_XYZ_VXYZ_R_OMEGA_WALL = 2 };
+
+/* neighbor_obs_type (quad_utils.py:40-58) */
+enum { QS_NEIGHBOR_NONE = 0, QS_NEIGHBOR_POS_VEL = 1 };
+
+/* noise source: counter-based Philox on the device (production) */
+enum { QS_SENSE_NOISE_NONE = 0, QS_SENSE_NOISE_DEFAULT = 1 };
+
+/* qs_set_param keys */
+enum { QS_PARAM_REW_POS = 0, QS_PARAM_REW_EFFORT, QS_PARAM_REW_CRASH, QS_PARAM_REW_ORIENT, QS_PARAM_REW_SPIN,
+       QS_PARAM_REW_QUADCOL_BIN, QS_PARAM_REW_QUADCOL_BIN_SMOOTH_MAX, QS_PARAM_REW_QUADCOL_BIN_OBST,
+       QS_PARAM_COUNT };
+
+/*
+ * Flat, POD configuration.  Host code evaluates the reference's construction-time Python once
+ * (quad_models.py / inertia.py / quadrotor_dynamics.py:106-168 / quadrotor_single.py:139-234) and
+ * passes the resulting constants here.  Doubles on purpose: the library rounds to fp32 itself.
+ */
+typedef struct qs_config {
+    int32_t api_version;          /* must be QS_API_VERSION */
+    int32_t num_envs;             /* N, environments on this device */
+    int32_t num_agents;           /* K <= QS_MAX_AGENTS */
+    int32_t scenario;             /* QS_SCENARIO_* */
+    int32_t obs_repr;             /* QS_OBS_* */
+    int32_t neighbor_obs_type;    /* QS_NEIGHBOR_* */
+    int32_t neighbor_visible_num; /* resolved: 0..K-1 (reference's -1 means K-1) */
+    int32_t use_obstacles;        /* quadrotor_multi.py:128-140 */
+    int32_t use_downwash;         /* quadrotor_multi.py:663-668 */
+    int32_t apply_collision_force;/* quadrotor_multi.py:227 */
+    int32_t sense_noise;          /* QS_SENSE_NOISE_* (quadrotor_single.py:236-247) */
+    int32_t ep_len;               /* int(ep_time / (dt * sim_steps)), quadrotor_single.py:158 */
+    int32_t sim_steps;            /* physics sub-steps per control step (2) */
+    int32_t svd_period;           /* sub-steps between re-orthonormalisations (quadrotor_dynamics.py:554-558) */
+    int32_t obst_area_len;        /* int(obst_spawn_area[0]) */
+    int32_t obst_area_wid;        /* int(obst_spawn_area[1]) */
+    int32_t num_obstacles;        /* int(density * area), quadrotor_multi.py:138 */
+    int32_t reserved0;
+    uint64_t seed;                /* Philox key */
+    int64_t env_id_offset;        /* global id of local env 0 (multi-GPU sharding keeps streams G-independent) */
+
+    double dt;                    /* 1 / sim_freq = 0.005 */
+    double room_dims[3];          /* length, width, height -> box [-L/2,L/2]x[-W/2,W/2]x[0,H] */
+    double gravity;               /* 9.81 */
+    /* QuadrotorDynamics.update_model, quadrotor_dynamics.py:106-168 */
+    double mass;
+    double inertia[3];
+    double thrust_max[4];
+    double torque_max[4];
+    double prop_cross[4][3];      /* np.cross(prop_pos, [0,0,1]) */
+    double prop_ccw[4];
+    double arm;                   /* ||motor_xyz[:2]||, also the numba floor threshold (quadrotor_dynamics.py:385) */
+    double motor_tau_up;          /* 4*dt/(damp_time_up+1e-6) */
+    double motor_tau_down;
+    double motor_linearity;
+    double vel_damp;
+    double damp_omega_quadratic;
+    double omega_max;             /* 40 */
+    double floor_mu;              /* 0.6 */
+    double ou_theta;              /* 0.15  (numba_utils.py:77-105) */
+    double ou_sigma;              /* 0.2 * thrust_noise_ratio */
+    /* SensorNoise defaults, sensor_noise.py:69-76 */
+    double sense_pos_std;         /* 0.005 */
+    double sense_vel_std;         /* 0.01 */
+    double sense_gyro_std;        /* 0.000175 */
+    /* reward coefficients, quadrotor_multi.py:101-112 */
+    double rew_pos, rew_effort, rew_crash, rew_orient, rew_spin;
+    double rew_quadcol_bin, rew_quadcol_bin_smooth_max, rew_quadcol_bin_obst;
+    /* collisions, quadrotor_multi.py:164-165 */
+    double collision_hitbox_radius;   /* x arm */
+    double collision_falloff_radius;  /* x arm */
+    /* reset, quadrotor_single.py:215-218,406-418 */
+    double spawn_box;             /* 2.0 (0.1 with obstacles) */
+    double spawn_min_z;           /* 0.75 */
+    /* obstacles, obstacles/obstacles.py:8-14 */
+    double obst_size;             /* diameter */
+    double sdf_resolution;        /* 0.1 */
+    double approach_goal_metric;  /* scenarios/base.py:35 (0.5); o_static_same_goal uses 1.0 */
+} qs_config;
+
+/* SoA view used by qs_get_state / qs_set_state.  Every pointer is a DEVICE pointer to a dense
+ * row-major array, or NULL to skip that field.  Shapes: [N*K, c] unless noted. */
+typedef struct qs_state_view {
+    float *pos;          /* [N*K,3] */
+    float *vel;          /* [N*K,3] */
+    float *rot;          /* [N*K,9] row-major body->world */
+    float *omega;        /* [N*K,3] body frame */
+    float *rot_damp;     /* [N*K,4] thrust_rot_damp */
+    float *cmds_damp;    /* [N*K,4] thrust_cmds_damp */
+    float *ou;           /* [N*K,4] OU thrust-noise state */
+    float *goal;         /* [N*K,3] */
+    int32_t *flags;      /* [N*K]   bit0 on_floor, bit1 crashed_floor, bit2 crashed_wall, bit3 crashed_ceiling,
+                                    bit4 prev_new_wall, bit5 prev_new_ceiling, bit6 prev_new_room, bit7 prev_obst_hit */
+    uint32_t *col_mask;  /* [N*K]   previous-step collision row (bit j set: pair (i,j) collided last step) */
+    int32_t *tick;       /* [N]     per-env episode tick */
+    int32_t *svd_ctr;    /* [N]     sub-steps since the last re-orthonormalisation */
+    uint32_t *step_ctr;  /* [N]     control steps since creation (RNG counter) */
+    float *obst_xy;      /* [N, QS_MAX_OBSTACLES, 2] obstacle centres (first num_obstacles valid) */
+} qs_state_view;
+
+/* Per-rollout aggregate of the reference's per-episode 'episode_extra_stats' (quadrotor_multi.py:739-831):
+ * sums over all episodes that finished since the last qs_episode_stats(reset=1). */
+typedef struct qs_stats {
+    int64_t episodes;
+    int64_t num_collisions;
+    int64_t num_collisions_after_settle;
+    int64_t num_collisions_final_5s;
+    int64_t num_collisions_with_room;
+    int64_t num_collisions_with_floor;
+    int64_t num_collisions_with_wall;
+    int64_t num_collisions_with_ceiling;
+    int64_t num_collisions_obst_quad;
+    int64_t num_collisions_obst_quad_after_settle;
+    int64_t agents_success;       /* sum over episodes of #agents with no collision and reached goal */
+    int64_t agents_deadlock;
+    int64_t agents_collided;
+    int64_t nonfinite_resets;     /* envs force-reset because a NaN/Inf appeared in their state */
+    double  distance_to_goal_1s;  /* sum over episodes and agents of the per-agent mean distance in the last 1 s */
+    double  distance_to_goal_3s;
+    double  distance_to_goal_5s;
+    double  reward_sum;           /* sum of all per-agent rewards of finished episodes */
+} qs_stats;
+
+typedef struct qs_env qs_env;
+
+size_t      qs_config_size(void);     /* sizeof(qs_config), for binding self-checks */
+size_t      qs_stats_size(void);
+int         qs_api_version(void);
+const char *qs_last_error(const qs_env *env);   /* env may be NULL: last creation error */
+
+int qs_create(const qs_config *cfg, int device, qs_env **out);
+int qs_destroy(qs_env *env);
+
+int qs_num_envs(const qs_env *env);
+int qs_num_agents(const qs_env *env);
+int qs_obs_dim(const qs_env *env);
+int qs_act_dim(const qs_env *env);
+/* number of kernels the library has launched since creation (bench.py's gpu_launches claim) */
+int64_t qs_launch_count(const qs_env *env);
+
+/* reset all envs (env_mask == NULL) or those with env_mask[e] != 0 (device uint8 [N]); writes obs [N*K,D]
+ * (rows of envs that were not reset are left untouched). */
+int qs_reset(qs_env *env, const uint8_t *env_mask, float *obs, void *stream);
+
+/* One control step for every env.
+ *   actions      [N*K,A] device float32 (raw policy output; clipped inside like RawControl.step)
+ *   obs          [N*K,D] device float32: next observation; for envs that finished, the observation after
+ *                        the automatic reset (quadrotor_multi.py:836, subproc_vec_env_custom.py:43-46)
+ *   rew          [N*K]   device float32
+ *   done         [N*K]   device uint8 (all K agents of a finished env are 1, quadrotor_multi.py:838)
+ *   terminal_obs [N*K,D] device float32 or NULL: last observation of the finished episode (rows of unfinished
+ *                        envs untouched) -> infos[i]["terminal_observation"]
+ */
+int qs_step(qs_env *env, const float *actions, float *obs, float *rew, uint8_t *done,
+            float *terminal_obs, void *stream);
+
+/* Same, HOST buffers (pageable or pinned).  H2D of actions and D2H of obs/rew/done happen inside. */
+int qs_reset_host(qs_env *env, float *obs_host, void *stream);
+int qs_step_host(qs_env *env, const float *actions_host, float *obs_host, float *rew_host,
+                 uint8_t *done_host, void *stream);
+
+int qs_get_state(qs_env *env, const qs_state_view *view, void *stream);
+int qs_set_state(qs_env *env, const qs_state_view *view, void *stream);
+
+/* scalar parameter update (QS_PARAM_*), takes effect from the next step */
+int qs_set_param(qs_env *env, int key, double value);
+
+/* copies the aggregate episode statistics to *out (host); synchronises `stream`.  reset != 0 zeroes them. */
+int qs_episode_stats(qs_env *env, qs_stats *out, int reset, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADSIM_H_ */

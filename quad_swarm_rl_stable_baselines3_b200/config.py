@@ -1,0 +1,218 @@
+"""Configuration: the reference's constructor kwargs flattened to the POD `qs_config` of include/quadsim.h.
+
+`QuadSimConfig` takes the same names as `QuadrotorEnvMulti.__init__`
+(gym_art/quadrotor_multi/quadrotor_multi.py:27-45) and the env factory
+`make_quadrotor_env_multi` (swarm_rl/env_wrappers/quad_utils.py:20-66) where they exist.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Sequence
+
+from . import quad_model
+
+QS_API_VERSION = 1
+QS_MAX_AGENTS = 32
+QS_MAX_OBSTACLES = 64
+
+SCENARIOS = {"static_same_goal": 0, "o_mix": 1, "o_random": 2, "o_static_same_goal": 3}
+OBS_REPR = {"xyz_vxyz_R_omega": 0, "xyz_vxyz_R_omega_floor": 1, "xyz_vxyz_R_omega_wall": 2}
+OBS_REPR_DIM = {"xyz_vxyz_R_omega": 18, "xyz_vxyz_R_omega_floor": 19, "xyz_vxyz_R_omega_wall": 24}  # quad_utils.py:30-38
+NEIGHBOR_OBS = {"none": 0, "pos_vel": 1}
+NEIGHBOR_OBS_DIM = {"none": 0, "pos_vel": 6}                                                       # quad_utils.py:40-58
+PARAM_KEYS = {"pos": 0, "effort": 1, "crash": 2, "orient": 3, "spin": 4,
+              "quadcol_bin": 5, "quadcol_bin_smooth_max": 6, "quadcol_bin_obst": 7}
+
+
+class QsConfigC(C.Structure):
+    """Binary mirror of `struct qs_config` (include/quadsim.h).  tests/test_capi_cpu.py checks sizeof agrees."""
+    _fields_ = [
+        ("api_version", C.c_int32), ("num_envs", C.c_int32), ("num_agents", C.c_int32), ("scenario", C.c_int32),
+        ("obs_repr", C.c_int32), ("neighbor_obs_type", C.c_int32), ("neighbor_visible_num", C.c_int32),
+        ("use_obstacles", C.c_int32), ("use_downwash", C.c_int32), ("apply_collision_force", C.c_int32),
+        ("sense_noise", C.c_int32), ("ep_len", C.c_int32), ("sim_steps", C.c_int32), ("svd_period", C.c_int32),
+        ("obst_area_len", C.c_int32), ("obst_area_wid", C.c_int32), ("num_obstacles", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
+        ("dt", C.c_double), ("room_dims", C.c_double * 3), ("gravity", C.c_double),
+        ("mass", C.c_double), ("inertia", C.c_double * 3), ("thrust_max", C.c_double * 4),
+        ("torque_max", C.c_double * 4), ("prop_cross", (C.c_double * 3) * 4), ("prop_ccw", C.c_double * 4),
+        ("arm", C.c_double), ("motor_tau_up", C.c_double), ("motor_tau_down", C.c_double),
+        ("motor_linearity", C.c_double), ("vel_damp", C.c_double), ("damp_omega_quadratic", C.c_double),
+        ("omega_max", C.c_double), ("floor_mu", C.c_double), ("ou_theta", C.c_double), ("ou_sigma", C.c_double),
+        ("sense_pos_std", C.c_double), ("sense_vel_std", C.c_double), ("sense_gyro_std", C.c_double),
+        ("rew_pos", C.c_double), ("rew_effort", C.c_double), ("rew_crash", C.c_double), ("rew_orient", C.c_double),
+        ("rew_spin", C.c_double), ("rew_quadcol_bin", C.c_double), ("rew_quadcol_bin_smooth_max", C.c_double),
+        ("rew_quadcol_bin_obst", C.c_double),
+        ("collision_hitbox_radius", C.c_double), ("collision_falloff_radius", C.c_double),
+        ("spawn_box", C.c_double), ("spawn_min_z", C.c_double),
+        ("obst_size", C.c_double), ("sdf_resolution", C.c_double), ("approach_goal_metric", C.c_double),
+    ]
+
+
+class QsStatsC(C.Structure):
+    """Binary mirror of `struct qs_stats`."""
+    _fields_ = [(n, C.c_int64) for n in (
+        "episodes", "num_collisions", "num_collisions_after_settle", "num_collisions_final_5s",
+        "num_collisions_with_room", "num_collisions_with_floor", "num_collisions_with_wall",
+        "num_collisions_with_ceiling", "num_collisions_obst_quad", "num_collisions_obst_quad_after_settle",
+        "agents_success", "agents_deadlock", "agents_collided", "nonfinite_resets")] + [
+        (n, C.c_double) for n in ("distance_to_goal_1s", "distance_to_goal_3s", "distance_to_goal_5s", "reward_sum")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class QsStateViewC(C.Structure):
+    """Binary mirror of `struct qs_state_view`: raw device addresses."""
+    FIELDS = ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou", "goal", "flags", "col_mask",
+              "tick", "svd_ctr", "step_ctr", "obst_xy")
+    _fields_ = [(n, C.c_void_p) for n in FIELDS]
+
+
+# default reward coefficients: quadrotor_multi.py:101-104 overlaid with the upstream training recipe
+# (swarm_rl/runs/quad_multi_mix_baseline.py:13-16: collision reward 5, smooth max penalty 10)
+DEFAULT_REW_COEFF = dict(pos=1.0, effort=0.05, crash=1.0, orient=1.0, spin=0.1,
+                         quadcol_bin=5.0, quadcol_bin_smooth_max=10.0, quadcol_bin_obst=5.0)
+
+
+@dataclass
+class QuadSimConfig:
+    num_envs: int = 1
+    num_agents: int = 8                       # quads_num_agents
+    quads_mode: str = "static_same_goal"      # 'static_same_goal' | 'mix' (with obstacles) | 'o_random' | 'o_static_same_goal'
+    obs_repr: str = "xyz_vxyz_R_omega"
+    neighbor_obs_type: str = "pos_vel"
+    neighbor_visible_num: int = 6             # -1 = all others
+    collision_hitbox_radius: float = 2.0
+    collision_falloff_radius: float = 4.0
+    use_obstacles: bool = False
+    obst_density: float = 0.2
+    obst_size: float = 0.6
+    obst_spawn_area: Sequence[float] = (8.0, 8.0)
+    use_downwash: bool = False
+    apply_collision_force: bool = True
+    room_dims: Sequence[float] = (10.0, 10.0, 10.0)
+    ep_time: float = 15.0                     # quads_episode_duration
+    sim_freq: float = 200.0
+    sim_steps: int = 2
+    sense_noise: Optional[str] = "default"    # None | 'default'
+    rew_coeff: Dict[str, float] = field(default_factory=dict)
+    seed: int = 0
+    env_id_offset: int = 0
+    motor: quad_model.MotorParams = field(default_factory=quad_model.MotorParams)
+    geometry: quad_model.QuadGeometry = field(default_factory=quad_model.QuadGeometry)
+
+    # ---- derived ---------------------------------------------------------------------------
+    @property
+    def visible(self) -> int:
+        if self.neighbor_obs_type == "none":
+            return 0
+        v = self.num_agents - 1 if self.neighbor_visible_num == -1 else self.neighbor_visible_num
+        if not 0 <= v <= self.num_agents - 1:
+            raise ValueError("Incorrect number of neigbors")      # quadrotor_multi.py:375
+        return v
+
+    @property
+    def obs_dim(self) -> int:
+        return (OBS_REPR_DIM[self.obs_repr] + NEIGHBOR_OBS_DIM[self.neighbor_obs_type] * self.visible
+                + (9 if self.use_obstacles else 0))
+
+    @property
+    def act_dim(self) -> int:
+        return 4
+
+    @property
+    def dt(self) -> float:
+        return 1.0 / self.sim_freq
+
+    @property
+    def ep_len(self) -> int:
+        return int(self.ep_time / (self.dt * self.sim_steps))     # quadrotor_single.py:158
+
+    @property
+    def num_obstacles(self) -> int:
+        if not self.use_obstacles:
+            return 0
+        return int(self.obst_density * self.obst_spawn_area[0] * self.obst_spawn_area[1])  # quadrotor_multi.py:138
+
+    def scenario_id(self) -> int:
+        mode = self.quads_mode
+        if self.use_obstacles and mode == "mix":
+            mode = "o_mix"
+        if mode not in SCENARIOS:
+            raise ValueError(f"quads_mode {self.quads_mode!r} is not available on the device "
+                             f"(supported: static_same_goal; with obstacles: mix, o_random, o_static_same_goal)")
+        if self.use_obstacles != mode.startswith("o_"):
+            raise ValueError(f"quads_mode {self.quads_mode!r} inconsistent with use_obstacles={self.use_obstacles}")
+        return SCENARIOS[mode]
+
+    def to_c(self) -> QsConfigC:
+        if not 1 <= self.num_agents <= QS_MAX_AGENTS:
+            raise ValueError(f"num_agents must be in [1, {QS_MAX_AGENTS}]")
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        if self.obs_repr not in OBS_REPR:
+            raise ValueError(f"obs_repr {self.obs_repr!r} not supported")
+        if self.neighbor_obs_type not in NEIGHBOR_OBS:
+            raise ValueError(f"neighbor_obs_type {self.neighbor_obs_type!r} not supported")
+        rew = dict(DEFAULT_REW_COEFF)
+        unknown = set(self.rew_coeff) - set(rew) - {"action_change", "yaw", "rot", "attitude", "vel"}
+        if unknown:
+            raise AssertionError(f"unknown rew_coeff keys {sorted(unknown)}")      # quadrotor_multi.py:109,116
+        rew.update({k: float(v) for k, v in self.rew_coeff.items() if k in rew})
+        q = quad_model.crazyflie_constants(self.geometry, self.motor, self.dt)
+        c = QsConfigC()
+        c.api_version = QS_API_VERSION
+        c.num_envs, c.num_agents = self.num_envs, self.num_agents
+        c.scenario = self.scenario_id()
+        c.obs_repr = OBS_REPR[self.obs_repr]
+        c.neighbor_obs_type = NEIGHBOR_OBS[self.neighbor_obs_type] if self.visible > 0 else 0
+        c.neighbor_visible_num = self.visible
+        c.use_obstacles = int(self.use_obstacles)
+        c.use_downwash = int(self.use_downwash)
+        c.apply_collision_force = int(self.apply_collision_force)
+        c.sense_noise = 0 if self.sense_noise is None else 1
+        if self.sense_noise not in (None, "default"):
+            raise ValueError("sense_noise must be None or 'default'")
+        c.ep_len, c.sim_steps = self.ep_len, self.sim_steps
+        c.svd_period = quad_model.svd_period(self.dt)
+        c.obst_area_len, c.obst_area_wid = int(self.obst_spawn_area[0]), int(self.obst_spawn_area[1])
+        c.num_obstacles = self.num_obstacles
+        if c.num_obstacles > QS_MAX_OBSTACLES or c.obst_area_len * c.obst_area_wid > 64:
+            raise ValueError("obstacle grid too large (<= 64 cells, <= 64 obstacles)")
+        if self.use_obstacles and c.obst_area_len * c.obst_area_wid - c.num_obstacles < self.num_agents:
+            raise ValueError("not enough free cells to spawn every drone in its own cell")
+        c.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        c.env_id_offset = self.env_id_offset
+        c.dt = self.dt
+        c.room_dims[:] = [float(v) for v in self.room_dims]
+        c.gravity = quad_model.GRAV
+        c.mass = q.mass
+        c.inertia[:] = q.inertia
+        c.thrust_max[:] = q.thrust_max
+        c.torque_max[:] = q.torque_max
+        for i in range(4):
+            c.prop_cross[i][:] = q.prop_cross[i]
+        c.prop_ccw[:] = q.prop_ccw
+        c.arm = q.arm
+        c.motor_tau_up, c.motor_tau_down = q.motor_tau_up, q.motor_tau_down
+        c.motor_linearity = q.motor_linearity
+        c.vel_damp, c.damp_omega_quadratic = q.vel_damp, q.damp_omega_quadratic
+        c.omega_max, c.floor_mu = 40.0, 0.6                       # quadrotor_dynamics.py:49,77
+        c.ou_theta, c.ou_sigma = 0.15, q.ou_sigma                 # numba_utils.py:80, quadrotor_dynamics.py:173
+        c.sense_pos_std, c.sense_vel_std, c.sense_gyro_std = 0.005, 0.01, 0.000175   # sensor_noise.py:70-74
+        c.rew_pos, c.rew_effort, c.rew_crash = rew["pos"], rew["effort"], rew["crash"]
+        c.rew_orient, c.rew_spin = rew["orient"], rew["spin"]
+        c.rew_quadcol_bin = rew["quadcol_bin"]
+        c.rew_quadcol_bin_smooth_max = rew["quadcol_bin_smooth_max"]
+        c.rew_quadcol_bin_obst = rew["quadcol_bin_obst"]
+        c.collision_hitbox_radius = self.collision_hitbox_radius
+        c.collision_falloff_radius = self.collision_falloff_radius
+        c.spawn_box = 0.1 if self.use_obstacles else 2.0          # quadrotor_single.py:215-218
+        c.spawn_min_z = 0.75                                      # quadrotor_single.py:416-417
+        c.obst_size = self.obst_size
+        c.sdf_resolution = 0.1                                    # obstacles/obstacles.py:13
+        c.approach_goal_metric = 0.5                              # scenarios/base.py:35
+        return c

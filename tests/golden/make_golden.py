@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference from /root/reference.
+
+Run in the build container (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+Two kinds of fixtures:
+
+  * ``trace_<name>.npz`` -- `QuadrotorEnvMulti.step` traces with numba's JIT disabled so that every random draw
+    on the hot path is taped (oracle/ref_harness.py).  Per step: actions, the dynamics snapshot after the step,
+    returned obs/reward/done, and the unit draws consumed (normals / uniforms / choice ids, reference order).
+  * ``dyn_jit.npz`` -- `QuadrotorDynamics.step` driven directly with the numba JIT ON (the reference's real code
+    path), thrust noise off: free flight, the 100-sub-step SVD re-orthonormalisation, floor contact and sliding.
+
+tests/test_oracle_golden.py replays them through oracle/quadsim_oracle.c.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+STATE_KEYS = ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou", "on_floor", "crashed_floor",
+              "crashed_wall", "crashed_ceiling", "goal")
+
+# name -> (env kwargs, steps, action scale/bias recipe)
+TRACES = {
+    # cfg2 shape: 8 quads, static_same_goal, 6 nearest neighbours, noise on; short episodes so resets are covered
+    "cfg2_k8": dict(env=dict(num_agents=8, ep_time=1.2), steps=260, act="uniform"),
+    # tight room: drones spawn outside the box -> wall / ceiling bounces, floor, pair collisions
+    "smallroom_k8": dict(env=dict(num_agents=8, room_dims=(3.0, 3.0, 3.0), ep_time=1.0), steps=220, act="high"),
+    # crowded: 16 quads in a small spawn volume -> drone-drone impulses (incl. drones in two new pairs)
+    "crowd_k16": dict(env=dict(num_agents=16, room_dims=(4.0, 4.0, 6.0), ep_time=1.0, neighbor_visible_num=6),
+                      steps=150, act="hover"),
+    # cfg3 shape: obstacles (mix -> o_random | o_static_same_goal), SDF obs, downwash, 2 neighbours
+    "cfg3_obst_k8": dict(env=dict(num_agents=8, quads_mode="mix", use_obstacles=True, use_downwash=True,
+                                  obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2, ep_time=1.0,
+                                  rew_coeff=dict(pos=1.0, effort=0.05, spin=0.1, vel=0.0, crash=1.0, orient=1.0,
+                                                 yaw=0.0, quadcol_bin=5.0, quadcol_bin_smooth_max=4.0,
+                                                 quadcol_bin_obst=5.0)),
+                         steps=330, act="hover"),
+    # cfg4 shape: 32 quads
+    "cfg4_k32": dict(env=dict(num_agents=32, ep_time=0.5), steps=70, act="uniform"),
+    # no sensor noise / all neighbours visible / wall obs
+    "nonoise_k4": dict(env=dict(num_agents=4, sense_noise=None, neighbor_visible_num=-1,
+                                obs_repr="xyz_vxyz_R_omega_wall", ep_time=0.6), steps=130, act="uniform"),
+}
+
+
+def gen_traces():
+    os.environ["NUMBA_DISABLE_JIT"] = "1"
+    import numpy as np
+    import ref_harness as rh
+
+    tape = rh.Tape(seed=1234)
+    rh.install_tape(tape)
+    for name, spec in TRACES.items():
+        K = spec["env"]["num_agents"]
+        env = rh.make_upstream_env(tape=tape, **spec["env"])
+        rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+        rec = {k: [] for k in ("actions", "obs", "rew", "done", "tn", "tu", "tc", "n_tn", "n_tu", "n_tc", "tick",
+                               "obst_xy", "scenario")}
+        snaps = {k: [] for k in STATE_KEYS}
+
+        def push_tape(m):
+            k, v = tape.since(m)
+            for key, kind in (("tn", 0), ("tu", 1), ("tc", 2)):
+                vals = v[k == kind]
+                rec[key].append(vals)
+                rec["n_" + key].append(len(vals))
+
+        def push_snap():
+            s = rh.snapshot(env)
+            for k in STATE_KEYS:
+                snaps[k].append(s[k])
+            rec["tick"].append(int(s["tick"][0]))
+            if env.use_obstacles:
+                rec["obst_xy"].append(np.array(env.obstacles.pos_arr)[:, :2].copy())
+                rec["scenario"].append(env.scenario.scenario.__class__.__name__)
+
+        m = tape.mark()
+        obs, _ = env.reset()
+        push_tape(m)
+        push_snap()
+        rec["obs"].append(np.array(obs, dtype=np.float64))
+        events = dict(done=0, impulse=0)
+        for s in range(spec["steps"]):
+            if spec["act"] == "uniform":
+                a = rs.uniform(-1.0, 1.0, (K, 4))
+            elif spec["act"] == "high":          # mostly climbing -> ceiling / wall hits
+                a = rs.uniform(-0.2, 1.3, (K, 4))
+            else:                                # near hover, small differential -> long free flight, collisions
+                a = 0.05 + rs.uniform(-0.15, 0.15, (K, 4))
+            m = tape.mark()
+            obs, rew, done, infos = env.step(a)
+            push_tape(m)
+            push_snap()
+            rec["actions"].append(a)
+            rec["obs"].append(np.array(obs, dtype=np.float64))
+            rec["rew"].append(np.array(rew, dtype=np.float64))
+            rec["done"].append(np.array(done, dtype=bool))
+            events["done"] += int(any(done))
+        out = dict(
+            actions=np.array(rec["actions"]), obs=np.array(rec["obs"]), rew=np.array(rec["rew"]),
+            done=np.array(rec["done"]), tick=np.array(rec["tick"]),
+            tn=np.concatenate(rec["tn"]), tu=np.concatenate(rec["tu"]), tc=np.concatenate(rec["tc"]),
+            n_tn=np.array(rec["n_tn"]), n_tu=np.array(rec["n_tu"]), n_tc=np.array(rec["n_tc"]),
+        )
+        for k in STATE_KEYS:
+            out["s_" + k] = np.array(snaps[k])
+        if env.use_obstacles:
+            out["obst_xy"] = np.array(rec["obst_xy"])
+            out["scenario"] = np.array(rec["scenario"])
+        out["env_kwargs"] = np.array(repr(spec["env"]))
+        path = os.path.join(HERE, f"trace_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: steps={spec['steps']} dones={events['done']} floor={int(out['s_on_floor'].any(axis=1).sum())} "
+              f"wall={int(out['s_crashed_wall'].sum())} ceil={int(out['s_crashed_ceiling'].sum())} "
+              f"draws N={len(out['tn'])} U={len(out['tu'])} C={len(out['tc'])} -> {os.path.getsize(path) // 1024} KiB")
+
+
+def gen_dyn_jit():
+    """JIT ON: QuadrotorDynamics.step (quadrotor_dynamics.py:215-221) on one drone, thrust noise off."""
+    import numpy as np
+    import ref_harness as rh
+    rh.install_stubs()
+    from gym_art.quadrotor_multi.quadrotor_dynamics import QuadrotorDynamics
+    from gym_art.quadrotor_multi.quad_utils import rpy2R
+    import gym_art.quadrotor_multi.quadrotor_randomization as qr
+
+    params = qr.Crazyflie().sample()
+    params["noise"]["thrust_noise_ratio"] = 0.0
+    room_box = np.array([[-5.0, -5.0, 0.0], [5.0, 5.0, 10.0]])
+    rs = np.random.RandomState(7)
+    runs = []
+    for run in range(4):
+        dyn = QuadrotorDynamics(model_params=params, dynamics_steps_num=2, room_box=room_box, use_numba=True, dt=0.005)
+        pos = np.array([rs.uniform(-1, 1), rs.uniform(-1, 1), rs.uniform(0.3, 2.5)])
+        vel = rs.uniform(-0.5, 0.5, 3)
+        rot = rpy2R(*rs.uniform(-0.4, 0.4, 3))
+        if run == 3:                                   # upside down -> random-yaw branch never fires w/o RNG tap; keep z>0
+            rot = rpy2R(0.2, 2.6, -1.0)
+            pos[2] = 3.0
+        omega = rs.uniform(-1.0, 1.0, 3)
+        dyn.set_state(pos, vel, rot, omega)
+        dyn.reset()
+        dyn.on_floor = False
+        steps = 260
+        cmds = rs.uniform(0.0, 1.0, (steps, 4)) * (0.6 if run % 2 == 0 else 1.0)
+        tr = {k: [] for k in ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "on_floor", "crashed_floor", "acc")}
+
+        def snap():
+            tr["pos"].append(np.array(dyn.pos, dtype=np.float64)); tr["vel"].append(np.array(dyn.vel, dtype=np.float64))
+            tr["rot"].append(np.array(dyn.rot, dtype=np.float64).reshape(9)); tr["omega"].append(np.array(dyn.omega, dtype=np.float64))
+            tr["rot_damp"].append(np.array(dyn.thrust_rot_damp, dtype=np.float64))
+            tr["cmds_damp"].append(np.array(dyn.thrust_cmds_damp, dtype=np.float64))
+            tr["on_floor"].append(bool(dyn.on_floor)); tr["crashed_floor"].append(bool(dyn.crashed_floor))
+            tr["acc"].append(np.array(dyn.acc, dtype=np.float64))
+
+        snap()
+        for s in range(steps):
+            dyn.step(cmds[s], 0.005)
+            snap()
+        runs.append(dict(cmds=cmds, **{k: np.array(v) for k, v in tr.items()}))
+    out = {}
+    for r, d in enumerate(runs):
+        for k, v in d.items():
+            out[f"r{r}_{k}"] = v
+    out["n_runs"] = np.array(len(runs))
+    out["consts"] = np.array([dyn.mass, *dyn.inertia, *dyn.thrust_max, *dyn.torque_max, dyn.arm, dyn.motor_tau_up,
+                              *dyn.prop_crossproducts.reshape(-1)])
+    path = os.path.join(HERE, "dyn_jit.npz")
+    np.savez_compressed(path, **out)
+    print("dyn_jit:", {r: int(d["on_floor"].sum()) for r, d in enumerate(runs)}, "->", os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "traces":
+        gen_traces()
+    elif which == "dyn":
+        gen_dyn_jit()
+    else:   # separate interpreters: NUMBA_DISABLE_JIT must be decided before numba is imported
+        subprocess.check_call([sys.executable, __file__, "dyn"])
+        subprocess.check_call([sys.executable, __file__, "traces"])

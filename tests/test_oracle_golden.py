@@ -1,0 +1,153 @@
+"""The CPU oracle (oracle/quadsim_oracle.c) against outputs of the reference itself.
+
+Fixtures are produced by tests/golden/make_golden.py from the unmodified reference in /root/reference
+(the reference's own tests hold no usable golden vectors for this path).
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+from oracle import OracleEnv
+from quad_swarm_rl_stable_baselines3_b200 import quad_model
+from quad_swarm_rl_stable_baselines3_b200.config import QuadSimConfig
+
+PHYS = ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou")
+
+
+def cfg_from_kwargs(kw):
+    kw = dict(kw)
+    rew = kw.pop("rew_coeff", None) or {}
+    rew = {k: v for k, v in rew.items()}
+    return QuadSimConfig(num_envs=1, rew_coeff=rew, **kw)
+
+
+def test_constants_match_reference(golden_dir):
+    """quad_model.py vs the reference's QuadLink / update_model (inertia.py:182-310, quadrotor_dynamics.py:106-168)."""
+    g = np.load(os.path.join(golden_dir, "dyn_jit.npz"))
+    q = quad_model.crazyflie_constants()
+    mine = np.array([q.mass, *q.inertia, *q.thrust_max, *q.torque_max, q.arm, q.motor_tau_up,
+                     *np.array(q.prop_cross).reshape(-1)])
+    np.testing.assert_allclose(mine, g["consts"], rtol=1e-12, atol=1e-18)
+    assert quad_model.svd_period(0.005) == 100
+
+
+def test_survey_known_answer_dynamics():
+    """one control step of QuadrotorDynamics.step from a hand-made state.
+    (set_state rounds omega to float32, quadrotor_dynamics.py:190, hence 1e-8 rather than 1e-13 on what omega feeds.)"""
+    o = OracleEnv(QuadSimConfig(num_envs=1, num_agents=1, neighbor_obs_type="none", neighbor_visible_num=0))
+    rot = [0.9541425672790118, -0.29881057511918196, -0.018005596439997374,
+           0.2951508833549871, 0.9490892608907772, -0.11007057243681952,
+           0.04997916927067833, 0.09970865087213879, 0.9937606691655043]
+    rd = np.array([0.7, 0.72, 0.68, 0.71])
+    o.set_state(pos=[0.3, -0.2, 2.0], vel=[0.1, -0.2, 0.3], rot=rot, omega=[0.5, -0.4, 0.3], rot_damp=rd,
+                cmds_damp=rd ** 2, ou=np.zeros(4), flags=[0])
+    o.dynamics_only(0, [0.6, 0.5, 0.55, 0.45])
+    s = o.get_state()
+    np.testing.assert_allclose(s["pos"][0], [0.3009955565579763, -0.2020262077779446, 2.002985078884568], rtol=1e-13)
+    np.testing.assert_allclose(s["vel"][0], [0.09815374185664064, -0.21064167712385498, 0.2943324935913465], rtol=1e-8)
+    np.testing.assert_allclose(s["omega"][0], [0.3368657149955732, -0.42912022001622524, 0.3058370554945566], rtol=1e-7)
+    np.testing.assert_allclose(s["rot"][0], [0.9531554796985265, -0.30178470374268573, -0.02050912254609862,
+                                              0.2975597188776914, 0.9476714420573863, -0.11565920460691105,
+                                              0.05434008853600427, 0.10413851590940512, 0.9930771995580635], rtol=1e-8)
+    np.testing.assert_allclose(s["rot_damp"][0], [0.7185661671889045, 0.7167910409603038, 0.6953364007391983,
+                                                   0.7002486915741181], rtol=1e-13)
+    np.testing.assert_allclose(s["cmds_damp"][0], [0.5163373366285527, 0.5137893964009559, 0.48349271019294304,
+                                                    0.4903482300512643], rtol=1e-13)
+
+
+def test_dynamics_jit_on(golden_dir):
+    """JIT-ON reference QuadrotorDynamics.step: free flight, SVD at sub-step 100, floor touch and sliding.
+    One-step teacher-forced comparison (floor friction chatter is chaotic, so free-running traces are only
+    compared until first floor contact)."""
+    g = np.load(os.path.join(golden_dir, "dyn_jit.npz"))
+    cfg = QuadSimConfig(num_envs=1, num_agents=1, neighbor_obs_type="none", neighbor_visible_num=0)
+    cfg.motor.thrust_noise_ratio = 0.0
+    for r in range(int(g["n_runs"])):
+        T = g[f"r{r}_cmds"].shape[0]
+        o = OracleEnv(cfg)
+        worst = 0.0
+        for s in range(T):
+            fl = int(g[f"r{r}_on_floor"][s])
+            o.set_state(pos=g[f"r{r}_pos"][s], vel=g[f"r{r}_vel"][s], rot=g[f"r{r}_rot"][s], omega=g[f"r{r}_omega"][s],
+                        rot_damp=g[f"r{r}_rot_damp"][s], cmds_damp=g[f"r{r}_cmds_damp"][s], ou=np.zeros(4), flags=[fl],
+                        svd_ctr=(2 * s) % 100)
+            a = 2.0 * g[f"r{r}_cmds"][s] - 1.0           # RawControl maps [-1,1] -> [0,1]
+            o.step(a[None, :])
+            st = o.get_state()
+            first_touch = (not g[f"r{r}_on_floor"][s]) and g[f"r{r}_on_floor"][s + 1]
+            for k in ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp"):
+                err = np.abs(st[k][0] - g[f"r{r}_{k}"][s + 1]).max()
+                if k == "rot" and first_touch and err > 2e-9:
+                    # touched down upside-down: the reference draws a random yaw from numba's private RNG
+                    # (quadrotor_dynamics.py:623-626), which cannot be taped -> both must be pure yaw rotations
+                    for R in (st[k][0], g[f"r{r}_rot"][s + 1]):
+                        assert abs(R[8] - 1.0) < 1e-12 and abs(R[0] - R[4]) < 1e-12 and abs(R[1] + R[3]) < 1e-12
+                    continue
+                worst = max(worst, err)
+                assert err < 2e-9, (r, s, k, err)
+            assert (st["flags"][0] & 1) == int(g[f"r{r}_on_floor"][s + 1]), (r, s)
+            assert ((st["flags"][0] >> 1) & 1) == int(g[f"r{r}_crashed_floor"][s + 1]), (r, s)
+        assert g[f"r{r}_on_floor"].sum() > 50           # the run does include floor contact
+
+
+TRACE_NAMES = ["cfg2_k8", "smallroom_k8", "crowd_k16", "cfg3_obst_k8", "cfg4_k32", "nonoise_k4"]
+
+
+@pytest.mark.parametrize("name", TRACE_NAMES)
+def test_env_trace(golden_dir, name):
+    """QuadrotorEnvMulti.reset/step traces (JIT off, every draw taped): the oracle replays the reference's own draws.
+    The physical state is re-synchronised to the reference before every step (teacher forcing; contact dynamics are
+    chaotic), while collision / room / episode bookkeeping free-runs across the whole trace."""
+    g = np.load(os.path.join(golden_dir, f"trace_{name}.npz"))
+    kw = ast.literal_eval(str(g["env_kwargs"]))
+    cfg = cfg_from_kwargs(kw)
+    K = cfg.num_agents
+    o = OracleEnv(cfg)
+    on, ou_, oc = np.cumsum(np.r_[0, g["n_tn"]]), np.cumsum(np.r_[0, g["n_tu"]]), np.cumsum(np.r_[0, g["n_tc"]])
+
+    def tape(i):
+        o.set_tape(g["tn"][on[i]:on[i + 1]], g["tu"][ou_[i]:ou_[i + 1]], g["tc"][oc[i]:oc[i + 1]])
+
+    def check_tape(i, what):
+        assert o.tape_pos() == (g["n_tn"][i], g["n_tu"][i], g["n_tc"][i]), (what, o.tape_pos(), g["n_tn"][i], g["n_tu"][i], g["n_tc"][i])
+
+    def check_state(i, what):
+        st = o.get_state()
+        for k in PHYS:
+            ref = g["s_" + k][i].reshape(K, -1)
+            np.testing.assert_allclose(st[k].reshape(K, -1), ref, rtol=0, atol=5e-9, err_msg=f"{what} {k}")
+        np.testing.assert_allclose(st["goal"], g["s_goal"][i], atol=1e-12, err_msg=f"{what} goal")
+        for bit, key in enumerate(("on_floor", "crashed_floor", "crashed_wall", "crashed_ceiling")):
+            assert np.array_equal((st["flags"] >> bit) & 1, g["s_" + key][i].astype(np.int32)), (what, key)
+        assert st["tick"] == g["tick"][i], what
+        if "obst_xy" in g.files:
+            np.testing.assert_allclose(st["obst_xy"], g["obst_xy"][i], atol=1e-12, err_msg=f"{what} obstacles")
+
+    tape(0)
+    obs = o.reset()
+    check_tape(0, "reset")
+    np.testing.assert_allclose(obs, g["obs"][0], rtol=0, atol=1e-9)
+    check_state(0, "reset")
+    n_done = n_impulse = 0
+    T = g["actions"].shape[0]
+    for s in range(T):
+        # teacher forcing of the physical state only
+        st = o.get_state()
+        fl = (st["flags"] & ~0xF)
+        for bit, key in enumerate(("on_floor", "crashed_floor", "crashed_wall", "crashed_ceiling")):
+            fl |= g["s_" + key][s].astype(np.int32) << bit
+        o.set_state(flags=fl, **{k: g["s_" + k][s] for k in PHYS})
+        tape(s + 1)
+        obs, rew, done = o.step(g["actions"][s])
+        check_tape(s + 1, f"step {s}")
+        check_state(s + 1, f"step {s}")
+        np.testing.assert_allclose(rew, g["rew"][s], rtol=0, atol=1e-9, err_msg=f"step {s} reward")
+        assert np.array_equal(done, g["done"][s]), f"step {s} done"
+        np.testing.assert_allclose(obs, g["obs"][s + 1], rtol=0, atol=1e-8, err_msg=f"step {s} obs")
+        n_done += int(done.any())
+        n_impulse += o.diag()["impulse_flag"]
+    assert n_done >= 1
+    if name in ("smallroom_k8", "crowd_k16", "cfg3_obst_k8"):
+        assert n_impulse >= 1
