@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- drone-steps/sec of the batched quadrotor-swarm step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...                 # CPU arm: the oracle port on all host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, weak scaling
+
+Workload (BASELINE.json configs[1]): 8-quad swarm, static_same_goal, pos_vel observations of the 6 nearest
+neighbours (obs 54), 4096 envs per GPU, sensor + thrust noise on, episodes of 1500 control steps (so the timed
+window contains auto-resets), synthetic i.i.d. U(-1,1) actions resident in HBM.  A "step" is one control step of
+every env = one launch of the fused step kernel.  The per-step working set (~14 MB) is smaller than the 126 MB L2,
+so L2 is flushed (a 256 MiB write) between timed steps and every step is timed with its own pair of CUDA events
+on the launching stream.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+AGENTS = 8
+# Algorithmic HBM bytes per drone-step for this workload (restated in DESIGN.md "Roofline"):
+# state 120 B read + 120 B written, goal 12 R, tick/flags 4 R+W, action 16 R, obs 54*4 W, reward 4 + done 1 W
+ALGO_BYTES_PER_DRONE_STEP = 497.0
+WORKLOAD = "cfg2: 8-quad static_same_goal, pos_vel x6 neighbours, obs 54, noise on, ep 1500 steps"
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic_per_launch():
+    """dram bytes per launch of the step kernel from the committed `ncu --set full` capture, if any."""
+    p = os.path.join(ROOT, "profiles", "step_kernel_cfg2_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(envs, agents, budget_s, threads):
+    """The CPU oracle (float64 C port of the reference's step, oracle/quadsim_oracle.c) on `threads` host threads,
+    one slice of independent envs per thread, same workload config.  Returns (drone-steps/s, description)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import OracleBatch
+    from quad_swarm_rl_stable_baselines3_b200.config import QuadSimConfig
+    cfg = QuadSimConfig(num_envs=envs, num_agents=agents, seed=0)
+    b = OracleBatch(cfg, threads=threads)
+    b.reset()
+    rs = np.random.RandomState(0)
+    acts = rs.uniform(-1, 1, (8, envs * agents, 4))
+    for i in range(3):
+        b.step(acts[i])
+    t0 = time.perf_counter()
+    b.step(acts[3]); b.step(acts[4])
+    per = (time.perf_counter() - t0) / 2
+    n = int(max(5, min(5000, budget_s / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    for i in range(n):
+        b.step(acts[i % 8])
+    dt = time.perf_counter() - t0
+    return envs * agents * n / dt, f"{envs} envs x {agents} drones x {n} control steps, {threads} threads, {dt:.1f} s"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host cores (the reference is pure Python and cannot
+    travel to the GPU box, so this is its C port, the oracle).  Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    envs = 512
+    budget = min(20.0, max(2.0, 0.02 * (args.steps + args.warmup)))
+    v, sample = cpu_port_throughput(envs, AGENTS, budget, threads)
+    line = {
+        "impl": "reference", "metric": "drone-steps/sec", "value": v, "unit": "drone-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * ENVS_PER_GPU * AGENTS / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "agents": AGENTS, "obs_dim": 54,
+                   "note": "CPU arm: C port of the reference step (oracle), all host threads, bounded sample; "
+                           "ms_per_step is the time this arm would need for one 4096-env step"},
+        "cpu_baseline": {"value": v, "unit": "drone-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "drone-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU, help="override for size sweeps (not the bench line)")
+    ap.add_argument("--no-flush", action="store_true", help="L2-warm back-to-back steps (informational only)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from quad_swarm_rl_stable_baselines3_b200.config import QuadSimConfig
+    from quad_swarm_rl_stable_baselines3_b200.sim import QuadSwarmSim
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_envs = args.envs_per_gpu
+    cfg = QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, seed=0, env_id_offset=rank * n_envs)
+    sim = QuadSwarmSim(cfg, device=dev)
+    sim.want_terminal_obs = False
+    nd = n_envs * AGENTS
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    POOL = 16
+    act_pool = (torch.rand((POOL, nd, 4), device=dev, generator=gen) * 2.0 - 1.0).contiguous()
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_loop(step_fn, steps, flush):
+        """per-step CUDA events on the launching stream; returns total ms over `steps` steps"""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            if flush:
+                flush_buf.fill_(float(i))
+            ev[i][0].record(stream)
+            step_fn(i)
+            ev[i][1].record(stream)
+        torch.cuda.synchronize(dev)
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+    sim.reset()
+    flush = not args.no_flush
+
+    # ---- device-resident path: value ----------------------------------------------------------------
+    def dev_step(i):
+        sim.step(act_pool[i % POOL])
+
+    for i in range(args.warmup):
+        dev_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = sim.launch_count
+    t_wall0 = time.perf_counter()
+    total_ms = timed_loop(dev_step, args.steps, flush)
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    launches = sim.launch_count - l0
+    # keep the GPU busy a little longer if the timed region was too short for nvidia-smi to sample it
+    clocks = None
+    if rank == 0:
+        if wall_s < 1.0:
+            t_end = time.perf_counter() + 1.0
+            j = 0
+            while time.perf_counter() < t_end:
+                dev_step(j); j += 1
+            torch.cuda.synchronize(dev)
+        clocks = sampler.stop()
+
+    # ---- host-buffer path through the public API: e2e ----------------------------------------------
+    host_acts = [np.ascontiguousarray(act_pool[i].cpu().numpy()) for i in range(POOL)]
+    out = (np.empty((nd, sim.D), dtype=np.float32), np.empty(nd, dtype=np.float32), np.empty(nd, dtype=np.uint8))
+
+    def host_step(i):
+        sim.step_host(host_acts[i % POOL], out)
+
+    e2e_steps = max(10, min(args.steps, 400))
+    for i in range(3):
+        host_step(i)
+    barrier()
+    e2e_ms = timed_loop(host_step, e2e_steps, flush)
+    barrier()
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = world * nd / (ms_per_step * 1e-3)
+        e2e_value = world * nd / (e2e_ms / e2e_steps * 1e-3)
+        peak, peak_src = measured_hbm_peak()
+        bytes_per_launch = ALGO_BYTES_PER_DRONE_STEP * nd
+        achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        cpu = None
+        if not args.skip_cpu:
+            threads = os.cpu_count() or 1
+            v, sample = cpu_port_throughput(512, AGENTS, 12.0, threads)
+            cpu = {"value": v, "unit": "drone-steps/s", "cores": threads, "kind": "port", "sample": sample}
+        line = {
+            "metric": "drone-steps/sec", "value": value, "unit": "drone-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n_envs, "agents": AGENTS, "obs_dim": sim.D,
+                       "act_dim": sim.A, "l2": "flushed between timed steps (256 MiB write)" if flush else "warm (not flushed)",
+                       "timing": "per-step CUDA events on the launching stream, max over ranks",
+                       "parallelism": f"env-sharded x{world}, no collective in the step"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "drone-steps/s", "h2d_bytes_per_step": nd * 4 * 4,
+                    "d2h_bytes_per_step": nd * (sim.D * 4 + 4 + 1), "steps": e2e_steps,
+                    "api": "QuadSwarmSim.step_host -> qs_step_host (pinned staging, H2D actions, D2H obs/rew/done)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": committed_traffic_per_launch(), "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "kernel": "qs::step_kernel<8>", "peak_source": peak_src},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

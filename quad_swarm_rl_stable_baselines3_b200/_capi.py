@@ -1,0 +1,79 @@
+"""ctypes binding of libquadsim_b200.so (include/quadsim.h).  No CPU fallback: if the CUDA library is missing or
+cannot be loaded, importing the simulator fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from .config import QsConfigC, QsStateViewC, QsStatsC
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libquadsim_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# every symbol include/quadsim.h declares
+EXPORTS = ("qs_config_size", "qs_stats_size", "qs_api_version", "qs_last_error", "qs_create", "qs_destroy",
+           "qs_num_envs", "qs_num_agents", "qs_obs_dim", "qs_act_dim", "qs_launch_count", "qs_reset", "qs_step",
+           "qs_reset_host", "qs_step_host", "qs_get_state", "qs_set_state", "qs_set_param", "qs_episode_stats")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, "quadsim.cu")]
+    deps = srcs + [os.path.join(CSRC, "quadsim_kernels.cuh"), os.path.join(os.path.dirname(_PKG), "include", "quadsim.h")]
+    if not force and os.path.exists(LIB_PATH) and all(
+            (not os.path.exists(d)) or os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built (run `python -c 'import __graft_entry__ as g; "
+            f"g.build()'` at the repo root).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u8p, fp = C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_float)
+    L.qs_config_size.restype = C.c_size_t
+    L.qs_stats_size.restype = C.c_size_t
+    L.qs_api_version.restype = i32
+    L.qs_last_error.restype = C.c_char_p
+    L.qs_last_error.argtypes = [vp]
+    L.qs_create.argtypes = [C.POINTER(QsConfigC), i32, C.POINTER(vp)]
+    L.qs_destroy.argtypes = [vp]
+    for n in ("qs_num_envs", "qs_num_agents", "qs_obs_dim", "qs_act_dim"):
+        getattr(L, n).argtypes = [vp]
+    L.qs_launch_count.argtypes = [vp]
+    L.qs_launch_count.restype = C.c_int64
+    L.qs_reset.argtypes = [vp, vp, vp, vp]
+    L.qs_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.qs_reset_host.argtypes = [vp, vp, vp]
+    L.qs_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.qs_get_state.argtypes = [vp, C.POINTER(QsStateViewC), vp]
+    L.qs_set_state.argtypes = [vp, C.POINTER(QsStateViewC), vp]
+    L.qs_set_param.argtypes = [vp, i32, C.c_double]
+    L.qs_episode_stats.argtypes = [vp, C.POINTER(QsStatsC), i32, vp]
+    L.qs_philox_probe.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32), fp]
+    if L.qs_config_size() != C.sizeof(QsConfigC) or L.qs_stats_size() != C.sizeof(QsStatsC):
+        raise RuntimeError("qs_config / qs_stats layout mismatch between config.py and include/quadsim.h")
+    _lib = L
+    return L
+
+
+def check(handle, rc: int, what: str):
+    if rc != 0:
+        msg = lib().qs_last_error(handle)
+        raise RuntimeError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

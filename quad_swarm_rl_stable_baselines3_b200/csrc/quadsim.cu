@@ -1,0 +1,351 @@
+// quadsim.cu -- C-ABI (include/quadsim.h) over the sm_100a kernels in quadsim_kernels.cuh.
+// Host side: owns the device state planes, converts qs_config to the kernel constant block, picks the launch shape.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "quadsim_kernels.cuh"
+
+using namespace qs;
+
+struct qs_env {
+    qs_config cfg;
+    DevConst dc;
+    DevPtrs dp;
+    int device;
+    int KG;                 // lanes per env
+    int block;              // threads per block
+    int grid;
+    size_t smem_bytes;
+    void *slab;             // one allocation for all device state
+    size_t slab_bytes;
+    // pinned host staging + device io buffers for the *_host entry points
+    float *h_act, *h_obs, *h_rew; uint8_t *h_done;
+    float *d_act, *d_obs, *d_rew; uint8_t *d_done;
+    long long launches;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(qs_env *e, int code, const std::string &msg)
+{
+    if (e) e->err = msg; else g_create_err = msg;
+    return code;
+}
+
+#define QS_CUDA(e, call)                                                                               \
+    do {                                                                                               \
+        cudaError_t _r = (call);                                                                       \
+        if (_r != cudaSuccess) return fail(e, QS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); \
+    } while (0)
+
+static int pow2_at_least(int k) { int p = 1; while (p < k) p <<= 1; return p; }
+
+static void fill_const(const qs_config &c, DevConst &d)
+{
+    memset(&d, 0, sizeof(d));
+    d.N = c.num_envs; d.K = c.num_agents; d.scenario = c.scenario; d.obs_repr = c.obs_repr;
+    d.nbr_type = c.neighbor_obs_type; d.V = c.neighbor_visible_num; d.use_obstacles = c.use_obstacles;
+    d.use_downwash = c.use_downwash; d.apply_force = c.apply_collision_force; d.sense_noise = c.sense_noise;
+    d.ep_len = c.ep_len; d.sim_steps = c.sim_steps; d.svd_period = c.svd_period;
+    d.obst_L = c.obst_area_len; d.obst_W = c.obst_area_wid; d.M = c.num_obstacles;
+    d.S = c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR ? 19 : (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_WALL ? 24 : 18);
+    d.D = d.S + (c.neighbor_obs_type == QS_NEIGHBOR_POS_VEL ? 6 * c.neighbor_visible_num : 0) + (c.use_obstacles ? 9 : 0);
+    d.key0 = (uint32_t)c.seed; d.key1 = (uint32_t)(c.seed >> 32);
+    d.env_id_offset = c.env_id_offset;
+    d.dt = (float)c.dt;
+    d.hx = (float)(c.room_dims[0] / 2); d.hy = (float)(c.room_dims[1] / 2); d.hz = (float)c.room_dims[2];
+    d.room_l = (float)c.room_dims[0]; d.room_w = (float)c.room_dims[1]; d.room_h = (float)c.room_dims[2];
+    d.gravity = (float)c.gravity; d.mass = (float)c.mass; d.inv_mass = (float)(1.0 / c.mass);
+    for (int a = 0; a < 3; ++a) { d.inertia[a] = (float)c.inertia[a]; d.inv_inertia[a] = (float)(1.0 / c.inertia[a]); }
+    for (int m = 0; m < 4; ++m) {
+        d.thrust_max[m] = (float)c.thrust_max[m]; d.torque_max[m] = (float)c.torque_max[m];
+        d.pcx[m] = (float)c.prop_cross[m][0]; d.pcy[m] = (float)c.prop_cross[m][1]; d.pcz[m] = (float)c.prop_cross[m][2];
+        d.ccw[m] = (float)c.prop_ccw[m];
+    }
+    d.arm = (float)c.arm; d.tau_up = (float)c.motor_tau_up; d.tau_down = (float)c.motor_tau_down; d.lin = (float)c.motor_linearity;
+    d.vel_damp = (float)c.vel_damp; d.damp_wq = (float)c.damp_omega_quadratic; d.omega_max = (float)c.omega_max; d.mu = (float)c.floor_mu;
+    d.ou_theta = (float)c.ou_theta; d.ou_sigma = (float)c.ou_sigma;
+    d.s_pos = (float)c.sense_pos_std; d.s_vel = (float)c.sense_vel_std; d.s_gyro = (float)c.sense_gyro_std;
+    d.rew_pos = (float)c.rew_pos; d.rew_effort = (float)c.rew_effort; d.rew_crash = (float)c.rew_crash;
+    d.rew_orient = (float)c.rew_orient; d.rew_spin = (float)c.rew_spin; d.rew_col = (float)c.rew_quadcol_bin;
+    d.rew_col_smooth = (float)c.rew_quadcol_bin_smooth_max; d.rew_col_obst = (float)c.rew_quadcol_bin_obst;
+    d.thr_col = (float)(c.collision_hitbox_radius * c.arm); d.thr_fall = (float)(c.collision_falloff_radius * c.arm);
+    d.thr_obst = (float)(c.arm + c.obst_size / 2.0); d.obst_rad = (float)(c.obst_size / 2.0); d.sdf_res = (float)c.sdf_resolution;
+    d.spawn_box = (float)c.spawn_box; d.spawn_min_z = (float)c.spawn_min_z; d.approach_metric = (float)c.approach_goal_metric;
+    double control_freq = std::floor(1.0 / c.dt + 0.5) / c.sim_steps;      // sim_freq / sim_steps (quadrotor_single.py:160)
+    d.grace_steps = (float)(1.5 * control_freq);                           // quadrotor_multi.py:156
+    d.final_grace_steps = (float)(5.0 * control_freq);                     // quadrotor_multi.py:160
+    d.control_dt = (float)(1.0 / control_freq);                            // quadrotor_multi.py:91
+}
+
+static int validate(const qs_config *c, std::string &why)
+{
+    if (c->api_version != QS_API_VERSION) { why = "api_version mismatch"; return 0; }
+    if (c->num_envs < 1) { why = "num_envs < 1"; return 0; }
+    if (c->num_agents < 1 || c->num_agents > QS_MAX_AGENTS) { why = "num_agents out of [1, 32]"; return 0; }
+    if (c->neighbor_visible_num < 0 || c->neighbor_visible_num > c->num_agents - 1) { why = "neighbor_visible_num out of range"; return 0; }
+    if (c->neighbor_obs_type != QS_NEIGHBOR_NONE && c->neighbor_obs_type != QS_NEIGHBOR_POS_VEL) { why = "unsupported neighbor_obs_type"; return 0; }
+    if (c->obs_repr < 0 || c->obs_repr > QS_OBS_XYZ_VXYZ_R_OMEGA_WALL) { why = "unsupported obs_repr"; return 0; }
+    if (c->sim_steps < 1 || c->sim_steps > 16 || !(c->dt > 0)) { why = "bad sim_steps / dt"; return 0; }
+    if (c->svd_period < 1 || c->ep_len < 1) { why = "bad svd_period / ep_len"; return 0; }
+    if (c->use_obstacles) {
+        if (c->scenario == QS_SCENARIO_STATIC_SAME_GOAL) { why = "use_obstacles needs an obstacle scenario"; return 0; }
+        int cells = c->obst_area_len * c->obst_area_wid;
+        if (cells < 1 || cells > 64 || c->num_obstacles < 0 || c->num_obstacles > QS_MAX_OBSTACLES) { why = "obstacle grid must have <= 64 cells"; return 0; }
+        if (cells - c->num_obstacles < c->num_agents) { why = "not enough free cells for the drones"; return 0; }
+    } else if (c->scenario != QS_SCENARIO_STATIC_SAME_GOAL) { why = "obstacle scenario without use_obstacles"; return 0; }
+    if (!(c->mass > 0) || !(c->inertia[0] > 0) || !(c->inertia[1] > 0) || !(c->inertia[2] > 0)) { why = "bad mass / inertia"; return 0; }
+    return 1;
+}
+
+template <typename... Args>
+static void set_smem_attr(size_t bytes, void (*kernel)(Args...))
+{
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#define QS_DISPATCH_KG(KGv, CALL)                 \
+    switch (KGv) {                                \
+        case 1: { constexpr int KG = 1; CALL; } break;   \
+        case 2: { constexpr int KG = 2; CALL; } break;   \
+        case 4: { constexpr int KG = 4; CALL; } break;   \
+        case 8: { constexpr int KG = 8; CALL; } break;   \
+        case 16: { constexpr int KG = 16; CALL; } break; \
+        default: { constexpr int KG = 32; CALL; } break; \
+    }
+
+extern "C" {
+
+size_t qs_config_size(void) { return sizeof(qs_config); }
+size_t qs_stats_size(void) { return sizeof(qs_stats); }
+int qs_api_version(void) { return QS_API_VERSION; }
+const char *qs_last_error(const qs_env *env) { return env ? env->err.c_str() : g_create_err.c_str(); }
+
+int qs_create(const qs_config *cfg, int device, qs_env **out)
+{
+    if (!cfg || !out) return fail(nullptr, QS_ERR_NULL, "qs_create: null argument");
+    *out = nullptr;
+    std::string why;
+    if (!validate(cfg, why)) return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: " + why);
+    int ndev = 0;
+    cudaError_t r = cudaGetDeviceCount(&ndev);
+    if (r != cudaSuccess || ndev == 0) return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: no CUDA device (") + cudaGetErrorString(r) + ")");
+    if (device < 0 || device >= ndev) return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: bad device index");
+    QS_CUDA(nullptr, cudaSetDevice(device));
+
+    qs_env *e = new qs_env();
+    e->cfg = *cfg; e->device = device; e->launches = 0;
+    e->h_act = e->h_obs = e->h_rew = nullptr; e->h_done = nullptr;
+    e->d_act = e->d_obs = e->d_rew = nullptr; e->d_done = nullptr;
+    fill_const(*cfg, e->dc);
+    const int N = cfg->num_envs, K = cfg->num_agents;
+    e->KG = pow2_at_least(K);
+    const long long lanes = (long long)N * e->KG;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // small batches: 64-thread blocks so that every SM gets work; large batches: 128
+    e->block = (lanes < (long long)sms * 2 * 128) ? 64 : 128;
+    if (e->block < e->KG) e->block = e->KG;
+    e->grid = (int)((lanes + e->block - 1) / e->block);
+    const int warps = e->block / 32 > 0 ? e->block / 32 : 1;
+    const int rows_per_warp = (32 / e->KG) * K;
+    e->smem_bytes = (size_t)warps * 256 * sizeof(float) + (size_t)warps * rows_per_warp * e->dc.D * sizeof(float);
+    if (e->smem_bytes > 200 * 1024) { delete e; return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: observation tile does not fit in shared memory"); }
+
+    // one slab: planes, per-env scalars, obstacle centres, stats
+    const size_t nd = (size_t)N * K;
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0, plane_off[PL_COUNT];
+    for (int p = 0; p < PL_COUNT; ++p) { plane_off[p] = off; off += align(nd * sizeof(float4)); }
+    size_t o_tick = off; off += align((size_t)N * sizeof(int));
+    size_t o_svd = off; off += align((size_t)N * sizeof(int));
+    size_t o_step = off; off += align((size_t)N * sizeof(uint32_t));
+    size_t o_ecnt = off; off += align((size_t)N * EC_COUNT * sizeof(int));
+    size_t o_obst = off; off += align((size_t)N * QS_MAX_OBSTACLES * sizeof(float2));
+    size_t o_stats = off; off += align(sizeof(qs_stats));
+    e->slab_bytes = off;
+    r = cudaMalloc(&e->slab, off);
+    if (r != cudaSuccess) { delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: cudaMalloc: ") + cudaGetErrorString(r)); }
+    cudaMemset(e->slab, 0, off);
+    char *b = (char *)e->slab;
+    for (int p = 0; p < PL_COUNT; ++p) e->dp.plane[p] = (float4 *)(b + plane_off[p]);
+    e->dp.tick = (int *)(b + o_tick); e->dp.svd_ctr = (int *)(b + o_svd); e->dp.step_ctr = (uint32_t *)(b + o_step);
+    e->dp.ecnt = (int *)(b + o_ecnt); e->dp.obst_xy = (float2 *)(b + o_obst); e->dp.stats = (qs_stats *)(b + o_stats);
+    // identity rotations so that an un-reset env is still a valid state
+    {
+        StateView v; memset(&v, 0, sizeof(v));
+        float *rot = nullptr;
+        cudaMalloc(&rot, nd * 9 * sizeof(float));
+        float *h = (float *)malloc(nd * 9 * sizeof(float));
+        for (size_t i = 0; i < nd; ++i) for (int a = 0; a < 9; ++a) h[9 * i + a] = (a % 4 == 0) ? 1.f : 0.f;
+        cudaMemcpy(rot, h, nd * 9 * sizeof(float), cudaMemcpyHostToDevice);
+        v.rot = rot;
+        state_io_kernel<<<(int)((nd + 127) / 128), 128>>>(e->dc, e->dp, v, 1);
+        cudaDeviceSynchronize();
+        cudaFree(rot); free(h);
+    }
+    QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, step_kernel<KG>); set_smem_attr(e->smem_bytes, reset_kernel<KG>));
+    r = cudaGetLastError();
+    if (r != cudaSuccess) { cudaFree(e->slab); delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: ") + cudaGetErrorString(r)); }
+    *out = e;
+    return QS_OK;
+}
+
+int qs_destroy(qs_env *e)
+{
+    if (!e) return QS_ERR_NULL;
+    cudaSetDevice(e->device);
+    cudaFree(e->slab);
+    if (e->h_act) cudaFreeHost(e->h_act);
+    if (e->h_obs) cudaFreeHost(e->h_obs);
+    if (e->h_rew) cudaFreeHost(e->h_rew);
+    if (e->h_done) cudaFreeHost(e->h_done);
+    if (e->d_act) cudaFree(e->d_act);
+    if (e->d_obs) cudaFree(e->d_obs);
+    if (e->d_rew) cudaFree(e->d_rew);
+    if (e->d_done) cudaFree(e->d_done);
+    delete e;
+    return QS_OK;
+}
+
+int qs_num_envs(const qs_env *e) { return e ? e->cfg.num_envs : QS_ERR_NULL; }
+int qs_num_agents(const qs_env *e) { return e ? e->cfg.num_agents : QS_ERR_NULL; }
+int qs_obs_dim(const qs_env *e) { return e ? e->dc.D : QS_ERR_NULL; }
+int qs_act_dim(const qs_env *e) { return e ? 4 : QS_ERR_NULL; }
+int64_t qs_launch_count(const qs_env *e) { return e ? e->launches : 0; }
+
+int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
+{
+    if (!e || !obs) return fail(e, QS_ERR_NULL, "qs_reset: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_DISPATCH_KG(e->KG, (reset_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs)));
+    e->launches += 1;
+    QS_CUDA(e, cudaGetLastError());
+    return QS_OK;
+}
+
+int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *done, float *terminal_obs, void *stream)
+{
+    if (!e || !actions || !obs || !rew || !done) return fail(e, QS_ERR_NULL, "qs_step: null argument");
+    if (((size_t)actions & 15) != 0) return fail(e, QS_ERR_SHAPE, "qs_step: actions must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_DISPATCH_KG(e->KG, (step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs)));
+    e->launches += 1;
+    QS_CUDA(e, cudaGetLastError());
+    return QS_OK;
+}
+
+static int ensure_host_buffers(qs_env *e)
+{
+    if (e->h_act) return QS_OK;
+    const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
+    QS_CUDA(e, cudaMallocHost(&e->h_act, nd * 4 * sizeof(float)));
+    QS_CUDA(e, cudaMallocHost(&e->h_obs, nd * D * sizeof(float)));
+    QS_CUDA(e, cudaMallocHost(&e->h_rew, nd * sizeof(float)));
+    QS_CUDA(e, cudaMallocHost(&e->h_done, nd));
+    QS_CUDA(e, cudaMalloc(&e->d_act, nd * 4 * sizeof(float)));
+    QS_CUDA(e, cudaMalloc(&e->d_obs, nd * D * sizeof(float)));
+    QS_CUDA(e, cudaMalloc(&e->d_rew, nd * sizeof(float)));
+    QS_CUDA(e, cudaMalloc(&e->d_done, nd));
+    return QS_OK;
+}
+
+int qs_reset_host(qs_env *e, float *obs_host, void *stream)
+{
+    if (!e || !obs_host) return fail(e, QS_ERR_NULL, "qs_reset_host: null argument");
+    int rc = ensure_host_buffers(e);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
+    rc = qs_reset(e, nullptr, e->d_obs, stream);
+    if (rc) return rc;
+    QS_CUDA(e, cudaMemcpyAsync(e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    QS_CUDA(e, cudaStreamSynchronize(s));
+    memcpy(obs_host, e->h_obs, nd * D * sizeof(float));
+    return QS_OK;
+}
+
+int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *rew_host, uint8_t *done_host, void *stream)
+{
+    if (!e || !actions_host || !obs_host || !rew_host || !done_host) return fail(e, QS_ERR_NULL, "qs_step_host: null argument");
+    int rc = ensure_host_buffers(e);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
+    memcpy(e->h_act, actions_host, nd * 4 * sizeof(float));
+    QS_CUDA(e, cudaMemcpyAsync(e->d_act, e->h_act, nd * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = qs_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, nullptr, stream);
+    if (rc) return rc;
+    QS_CUDA(e, cudaMemcpyAsync(e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    QS_CUDA(e, cudaMemcpyAsync(e->h_rew, e->d_rew, nd * sizeof(float), cudaMemcpyDeviceToHost, s));
+    QS_CUDA(e, cudaMemcpyAsync(e->h_done, e->d_done, nd, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(e, cudaStreamSynchronize(s));
+    memcpy(obs_host, e->h_obs, nd * D * sizeof(float));
+    memcpy(rew_host, e->h_rew, nd * sizeof(float));
+    memcpy(done_host, e->h_done, nd);
+    return QS_OK;
+}
+
+static int state_io(qs_env *e, const qs_state_view *view, void *stream, int set)
+{
+    if (!e || !view) return fail(e, QS_ERR_NULL, "qs_get/set_state: null argument");
+    StateView v;
+    v.pos = view->pos; v.vel = view->vel; v.rot = view->rot; v.omega = view->omega; v.rot_damp = view->rot_damp;
+    v.cmds_damp = view->cmds_damp; v.ou = view->ou; v.goal = view->goal; v.flags = view->flags; v.col_mask = view->col_mask;
+    v.tick = view->tick; v.svd_ctr = view->svd_ctr; v.step_ctr = view->step_ctr; v.obst_xy = view->obst_xy;
+    const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+    state_io_kernel<<<(int)((nd + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->dc, e->dp, v, set);
+    e->launches += 1;
+    QS_CUDA(e, cudaGetLastError());
+    return QS_OK;
+}
+int qs_get_state(qs_env *e, const qs_state_view *view, void *stream) { return state_io(e, view, stream, 0); }
+int qs_set_state(qs_env *e, const qs_state_view *view, void *stream) { return state_io(e, view, stream, 1); }
+
+int qs_set_param(qs_env *e, int key, double value)
+{
+    if (!e) return QS_ERR_NULL;
+    switch (key) {
+        case QS_PARAM_REW_POS: e->cfg.rew_pos = value; break;
+        case QS_PARAM_REW_EFFORT: e->cfg.rew_effort = value; break;
+        case QS_PARAM_REW_CRASH: e->cfg.rew_crash = value; break;
+        case QS_PARAM_REW_ORIENT: e->cfg.rew_orient = value; break;
+        case QS_PARAM_REW_SPIN: e->cfg.rew_spin = value; break;
+        case QS_PARAM_REW_QUADCOL_BIN: e->cfg.rew_quadcol_bin = value; break;
+        case QS_PARAM_REW_QUADCOL_BIN_SMOOTH_MAX: e->cfg.rew_quadcol_bin_smooth_max = value; break;
+        case QS_PARAM_REW_QUADCOL_BIN_OBST: e->cfg.rew_quadcol_bin_obst = value; break;
+        default: return fail(e, QS_ERR_BAD_CONFIG, "qs_set_param: unknown key");
+    }
+    fill_const(e->cfg, e->dc);
+    return QS_OK;
+}
+
+int qs_episode_stats(qs_env *e, qs_stats *out, int reset, void *stream)
+{
+    if (!e || !out) return fail(e, QS_ERR_NULL, "qs_episode_stats: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    QS_CUDA(e, cudaMemcpyAsync(out, e->dp.stats, sizeof(qs_stats), cudaMemcpyDeviceToHost, s));
+    if (reset) QS_CUDA(e, cudaMemsetAsync(e->dp.stats, 0, sizeof(qs_stats), s));
+    QS_CUDA(e, cudaStreamSynchronize(s));
+    return QS_OK;
+}
+
+// test hook: raw generator output (pins the RNG contract against the oracle); not part of the reference surface
+int qs_philox_probe(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4, float *fout6)
+{
+    uint32_t *d = nullptr; float *f = nullptr;
+    if (cudaMalloc(&d, 16) != cudaSuccess || cudaMalloc(&f, 24) != cudaSuccess) return QS_ERR_CUDA;
+    philox_probe_kernel<<<1, 1>>>(c0, c1, c2, c3, k0, k1, d, f);
+    cudaError_t r = cudaMemcpy(out4, d, 16, cudaMemcpyDeviceToHost);
+    if (r == cudaSuccess) r = cudaMemcpy(fout6, f, 24, cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(f);
+    return r == cudaSuccess ? QS_OK : QS_ERR_CUDA;
+}
+
+}  // extern "C"

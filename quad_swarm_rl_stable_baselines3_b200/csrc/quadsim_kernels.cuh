@@ -1,0 +1,1151 @@
+// quadsim_kernels.cuh -- sm_100a device code of the batched quadrotor-swarm simulator.
+//
+// One thread owns one drone; the K drones of an environment occupy KG = pow2(K) adjacent lanes of a warp, so every
+// cross-drone quantity (pair distances, collision rows, neighbour ranking, downwash, impulses) moves through
+// __shfl_sync on the group's lane mask.  State is structure-of-arrays in HBM as float4 planes (one 16-byte vector
+// load/store per thread per plane, 512 B per warp, fully coalesced); observations are staged per warp in shared
+// memory and leave as 16-byte coalesced stores.  There are no tensor-core instructions: nothing here is a contraction.
+//
+// The arithmetic restates, in fp32, the reference's per-control-step path; each device function cites the reference
+// file:line it follows (paths relative to gym_art/quadrotor_multi/ in priban42/quad-swarm-rl-stable-baselines3).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/quadsim.h"
+
+namespace qs {
+
+// ----------------------------------------------------------------------------------------------------------------
+// constants and pointers handed to the kernels (by value, __grid_constant__ -> constant bank)
+// ----------------------------------------------------------------------------------------------------------------
+struct DevConst {
+    int N, K, scenario, obs_repr, nbr_type, V, use_obstacles, use_downwash, apply_force, sense_noise;
+    int ep_len, sim_steps, svd_period, obst_L, obst_W, M, D, S;   // D obs dim, S self-obs dim
+    uint32_t key0, key1;
+    long long env_id_offset;
+    float dt, hx, hy, hz, room_l, room_w, room_h, gravity, mass, inv_mass;
+    float inertia[3], inv_inertia[3], thrust_max[4], torque_max[4], pcx[4], pcy[4], pcz[4], ccw[4];
+    float arm, tau_up, tau_down, lin, vel_damp, damp_wq, omega_max, mu, ou_theta, ou_sigma;
+    float s_pos, s_vel, s_gyro;
+    float rew_pos, rew_effort, rew_crash, rew_orient, rew_spin, rew_col, rew_col_smooth, rew_col_obst;
+    float thr_col, thr_fall, thr_obst, obst_rad, sdf_res;
+    float spawn_box, spawn_min_z, approach_metric, grace_steps, final_grace_steps, control_dt;
+};
+
+enum { PL_POS_VX = 0, PL_V_W, PL_W_R0, PL_R1, PL_R2_FLAGS, PL_ROT_DAMP, PL_CMDS_DAMP, PL_OU, PL_GOAL, PL_DIST_RING,
+       PL_DIST_SUMS, PL_COUNT };
+
+// per-env counters (int32 each)
+enum { EC_COL = 0, EC_COL_SETTLE, EC_COL_FINAL, EC_ROOM, EC_FLOOR, EC_WALL, EC_CEIL, EC_OBST, EC_OBST_SETTLE,
+       EC_SCENARIO, EC_COUNT };
+
+struct DevPtrs {
+    float4 *plane[PL_COUNT];   // each [N*K]
+    int *tick;                 // [N]
+    int *svd_ctr;              // [N]
+    uint32_t *step_ctr;        // [N]
+    int *ecnt;                 // [N, EC_COUNT]
+    float2 *obst_xy;           // [N, QS_MAX_OBSTACLES]
+    qs_stats *stats;           // device aggregate
+};
+
+// flag bits kept in PL_R2_FLAGS.z
+enum { F_ON_FLOOR = 1, F_CR_FLOOR = 2, F_CR_WALL = 4, F_CR_CEIL = 8, F_PREV_WALL = 16, F_PREV_CEIL = 32,
+       F_PREV_ROOM = 64, F_PREV_OBST = 128, F_REACHED = 256, F_COL_AGENT = 512, F_COL_OBST = 1024,
+       // transient (last sub-step): the drone sits exactly on a wall plane (collisions/room.py:14-15 `pos == room_box`)
+       F_AT_XLO = 2048, F_AT_XHI = 4096, F_AT_YLO = 8192, F_AT_YHI = 16384 };
+
+// RNG sites: DESIGN.md "RNG contract" (identical table in oracle/quadsim_oracle.c)
+enum { SITE_OU = 0, SITE_SENSOR = 1, SITE_SENSOR_IMPULSE = 2, SITE_SENSOR_RESET = 3, SITE_FLOOR_YAW = 4,
+       SITE_PAIR = 5, SITE_OBST = 6, SITE_WALL = 7, SITE_CEILING = 8, SITE_DOWNWASH = 9, SITE_SPAWN = 10,
+       SITE_SCENARIO = 11 };
+
+#define QS_FULL 0xffffffffu
+#define QS_PI_F 3.14159265358979323846f
+
+// ----------------------------------------------------------------------------------------------------------------
+// Philox4x32-10, keyed (seed), counter (env gid, step counter, site|drone<<8|aux<<16, block)
+// ----------------------------------------------------------------------------------------------------------------
+struct Rng {
+    uint32_t gid, step, k0, k1;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint4 rng_block(const Rng &g, int site, int drone, int aux, int block)
+{
+    uint32_t c2 = (uint32_t)site | ((uint32_t)drone << 8) | ((uint32_t)aux << 16);
+    return philox4x32_10(g.gid, g.step, c2, (uint32_t)block, g.k0, g.k1);
+}
+
+// ((x >> 9) + 0.5) * 2^-23 : exactly representable in fp32, in (0,1)
+__device__ __forceinline__ float u23(uint32_t x) { return fmaf((float)(x >> 9), 1.1920928955078125e-07f, 5.9604644775390625e-08f); }
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1)
+{
+    float rad = sqrtf(fmaxf(-2.0f * logf(u23(a)), 0.0f));
+    float s, c;
+    sincospif(2.0f * u23(b), &s, &c);
+    n0 = rad * c; n1 = rad * s;
+}
+
+// idx-th uniform of stream (site, drone, aux)
+__device__ __forceinline__ float rng_u(const Rng &g, int site, int drone, int aux, int idx)
+{
+    uint4 r = rng_block(g, site, drone, aux, idx >> 2);
+    uint32_t x = (idx & 2) ? ((idx & 1) ? r.w : r.z) : ((idx & 1) ? r.y : r.x);
+    return u23(x);
+}
+__device__ __forceinline__ void rng_u4(const Rng &g, int site, int drone, int aux, int block, float *u)
+{
+    uint4 r = rng_block(g, site, drone, aux, block);
+    u[0] = u23(r.x); u[1] = u23(r.y); u[2] = u23(r.z); u[3] = u23(r.w);
+}
+__device__ __forceinline__ void rng_n4(const Rng &g, int site, int drone, int aux, int block, float *n)
+{
+    uint4 r = rng_block(g, site, drone, aux, block);
+    box_muller(r.x, r.y, n[0], n[1]);
+    box_muller(r.z, r.w, n[2], n[3]);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// per-drone register state
+// ----------------------------------------------------------------------------------------------------------------
+struct Drone {
+    float p[3], v[3], w[3], R[9], rd[4], cd[4], ou[4], goal[3];
+    int flags;
+    uint32_t colmask;
+};
+
+__device__ __forceinline__ void load_drone(const DevPtrs &P, int gi, Drone &q)
+{
+    float4 a = P.plane[PL_POS_VX][gi], b = P.plane[PL_V_W][gi], c = P.plane[PL_W_R0][gi], d = P.plane[PL_R1][gi],
+           e = P.plane[PL_R2_FLAGS][gi], f = P.plane[PL_ROT_DAMP][gi], g = P.plane[PL_CMDS_DAMP][gi],
+           h = P.plane[PL_OU][gi], k = P.plane[PL_GOAL][gi];
+    q.p[0] = a.x; q.p[1] = a.y; q.p[2] = a.z; q.v[0] = a.w; q.v[1] = b.x; q.v[2] = b.y;
+    q.w[0] = b.z; q.w[1] = b.w; q.w[2] = c.x;
+    q.R[0] = c.y; q.R[1] = c.z; q.R[2] = c.w; q.R[3] = d.x; q.R[4] = d.y; q.R[5] = d.z; q.R[6] = d.w; q.R[7] = e.x; q.R[8] = e.y;
+    q.flags = __float_as_int(e.z); q.colmask = __float_as_uint(e.w);
+    q.rd[0] = f.x; q.rd[1] = f.y; q.rd[2] = f.z; q.rd[3] = f.w;
+    q.cd[0] = g.x; q.cd[1] = g.y; q.cd[2] = g.z; q.cd[3] = g.w;
+    q.ou[0] = h.x; q.ou[1] = h.y; q.ou[2] = h.z; q.ou[3] = h.w;
+    q.goal[0] = k.x; q.goal[1] = k.y; q.goal[2] = k.z;
+}
+
+__device__ __forceinline__ void store_drone(const DevPtrs &P, int gi, const Drone &q, bool store_goal)
+{
+    P.plane[PL_POS_VX][gi] = make_float4(q.p[0], q.p[1], q.p[2], q.v[0]);
+    P.plane[PL_V_W][gi] = make_float4(q.v[1], q.v[2], q.w[0], q.w[1]);
+    P.plane[PL_W_R0][gi] = make_float4(q.w[2], q.R[0], q.R[1], q.R[2]);
+    P.plane[PL_R1][gi] = make_float4(q.R[3], q.R[4], q.R[5], q.R[6]);
+    P.plane[PL_R2_FLAGS][gi] = make_float4(q.R[7], q.R[8], __int_as_float(q.flags), __uint_as_float(q.colmask));
+    P.plane[PL_ROT_DAMP][gi] = make_float4(q.rd[0], q.rd[1], q.rd[2], q.rd[3]);
+    P.plane[PL_CMDS_DAMP][gi] = make_float4(q.cd[0], q.cd[1], q.cd[2], q.cd[3]);
+    P.plane[PL_OU][gi] = make_float4(q.ou[0], q.ou[1], q.ou[2], q.ou[3]);
+    if (store_goal) P.plane[PL_GOAL][gi] = make_float4(q.goal[0], q.goal[1], q.goal[2], 0.0f);
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float norm3f(float a, float b, float c) { return sqrtf(a * a + b * b + c * c); }
+
+// unit vector (c, s) with angle atan2(y, x); atan2(0,0) = 0 -> (1, 0)
+__device__ __forceinline__ void unit_dir(float x, float y, float &c, float &s)
+{
+    float h = sqrtf(x * x + y * y);
+    if (h > 0.0f) { c = x / h; s = y / h; } else { c = 1.0f; s = 0.0f; }
+}
+__device__ __forceinline__ void set_yaw(float *R, float c, float s)
+{
+    R[0] = c; R[1] = -s; R[2] = 0.f; R[3] = s; R[4] = c; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
+}
+
+// U V^T of svd(R) == orthogonal polar factor (quadrotor_dynamics.py:556-557): Newton X <- (X + X^-T)/2.
+// R is within ~1e-5 of orthonormal after 100 Rodrigues steps, so 3 iterations reach fp32 round-off.
+__device__ __forceinline__ void polar_orthonormalise(float *X)
+{
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        float c00 = X[4] * X[8] - X[5] * X[7], c01 = X[5] * X[6] - X[3] * X[8], c02 = X[3] * X[7] - X[4] * X[6];
+        float c10 = X[2] * X[7] - X[1] * X[8], c11 = X[0] * X[8] - X[2] * X[6], c12 = X[1] * X[6] - X[0] * X[7];
+        float c20 = X[1] * X[5] - X[2] * X[4], c21 = X[2] * X[3] - X[0] * X[5], c22 = X[0] * X[4] - X[1] * X[3];
+        float id = 1.0f / (X[0] * c00 + X[1] * c01 + X[2] * c02);
+        X[0] = 0.5f * (X[0] + c00 * id); X[1] = 0.5f * (X[1] + c01 * id); X[2] = 0.5f * (X[2] + c02 * id);
+        X[3] = 0.5f * (X[3] + c10 * id); X[4] = 0.5f * (X[4] + c11 * id); X[5] = 0.5f * (X[5] + c12 * id);
+        X[6] = 0.5f * (X[6] + c20 * id); X[7] = 0.5f * (X[7] + c21 * id); X[8] = 0.5f * (X[8] + c22 * id);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// a1-a4  QuadrotorDynamics.step: one physics sub-step (quadrotor_dynamics.py:355-390, 504-656)
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g, int drone, Drone &q, const float *cmd,
+                                                 int substep, bool do_svd)
+{
+    const float dt = c.dt;
+    // motor lag in sqrt-thrust space + OU noise, thrust / torque (:511-540)
+    float tq0 = 0.f, tq1 = 0.f, tq2 = 0.f, thrust = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        float cm = cmd[m];
+        float tau = fminf((cm < q.cd[m]) ? c.tau_down : c.tau_up, 1.0f);
+        q.rd[m] = tau * (sqrtf(cm) - q.rd[m]) + q.rd[m];
+        float cdm = clampf(q.rd[m] * q.rd[m] + cm * q.ou[m], 0.0f, 1.0f);
+        q.cd[m] = cdm;
+        float th = c.thrust_max[m] * ((1.0f - c.lin) * cdm * cdm + c.lin * cdm);
+        tq0 += c.pcx[m] * th; tq1 += c.pcy[m] * th; tq2 += c.pcz[m] * th + c.torque_max[m] * c.ccw[m] * cdm;
+        thrust += th;
+    }
+    // Rodrigues rotation about the world-frame angular velocity (:544-551)
+    float wx = q.R[0] * q.w[0] + q.R[1] * q.w[1] + q.R[2] * q.w[2];
+    float wy = q.R[3] * q.w[0] + q.R[4] * q.w[1] + q.R[5] * q.w[2];
+    float wz = q.R[6] * q.w[0] + q.R[7] * q.w[1] + q.R[8] * q.w[2];
+    float wn = norm3f(wx, wy, wz);
+    if (wn != 0.0f) {
+        float inv = 1.0f / wn, kx = wx * inv, ky = wy * inv, kz = wz * inv;
+        float ang = wn * dt, s, ch;
+        sincosf(0.5f * ang, &s, &ch);
+        float sn = 2.0f * s * ch, oc = 2.0f * s * s;               // sin(ang), 1 - cos(ang) without cancellation
+        // dR = I + sn*K + oc*K^2,  K^2 = k k^T - I
+        float d00 = 1.f + oc * (kx * kx - 1.f), d01 = -sn * kz + oc * kx * ky, d02 = sn * ky + oc * kx * kz;
+        float d10 = sn * kz + oc * kx * ky, d11 = 1.f + oc * (ky * ky - 1.f), d12 = -sn * kx + oc * ky * kz;
+        float d20 = -sn * ky + oc * kx * kz, d21 = sn * kx + oc * ky * kz, d22 = 1.f + oc * (kz * kz - 1.f);
+        float n[9];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            n[j] = d00 * q.R[j] + d01 * q.R[3 + j] + d02 * q.R[6 + j];
+            n[3 + j] = d10 * q.R[j] + d11 * q.R[3 + j] + d12 * q.R[6 + j];
+            n[6 + j] = d20 * q.R[j] + d21 * q.R[3 + j] + d22 * q.R[6 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) q.R[j] = n[j];
+    }
+    if (do_svd) polar_orthonormalise(q.R);                           // :554-558
+    // omega (:562-567)
+    {
+        float i0 = c.inertia[0] * q.w[0], i1 = c.inertia[1] * q.w[1], i2 = c.inertia[2] * q.w[2];
+        float cr0 = -q.w[1] * i2 + q.w[2] * i1, cr1 = -q.w[2] * i0 + q.w[0] * i2, cr2 = -q.w[0] * i1 + q.w[1] * i0;
+        float wd0 = c.inv_inertia[0] * (cr0 + tq0), wd1 = c.inv_inertia[1] * (cr1 + tq1), wd2 = c.inv_inertia[2] * (cr2 + tq2);
+        float q0 = clampf(c.damp_wq * q.w[0] * q.w[0], 0.f, 1.f), q1 = clampf(c.damp_wq * q.w[1] * q.w[1], 0.f, 1.f),
+              q2 = clampf(c.damp_wq * q.w[2] * q.w[2], 0.f, 1.f);
+        q.w[0] = clampf(q.w[0] + (1.f - q0) * dt * wd0, -c.omega_max, c.omega_max);
+        q.w[1] = clampf(q.w[1] + (1.f - q1) * dt * wd1, -c.omega_max, c.omega_max);
+        q.w[2] = clampf(q.w[2] + (1.f - q2) * dt * wd2, -c.omega_max, c.omega_max);
+    }
+    // position, room clip and wall / ceiling flags (:570, :367-374).
+    // Threshold predicates are evaluated as  dt*v  vs  (bound - p): the difference is exact in fp32 near the bound
+    // (Sterbenz), so the decision equals the exact-arithmetic one on the same inputs even when |dt*v| is below the
+    // fp32 resolution of p (a drone resting against a wall, or lifting off the floor by 1e-10 m).
+    float dx = dt * q.v[0], dy = dt * q.v[1], dz = dt * q.v[2];
+    const float gx_hi = c.hx - q.p[0], gx_lo = -c.hx - q.p[0], gy_hi = c.hy - q.p[1], gy_lo = -c.hy - q.p[1], gz_hi = c.hz - q.p[2];
+    const bool floor_hit = dz <= (c.arm - q.p[2]);
+    int fl = q.flags & ~(F_CR_FLOOR | F_CR_WALL | F_CR_CEIL | F_AT_XLO | F_AT_XHI | F_AT_YLO | F_AT_YHI);
+    if (dx > gx_hi || dx < gx_lo || dy > gy_hi || dy < gy_lo) fl |= F_CR_WALL;
+    if (dz > gz_hi) fl |= F_CR_CEIL;
+    fl |= (dx <= gx_lo ? F_AT_XLO : 0) | (dx >= gx_hi ? F_AT_XHI : 0) | (dy <= gy_lo ? F_AT_YLO : 0) | (dy >= gy_hi ? F_AT_YHI : 0);
+    q.p[0] = clampf(q.p[0] + dx, -c.hx, c.hx); q.p[1] = clampf(q.p[1] + dy, -c.hy, c.hy); q.p[2] = clampf(q.p[2] + dz, 0.0f, c.hz);
+    // floor_interaction_numba (:576-646), floor threshold = arm (:385)
+    float fx = q.R[2] * thrust, fy = q.R[5] * thrust, fz = q.R[8] * thrust;   // R @ [0,0,T], old R
+    float ax, ay, az;
+    if (floor_hit) {
+        q.p[2] = c.arm;
+        if (fl & F_ON_FLOOR) {
+            float cy, sy;
+            unit_dir(q.R[0] + 1e-6f, q.R[3], cy, sy);
+            set_yaw(q.R, cy, sy);
+            float fr = c.mu * (c.mass * 9.81f - fz);
+            if (norm3f(q.v[0], q.v[1], q.v[2]) < 1e-6f) {
+                float fm = sqrtf(fx * fx + fy * fy);
+                float fn = fmaxf(fm - fr, 0.0f);
+                if (fn == 0.0f) { fx = 0.f; fy = 0.f; }
+                else { float cf, sf; unit_dir(fx, fy, cf, sf); fx = fn * cf; fy = fn * sf; }
+            } else {
+                float cf, sf;
+                unit_dir(q.v[0], q.v[1], cf, sf);                    // :608 numba path: friction opposes velocity
+                fx -= cf * fr; fy -= sf * fr;
+            }
+        } else {
+            fl |= F_ON_FLOOR | F_CR_FLOOR;
+            q.v[0] = q.v[1] = q.v[2] = 0.f; q.w[0] = q.w[1] = q.w[2] = 0.f;
+            float cy, sy;
+            if (q.R[8] < 0.f) {                                      // :623-626 upside down -> random yaw
+                float th = -1.0f + 2.0f * rng_u(g, SITE_FLOOR_YAW, drone, substep, 0);
+                sincospif(th, &sy, &cy);
+            } else {
+                unit_dir(q.R[0] + 1e-6f, q.R[3], cy, sy);
+            }
+            set_yaw(q.R, cy, sy);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { q.cd[m] = 0.f; q.rd[m] = 0.f; }
+        }
+        ax = fx * c.inv_mass; ay = fy * c.inv_mass; az = fmaxf(0.0f, -9.81f + fz * c.inv_mass);
+    } else {
+        fl &= ~F_ON_FLOOR;
+        ax = fx * c.inv_mass; ay = fy * c.inv_mass; az = -9.81f + fz * c.inv_mass;
+    }
+    q.flags = fl;
+    // compute_velocity_and_acceleration (:649-656); the accelerometer output never reaches an observation
+    float kd = 1.0f - c.vel_damp;
+    q.v[0] = kd * q.v[0] + dt * ax; q.v[1] = kd * q.v[1] + dt * ay; q.v[2] = kd * q.v[2] + dt * az;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// a9  self observation: SensorNoise.add_noise_numba + state_xyz_vxyz_R_omega* (sensor_noise.py:172-261, get_state.py:226-292)
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void self_obs(const DevConst &c, const Rng &g, int site, int drone, const Drone &q, float *o)
+{
+    float p0 = q.p[0], p1 = q.p[1], p2 = q.p[2], v0 = q.v[0], v1 = q.v[1], v2 = q.v[2], w0 = q.w[0], w1 = q.w[1], w2 = q.w[2];
+    if (c.sense_noise) {
+        float n[4], m[4], l0, l1;
+        rng_n4(g, site, drone, 0, 0, n);
+        rng_n4(g, site, drone, 0, 1, m);
+        uint4 r = rng_block(g, site, drone, 0, 2);
+        box_muller(r.x, r.y, l0, l1);
+        p0 += c.s_pos * n[0]; p1 += c.s_pos * n[1]; p2 += c.s_pos * n[2];
+        v0 += c.s_vel * n[3]; v1 += c.s_vel * m[0]; v2 += c.s_vel * m[1];
+        w0 += c.s_gyro * m[2]; w1 += c.s_gyro * m[3]; w2 += c.s_gyro * l0;
+        // R -> quaternion -> R round trip (sensor_noise.py:34-63, 205-210; quad_utils.py:162-168), zero rotation noise
+        const float *R = q.R;
+        float tr = R[0] + R[4] + R[8], qw, qx, qy, qz, S;
+        if (tr > 0.f) { S = sqrtf(tr + 1.0f) * 2.f; qw = 0.25f * S; qx = (R[7] - R[5]) / S; qy = (R[2] - R[6]) / S; qz = (R[3] - R[1]) / S; }
+        else if (R[0] > R[4] && R[0] > R[8]) { S = sqrtf(1.0f + R[0] - R[4] - R[8]) * 2.f; qw = (R[7] - R[5]) / S; qx = 0.25f * S; qy = (R[1] + R[3]) / S; qz = (R[2] + R[6]) / S; }
+        else if (R[4] > R[8]) { S = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2.f; qw = (R[2] - R[6]) / S; qx = (R[1] + R[3]) / S; qy = 0.25f * S; qz = (R[5] + R[7]) / S; }
+        else { S = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2.f; qw = (R[3] - R[1]) / S; qx = (R[2] + R[6]) / S; qy = (R[5] + R[7]) / S; qz = 0.25f * S; }
+        o[6] = 1.0f - 2.f * qy * qy - 2.f * qz * qz; o[7] = 2.f * qx * qy - 2.f * qz * qw; o[8] = 2.f * qx * qz + 2.f * qy * qw;
+        o[9] = 2.f * qx * qy + 2.f * qz * qw; o[10] = 1.0f - 2.f * qx * qx - 2.f * qz * qz; o[11] = 2.f * qy * qz - 2.f * qx * qw;
+        o[12] = 2.f * qx * qz - 2.f * qy * qw; o[13] = 2.f * qy * qz + 2.f * qx * qw; o[14] = 1.0f - 2.f * qx * qx - 2.f * qy * qy;
+    } else {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) o[6 + a] = q.R[a];
+    }
+    o[0] = p0 - q.goal[0]; o[1] = p1 - q.goal[1]; o[2] = p2 - q.goal[2];
+    o[3] = v0; o[4] = v1; o[5] = v2; o[15] = w0; o[16] = w1; o[17] = w2;
+    if (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR) o[18] = p2;
+    if (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_WALL) {
+        o[18] = clampf(p0 + c.hx, 0.f, 5.f); o[19] = clampf(p1 + c.hy, 0.f, 5.f); o[20] = clampf(p2, 0.f, 5.f);
+        o[21] = clampf(c.hx - p0, 0.f, 5.f); o[22] = clampf(c.hy - p1, 0.f, 5.f); o[23] = clampf(c.hz - p2, 0.f, 5.f);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// impulses (all lanes of a group compute the same event redundantly; the lanes involved keep the result)
+// ----------------------------------------------------------------------------------------------------------------
+// compute_new_vel, collisions/utils.py:8-19
+__device__ __forceinline__ void compute_new_vel(float max_mag, float *v, const float *shift, float decay)
+{
+    float n0 = v[0] + shift[0], n1 = v[1] + shift[1], n2 = v[2] + shift[2];
+    float mag = norm3f(n0, n1, n2), den = (mag == 0.0f) ? mag + 1e-5f : mag;
+    float d0 = n0 / den, d1 = n1 / den, d2 = n2 / den;
+    mag = fminf(mag * decay, max_mag);
+    v[0] += d0 * mag - v[0]; v[1] += d1 * mag - v[1]; v[2] += d2 * mag - v[2];
+}
+// compute_new_omega, collisions/utils.py:22-33
+__device__ __forceinline__ void compute_new_omega(const float *u4, float magn_scale, float *out)
+{
+    float omax = magn_scale * QS_PI_F;
+    float a = -1.f + 2.f * u4[0], b = -1.f + 2.f * u4[1], cc = -1.f + 2.f * u4[2];
+    float mag = norm3f(a, b, cc), den = (mag == 0.0f) ? mag + 1e-5f : mag;
+    float m2 = 0.5f * omax + 0.5f * omax * u4[3];
+    out[0] = a / den * m2; out[1] = b / den * m2; out[2] = cc / den * m2;
+}
+
+// perform_collision_between_drones, collisions/quadrotors.py:9-59.  Inputs are drone i ("1") and drone j ("2").
+__device__ __noinline__ void pair_impulse(const Rng &g, int i, int j, const float *p1, const float *p2, float *v1, float *v2,
+                                          float *w1, float *w2)
+{
+    float n0 = p1[0] - p2[0], n1 = p1[1] - p2[1], n2 = p1[2] - p2[2];
+    float nm = norm3f(n0, n1, n2), den = (nm == 0.0f) ? nm + 1e-5f : nm;
+    n0 /= den; n1 /= den; n2 /= den;
+    float a1 = v1[0] * n0 + v1[1] * n1 + v1[2] * n2, a2 = v2[0] * n0 + v2[1] * n1 + v2[2] * n2;
+    float vc[3] = { (a2 - a1) * n0, (a2 - a1) * n1, (a2 - a1) * n2 };
+    float s1[3] = { vc[0], vc[1], vc[2] }, s2[3] = { -vc[0], -vc[1], -vc[2] };
+    for (int att = 0; att < 3; ++att) {
+        float x[4], y[4], z[4];
+        rng_n4(g, SITE_PAIR, i, j, att * 3 + 0, x);
+        rng_n4(g, SITE_PAIR, i, j, att * 3 + 1, y);
+        rng_n4(g, SITE_PAIR, i, j, att * 3 + 2, z);
+        float cons[3] = { 0.8f * x[0], 0.8f * x[1], 0.8f * x[2] };
+        float e1[3] = { cons[0] + 0.15f * x[3], cons[1] + 0.15f * y[0], cons[2] + 0.15f * y[1] };
+        float e2[3] = { -cons[0] + 0.15f * y[2], -cons[1] + 0.15f * y[3], -cons[2] + 0.15f * z[0] };
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s1[a] = vc[a] + e1[a]; s2[a] = -vc[a] + e2[a]; }
+        float t1 = (v1[0] + s1[0]) * n0 + (v1[1] + s1[1]) * n1 + (v1[2] + s1[2]) * n2;
+        float t2 = (v2[0] + s2[0]) * n0 + (v2[1] + s2[1]) * n1 + (v2[2] + s2[2]) * n2;
+        if (t1 > 0.f && 0.f > t2) break;
+    }
+    float maxv = fmaxf(norm3f(v1[0], v1[1], v1[2]), norm3f(v2[0], v2[1], v2[2]));
+    float u[4], t[4];
+    rng_u4(g, SITE_PAIR, i, j, 9, u);                                 // idx 36..39
+    rng_u4(g, SITE_PAIR, i, j, 10, t);                                // idx 40..43
+    compute_new_vel(maxv, v1, s1, 0.2f + 0.6f * u[0]);
+    compute_new_vel(maxv, v2, s2, 0.2f + 0.6f * u[1]);
+    float u4[4] = { u[2], u[3], t[0], t[1] }, w[3];
+    compute_new_omega(u4, 20.0f, w);
+    w1[0] += w[0]; w1[1] += w[1]; w1[2] += w[2];
+    w2[0] -= w[0]; w2[1] -= w[1]; w2[2] -= w[2];
+}
+
+// perform_collision_with_obstacle, collisions/obstacles.py:9-50
+__device__ __noinline__ void obstacle_impulse(const DevConst &c, const Rng &g, int drone, Drone &q, float ox, float oy)
+{
+    float n0 = q.p[0] - ox, n1 = q.p[1] - oy;
+    float nm = sqrtf(n0 * n0 + n1 * n1), den = (nm == 0.0f) ? nm + 1e-5f : nm;
+    n0 /= den; n1 /= den;
+    float vm = norm3f(q.v[0], q.v[1], q.v[2]);
+    float nv[3] = { vm * n0, vm * n1, 0.f }, noise[3] = { 0.f, 0.f, 0.f };
+    for (int att = 0; att < 3; ++att) {
+        float x[4], y[4];
+        rng_n4(g, SITE_OBST, drone, 0, att * 2, x);
+        rng_n4(g, SITE_OBST, drone, 0, att * 2 + 1, y);
+        float t[3] = { 0.1f * x[0] + 0.05f * x[3], 0.1f * x[1] + 0.05f * y[0], 0.1f * x[2] + 0.05f * y[1] };
+        if ((nv[0] + t[0]) * n0 + (nv[1] + t[1]) * n1 > 0.f) { noise[0] = t[0]; noise[1] = t[1]; noise[2] = t[2]; break; }
+    }
+    float dz = q.p[2] - 0.5f * c.room_h;
+    float d3 = norm3f(q.p[0] - ox, q.p[1] - oy, dz);
+    float shift[3] = { nv[0] - q.v[0] + noise[0], nv[1] - q.v[1] + noise[1], nv[2] - q.v[2] + noise[2] };
+    float u[4], t[4];
+    rng_u4(g, SITE_OBST, drone, 0, 6, u);                             // idx 24..27
+    rng_u4(g, SITE_OBST, drone, 0, 7, t);                             // idx 28..31
+    float decay = (d3 < c.obst_rad) ? 1.0f : 0.2f + 0.6f * u[0];
+    compute_new_vel(vm, q.v, shift, decay);
+    float u4[4] = { u[1], u[2], u[3], t[0] }, w[3];
+    compute_new_omega(u4, 1.0f, w);
+    q.w[0] += w[0]; q.w[1] += w[1]; q.w[2] += w[2];
+}
+
+// perform_collision_with_wall / _ceiling, collisions/room.py:6-45, 91-113
+__device__ __noinline__ void room_impulse(const DevConst &c, const Rng &g, int drone, Drone &q, bool is_wall)
+{
+    int site = is_wall ? SITE_WALL : SITE_CEILING;
+    float u[12];
+    rng_u4(g, site, drone, 0, 0, u); rng_u4(g, site, drone, 0, 1, u + 4); rng_u4(g, site, drone, 0, 2, u + 8);
+    float sp = norm3f(q.v[0], q.v[1], q.v[2]);
+    float lo = 0.2f * sp, hi = 0.8f * sp;
+    float real = clampf(lo + (hi - lo) * u[0], 0.1f, 6.0f);
+    float d0 = -1.f + 2.f * u[1], d1 = -1.f + 2.f * u[2], d2;
+    int k;
+    if (is_wall) {
+        if (q.flags & F_AT_XLO) d0 = 0.1f + 0.9f * u[4]; else if (q.flags & F_AT_XHI) d0 = -1.0f + 0.9f * u[4];
+        if (q.flags & F_AT_YLO) d1 = 0.1f + 0.9f * u[5]; else if (q.flags & F_AT_YHI) d1 = -1.0f + 0.9f * u[5];
+        k = 6;
+    } else k = 4;
+    d2 = -1.0f + 0.5f * u[k];
+    float dm = norm3f(d0, d1, d2) + 1e-5f;
+    q.v[0] = real * (d0 / dm); q.v[1] = real * (d1 / dm); q.v[2] = real * (d2 / dm);
+    float w0 = -1.f + 2.f * u[k + 1], w1 = -1.f + 2.f * u[k + 2], w2 = -1.f + 2.f * u[k + 3];
+    float wm = norm3f(w0, w1, w2) + 1e-5f;
+    float omax = 20.f * QS_PI_F, mag = 0.5f * omax + 0.5f * omax * u[k + 4];
+    q.w[0] += w0 / wm * mag; q.w[1] += w1 / wm * mag; q.w[2] += w2 / wm * mag;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// reset
+// ----------------------------------------------------------------------------------------------------------------
+// get_cell_centers, obstacles/utils.py:47-58
+__device__ __forceinline__ void cell_center(const DevConst &c, int index, float &x, float &y)
+{
+    int i = index / c.obst_W, jj = index - i * c.obst_W, j = c.obst_W - 1 - jj;
+    x = (float)i + 0.5f - (float)(c.obst_L / 2);
+    y = (float)j + 0.5f - (float)(c.obst_W / 2);
+}
+
+// k distinct ids of n via partial Fisher-Yates (oracle rnd_choice).  Returns through `a` (first k entries).
+__device__ __forceinline__ void choice_fy(const Rng &g, int aux, int n, int k, unsigned char *a)
+{
+    for (int i = 0; i < n; ++i) a[i] = (unsigned char)i;
+    for (int t = 0; t < k; ++t) {
+        float u = rng_u(g, SITE_SCENARIO, 0xFF, aux, t);
+        int r = t + (int)floorf(u * (float)(n - t));
+        r = min(r, n - 1);
+        unsigned char tmp = a[t]; a[t] = a[r]; a[r] = tmp;
+    }
+}
+
+// obst_generation_given_density (quadrotor_multi.py:405-426) + Scenario_o_random / o_static_same_goal .reset
+// (scenarios/obstacles/o_random.py:26-52, o_static_same_goal.py:27-48, o_base.py:69-81,124-153).
+// Every lane of the group evaluates it redundantly (same keys -> same values); lane `drone` keeps its own spawn/goal.
+__device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rng &g, int drone, bool leader, float2 *obst_xy,
+                                                     float *spawn, float *goal, int &scenario_now)
+{
+    const int L = c.obst_L, W = c.obst_W, M = c.M, K = c.K;
+    unsigned char a[64];
+    choice_fy(g, 0, L * W, M, a);
+    unsigned long long map = 0ull;                                      // bit rid*W + cid
+    for (int m = 0; m < M; ++m) {
+        int rid = a[m] / W, cid = a[m] - rid * W;
+        map |= 1ull << (rid * W + cid);
+        if (leader) { float x, y; cell_center(c, rid + L * cid, x, y); obst_xy[m] = make_float2(x, y); }
+    }
+    int scen = c.scenario;
+    if (scen == QS_SCENARIO_O_MIX) {
+        int mode_index = (int)floorf(rng_u(g, SITE_SCENARIO, 0xFF, 1, 0) * 100.0f);
+        scen = (mode_index % 2 == 0) ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
+    }
+    scenario_now = scen;
+    unsigned char freec[64];
+    int nf = 0;
+    for (int cell = 0; cell < L * W; ++cell) if (!((map >> cell) & 1ull)) freec[nf++] = (unsigned char)cell;   // row-major (rid, cid)
+    {
+        choice_fy(g, 2, nf, K, a);
+        int cell = freec[a[drone < K ? drone : 0]], rid = cell / W, cid = cell - rid * W;
+        cell_center(c, rid + L * cid, spawn[0], spawn[1]);
+        spawn[2] = 1.0f + 2.0f * rng_u(g, SITE_SCENARIO, 0xFF, 3, drone);
+    }
+    if (scen == QS_SCENARIO_O_STATIC_SAME_GOAL) {
+        // largest empty square; dp row/col 0 copy the obstacle map itself (o_base.py:134-136)
+        int dp[64], max_size = 0, cx = 0, cy = 0;
+        for (int j = 0; j < W; ++j) dp[j] = (int)((map >> j) & 1ull);
+        for (int r = 1; r < L; ++r) {
+            dp[r * W] = (int)((map >> (r * W)) & 1ull);
+            for (int j = 1; j < W; ++j) {
+                int v = 0;
+                if (!((map >> (r * W + j)) & 1ull)) {
+                    v = min(min(dp[(r - 1) * W + j], dp[r * W + j - 1]), dp[(r - 1) * W + j - 1]) + 1;
+                    if (v > max_size) { max_size = v; cx = r - (max_size - 1) / 2; cy = j - (max_size - 1) / 2; }
+                }
+                dp[r * W + j] = v;
+            }
+        }
+        cell_center(c, cx + W * cy, goal[0], goal[1]);
+        goal[2] = 1.5f + 1.5f * rng_u(g, SITE_SCENARIO, 0xFF, 4, 0);
+    } else {
+        choice_fy(g, 5, nf, K, a);
+        int cell = freec[a[drone < K ? drone : 0]], rid = cell / W, cid = cell - rid * W;
+        cell_center(c, rid + L * cid, goal[0], goal[1]);
+        goal[2] = 1.0f + 2.0f * rng_u(g, SITE_SCENARIO, 0xFF, 6, drone);
+    }
+}
+
+// QuadrotorSingle._reset, quadrotor_single.py:401-469
+__device__ __noinline__ void drone_reset(const DevConst &c, const Rng &g, int drone, const float *spawn, Drone &q)
+{
+    float u[4];
+    rng_u4(g, SITE_SPAWN, drone, 0, 0, u);
+    q.p[0] = (-c.spawn_box + 2.0f * c.spawn_box * u[0]) + spawn[0];
+    q.p[1] = (-c.spawn_box + 2.0f * c.spawn_box * u[1]) + spawn[1];
+    q.p[2] = fmaxf((-c.spawn_box + 2.0f * c.spawn_box * u[2]) + spawn[2], c.spawn_min_z);
+    float hx = -q.p[0], hy = -q.p[1], hn = sqrtf(hx * hx + hy * hy);
+    if (!(hn < 0.00001f)) { hx /= hn; hy /= hn; }
+    float cy, sy;
+    unit_dir(hx, hy, cy, sy);                                           // fallback: face the origin
+    bool found = false;
+    for (int blk = 0; blk < 16 && !found; ++blk) {                      // randyaw() rejection loop (:454-456)
+        rng_u4(g, SITE_SPAWN, drone, 1, blk, u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (!found) {
+                float s, cc;
+                sincospif(-1.0f + 2.0f * u[t], &s, &cc);
+                if (!(cc * hx + s * hy < 0.5f)) { cy = cc; sy = s; found = true; }
+            }
+        }
+    }
+    set_yaw(q.R, cy, sy);
+    q.v[0] = q.v[1] = q.v[2] = 0.f; q.w[0] = q.w[1] = q.w[2] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { q.rd[m] = 0.f; q.cd[m] = 0.f; }
+    q.flags = 0; q.colmask = 0u;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// group helpers
+// ----------------------------------------------------------------------------------------------------------------
+template <int KG>
+__device__ __forceinline__ uint32_t group_mask(int lane) { return (KG == 32) ? QS_FULL : (((1u << KG) - 1u) << (lane & ~(KG - 1))); }
+
+// neighbour + obstacle part of the observation, written into the warp's shared-memory tile row `o`.
+// vs: the velocity snapshot the reference's `self.vel` holds (stale at reset, quadrotor_multi.py:477).
+// `stage` is this warp's 32 x 2 float4 exchange buffer: every lane publishes (pos, vs), the group syncs, and each lane
+// reads its K-1 neighbours as broadcast 16-byte shared-memory loads.
+template <int KG>
+__device__ __forceinline__ void group_obs_tail(const DevConst &c, const DevPtrs &P, int env, int d, int lane, uint32_t gmask, bool valid,
+                                               const Drone &q, const float *vs, float *o, float4 *stage)
+{
+    const int base = lane & ~(KG - 1);
+    if (c.nbr_type == QS_NEIGHBOR_POS_VEL && KG > 1) {
+        // a15: neighborhood_indices + get_rel_pos_vel_item + clip (quadrotor_multi.py:275-380)
+        __syncwarp(gmask);
+        stage[2 * lane] = make_float4(q.p[0], q.p[1], q.p[2], 0.f);
+        stage[2 * lane + 1] = make_float4(vs[0], vs[1], vs[2], 0.f);
+        __syncwarp(gmask);
+        const float INF = __int_as_float(0x7f800000);
+        if (c.V < c.K - 1) {
+            // rank by ||[dp, dv]|| (6-vector, :357-359), max(.,0.01); V rounds of first-minimum selection == stable argsort[:V]
+            float met[KG];
+#pragma unroll
+            for (int j = 0; j < KG; ++j) {
+                float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                float r0 = a.x - q.p[0], r1 = a.y - q.p[1], r2 = a.z - q.p[2], r3 = b.x - vs[0], r4 = b.y - vs[1], r5 = b.z - vs[2];
+                float ss = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5;
+                met[j] = (j < c.K && j != d) ? fmaxf(sqrtf(ss), 0.01f) : INF;
+            }
+            for (int sidx = 0; sidx < c.V; ++sidx) {
+                float best = INF; int jb = 0;
+#pragma unroll
+                for (int j = 0; j < KG; ++j) if (met[j] < best) { best = met[j]; jb = j; }
+#pragma unroll
+                for (int j = 0; j < KG; ++j) met[j] = (j == jb) ? INF : met[j];
+                if (valid) {
+                    float4 a = stage[2 * (base + jb)], b = stage[2 * (base + jb) + 1];
+                    float *r = o + c.S + 6 * sidx;
+                    r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                    r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                }
+            }
+        } else if (valid) {
+            for (int j = 0; j < c.K; ++j) {                                // all others, index order (:350-351)
+                if (j == d) continue;
+                int sidx = j - (j > d ? 1 : 0);
+                float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                float *r = o + c.S + 6 * sidx;
+                r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+            }
+        }
+    }
+    if (c.use_obstacles && valid) {
+        // a14: get_surround_sdfs, obstacles/utils.py:5-27 (min over obstacles commutes with sqrt)
+        const float2 *ob = P.obst_xy + (size_t)env * QS_MAX_OBSTACLES;
+        float gx[3] = { q.p[0] - c.sdf_res, q.p[0], q.p[0] + c.sdf_res }, gy[3] = { q.p[1] - c.sdf_res, q.p[1], q.p[1] + c.sdf_res };
+        float md[9];
+#pragma unroll
+        for (int a = 0; a < 9; ++a) md[a] = 10000.0f;                   // (100)^2
+        for (int m = 0; m < c.M; ++m) {
+            float2 xy = ob[m];
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    float dx = gx[a] - xy.x, dy = gy[b] - xy.y;
+                    md[a * 3 + b] = fminf(md[a * 3 + b], dx * dx + dy * dy);
+                }
+        }
+        float *r = o + c.S + ((c.nbr_type == QS_NEIGHBOR_POS_VEL) ? 6 * c.V : 0);
+#pragma unroll
+        for (int a = 0; a < 9; ++a) r[a] = sqrtf(md[a]) - c.obst_rad;
+    }
+}
+
+// Reset of one environment (QuadrotorEnvMulti.reset, quadrotor_multi.py:440-519), executed by the env's lane group.
+template <int KG>
+__device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P, const Rng &g, int env, int d, bool valid, Drone &q,
+                                            int &scenario_now)
+{
+    float spawn[3];
+    if (c.use_obstacles) {
+        obstacle_scenario_reset(c, g, d, valid && d == 0, P.obst_xy + (size_t)env * QS_MAX_OBSTACLES, spawn, q.goal, scenario_now);
+    } else {
+        q.goal[0] = 0.f; q.goal[1] = 0.f; q.goal[2] = 2.0f;               // static_same_goal: formation size 0 (scenarios/utils.py:30)
+        spawn[0] = 0.f; spawn[1] = 0.f; spawn[2] = 2.0f;
+        scenario_now = QS_SCENARIO_STATIC_SAME_GOAL;
+    }
+    drone_reset(c, g, d, spawn, q);
+}
+
+// coalesced copy of the warp's observation tile (rows contiguous in global memory) out of shared memory
+__device__ __forceinline__ void warp_store_tile(const float *tile, float *dst, int count, int lane)
+{
+    if (((((size_t)dst) & 15) == 0) && ((count & 3) == 0)) {
+        const float4 *s = reinterpret_cast<const float4 *>(tile);
+        float4 *o = reinterpret_cast<float4 *>(dst);
+        for (int i = lane; i < (count >> 2); i += 32) __stcs(o + i, s[i]);
+    } else {
+        for (int i = lane; i < count; i += 32) __stcs(dst + i, tile[i]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// The step kernel: QuadrotorEnvMulti.step (quadrotor_multi.py:521-842) for every env, one launch.
+// ----------------------------------------------------------------------------------------------------------------
+template <int KG>
+__global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
+                                                   const float4 *__restrict__ actions, float *__restrict__ obs,
+                                                   float *__restrict__ rew, uint8_t *__restrict__ done, float *__restrict__ term_obs)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env = tid / KG, d = tid % KG;
+    const bool valid = env < c.N && d < c.K;
+    const int gi = env * c.K + d;
+    const uint32_t gmask = group_mask<KG>(lane);
+    const int base = lane & ~(KG - 1);
+    constexpr int GPW = 32 / KG;                                        // env groups per warp
+    const int rows_per_warp = GPW * c.K;
+    float4 *stage = reinterpret_cast<float4 *>(smem) + (size_t)warp_in_block * 64;          // 32 lanes x 2 float4
+    float *tile = smem + (size_t)(blockDim.x >> 5) * 256 + (size_t)warp_in_block * rows_per_warp * c.D;   // this warp's obs rows
+    const int row = (lane / KG) * c.K + d;
+    float *orow = tile + (size_t)row * c.D;
+    const int warp_env0 = (tid - lane) / KG;                            // first env of this warp
+    const int warp_rows = max(0, min(GPW, c.N - warp_env0)) * c.K;      // valid rows of this warp
+
+    Drone q;
+    float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
+    int tick = 0, svd = 0;
+    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
+    int scen_now = 0;
+    if (env < c.N) {                                                    // env-level scalars: every lane of the group
+        tick = P.tick[env]; svd = P.svd_ctr[env];
+        if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
+        g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
+    }
+    if (valid) {
+        load_drone(P, gi, q);
+        act = __ldcs(actions + gi);
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { q.p[a] = 1.0e6f * (float)(lane + 1); q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
+#pragma unroll
+        for (int a = 0; a < 9; ++a) q.R[a] = (a % 4 == 0) ? 1.f : 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { q.rd[a] = q.cd[a] = q.ou[a] = 0.f; }
+        q.flags = 0; q.colmask = 0;
+    }
+
+    // ---- per-drone: RawControl.step -> QuadrotorDynamics.step (quadrotor_control.py:53-57, quadrotor_dynamics.py:215-221)
+    const int time_remain = c.ep_len - tick;                           // quadrotor_single.py:361
+    float a4[4] = { act.x, act.y, act.z, act.w }, cmd[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) cmd[m] = 0.5f * (clampf(a4[m], -1.0f, 1.0f) + 1.0f);
+    if (valid) {
+        float n[4];
+        rng_n4(g, SITE_OU, d, 0, 0, n);                                // OUNoiseNumba.noise, numba_utils.py:101-105
+#pragma unroll
+        for (int m = 0; m < 4; ++m) q.ou[m] = q.ou[m] + (c.ou_theta * (0.0f - q.ou[m]) + c.ou_sigma * n[m]);
+        for (int s = 0; s < c.sim_steps; ++s) {
+            svd += 1;
+            bool fire = svd >= c.svd_period;
+            if (fire) svd = 0;
+            dynamics_substep(c, g, d, q, cmd, s, fire);
+        }
+    }
+    // ---- compute_reward_weighted (quadrotor_single.py:34-92), dt = physics dt
+    const bool on_floor = (q.flags & F_ON_FLOOR) != 0;
+    const float dist = norm3f(q.goal[0] - q.p[0], q.goal[1] - q.p[1], q.goal[2] - q.p[2]);
+    float reward;
+    {
+        float effort = sqrtf(a4[0] * a4[0] + a4[1] * a4[1] + a4[2] * a4[2] + a4[3] * a4[3]);
+        float orient = on_floor ? 1.0f : -q.R[8];
+        float spin = norm3f(q.w[0], q.w[1], q.w[2]);
+        float crash = on_floor ? 1.0f : 0.0f;
+        reward = -c.dt * (c.rew_pos * dist + c.rew_effort * effort + c.rew_crash * crash + c.rew_orient * orient + c.rew_spin * spin);
+    }
+    tick += 1;
+    // a non-finite state cannot be stepped further: force-reset the env and count it (reference raises, quadrotor_single.py:87-90)
+    float chk = q.p[0] + q.p[1] + q.p[2] + q.v[0] + q.v[1] + q.v[2] + q.w[0] + q.w[1] + q.w[2] + q.R[0] + q.R[4] + q.R[8] + reward;
+    const bool bad = valid && !isfinite(chk);
+    const uint32_t bad_ballot = __ballot_sync(QS_FULL, bad) & gmask;
+    const bool all_done = (tick > c.ep_len) || (bad_ballot != 0u);     // quadrotor_single.py:366-367
+
+    // ---- 1.1 drone-drone collisions (collisions/quadrotors.py:63-103, quadrotor_multi.py:537-568)
+    uint32_t rowmask = 0u;
+    float prox = 0.f;
+    if (KG > 1) {
+        const float pen_ratio = -c.rew_col_smooth / c.thr_fall;
+        stage[2 * lane] = make_float4(q.p[0], q.p[1], q.p[2], 0.f);
+        __syncwarp(gmask);
+#pragma unroll
+        for (int j = 0; j < KG; ++j) {
+            float4 o4 = stage[2 * (base + j)];
+            float dx = q.p[0] - o4.x, dy = q.p[1] - o4.y, dz = q.p[2] - o4.z;
+            float dd = sqrtf(dx * dx + dy * dy + dz * dz);
+            bool other = (j != d) && (j < c.K) && valid;
+            if (other && dd <= c.thr_col) rowmask |= 1u << j;
+            if (other && dd <= c.thr_fall) prox += pen_ratio * dd + c.rew_col_smooth;
+        }
+    }
+    const uint32_t new_pairs = rowmask & ~q.colmask;                   // :545-546
+    const bool is_unique = (rowmask != 0u) && (q.colmask == 0u);       // setdiff1d over flattened ids, :548
+    const uint32_t uniq_ballot = __ballot_sync(QS_FULL, is_unique) & gmask;
+    const int n_unique = __popc(uniq_ballot);
+    const bool unique_any_nonzero = (uniq_ballot & ~(1u << base)) != 0u;   // `.any()` drops a lone agent 0, :611
+    const int col_tick = n_unique >> 1;                                // :557
+    const bool settled = (float)tick >= c.grace_steps;
+    if (col_tick > 0 && settled && is_unique) q.flags |= F_COL_AGENT;  // agent_col_agent, :560-563
+
+    // ---- 1.2 obstacles (obstacles/utils.py:31-43, quadrotor_multi.py:571-597)
+    int obst_hit = -1;
+    bool obst_new = false;
+    if (c.use_obstacles) {
+        if (valid) {
+            const float2 *ob = P.obst_xy + (size_t)env * QS_MAX_OBSTACLES;
+            for (int m = 0; m < c.M; ++m) {
+                float2 xy = ob[m];
+                float dx = q.p[0] - xy.x, dy = q.p[1] - xy.y;
+                if (sqrtf(dx * dx + dy * dy) <= c.thr_obst) { obst_hit = m; break; }
+            }
+        }
+        obst_new = (obst_hit >= 0) && !(q.flags & F_PREV_OBST);
+        q.flags = (obst_hit >= 0) ? (q.flags | F_PREV_OBST) : (q.flags & ~F_PREV_OBST);
+    }
+    const uint32_t obst_ballot = __ballot_sync(QS_FULL, obst_new) & gmask;
+    const int n_obst_new = __popc(obst_ballot);
+    if (n_obst_new > 0 && settled && obst_new) q.flags |= F_COL_OBST;
+
+    // ---- 1.3 room (quadrotor_multi.py:390-403, 600-606): prev lists hold last step's NEW crashes
+    const bool new_wall = (q.flags & F_CR_WALL) && !(q.flags & F_PREV_WALL);
+    const bool new_ceil = (q.flags & F_CR_CEIL) && !(q.flags & F_PREV_CEIL);
+    const bool cr_floor = (q.flags & F_CR_FLOOR) != 0;
+    const bool new_room = (cr_floor || new_wall || new_ceil) && !(q.flags & F_PREV_ROOM);
+    q.flags = (q.flags & ~(F_PREV_WALL | F_PREV_CEIL | F_PREV_ROOM)) | (new_wall ? F_PREV_WALL : 0) | (new_ceil ? F_PREV_CEIL : 0) |
+              (new_room ? F_PREV_ROOM : 0);
+    const uint32_t wall_ballot = __ballot_sync(QS_FULL, new_wall) & gmask;
+    const uint32_t ceil_ballot = __ballot_sync(QS_FULL, new_ceil) & gmask;
+    const uint32_t floor_ballot = __ballot_sync(QS_FULL, cr_floor && valid) & gmask;
+    const uint32_t room_ballot = __ballot_sync(QS_FULL, new_room) & gmask;
+    const uint32_t pair_ballot = __ballot_sync(QS_FULL, new_pairs != 0u) & gmask;
+
+    // ---- 2. rewards (quadrotor_multi.py:610-655)
+    reward += c.rew_col * ((unique_any_nonzero && is_unique) ? -1.0f : 0.0f);
+    reward += -1.0f * (c.control_dt * prox);
+    if (c.use_obstacles) reward += c.rew_col_obst * (obst_new ? -1.0f : 0.0f);
+
+    // distance_to_goal log: reached-goal flag from the mean of the last 5 entries, and the 1/3/5 s windows (:651-655, 762-767)
+    if (valid) {
+        float dlog = c.dt * dist;                                      // -rewraw_pos
+        float4 ring = P.plane[PL_DIST_RING][gi];
+        if (tick >= 5 && !(q.flags & F_REACHED)) {
+            float m5 = (ring.x + ring.y + ring.z + ring.w + dlog) / 5.0f;
+            float metric = (c.use_obstacles && scen_now == QS_SCENARIO_O_STATIC_SAME_GOAL) ? 1.0f : c.approach_metric;
+            if (m5 / c.dt < metric) q.flags |= F_REACHED;
+        }
+        P.plane[PL_DIST_RING][gi] = make_float4(ring.y, ring.z, ring.w, dlog);
+        int steps_left = c.ep_len + 1 - tick;
+        if (steps_left < 500) {
+            float4 sums = P.plane[PL_DIST_SUMS][gi];
+            if (steps_left < 100) sums.x += dlog;
+            if (steps_left < 300) sums.y += dlog;
+            sums.z += dlog;
+            P.plane[PL_DIST_SUMS][gi] = sums;
+        }
+    }
+
+    // ---- 3. impulses (quadrotor_multi.py:659-698): rare, group-divergent
+    bool flag = false;
+    if (c.use_downwash && KG > 1) {
+        // perform_downwash, aerodynamics/downwash.py:4-66: lane j accumulates the pushes of every source i in index order
+        float ua = 0.f, uw = 0.f;
+        if (valid) { float u[4]; rng_u4(g, SITE_DOWNWASH, d, 0xFF, 0, u); ua = u[0]; uw = u[1]; }
+        const float zx0 = q.R[2], zy0 = q.R[5], zz0 = q.R[8], px0 = q.p[0], py0 = q.p[1], pz0 = q.p[2];
+        bool hit = false;
+#pragma unroll
+        for (int i = 0; i < KG; ++i) {
+            float px = __shfl_sync(gmask, px0, base + i), py = __shfl_sync(gmask, py0, base + i), pz = __shfl_sync(gmask, pz0, base + i);
+            float zx = __shfl_sync(gmask, zx0, base + i), zy = __shfl_sync(gmask, zy0, base + i), zz = __shfl_sync(gmask, zz0, base + i);
+            float sa = __shfl_sync(gmask, ua, base + i), sw = __shfl_sync(gmask, uw, base + i);
+            if (i < c.K && i != d && valid) {
+                float rx = px0 - px, ry = py0 - py, rz = pz0 - pz;
+                float dd = norm3f(rx, ry, rz);
+                float relz = rx * zx + ry * zy + rz * zz;
+                float rxy = sqrtf(dd * dd - relz * relz);
+                if (-0.7f < relz && relz < 0.f && rxy < 0.1f) {
+                    float acc = fmaxf(1e-6f, (6.0f / 17.0f) * (-10.0f * dd + 7.0f) + (-0.1f + 0.2f * sa));
+                    float ow = fmaxf(1e-6f, 0.3f * (dd - 1.0f) * (dd - 1.0f) + (-0.01f + 0.02f * sw));
+                    float u[4], t[4];
+                    rng_u4(g, SITE_DOWNWASH, i, d, 0, u); rng_u4(g, SITE_DOWNWASH, i, d, 1, t);
+                    float nx = zx + (-0.1f + 0.2f * u[0]), ny = zy + (-0.1f + 0.2f * u[1]), nz = zz + (-0.1f + 0.2f * u[2]);
+                    float nm = norm3f(nx, ny, nz), den = (nm == 0.f) ? nm + 1e-6f : nm;
+                    float wx = -1.f + 2.f * u[3], wy = -1.f + 2.f * t[0], wz = -1.f + 2.f * t[1];
+                    float wm = norm3f(wx, wy, wz), wden = (wm == 0.f) ? wm + 1e-6f : wm;
+                    q.v[0] += acc * (-nx / den) * c.control_dt; q.v[1] += acc * (-ny / den) * c.control_dt; q.v[2] += acc * (-nz / den) * c.control_dt;
+                    q.w[0] += ow * (wx / wden) * c.control_dt; q.w[1] += ow * (wy / wden) * c.control_dt; q.w[2] += ow * (wz / wden) * c.control_dt;
+                    hit = true;
+                }
+            }
+        }
+        flag = (__ballot_sync(QS_FULL, hit) & gmask) != 0u;
+    }
+    if (c.apply_force) {
+        if (pair_ballot) {
+            // new pairs in (i, j) lexicographic order; a drone in two pairs is updated twice (:674-677)
+            for (int i = 0; i < c.K - 1; ++i) {
+                uint32_t rowi = __shfl_sync(gmask, new_pairs, base + i) & ~((2u << i) - 1u);   // j > i
+                while (rowi) {
+                    int j = __ffs(rowi) - 1;
+                    rowi &= rowi - 1;
+                    float p1[3], p2[3], v1[3], v2[3], w1[3], w2[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        p1[a] = __shfl_sync(gmask, q.p[a], base + i); p2[a] = __shfl_sync(gmask, q.p[a], base + j);
+                        v1[a] = __shfl_sync(gmask, q.v[a], base + i); v2[a] = __shfl_sync(gmask, q.v[a], base + j);
+                        w1[a] = __shfl_sync(gmask, q.w[a], base + i); w2[a] = __shfl_sync(gmask, q.w[a], base + j);
+                    }
+                    pair_impulse(g, i, j, p1, p2, v1, v2, w1, w2);
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        if (d == i) { q.v[a] = v1[a]; q.w[a] = w1[a]; }
+                        if (d == j) { q.v[a] = v2[a]; q.w[a] = w2[a]; }
+                    }
+                }
+            }
+            flag = true;
+        }
+        if (c.use_obstacles && obst_ballot) {
+            if (obst_new) { float2 xy = P.obst_xy[(size_t)env * QS_MAX_OBSTACLES + obst_hit]; obstacle_impulse(c, g, d, q, xy.x, xy.y); }
+            flag = true;
+        }
+        if (wall_ballot | ceil_ballot) {
+            if (new_wall) room_impulse(c, g, d, q, true);
+            if (new_ceil) room_impulse(c, g, d, q, false);
+            flag = true;
+        }
+    }
+    q.colmask = rowmask;                                               // :568
+
+    // ---- episode counters (leader lane) (:557-565, 578-581, 631-635)
+    if (valid && d == 0) {
+        int *ec = P.ecnt + env * EC_COUNT;
+        if (col_tick > 0) {
+            ec[EC_COL] += col_tick;
+            if (settled) ec[EC_COL_SETTLE] += col_tick;
+            if ((float)time_remain <= c.final_grace_steps) ec[EC_COL_FINAL] += col_tick;
+        }
+        if (n_obst_new > 0) { ec[EC_OBST] += n_obst_new; if (settled) ec[EC_OBST_SETTLE] += n_obst_new; }
+        if (settled && (room_ballot | floor_ballot | wall_ballot | ceil_ballot)) {
+            ec[EC_ROOM] += __popc(room_ballot); ec[EC_FLOOR] += __popc(floor_ballot);
+            ec[EC_WALL] += __popc(wall_ballot); ec[EC_CEIL] += __popc(ceil_ballot);
+        }
+    }
+
+    // ---- 5. observations (:703-720).  Self obs carries fresh sensor noise if any impulse fired (:711-712)
+    float vs[3] = { q.v[0], q.v[1], q.v[2] };                          // self.vel snapshot, :705-709
+    if (valid) self_obs(c, g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d, q, orow);
+    group_obs_tail<KG>(c, P, env, d, lane, gmask, valid, q, vs, orow, stage);
+    if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }
+
+    // ---- 7. dones (:739-838): episode stats, then the env resets itself and returns the new episode's first observation
+    const uint32_t done_ballot = __ballot_sync(QS_FULL, all_done && valid);
+    if (done_ballot) {
+        __syncwarp();
+        if (term_obs != nullptr) {
+            // terminal observation of the finished episode (rows of envs that go on are left untouched)
+            for (int r = 0; r < warp_rows; ++r) {
+                int src_lane = (r / c.K) * KG;                         // leader lane of that row's env
+                if ((done_ballot >> src_lane) & 1u) {
+                    const float *s = tile + (size_t)r * c.D;
+                    float *t = term_obs + ((size_t)warp_env0 * c.K + r) * c.D;
+                    for (int k = lane; k < c.D; k += 32) t[k] = s[k];
+                }
+            }
+            __syncwarp();
+        }
+        if (all_done) {
+            int *ec = P.ecnt + env * EC_COUNT;
+            qs_stats *st = P.stats;
+            {
+                bool col = (q.flags & (F_COL_AGENT | F_COL_OBST)) != 0, reached = (q.flags & F_REACHED) != 0;
+                uint32_t b_succ = __ballot_sync(gmask, !col && reached && valid) & gmask;
+                uint32_t b_dead = __ballot_sync(gmask, !col && !reached && valid) & gmask;
+                uint32_t b_col = __ballot_sync(gmask, col && valid) & gmask;
+                float4 sums = valid ? P.plane[PL_DIST_SUMS][gi] : make_float4(0.f, 0.f, 0.f, 0.f);
+                float inv_dt = 1.0f / c.dt;
+                float m1 = inv_dt * sums.x / (float)min(100, tick), m3 = inv_dt * sums.y / (float)min(300, tick), m5 = inv_dt * sums.z / (float)min(500, tick);
+#pragma unroll
+                for (int off = KG / 2; off > 0; off >>= 1) {
+                    m1 += __shfl_xor_sync(gmask, m1, off); m3 += __shfl_xor_sync(gmask, m3, off); m5 += __shfl_xor_sync(gmask, m5, off);
+                }
+                if (valid && d == 0) {
+                    atomicAdd((unsigned long long *)&st->episodes, 1ull);
+                    atomicAdd((unsigned long long *)&st->num_collisions, (unsigned long long)ec[EC_COL]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_after_settle, (unsigned long long)ec[EC_COL_SETTLE]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_final_5s, (unsigned long long)ec[EC_COL_FINAL]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_with_room, (unsigned long long)ec[EC_ROOM]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_with_floor, (unsigned long long)ec[EC_FLOOR]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_with_wall, (unsigned long long)ec[EC_WALL]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_with_ceiling, (unsigned long long)ec[EC_CEIL]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_obst_quad, (unsigned long long)ec[EC_OBST]);
+                    atomicAdd((unsigned long long *)&st->num_collisions_obst_quad_after_settle, (unsigned long long)ec[EC_OBST_SETTLE]);
+                    atomicAdd((unsigned long long *)&st->agents_success, (unsigned long long)__popc(b_succ));
+                    atomicAdd((unsigned long long *)&st->agents_deadlock, (unsigned long long)__popc(b_dead));
+                    atomicAdd((unsigned long long *)&st->agents_collided, (unsigned long long)__popc(b_col));
+                    if (bad_ballot) atomicAdd((unsigned long long *)&st->nonfinite_resets, 1ull);
+                    atomicAdd(&st->distance_to_goal_1s, (double)m1);
+                    atomicAdd(&st->distance_to_goal_3s, (double)m3);
+                    atomicAdd(&st->distance_to_goal_5s, (double)m5);
+                }
+            }
+            int scen = 0;
+            if (bad_ballot) {                                           // do not let NaNs leak through the persistent noise state
+#pragma unroll
+                for (int m = 0; m < 4; ++m) q.ou[m] = isfinite(q.ou[m]) ? q.ou[m] : 0.f;
+                if (!isfinite(vs[0] + vs[1] + vs[2])) { vs[0] = vs[1] = vs[2] = 0.f; }
+            }
+            group_reset<KG>(c, P, g, env, d, valid, q, scen);
+            tick = 0;
+            if (valid) {
+                if (d == 0) {
+#pragma unroll
+                    for (int k = 0; k < EC_COUNT; ++k) ec[k] = 0;
+                    ec[EC_SCENARIO] = scen;
+                }
+                P.plane[PL_DIST_RING][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                P.plane[PL_DIST_SUMS][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __threadfence_block();                                      // obstacle centres written by the leader lane
+            __syncwarp(gmask);
+            if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
+            group_obs_tail<KG>(c, P, env, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
+        }
+        __syncwarp();
+    }
+
+    // ---- write back
+    if (valid) {
+        store_drone(P, gi, q, all_done);
+        if (d == 0) { P.tick[env] = tick; P.svd_ctr[env] = svd; P.step_ctr[env] = g.step + 1u; }
+    }
+    __syncwarp();
+    if (warp_rows > 0) warp_store_tile(tile, obs + (size_t)warp_env0 * c.K * c.D, warp_rows * c.D, lane);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// explicit reset (QuadrotorEnvMulti.reset through VecEnv.reset)
+// ----------------------------------------------------------------------------------------------------------------
+template <int KG>
+__global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
+                                                    const uint8_t *__restrict__ env_mask, float *__restrict__ obs)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int env = tid / KG, d = tid % KG;
+    const bool in_range = env < c.N && d < c.K;
+    const bool valid = in_range && (env_mask == nullptr || env_mask[env] != 0);
+    const int gi = env * c.K + d;
+    const uint32_t gmask = group_mask<KG>(lane);
+    constexpr int GPW = 32 / KG;
+    const int rows_per_warp = GPW * c.K;
+    float4 *stage = reinterpret_cast<float4 *>(smem) + (size_t)warp_in_block * 64;
+    float *tile = smem + (size_t)(blockDim.x >> 5) * 256 + (size_t)warp_in_block * rows_per_warp * c.D;
+    const int row = (lane / KG) * c.K + d;
+    float *orow = tile + (size_t)row * c.D;
+
+    Drone q;
+    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
+    float vs[3] = { 0.f, 0.f, 0.f };
+    if (in_range) {
+        load_drone(P, gi, q);
+        vs[0] = q.v[0]; vs[1] = q.v[1]; vs[2] = q.v[2];                 // self.vel is not refreshed by reset (quadrotor_multi.py:477)
+        g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
+    } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { q.p[a] = 0.f; q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
+#pragma unroll
+        for (int a = 0; a < 9; ++a) q.R[a] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { q.rd[a] = q.cd[a] = q.ou[a] = 0.f; }
+        q.flags = 0; q.colmask = 0;
+    }
+    int scen = 0;
+    if (valid) {
+        group_reset<KG>(c, P, g, env, d, true, q, scen);
+        if (d == 0) {
+            int *ec = P.ecnt + env * EC_COUNT;
+#pragma unroll
+            for (int k = 0; k < EC_COUNT; ++k) ec[k] = 0;
+            ec[EC_SCENARIO] = scen;
+            P.tick[env] = 0; P.step_ctr[env] = g.step + 1u;
+        }
+        P.plane[PL_DIST_RING][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        P.plane[PL_DIST_SUMS][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_drone(P, gi, q, true);
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
+    group_obs_tail<KG>(c, P, env, d, lane, gmask, valid, q, vs, orow, stage);
+    __syncwarp();
+    // rows of envs that were not reset stay untouched: per-row masked copy
+    const int warp_env0 = (tid - lane) / KG;
+    const int warp_rows = max(0, min(GPW, c.N - warp_env0)) * c.K;
+    for (int r = 0; r < warp_rows; ++r) {
+        int e = warp_env0 + r / c.K;
+        if (env_mask == nullptr || env_mask[e] != 0) {
+            const float *s = tile + (size_t)r * c.D;
+            float *t = obs + ((size_t)warp_env0 * c.K + r) * c.D;
+            for (int k = lane; k < c.D; k += 32) t[k] = s[k];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// state pack / unpack (qs_get_state / qs_set_state)
+// ----------------------------------------------------------------------------------------------------------------
+struct StateView {
+    float *pos, *vel, *rot, *omega, *rot_damp, *cmds_damp, *ou, *goal;
+    int *flags; uint32_t *col_mask; int *tick, *svd_ctr; uint32_t *step_ctr; float *obst_xy;
+};
+
+__global__ void state_io_kernel(DevConst c, DevPtrs P, StateView v, int set)
+{
+    int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    int nd = c.N * c.K;
+    if (gi < nd) {
+        Drone q;
+        load_drone(P, gi, q);
+        if (set) {
+            if (v.pos) for (int a = 0; a < 3; ++a) q.p[a] = v.pos[3 * gi + a];
+            if (v.vel) for (int a = 0; a < 3; ++a) q.v[a] = v.vel[3 * gi + a];
+            if (v.omega) for (int a = 0; a < 3; ++a) q.w[a] = v.omega[3 * gi + a];
+            if (v.rot) for (int a = 0; a < 9; ++a) q.R[a] = v.rot[9 * gi + a];
+            if (v.rot_damp) for (int a = 0; a < 4; ++a) q.rd[a] = v.rot_damp[4 * gi + a];
+            if (v.cmds_damp) for (int a = 0; a < 4; ++a) q.cd[a] = v.cmds_damp[4 * gi + a];
+            if (v.ou) for (int a = 0; a < 4; ++a) q.ou[a] = v.ou[4 * gi + a];
+            if (v.goal) for (int a = 0; a < 3; ++a) q.goal[a] = v.goal[3 * gi + a];
+            if (v.flags) q.flags = v.flags[gi];
+            if (v.col_mask) q.colmask = v.col_mask[gi];
+            store_drone(P, gi, q, true);
+        } else {
+            if (v.pos) for (int a = 0; a < 3; ++a) v.pos[3 * gi + a] = q.p[a];
+            if (v.vel) for (int a = 0; a < 3; ++a) v.vel[3 * gi + a] = q.v[a];
+            if (v.omega) for (int a = 0; a < 3; ++a) v.omega[3 * gi + a] = q.w[a];
+            if (v.rot) for (int a = 0; a < 9; ++a) v.rot[9 * gi + a] = q.R[a];
+            if (v.rot_damp) for (int a = 0; a < 4; ++a) v.rot_damp[4 * gi + a] = q.rd[a];
+            if (v.cmds_damp) for (int a = 0; a < 4; ++a) v.cmds_damp[4 * gi + a] = q.cd[a];
+            if (v.ou) for (int a = 0; a < 4; ++a) v.ou[4 * gi + a] = q.ou[a];
+            if (v.goal) for (int a = 0; a < 3; ++a) v.goal[3 * gi + a] = q.goal[a];
+            if (v.flags) v.flags[gi] = q.flags;
+            if (v.col_mask) v.col_mask[gi] = q.colmask;
+        }
+    }
+    if (gi < c.N) {
+        if (set) {
+            if (v.tick) P.tick[gi] = v.tick[gi];
+            if (v.svd_ctr) P.svd_ctr[gi] = v.svd_ctr[gi];
+            if (v.step_ctr) P.step_ctr[gi] = v.step_ctr[gi];
+        } else {
+            if (v.tick) v.tick[gi] = P.tick[gi];
+            if (v.svd_ctr) v.svd_ctr[gi] = P.svd_ctr[gi];
+            if (v.step_ctr) v.step_ctr[gi] = P.step_ctr[gi];
+        }
+    }
+    if (v.obst_xy) {
+        int tot = c.N * QS_MAX_OBSTACLES;
+        for (int k = gi; k < tot; k += gridDim.x * blockDim.x) {
+            if (set) P.obst_xy[k] = make_float2(v.obst_xy[2 * k], v.obst_xy[2 * k + 1]);
+            else { float2 xy = P.obst_xy[k]; v.obst_xy[2 * k] = xy.x; v.obst_xy[2 * k + 1] = xy.y; }
+        }
+    }
+}
+
+// raw generator probe used by the tests to pin the RNG contract bit-for-bit against the oracle
+__global__ void philox_probe_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out, float *fout)
+{
+    uint4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+    fout[0] = u23(r.x); fout[1] = u23(r.y);
+    box_muller(r.x, r.y, fout[2], fout[3]);
+    box_muller(r.z, r.w, fout[4], fout[5]);
+}
+
+}  // namespace qs

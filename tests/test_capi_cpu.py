@@ -1,0 +1,75 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol include/quadsim.h declares, the
+ctypes mirrors match the header's struct sizes, and host-side config logic behaves like the reference's constructor."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from quad_swarm_rl_stable_baselines3_b200 import _capi
+from quad_swarm_rl_stable_baselines3_b200.config import QsConfigC, QsStatsC, QuadSimConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _capi.build()
+    return _capi.lib()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "quadsim.h")).read()
+    declared = set(re.findall(r"\b(qs_[a-z_]+)\s*\(", hdr))
+    declared -= {"qs_status"}
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layouts(lib):
+    assert lib.qs_config_size() == C.sizeof(QsConfigC)
+    assert lib.qs_stats_size() == C.sizeof(QsStatsC)
+    assert lib.qs_api_version() == 1
+
+
+def test_create_without_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    cfg = QuadSimConfig(num_envs=2).to_c()
+    rc = lib.qs_create(C.byref(cfg), 0, C.byref(h))
+    assert rc < 0 and not h.value
+    assert b"CUDA" in lib.qs_last_error(None)
+    from quad_swarm_rl_stable_baselines3_b200.sim import QuadSwarmSim
+    with pytest.raises(RuntimeError, match="CUDA"):
+        QuadSwarmSim(QuadSimConfig(num_envs=2))
+
+
+def test_bad_config_rejected(lib):
+    c = QuadSimConfig(num_envs=2).to_c()
+    c.num_agents = 40
+    h = C.c_void_p()
+    assert lib.qs_create(C.byref(c), 0, C.byref(h)) == -1
+    assert b"num_agents" in lib.qs_last_error(None)
+    assert lib.qs_create(None, 0, C.byref(h)) == -4
+
+
+def test_config_derivations():
+    c = QuadSimConfig(num_envs=3, num_agents=8)
+    assert c.obs_dim == 54 and c.ep_len == 1500 and c.visible == 6
+    c3 = QuadSimConfig(num_agents=8, quads_mode="mix", use_obstacles=True, obs_repr="xyz_vxyz_R_omega_floor",
+                       neighbor_visible_num=2)
+    assert c3.obs_dim == 40 and c3.num_obstacles == 12 and c3.to_c().spawn_box == 0.1   # cfg3
+    assert QuadSimConfig(num_agents=32).obs_dim == 54                            # cfg4
+    assert QuadSimConfig(num_agents=4, neighbor_visible_num=-1).visible == 3
+    with pytest.raises(ValueError):
+        QuadSimConfig(num_agents=4, neighbor_visible_num=6).to_c()
+    with pytest.raises(ValueError):
+        QuadSimConfig(quads_mode="swap_goals").to_c()
+    with pytest.raises(AssertionError):
+        QuadSimConfig(rew_coeff=dict(typo=1.0)).to_c()
+    cc = c.to_c()
+    assert abs(cc.collision_hitbox_radius * cc.arm - 0.09192388155425119) < 1e-15
+    assert cc.svd_period == 100
