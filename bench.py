@@ -5,12 +5,14 @@
     python bench.py --impl reference [--gpus N] ...                 # CPU arm: the oracle port on all host cores
     torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, weak scaling
 
-Workload (BASELINE.json configs[1]): 8-quad swarm, static_same_goal, pos_vel observations of the 6 nearest
-neighbours (obs 54), 4096 envs per GPU, sensor + thrust noise on, episodes of 1500 control steps (so the timed
-window contains auto-resets), synthetic i.i.d. U(-1,1) actions resident in HBM.  A "step" is one control step of
-every env = one launch of the fused step kernel.  The per-step working set (~14 MB) is smaller than the 126 MB L2,
-so L2 is flushed (a 256 MiB write) between timed steps and every step is timed with its own pair of CUDA events
-on the launching stream.  Prints ONE JSON line (rank 0).
+Workload = the simulator leg of BASELINE.json configs[4] ("synthetic random-action throughput sweep: 65536 envs x
+8 quads"), with the environment of configs[1]: 8-quad swarm, static_same_goal, pos_vel observations of the 6 nearest
+neighbours (obs 54), sensor + thrust noise on, episodes of 1500 control steps (the timed window contains auto-resets),
+synthetic i.i.d. U(-1,1) actions resident in HBM.  65536 envs PER GPU (weak scaling: env shards are independent, no
+collective in the step).  A "step" is one control step of every env = one launch of the fused step kernel.  The
+per-step working set (260 MB of state + observations) is larger than the 126 MB L2, so steps run back to back without
+an L2 flush.  The 4096-envs-per-GPU point of configs[1] is measured too (per-step events, L2 flushed between steps)
+and reported under "cfg2_4096".  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -23,12 +25,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ENVS_PER_GPU = 4096
+ENVS_PER_GPU = 65536
+ENVS_CFG2 = 4096
 AGENTS = 8
 # Algorithmic HBM bytes per drone-step for this workload (restated in DESIGN.md "Roofline"):
 # state 120 B read + 120 B written, goal 12 R, tick/flags 4 R+W, action 16 R, obs 54*4 W, reward 4 + done 1 W
 ALGO_BYTES_PER_DRONE_STEP = 497.0
-WORKLOAD = "cfg2: 8-quad static_same_goal, pos_vel x6 neighbours, obs 54, noise on, ep 1500 steps"
+WORKLOAD = ("cfg5 simulator leg: 65536 envs x 8 quads per GPU, env = cfg2 (static_same_goal, pos_vel x6 neighbours, "
+            "obs 54, noise on, ep 1500 steps)")
 
 
 def measured_hbm_peak():
@@ -140,7 +144,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "agents": AGENTS, "obs_dim": 54,
                    "note": "CPU arm: C port of the reference step (oracle), all host threads, bounded sample; "
-                           "ms_per_step is the time this arm would need for one 4096-env step"},
+                           "ms_per_step is the time this arm would need for one 65536-env step"},
         "cpu_baseline": {"value": v, "unit": "drone-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "drone-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -151,12 +155,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU, help="override for size sweeps (not the bench line)")
-    ap.add_argument("--no-flush", action="store_true", help="L2-warm back-to-back steps (informational only)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-small", action="store_true", help="skip the 4096-env cfg2 point")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -179,16 +183,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_envs = args.envs_per_gpu
-    cfg = QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, seed=0, env_id_offset=rank * n_envs)
-    sim = QuadSwarmSim(cfg, device=dev)
-    sim.want_terminal_obs = False
-    nd = n_envs * AGENTS
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    POOL = 16
-    act_pool = (torch.rand((POOL, nd, 4), device=dev, generator=gen) * 2.0 - 1.0).contiguous()
-    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -196,66 +190,97 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed_loop(step_fn, steps, flush):
-        """per-step CUDA events on the launching stream; returns total ms over `steps` steps"""
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for i in range(steps):
-            if flush:
-                flush_buf.fill_(float(i))
-            ev[i][0].record(stream)
-            step_fn(i)
-            ev[i][1].record(stream)
-        torch.cuda.synchronize(dev)
-        return sum(a.elapsed_time(b) for a, b in ev)
+    def make(n_envs):
+        cfg = QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, seed=0, env_id_offset=rank * n_envs)
+        sim = QuadSwarmSim(cfg, device=dev)
+        sim.want_terminal_obs = False
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        pool = (torch.rand((POOL, n_envs * AGENTS, 4), device=dev, generator=gen) * 2.0 - 1.0).contiguous()
+        sim.reset()
+        return sim, pool
 
-    sim.reset()
-    flush = not args.no_flush
+    POOL = 8
+    n_envs = args.envs_per_gpu
+    nd = n_envs * AGENTS
+    sim, act_pool = make(n_envs)
 
-    # ---- device-resident path: value ----------------------------------------------------------------
-    def dev_step(i):
-        sim.step(act_pool[i % POOL])
-
+    # ---- device-resident path: value.  K back-to-back steps, one CUDA-event pair on the launching stream ---------
     for i in range(args.warmup):
-        dev_step(i)
+        sim.step(act_pool[i % POOL])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = sim.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    total_ms = timed_loop(dev_step, args.steps, flush)
+    e0.record(stream)
+    for i in range(args.steps):
+        sim.step(act_pool[i % POOL])
+    e1.record(stream)
     barrier()
     wall_s = time.perf_counter() - t_wall0
+    total_ms = e0.elapsed_time(e1)
     launches = sim.launch_count - l0
-    # keep the GPU busy a little longer if the timed region was too short for nvidia-smi to sample it
     clocks = None
     if rank == 0:
-        if wall_s < 1.0:
-            t_end = time.perf_counter() + 1.0
+        if wall_s < 1.5:      # keep the GPU under the same load a little longer so that nvidia-smi samples it
+            t_end = time.perf_counter() + 1.5
             j = 0
             while time.perf_counter() < t_end:
-                dev_step(j); j += 1
+                sim.step(act_pool[j % POOL]); j += 1
             torch.cuda.synchronize(dev)
         clocks = sampler.stop()
 
-    # ---- host-buffer path through the public API: e2e ----------------------------------------------
-    host_acts = [np.ascontiguousarray(act_pool[i].cpu().numpy()) for i in range(POOL)]
-    out = (np.empty((nd, sim.D), dtype=np.float32), np.empty(nd, dtype=np.float32), np.empty(nd, dtype=np.uint8))
-
-    def host_step(i):
-        sim.step_host(host_acts[i % POOL], out)
-
-    e2e_steps = max(10, min(args.steps, 400))
+    # ---- host-buffer path through the public API: e2e (pinned numpy in, pinned numpy out, every step) ------------
+    host_acts = []
+    for i in range(POOL):
+        t = torch.empty((nd, 4), dtype=torch.float32, pin_memory=True)
+        t.copy_(act_pool[i])
+        host_acts.append(t.numpy())
+    out_t = (torch.empty((nd, sim.D), dtype=torch.float32, pin_memory=True),
+             torch.empty((nd,), dtype=torch.float32, pin_memory=True), torch.empty((nd,), dtype=torch.uint8, pin_memory=True))
+    out = tuple(t.numpy() for t in out_t)
+    e2e_steps = max(10, min(args.steps, 200))
     for i in range(3):
-        host_step(i)
+        sim.step_host(host_acts[i % POOL], out)
     barrier()
-    e2e_ms = timed_loop(host_step, e2e_steps, flush)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(e2e_steps):
+        sim.step_host(host_acts[i % POOL], out)
+    e1.record(stream)
     barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))     # the call is synchronous: host clock == device clock
 
-    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    # ---- cfg2 point: 4096 envs per GPU, per-step events, L2 flushed between steps -------------------------------
+    small_ms = None
+    if not args.skip_small:
+        del sim, act_pool
+        sim2, pool2 = make(ENVS_CFG2)
+        flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+        for i in range(20):
+            sim2.step(pool2[i % POOL])
+        ns = min(args.steps, 300)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ns)]
+        barrier()
+        for i in range(ns):
+            flush_buf.fill_(float(i))
+            ev[i][0].record(stream)
+            sim2.step(pool2[i % POOL])
+            ev[i][1].record(stream)
+        barrier()
+        small_ms = sum(a.elapsed_time(b) for a, b in ev) / ns
+        d_small = sim2.D
+        del sim2, pool2, flush_buf
+    else:
+        d_small = 54
+
+    t = torch.tensor([total_ms, e2e_ms, small_ms or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, small_ms_max = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -273,20 +298,29 @@ def main():
             "metric": "drone-steps/sec", "value": value, "unit": "drone-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n_envs, "agents": AGENTS, "obs_dim": sim.D,
-                       "act_dim": sim.A, "l2": "flushed between timed steps (256 MiB write)" if flush else "warm (not flushed)",
-                       "timing": "per-step CUDA events on the launching stream, max over ranks",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n_envs, "agents": AGENTS, "obs_dim": d_small,
+                       "act_dim": 4, "l2": "inputs larger than L2 (260 MB touched per step vs 126 MB L2), no flush",
+                       "timing": "one CUDA-event pair around the K back-to-back steps on the launching stream, max over ranks",
                        "parallelism": f"env-sharded x{world}, no collective in the step"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "drone-steps/s", "h2d_bytes_per_step": nd * 4 * 4,
-                    "d2h_bytes_per_step": nd * (sim.D * 4 + 4 + 1), "steps": e2e_steps,
-                    "api": "QuadSwarmSim.step_host -> qs_step_host (pinned staging, H2D actions, D2H obs/rew/done)"},
+                    "d2h_bytes_per_step": nd * (d_small * 4 + 4 + 1), "steps": e2e_steps,
+                    "api": "QuadSwarmSim.step_host -> qs_step_host: pinned numpy actions H2D, step kernel, "
+                           "obs/rew/done D2H into pinned numpy, stream sync, every step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": committed_traffic_per_launch(), "algorithmic_bytes_per_launch": bytes_per_launch,
                          "kernel": "qs::step_kernel<8>", "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
+        if small_ms is not None:
+            nd2 = ENVS_CFG2 * AGENTS
+            ach2 = ALGO_BYTES_PER_DRONE_STEP * nd2 / (small_ms_max * 1e-3) / 1e9
+            line["cfg2_4096"] = {"workload": "configs[1]: 4096 envs x 8 quads per GPU, same env", "ms_per_step": small_ms_max,
+                                 "value": world * nd2 / (small_ms_max * 1e-3), "unit": "drone-steps/s",
+                                 "l2": "flushed between timed steps (256 MiB write), per-step CUDA events",
+                                 "roofline_frac": ach2 / peak,
+                                 "note": "32768 threads = 0.43 waves of 148 SMs: bounded by one thread's latency chain, not by HBM"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -215,7 +215,9 @@ int qs_reset(qs_env *env, const uint8_t *env_mask, float *obs, void *stream);
 int qs_step(qs_env *env, const float *actions, float *obs, float *rew, uint8_t *done,
             float *terminal_obs, void *stream);
 
-/* Same, HOST buffers (pageable or pinned).  H2D of actions and D2H of obs/rew/done happen inside. */
+/* Same, HOST buffers.  H2D of actions and D2H of obs/rew/done happen inside; the call returns after the stream has
+ * drained.  Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are DMA'd directly, pageable ones
+ * are staged through pinned buffers owned by the handle (one extra host memcpy each way). */
 int qs_reset_host(qs_env *env, float *obs_host, void *stream);
 int qs_step_host(qs_env *env, const float *actions_host, float *obs_host, float *rew_host,
                  uint8_t *done_host, void *stream);

@@ -256,6 +256,15 @@ static int ensure_host_buffers(qs_env *e)
     return QS_OK;
 }
 
+// true if `p` is page-locked host memory the copy engines can reach directly (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory); pageable buffers go through the handle's pinned staging area instead.
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int qs_reset_host(qs_env *e, float *obs_host, void *stream)
 {
     if (!e || !obs_host) return fail(e, QS_ERR_NULL, "qs_reset_host: null argument");
@@ -265,9 +274,10 @@ int qs_reset_host(qs_env *e, float *obs_host, void *stream)
     const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
     rc = qs_reset(e, nullptr, e->d_obs, stream);
     if (rc) return rc;
-    QS_CUDA(e, cudaMemcpyAsync(e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    const bool direct = is_pinned(obs_host);
+    QS_CUDA(e, cudaMemcpyAsync(direct ? obs_host : e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaStreamSynchronize(s));
-    memcpy(obs_host, e->h_obs, nd * D * sizeof(float));
+    if (!direct) memcpy(obs_host, e->h_obs, nd * D * sizeof(float));
     return QS_OK;
 }
 
@@ -278,17 +288,19 @@ int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *r
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
-    memcpy(e->h_act, actions_host, nd * 4 * sizeof(float));
-    QS_CUDA(e, cudaMemcpyAsync(e->d_act, e->h_act, nd * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    // page-locked caller buffers are DMA'd directly; pageable ones are staged through the handle's pinned buffers
+    const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rew_host), pd = is_pinned(done_host);
+    if (!pa) memcpy(e->h_act, actions_host, nd * 4 * sizeof(float));
+    QS_CUDA(e, cudaMemcpyAsync(e->d_act, pa ? actions_host : e->h_act, nd * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = qs_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, nullptr, stream);
     if (rc) return rc;
-    QS_CUDA(e, cudaMemcpyAsync(e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
-    QS_CUDA(e, cudaMemcpyAsync(e->h_rew, e->d_rew, nd * sizeof(float), cudaMemcpyDeviceToHost, s));
-    QS_CUDA(e, cudaMemcpyAsync(e->h_done, e->d_done, nd, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(e, cudaMemcpyAsync(pr ? rew_host : e->h_rew, e->d_rew, nd * sizeof(float), cudaMemcpyDeviceToHost, s));
+    QS_CUDA(e, cudaMemcpyAsync(pd ? done_host : e->h_done, e->d_done, nd, cudaMemcpyDeviceToHost, s));
+    QS_CUDA(e, cudaMemcpyAsync(po ? obs_host : e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaStreamSynchronize(s));
-    memcpy(obs_host, e->h_obs, nd * D * sizeof(float));
-    memcpy(rew_host, e->h_rew, nd * sizeof(float));
-    memcpy(done_host, e->h_done, nd);
+    if (!po) memcpy(obs_host, e->h_obs, nd * D * sizeof(float));
+    if (!pr) memcpy(rew_host, e->h_rew, nd * sizeof(float));
+    if (!pd) memcpy(done_host, e->h_done, nd);
     return QS_OK;
 }
 

@@ -14,6 +14,9 @@
 
 #include "../../include/quadsim.h"
 
+#define QS_FULL 0xffffffffu
+#define QS_PI_F 3.14159265358979323846f
+
 namespace qs {
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -61,8 +64,6 @@ enum { SITE_OU = 0, SITE_SENSOR = 1, SITE_SENSOR_IMPULSE = 2, SITE_SENSOR_RESET 
        SITE_PAIR = 5, SITE_OBST = 6, SITE_WALL = 7, SITE_CEILING = 8, SITE_DOWNWASH = 9, SITE_SPAWN = 10,
        SITE_SCENARIO = 11 };
 
-#define QS_FULL 0xffffffffu
-#define QS_PI_F 3.14159265358979323846f
 
 // ----------------------------------------------------------------------------------------------------------------
 // Philox4x32-10, keyed (seed), counter (env gid, step counter, site|drone<<8|aux<<16, block)
@@ -92,12 +93,14 @@ __device__ __forceinline__ uint4 rng_block(const Rng &g, int site, int drone, in
 // ((x >> 9) + 0.5) * 2^-23 : exactly representable in fp32, in (0,1)
 __device__ __forceinline__ float u23(uint32_t x) { return fmaf((float)(x >> 9), 1.1920928955078125e-07f, 5.9604644775390625e-08f); }
 
+// Box-Muller on the SFU: lg2.approx / sin.approx / cos.approx (abs error ~2^-21 on the unit draws, i.e. <= 1e-8 after
+// scaling by the noise sigmas).  u in (0,1) so the log is finite; the angle is mapped to (-pi, pi) where the
+// approximations are tightest: cos(2 pi u) = -cos(pi (2u-1)), sin(2 pi u) = -sin(pi (2u-1)).
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1)
 {
-    float rad = sqrtf(fmaxf(-2.0f * logf(u23(a)), 0.0f));
-    float s, c;
-    sincospif(2.0f * u23(b), &s, &c);
-    n0 = rad * c; n1 = rad * s;
+    float rad = sqrtf(fmaxf(-1.3862943611198906f * __log2f(u23(a)), 0.0f));     // -2 ln u = -2 ln2 log2 u
+    float ang = QS_PI_F * fmaf(2.0f, u23(b), -1.0f);
+    n0 = -rad * __cosf(ang); n1 = -rad * __sinf(ang);
 }
 
 // idx-th uniform of stream (site, drone, aux)
@@ -299,6 +302,15 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
     q.v[0] = kd * q.v[0] + dt * ax; q.v[1] = kd * q.v[1] + dt * ay; q.v[2] = kd * q.v[2] + dt * az;
 }
 
+// rot2quat branches for trace <= 0 (sensor_noise.py:44-62)
+__device__ __noinline__ void rot2quat_rare(const float *R, float &qw, float &qx, float &qy, float &qz)
+{
+    float S;
+    if (R[0] > R[4] && R[0] > R[8]) { S = sqrtf(1.0f + R[0] - R[4] - R[8]) * 2.f; qw = (R[7] - R[5]) / S; qx = 0.25f * S; qy = (R[1] + R[3]) / S; qz = (R[2] + R[6]) / S; }
+    else if (R[4] > R[8]) { S = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2.f; qw = (R[2] - R[6]) / S; qx = (R[1] + R[3]) / S; qy = 0.25f * S; qz = (R[5] + R[7]) / S; }
+    else { S = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2.f; qw = (R[3] - R[1]) / S; qx = (R[2] + R[6]) / S; qy = (R[5] + R[7]) / S; qz = 0.25f * S; }
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // a9  self observation: SensorNoise.add_noise_numba + state_xyz_vxyz_R_omega* (sensor_noise.py:172-261, get_state.py:226-292)
 // ----------------------------------------------------------------------------------------------------------------
@@ -317,10 +329,8 @@ __device__ __forceinline__ void self_obs(const DevConst &c, const Rng &g, int si
         // R -> quaternion -> R round trip (sensor_noise.py:34-63, 205-210; quad_utils.py:162-168), zero rotation noise
         const float *R = q.R;
         float tr = R[0] + R[4] + R[8], qw, qx, qy, qz, S;
-        if (tr > 0.f) { S = sqrtf(tr + 1.0f) * 2.f; qw = 0.25f * S; qx = (R[7] - R[5]) / S; qy = (R[2] - R[6]) / S; qz = (R[3] - R[1]) / S; }
-        else if (R[0] > R[4] && R[0] > R[8]) { S = sqrtf(1.0f + R[0] - R[4] - R[8]) * 2.f; qw = (R[7] - R[5]) / S; qx = 0.25f * S; qy = (R[1] + R[3]) / S; qz = (R[2] + R[6]) / S; }
-        else if (R[4] > R[8]) { S = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2.f; qw = (R[2] - R[6]) / S; qx = (R[1] + R[3]) / S; qy = 0.25f * S; qz = (R[5] + R[7]) / S; }
-        else { S = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2.f; qw = (R[3] - R[1]) / S; qx = (R[2] + R[6]) / S; qy = (R[5] + R[7]) / S; qz = 0.25f * S; }
+        if (tr > 0.f) { S = sqrtf(tr + 1.0f) * 2.f; float iS = 1.0f / S; qw = 0.25f * S; qx = (R[7] - R[5]) * iS; qy = (R[2] - R[6]) * iS; qz = (R[3] - R[1]) * iS; }
+        else rot2quat_rare(R, qw, qx, qy, qz);                            // tilted past ~120 deg: out of line
         o[6] = 1.0f - 2.f * qy * qy - 2.f * qz * qz; o[7] = 2.f * qx * qy - 2.f * qz * qw; o[8] = 2.f * qx * qz + 2.f * qy * qw;
         o[9] = 2.f * qx * qy + 2.f * qz * qw; o[10] = 1.0f - 2.f * qx * qx - 2.f * qz * qz; o[11] = 2.f * qy * qz - 2.f * qx * qw;
         o[12] = 2.f * qx * qz - 2.f * qy * qw; o[13] = 2.f * qy * qz + 2.f * qx * qw; o[14] = 1.0f - 2.f * qx * qx - 2.f * qy * qy;
@@ -580,26 +590,37 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const DevPtrs 
         __syncwarp(gmask);
         const float INF = __int_as_float(0x7f800000);
         if (c.V < c.K - 1) {
-            // rank by ||[dp, dv]|| (6-vector, :357-359), max(.,0.01); V rounds of first-minimum selection == stable argsort[:V]
+            // rank by ||[dp, dv]|| (6-vector, :357-359), max(., 0.01).  The ranking is done on the squared metric
+            // (monotone, so the order is the same away from ties) and as a stable rank count -- candidate a precedes b
+            // iff met[a] <= met[b] for a < b -- which equals argsort(kind='stable')[:V] (first-minimum selection).
             float met[KG];
 #pragma unroll
             for (int j = 0; j < KG; ++j) {
                 float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
                 float r0 = a.x - q.p[0], r1 = a.y - q.p[1], r2 = a.z - q.p[2], r3 = b.x - vs[0], r4 = b.y - vs[1], r5 = b.z - vs[2];
                 float ss = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5;
-                met[j] = (j < c.K && j != d) ? fmaxf(sqrtf(ss), 0.01f) : INF;
+                met[j] = (j < c.K && j != d) ? fmaxf(ss, 1.0e-4f) : INF;
             }
-            for (int sidx = 0; sidx < c.V; ++sidx) {
-                float best = INF; int jb = 0;
+            int rank[KG];
 #pragma unroll
-                for (int j = 0; j < KG; ++j) if (met[j] < best) { best = met[j]; jb = j; }
+            for (int j = 0; j < KG; ++j) rank[j] = 0;
 #pragma unroll
-                for (int j = 0; j < KG; ++j) met[j] = (j == jb) ? INF : met[j];
-                if (valid) {
-                    float4 a = stage[2 * (base + jb)], b = stage[2 * (base + jb) + 1];
-                    float *r = o + c.S + 6 * sidx;
-                    r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
-                    r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+            for (int a = 0; a < KG; ++a)
+#pragma unroll
+                for (int b = a + 1; b < KG; ++b) {
+                    bool b_first = met[b] < met[a];
+                    rank[a] += b_first ? 1 : 0;
+                    rank[b] += b_first ? 0 : 1;
+                }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < KG; ++j) {
+                    if (rank[j] < c.V && met[j] < INF) {
+                        float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                        float *r = o + c.S + 6 * rank[j];
+                        r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                        r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                    }
                 }
             }
         } else if (valid) {
@@ -754,14 +775,19 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevCo
         const float pen_ratio = -c.rew_col_smooth / c.thr_fall;
         stage[2 * lane] = make_float4(q.p[0], q.p[1], q.p[2], 0.f);
         __syncwarp(gmask);
+        // pre-filter on the squared distance (slightly widened), exact `<=` tests on the rounded distance only for near pairs
+        const float thr_far = fmaxf(c.thr_col, c.thr_fall), fall2 = thr_far * thr_far * 1.0001f;
 #pragma unroll
         for (int j = 0; j < KG; ++j) {
             float4 o4 = stage[2 * (base + j)];
             float dx = q.p[0] - o4.x, dy = q.p[1] - o4.y, dz = q.p[2] - o4.z;
-            float dd = sqrtf(dx * dx + dy * dy + dz * dz);
+            float d2 = dx * dx + dy * dy + dz * dz;
             bool other = (j != d) && (j < c.K) && valid;
-            if (other && dd <= c.thr_col) rowmask |= 1u << j;
-            if (other && dd <= c.thr_fall) prox += pen_ratio * dd + c.rew_col_smooth;
+            if (other && d2 <= fall2) {
+                float dd = __fsqrt_rn(d2);
+                if (dd <= c.thr_col) rowmask |= 1u << j;
+                if (dd <= c.thr_fall) prox += pen_ratio * dd + c.rew_col_smooth;
+            }
         }
     }
     const uint32_t new_pairs = rowmask & ~q.colmask;                   // :545-546
@@ -779,10 +805,11 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevCo
     if (c.use_obstacles) {
         if (valid) {
             const float2 *ob = P.obst_xy + (size_t)env * QS_MAX_OBSTACLES;
+            const float obst2 = c.thr_obst * c.thr_obst * 1.0001f;
             for (int m = 0; m < c.M; ++m) {
                 float2 xy = ob[m];
-                float dx = q.p[0] - xy.x, dy = q.p[1] - xy.y;
-                if (sqrtf(dx * dx + dy * dy) <= c.thr_obst) { obst_hit = m; break; }
+                float dx = q.p[0] - xy.x, dy = q.p[1] - xy.y, d2 = dx * dx + dy * dy;
+                if (d2 <= obst2 && __fsqrt_rn(d2) <= c.thr_obst) { obst_hit = m; break; }
             }
         }
         obst_new = (obst_hit >= 0) && !(q.flags & F_PREV_OBST);
