@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define QS_API_VERSION 1
+#define QS_API_VERSION 2
 #define QS_MAX_AGENTS 32      /* drones per env handled by the warp-group kernels */
 #define QS_MAX_OBSTACLES 64
 
@@ -57,13 +57,26 @@ typedef enum qs_status {
 enum { QS_SCENARIO_STATIC_SAME_GOAL = 0,      /* scenarios/static_same_goal.py */
        QS_SCENARIO_O_MIX = 1,                 /* scenarios/mix.py with obstacles: o_random | o_static_same_goal per episode */
        QS_SCENARIO_O_RANDOM = 2,              /* scenarios/obstacles/o_random.py */
-       QS_SCENARIO_O_STATIC_SAME_GOAL = 3 };  /* scenarios/obstacles/o_static_same_goal.py */
+       QS_SCENARIO_O_STATIC_SAME_GOAL = 3,    /* scenarios/obstacles/o_static_same_goal.py */
+       QS_SCENARIO_DYNAMIC_REPULSIVE = 4 };   /* scenarios/dynamic_repulsive.py (fork mode: pursuit of a repelled evader) */
+
+/* env_mode: which of the reference's two live env variants the handle reproduces */
+enum { QS_MODE_UPSTREAM = 0,   /* gym_art/quadrotor_multi/quadrotor_multi.py + quadrotor_single.py (RawControl, 4 motor thrusts) */
+       QS_MODE_FORK = 1 };     /* quadrotor_multi_rewards.py + quadrotor_single_rewards.py: PID pre-controller, 2-D action,
+                                  `substeps` control steps per call, capture reward (what swarm_rl/sb_train.py trains on) */
 
 /* obs_repr (gym_art/quadrotor_multi/quad_utils.py:30-38, get_state.py:226-292) */
-enum { QS_OBS_XYZ_VXYZ_R_OMEGA = 0, QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR = 1, QS_OBS_XYZ_VXYZ_R_OMEGA_WALL = 2 };
+enum { QS_OBS_XYZ_VXYZ_R_OMEGA = 0, QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR = 1, QS_OBS_XYZ_VXYZ_R_OMEGA_WALL = 2,
+       /* fork 2-D representations (get_state.py:7-103), QS_MODE_FORK only */
+       QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_ANGLE_ANGLEDOT = 3,   /* 6 floats, get_state.py:37-69 */
+       QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_SANGLE_ANGLEDOT = 4,  /* 7 floats, get_state.py:71-103 */
+       QS_OBS_AW_AWDOT_DIST_DISTDOT_ANGLE_ANGLEDOT = 5 };       /* 6 floats, get_state.py:7-35 */
 
 /* neighbor_obs_type (quad_utils.py:40-58) */
-enum { QS_NEIGHBOR_NONE = 0, QS_NEIGHBOR_POS_VEL = 1 };
+enum { QS_NEIGHBOR_NONE = 0, QS_NEIGHBOR_POS_VEL = 1,
+       /* fork types (quadrotor_multi_rewards.py:326-358), QS_MODE_FORK only */
+       QS_NEIGHBOR_DIST_ANGLE = 2,      /* [|dp|, bearing - heading] */
+       QS_NEIGHBOR_DIST_SANGLE = 3 };   /* [|dp|, cos, sin of the relative bearing] */
 
 /* noise source: counter-based Philox on the device (production) */
 enum { QS_SENSE_NOISE_NONE = 0, QS_SENSE_NOISE_DEFAULT = 1 };
@@ -71,7 +84,38 @@ enum { QS_SENSE_NOISE_NONE = 0, QS_SENSE_NOISE_DEFAULT = 1 };
 /* qs_set_param keys */
 enum { QS_PARAM_REW_POS = 0, QS_PARAM_REW_EFFORT, QS_PARAM_REW_CRASH, QS_PARAM_REW_ORIENT, QS_PARAM_REW_SPIN,
        QS_PARAM_REW_QUADCOL_BIN, QS_PARAM_REW_QUADCOL_BIN_SMOOTH_MAX, QS_PARAM_REW_QUADCOL_BIN_OBST,
+       QS_PARAM_CAPTURE_RADIUS,   /* set_capture_radius, quadrotor_multi_rewards.py:210-211 */
        QS_PARAM_COUNT };
+
+/* Constants of the fork's pre-controller and pursuit task, evaluated once on the host from the reference's
+ * construction-time code (fork_model.py) -- only read when env_mode == QS_MODE_FORK. */
+typedef struct qs_fork_config {
+    int32_t substeps;             /* control steps per step() call: 8, quadrotor_multi_rewards.py:633 */
+    int32_t reserved;
+    double capture_radius;        /* initial_capture_radius, quadrotor_multi_rewards.py:205-208 */
+    double rew_existence;         /* -0.1  (:744) */
+    double rew_captor;            /* 100   (:741) */
+    double rew_helper;            /* 100   (:743) */
+    double max_angular_rate;      /* pi*80/180 rad/s, Controller/Controller.py:31 */
+    double chaser_speed;          /* 0.2 m/s, Controller/Controller.py:89 */
+    double evader_v_max;          /* 0.5,  scenarios/dynamic_repulsive.py:31 */
+    double evader_dt;             /* 1/200, :32 */
+    double evader_arena;          /* 5,    :35 */
+    double spawn_ring;            /* 0.5,  :75 */
+    double evader_r_min;          /* 2,    :79 */
+    double evader_r_span;         /* 3,    :79 */
+    /* 12 PIDs in cascade order: position x,y,z; velocity x,y,z; attitude x,y,z; rate x,y,z.
+     * Columns: kp, kd, ki, saturation (<=0: none), antiwindup (<=0: none).  Controller/Pid.py:7-26 and the
+     * initialize_pids() of Position/Velocity/Attitude/RateController.py. */
+    double pid[12][5];
+    double rate_out_scale;        /* 800, Controller/RateController.py:84-86 */
+    double mixer[4][4];           /* allocation_matrix_inv [motor][roll,pitch,yaw,throttle], Controller/Mixer.py:31-65 */
+    double ctrl_mass;             /* ModelParams.mass 0.028, Controller/MultirotorModel.py:14 */
+    double ctrl_g;                /* 9.81 */
+    double ctrl_kf;               /* 1.25e-9 */
+    double ctrl_min_rpm;          /* 1170 */
+    double ctrl_max_rpm;          /* 13000 */
+} qs_fork_config;
 
 /*
  * Flat, POD configuration.  Host code evaluates the reference's construction-time Python once
@@ -96,7 +140,7 @@ typedef struct qs_config {
     int32_t obst_area_len;        /* int(obst_spawn_area[0]) */
     int32_t obst_area_wid;        /* int(obst_spawn_area[1]) */
     int32_t num_obstacles;        /* int(density * area), quadrotor_multi.py:138 */
-    int32_t reserved0;
+    int32_t env_mode;             /* QS_MODE_* */
     uint64_t seed;                /* Philox key */
     int64_t env_id_offset;        /* global id of local env 0 (multi-GPU sharding keeps streams G-independent) */
 
@@ -137,6 +181,7 @@ typedef struct qs_config {
     double obst_size;             /* diameter */
     double sdf_resolution;        /* 0.1 */
     double approach_goal_metric;  /* scenarios/base.py:35 (0.5); o_static_same_goal uses 1.0 */
+    qs_fork_config fork;          /* QS_MODE_FORK only */
 } qs_config;
 
 /* SoA view used by qs_get_state / qs_set_state.  Every pointer is a DEVICE pointer to a dense
@@ -157,6 +202,10 @@ typedef struct qs_state_view {
     int32_t *svd_ctr;    /* [N]     sub-steps since the last re-orthonormalisation */
     uint32_t *step_ctr;  /* [N]     control steps since creation (RNG counter) */
     float *obst_xy;      /* [N, QS_MAX_OBSTACLES, 2] obstacle centres (first num_obstacles valid) */
+    /* fork mode (NULL / ignored otherwise) */
+    float *pid;          /* [N*K,24] (last_error, integral) of the 12 PIDs in cascade order */
+    float *heading;      /* [N*K,2]  pre_controller.angle, pre_controller.angular_velocity */
+    float *evader;       /* [N,2]    Scenario_dynamic_repulsive.pos */
 } qs_state_view;
 
 /* Per-rollout aggregate of the reference's per-episode 'episode_extra_stats' (quadrotor_multi.py:739-831):
@@ -176,6 +225,7 @@ typedef struct qs_stats {
     int64_t agents_deadlock;
     int64_t agents_collided;
     int64_t nonfinite_resets;     /* envs force-reset because a NaN/Inf appeared in their state */
+    int64_t episodes_success;     /* fork mode: episodes that ended with the target caught (reset_info["success"]) */
     double  distance_to_goal_1s;  /* sum over episodes and agents of the per-agent mean distance in the last 1 s */
     double  distance_to_goal_3s;
     double  distance_to_goal_5s;
@@ -211,16 +261,22 @@ int qs_reset(qs_env *env, const uint8_t *env_mask, float *obs, void *stream);
  *   done         [N*K]   device uint8 (all K agents of a finished env are 1, quadrotor_multi.py:838)
  *   terminal_obs [N*K,D] device float32 or NULL: last observation of the finished episode (rows of unfinished
  *                        envs untouched) -> infos[i]["terminal_observation"]
+ *   reset_success [N]    device uint8 or NULL: for envs that finished this step, reset_info["success"] of the episode
+ *                        that ended (fork mode: the target was caught, quadrotor_multi_rewards.py:625-627; upstream
+ *                        mode: 0); entries of unfinished envs are untouched -> VecEnv.reset_infos
+ * In QS_MODE_FORK one call advances every env by fork.substeps control steps (fewer if the episode ends inside,
+ * quadrotor_multi_rewards.py:633,986-987), A = 2, and the reward is the last executed sub-step's (:634).
  */
 int qs_step(qs_env *env, const float *actions, float *obs, float *rew, uint8_t *done,
-            float *terminal_obs, void *stream);
+            float *terminal_obs, uint8_t *reset_success, void *stream);
 
 /* Same, HOST buffers.  H2D of actions and D2H of obs/rew/done happen inside; the call returns after the stream has
  * drained.  Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are DMA'd directly, pageable ones
  * are staged through pinned buffers owned by the handle (one extra host memcpy each way). */
 int qs_reset_host(qs_env *env, float *obs_host, void *stream);
 int qs_step_host(qs_env *env, const float *actions_host, float *obs_host, float *rew_host,
-                 uint8_t *done_host, void *stream);
+                 uint8_t *done_host, float *terminal_obs_host /* nullable */, uint8_t *reset_success_host /* nullable */,
+                 void *stream);
 
 int qs_get_state(qs_env *env, const qs_state_view *view, void *stream);
 int qs_set_state(qs_env *env, const qs_state_view *view, void *stream);

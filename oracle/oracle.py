@@ -44,7 +44,10 @@ def lib():
         L.qo_set_tape.argtypes = [C.c_void_p, dp, C.c_int, dp, C.c_int, dp, C.c_int]
         L.qo_tape_pos.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
         L.qo_reset.argtypes = [C.c_void_p, dp]
-        L.qo_step.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_uint8), dp]
+        L.qo_step.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_uint8), dp, C.POINTER(C.c_uint8)]
+        L.qo_act_dim.argtypes = [C.c_void_p]
+        L.qo_get_fork_state.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_int32)]
+        L.qo_set_fork_state.argtypes = [C.c_void_p, dp, dp, dp, C.POINTER(C.c_int32)]
         L.qo_dynamics_only.argtypes = [C.c_void_p, C.c_int, dp]
         L.qo_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 11
         L.qo_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 11
@@ -90,6 +93,8 @@ class OracleEnv:
         if not self.h:
             raise RuntimeError("qo_create failed")
         self.D = lib().qo_obs_dim(self.h)
+        self.A = lib().qo_act_dim(self.h)
+        self.last_reset_success = None
         self._tape = None
 
     def __del__(self):
@@ -123,12 +128,14 @@ class OracleEnv:
         return obs
 
     def step(self, actions, want_terminal=False):
-        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.K, 4)
+        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.K, self.A)
         obs = np.zeros((self.K, self.D))
         rew = np.zeros(self.K)
         done = np.zeros(self.K, dtype=np.uint8)
         term = np.zeros((self.K, self.D)) if want_terminal else None
-        lib().qo_step(self.h, _dp(a), _dp(obs), _dp(rew), done.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(term))
+        succ = C.c_uint8(255)
+        lib().qo_step(self.h, _dp(a), _dp(obs), _dp(rew), done.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(term), C.byref(succ))
+        self.last_reset_success = None if succ.value == 255 else bool(succ.value)   # reset_info["success"] if the env reset
         if want_terminal:
             return obs, rew, done.astype(bool), term
         return obs, rew, done.astype(bool)
@@ -166,6 +173,20 @@ class OracleEnv:
         if kw.get("obst_xy") is not None:
             xy = np.ascontiguousarray(kw["obst_xy"], dtype=np.float64).reshape(-1, 2)
             lib().qo_set_obstacles(self.h, _dp(xy), xy.shape[0])
+
+    def get_fork_state(self):
+        pid, heading, evader, fl = np.zeros((self.K, 24)), np.zeros((self.K, 2)), np.zeros(2), (C.c_int32 * 2)()
+        lib().qo_get_fork_state(self.h, _dp(pid), _dp(heading), _dp(evader), fl)
+        return dict(pid=pid, heading=heading, evader=evader, episode_success=bool(fl[0]), chasers_placed=bool(fl[1]))
+
+    def set_fork_state(self, pid=None, heading=None, evader=None, episode_success=None, chasers_placed=None):
+        keep = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (pid, heading, evader)]
+        fl = None
+        if episode_success is not None or chasers_placed is not None:
+            cur = self.get_fork_state()
+            fl = (C.c_int32 * 2)(int(cur["episode_success"] if episode_success is None else episode_success),
+                                 int(cur["chasers_placed"] if chasers_placed is None else chasers_placed))
+        lib().qo_set_fork_state(self.h, *[_dp(a) for a in keep], fl)
 
     def stats(self):
         s = QsStatsC()
@@ -208,7 +229,7 @@ class OracleBatch:
         return self.obs
 
     def step(self, actions):
-        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.N * self.K, 4)
+        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.N * self.K, self.envs[0].A)
         K, D = self.K, self.D
         u8 = C.POINTER(C.c_uint8)
 

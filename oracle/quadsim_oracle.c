@@ -45,6 +45,8 @@ typedef struct {
     double sum1, sum3, sum5; int n1, n3, n5;
     int reached_goal, col_agent_ok, col_obst_ok;
     double ep_reward;
+    /* fork mode: pre_controller state.  pid[2k] = last_error, pid[2k+1] = integral of PID k (cascade order) */
+    double pid[24], angle, ang_vel;
 } qo_drone;
 
 typedef struct qo_env {
@@ -59,6 +61,10 @@ typedef struct qo_env {
     double obst_xy[QS_MAX_OBSTACLES][2];
     int n_obst;
     int scenario_now;                   /* QS_SCENARIO_O_RANDOM / O_STATIC_SAME_GOAL / STATIC_SAME_GOAL */
+    double evader[2];                   /* fork mode: Scenario_dynamic_repulsive.pos */
+    int episode_success;                /* fork mode: quadrotor_multi_rewards.py:757,625-627 */
+    int chasers_placed;                 /* fork mode: 0 until the first reset has given the dynamics a position; the evader's very
+                                           first step ignores the chasers (`hasattr(env.dynamics, "pos")`, dynamic_repulsive.py:44) */
     double approach_metric;
     /* per-episode counters (quadrotor_multi.py:153-171) */
     int collisions_per_episode, collisions_after_settle, collisions_final_5s;
@@ -887,6 +893,8 @@ static void env_step(qo_env *e, const double *actions, double *obs, double *rew,
     e->step_ctr += 1;
 }
 
+#include "fork_oracle.inc"
+
 /* ------------------------------------------------------------------------------------------------ */
 /* exported API (ctypes)                                                                              */
 /* ------------------------------------------------------------------------------------------------ */
@@ -902,7 +910,11 @@ qo_env *qo_create(const qs_config *cfg, int env_index)
     return e;
 }
 void qo_destroy(qo_env *e) { free(e); }
-int qo_obs_dim(const qo_env *e) { return obs_dim(&e->c); }
+static int is_fork(const qo_env *e) { return e->c.env_mode == QS_MODE_FORK; }
+static int any_obs_dim(const qs_config *c) { return c->env_mode == QS_MODE_FORK ? fork_obs_dim(c) : obs_dim(c); }
+static int any_act_dim(const qs_config *c) { return c->env_mode == QS_MODE_FORK ? 2 : 4; }
+int qo_obs_dim(const qo_env *e) { return any_obs_dim(&e->c); }
+int qo_act_dim(const qo_env *e) { return any_act_dim(&e->c); }
 
 void qo_set_tape(qo_env *e, const double *normals, int nn, const double *uniforms, int nu, const double *choices, int nc)
 {
@@ -913,10 +925,30 @@ void qo_set_tape(qo_env *e, const double *normals, int nn, const double *uniform
 /* how far the tape was consumed (tests assert it was consumed exactly) */
 void qo_tape_pos(const qo_env *e, int *in_, int *iu, int *ic) { *in_ = e->in_; *iu = e->iu; *ic = e->ic; }
 
-void qo_reset(qo_env *e, double *obs) { env_reset(e, obs); e->step_ctr += 1; }
-void qo_step(qo_env *e, const double *actions, double *obs, double *rew, uint8_t *done, double *terminal_obs)
+void qo_reset(qo_env *e, double *obs) { if (is_fork(e)) fork_env_reset(e, obs); else env_reset(e, obs); e->step_ctr += 1; }
+void qo_step(qo_env *e, const double *actions, double *obs, double *rew, uint8_t *done, double *terminal_obs, uint8_t *reset_success)
 {
-    env_step(e, actions, obs, rew, done, terminal_obs);
+    if (is_fork(e)) fork_env_step(e, actions, obs, rew, done, terminal_obs, reset_success);
+    else { env_step(e, actions, obs, rew, done, terminal_obs); if (reset_success && done[0]) *reset_success = 0; }
+}
+/* fork-mode state: pid [K,24], heading [K,2] = (angle, angular_velocity), evader [2] */
+void qo_get_fork_state(const qo_env *e, double *pid, double *heading, double *evader, int32_t *env_flags /* [2]: episode_success, chasers_placed */)
+{
+    for (int i = 0; i < e->K; ++i) {
+        if (pid) memcpy(pid + 24 * i, e->d[i].pid, sizeof(double) * 24);
+        if (heading) { heading[2 * i] = e->d[i].angle; heading[2 * i + 1] = e->d[i].ang_vel; }
+    }
+    if (evader) { evader[0] = e->evader[0]; evader[1] = e->evader[1]; }
+    if (env_flags) { env_flags[0] = e->episode_success; env_flags[1] = e->chasers_placed; }
+}
+void qo_set_fork_state(qo_env *e, const double *pid, const double *heading, const double *evader, const int32_t *env_flags)
+{
+    if (env_flags) { e->episode_success = env_flags[0]; e->chasers_placed = env_flags[1]; }
+    for (int i = 0; i < e->K; ++i) {
+        if (pid) memcpy(e->d[i].pid, pid + 24 * i, sizeof(double) * 24);
+        if (heading) { e->d[i].angle = heading[2 * i]; e->d[i].ang_vel = heading[2 * i + 1]; }
+    }
+    if (evader) { e->evader[0] = evader[0]; e->evader[1] = evader[1]; }
 }
 
 /* one free-flight control step of drone 0 only (golden vector A.1 of SURVEY.md) */
@@ -984,7 +1016,8 @@ void qo_get_diag(const qo_env *e, uint32_t *new_pairs, int32_t *neighbors, int32
 void qo_set_param(qo_env *e, int key, double v)
 {
     double *p[QS_PARAM_COUNT] = { &e->c.rew_pos, &e->c.rew_effort, &e->c.rew_crash, &e->c.rew_orient, &e->c.rew_spin,
-                                  &e->c.rew_quadcol_bin, &e->c.rew_quadcol_bin_smooth_max, &e->c.rew_quadcol_bin_obst };
+                                  &e->c.rew_quadcol_bin, &e->c.rew_quadcol_bin_smooth_max, &e->c.rew_quadcol_bin_obst,
+                                  &e->c.fork.capture_radius };
     if (key >= 0 && key < QS_PARAM_COUNT) *p[key] = v;
 }
 
@@ -997,13 +1030,13 @@ void qo_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, 
 void qo_batch_step(qo_env **envs, int n, const double *actions, double *obs, double *rew, uint8_t *done)
 {
     if (n <= 0) return;
-    int K = envs[0]->K, D = obs_dim(&envs[0]->c);
+    int K = envs[0]->K, D = any_obs_dim(&envs[0]->c), A = any_act_dim(&envs[0]->c);
     for (int k = 0; k < n; ++k)
-        env_step(envs[k], actions + (size_t)k * K * 4, obs + (size_t)k * K * D, rew + (size_t)k * K, done + (size_t)k * K, NULL);
+        qo_step(envs[k], actions + (size_t)k * K * A, obs + (size_t)k * K * D, rew + (size_t)k * K, done + (size_t)k * K, NULL, NULL);
 }
 void qo_batch_reset(qo_env **envs, int n, double *obs)
 {
     if (n <= 0) return;
-    int K = envs[0]->K, D = obs_dim(&envs[0]->c);
-    for (int k = 0; k < n; ++k) { env_reset(envs[k], obs + (size_t)k * K * D); envs[k]->step_ctr += 1; }
+    int K = envs[0]->K, D = any_obs_dim(&envs[0]->c);
+    for (int k = 0; k < n; ++k) qo_reset(envs[k], obs + (size_t)k * K * D);
 }

@@ -282,3 +282,57 @@ def snapshot(env):
         tick=np.array([e.tick for e in env.envs], dtype=np.int64),
         since_last_svd=np.array([x.since_last_svd for x in d], dtype=np.float64),
     )
+
+
+# --------------------------------------------------------------------------------------
+# fork env (swarm_rl/sb_train.py path): quadrotor_multi_rewards.QuadrotorEnvMulti(QuadrotorEnvConfig)
+# --------------------------------------------------------------------------------------
+def make_fork_env(tape=None, **overrides):
+    """``quadrotor_multi_rewards.QuadrotorEnvMulti`` built from ``swarm_rl.global_cfg.QuadrotorEnvConfig`` exactly as
+    ``SB3QuadrotorEnv._make_env`` does (swarm_rl/env_wrappers/sb3_quad_env.py:36-41).  ``overrides`` are dataclass
+    field values (num_agents, episode_duration, obs_repr, neighbor_obs_type, neighbor_visible_num, room_dims, ...)."""
+    install_stubs()
+    from swarm_rl.global_cfg import QuadrotorEnvConfig
+    from gym_art.quadrotor_multi import quadrotor_multi_rewards as qmr
+    cfg = QuadrotorEnvConfig()
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise KeyError(k)
+        setattr(cfg, k, v)
+    if cfg.seed is None:
+        cfg.seed = 0
+    env = qmr.QuadrotorEnvMulti(cfg)
+    # reference bug (SURVEY.md H4): Scenario_dynamic_repulsive.pos starts as an *int* array (dynamic_repulsive.py:34), so
+    # the first episode's evader position is garbage (nan cast to int).  From the second reset on it is float64.  The
+    # fixtures start from the float state every later episode has.
+    env.scenario.pos = np.zeros(2, dtype=np.float64)
+    if os.environ.get("NUMBA_DISABLE_JIT") == "1":
+        for e in env.envs:
+            n = e.dynamics.thrust_noise
+            n.theta, n.sigma, n.mu = np.float32(n.theta), np.float32(n.sigma), np.float32(n.mu)
+    if tape is not None:
+        gen = TapeGenerator(tape)
+        env.rng = gen
+        env.scenario.rng = gen
+        for e in env.envs:
+            e.rng = gen
+            e.dynamics.rng = gen
+    return env
+
+
+def fork_snapshot(env):
+    """dynamics snapshot + the fork's extra per-drone state (pre-controller angle, 12 PIDs) and the evader position."""
+    s = snapshot(env)
+    pid_state = []
+    for e in env.envs:
+        c = e.pre_controller
+        row = []
+        for ctl in (c.position_controller, c.velocity_controller, c.attitude_controller, c.rate_controller):
+            for p in (ctl.pid_x, ctl.pid_y, ctl.pid_z):
+                row += [p.last_error, p.integral]
+        pid_state.append(row)
+    s["pid"] = np.array(pid_state, dtype=np.float64)                       # [K, 24]
+    s["angle"] = np.array([e.pre_controller.angle for e in env.envs], dtype=np.float64)
+    s["ang_vel"] = np.array([e.pre_controller.angular_velocity for e in env.envs], dtype=np.float64)
+    s["evader"] = np.array(env.scenario.pos, dtype=np.float64)
+    return s

@@ -9,7 +9,8 @@ import subprocess
 from .config import QsConfigC, QsStateViewC, QsStatsC
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libquadsim_b200.so")
+# QS_LIB_PATH: load another build of the same sources (tuning sweeps under build/variants/); default is the in-tree library
+LIB_PATH = os.environ.get("QS_LIB_PATH") or os.path.join(_PKG, "libquadsim_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -24,17 +25,18 @@ EXPORTS = ("qs_config_size", "qs_stats_size", "qs_api_version", "qs_last_error",
            "qs_reset_host", "qs_step_host", "qs_get_state", "qs_set_state", "qs_set_param", "qs_episode_stats")
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, "quadsim.cu")]
     deps = srcs + [os.path.join(CSRC, "quadsim_kernels.cuh"), os.path.join(os.path.dirname(_PKG), "include", "quadsim.h")]
-    if not force and os.path.exists(LIB_PATH) and all(
+    if not force and out is None and os.path.exists(LIB_PATH) and all(
             (not os.path.exists(d)) or os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    target = out or LIB_PATH
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + srcs
     subprocess.check_call(cmd)
-    return LIB_PATH
+    return target
 
 
 _lib = None

@@ -10,19 +10,36 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Sequence
 
-from . import quad_model
+from . import fork_model, quad_model
 
-QS_API_VERSION = 1
+QS_API_VERSION = 2
 QS_MAX_AGENTS = 32
 QS_MAX_OBSTACLES = 64
 
-SCENARIOS = {"static_same_goal": 0, "o_mix": 1, "o_random": 2, "o_static_same_goal": 3}
-OBS_REPR = {"xyz_vxyz_R_omega": 0, "xyz_vxyz_R_omega_floor": 1, "xyz_vxyz_R_omega_wall": 2}
-OBS_REPR_DIM = {"xyz_vxyz_R_omega": 18, "xyz_vxyz_R_omega_floor": 19, "xyz_vxyz_R_omega_wall": 24}  # quad_utils.py:30-38
-NEIGHBOR_OBS = {"none": 0, "pos_vel": 1}
-NEIGHBOR_OBS_DIM = {"none": 0, "pos_vel": 6}                                                       # quad_utils.py:40-58
+SCENARIOS = {"static_same_goal": 0, "o_mix": 1, "o_random": 2, "o_static_same_goal": 3, "dynamic_repulsive": 4}
+ENV_MODES = {"upstream": 0, "fork": 1}
+OBS_REPR = {"xyz_vxyz_R_omega": 0, "xyz_vxyz_R_omega_floor": 1, "xyz_vxyz_R_omega_wall": 2,
+            "cdist_cdistdot_dist_distdot_angle_angledot": 3, "cdist_cdistdot_dist_distdot_sangle_angledot": 4,
+            "aw_awdot_dist_distdot_angle_angledot": 5}
+OBS_REPR_DIM = {"xyz_vxyz_R_omega": 18, "xyz_vxyz_R_omega_floor": 19, "xyz_vxyz_R_omega_wall": 24,       # quad_utils.py:30-38
+                "cdist_cdistdot_dist_distdot_angle_angledot": 6, "cdist_cdistdot_dist_distdot_sangle_angledot": 7,
+                "aw_awdot_dist_distdot_angle_angledot": 6}
+FORK_OBS_REPR = {k for k, v in OBS_REPR.items() if v >= 3}
+NEIGHBOR_OBS = {"none": 0, "pos_vel": 1, "dist_angle": 2, "dist_sangle": 3}
+NEIGHBOR_OBS_DIM = {"none": 0, "pos_vel": 6, "dist_angle": 2, "dist_sangle": 3}                      # quad_utils.py:40-58
+FORK_NEIGHBOR_OBS = {"none", "dist_angle", "dist_sangle"}
 PARAM_KEYS = {"pos": 0, "effort": 1, "crash": 2, "orient": 3, "spin": 4,
-              "quadcol_bin": 5, "quadcol_bin_smooth_max": 6, "quadcol_bin_obst": 7}
+              "quadcol_bin": 5, "quadcol_bin_smooth_max": 6, "quadcol_bin_obst": 7, "capture_radius": 8}
+
+
+class QsForkConfigC(C.Structure):
+    """Binary mirror of `struct qs_fork_config`."""
+    _fields_ = [("substeps", C.c_int32), ("reserved", C.c_int32)] + [(n, C.c_double) for n in (
+        "capture_radius", "rew_existence", "rew_captor", "rew_helper", "max_angular_rate", "chaser_speed",
+        "evader_v_max", "evader_dt", "evader_arena", "spawn_ring", "evader_r_min", "evader_r_span")] + [
+        ("pid", (C.c_double * 5) * 12), ("rate_out_scale", C.c_double), ("mixer", (C.c_double * 4) * 4),
+        ("ctrl_mass", C.c_double), ("ctrl_g", C.c_double), ("ctrl_kf", C.c_double), ("ctrl_min_rpm", C.c_double),
+        ("ctrl_max_rpm", C.c_double)]
 
 
 class QsConfigC(C.Structure):
@@ -33,7 +50,7 @@ class QsConfigC(C.Structure):
         ("use_obstacles", C.c_int32), ("use_downwash", C.c_int32), ("apply_collision_force", C.c_int32),
         ("sense_noise", C.c_int32), ("ep_len", C.c_int32), ("sim_steps", C.c_int32), ("svd_period", C.c_int32),
         ("obst_area_len", C.c_int32), ("obst_area_wid", C.c_int32), ("num_obstacles", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("env_mode", C.c_int32),
         ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
         ("dt", C.c_double), ("room_dims", C.c_double * 3), ("gravity", C.c_double),
         ("mass", C.c_double), ("inertia", C.c_double * 3), ("thrust_max", C.c_double * 4),
@@ -48,6 +65,7 @@ class QsConfigC(C.Structure):
         ("collision_hitbox_radius", C.c_double), ("collision_falloff_radius", C.c_double),
         ("spawn_box", C.c_double), ("spawn_min_z", C.c_double),
         ("obst_size", C.c_double), ("sdf_resolution", C.c_double), ("approach_goal_metric", C.c_double),
+        ("fork", QsForkConfigC),
     ]
 
 
@@ -57,7 +75,7 @@ class QsStatsC(C.Structure):
         "episodes", "num_collisions", "num_collisions_after_settle", "num_collisions_final_5s",
         "num_collisions_with_room", "num_collisions_with_floor", "num_collisions_with_wall",
         "num_collisions_with_ceiling", "num_collisions_obst_quad", "num_collisions_obst_quad_after_settle",
-        "agents_success", "agents_deadlock", "agents_collided", "nonfinite_resets")] + [
+        "agents_success", "agents_deadlock", "agents_collided", "nonfinite_resets", "episodes_success")] + [
         (n, C.c_double) for n in ("distance_to_goal_1s", "distance_to_goal_3s", "distance_to_goal_5s", "reward_sum")]
 
     def as_dict(self):
@@ -67,7 +85,7 @@ class QsStatsC(C.Structure):
 class QsStateViewC(C.Structure):
     """Binary mirror of `struct qs_state_view`: raw device addresses."""
     FIELDS = ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou", "goal", "flags", "col_mask",
-              "tick", "svd_ctr", "step_ctr", "obst_xy")
+              "tick", "svd_ctr", "step_ctr", "obst_xy", "pid", "heading", "evader")
     _fields_ = [(n, C.c_void_p) for n in FIELDS]
 
 
@@ -103,6 +121,36 @@ class QuadSimConfig:
     env_id_offset: int = 0
     motor: quad_model.MotorParams = field(default_factory=quad_model.MotorParams)
     geometry: quad_model.QuadGeometry = field(default_factory=quad_model.QuadGeometry)
+    env_mode: str = "upstream"                # 'upstream' (quadrotor_multi.py) | 'fork' (quadrotor_multi_rewards.py)
+    fork: fork_model.ForkParams = field(default_factory=fork_model.ForkParams)
+
+    @classmethod
+    def fork_default(cls, **kw) -> "QuadSimConfig":
+        """The env `swarm_rl/sb_train.py` trains on: defaults of `swarm_rl/global_cfg.py:QuadrotorEnvConfig`
+        (4 agents, dynamic_repulsive, 2-D observations, room 15x15x3, 30 s episodes, collision forces off)."""
+        base = dict(env_mode="fork", num_agents=4, quads_mode="dynamic_repulsive",
+                    obs_repr="cdist_cdistdot_dist_distdot_angle_angledot", neighbor_obs_type="dist_angle",
+                    neighbor_visible_num=-1, room_dims=(15.0, 15.0, 3.0), ep_time=30.0,
+                    apply_collision_force=False)                  # quadrotor_multi_rewards.py:203
+        capture_radius = kw.pop("capture_radius", None)
+        base.update(kw)
+        cfg = cls(**base)
+        if capture_radius is not None:
+            cfg.fork.capture_radius = float(capture_radius)
+        return cfg
+
+    @classmethod
+    def from_reference_cfg(cls, rcfg, num_envs: int, **kw) -> "QuadSimConfig":
+        """Map a `swarm_rl.global_cfg.QuadrotorEnvConfig` (duck-typed) to the fork-mode configuration."""
+        cap = getattr(rcfg, "initial_capture_radius", None)
+        return cls.fork_default(
+            num_envs=num_envs, num_agents=rcfg.num_agents, quads_mode=rcfg.quads_mode, obs_repr=rcfg.obs_repr,
+            neighbor_obs_type=rcfg.neighbor_obs_type, neighbor_visible_num=rcfg.neighbor_visible_num,
+            room_dims=tuple(float(v) for v in rcfg.room_dims), ep_time=float(rcfg.episode_duration),
+            collision_hitbox_radius=rcfg.collision_hitbox_radius, collision_falloff_radius=rcfg.collision_falloff_radius,
+            use_downwash=bool(rcfg.use_downwash), sim_freq=float(rcfg.sim_freq), sim_steps=int(rcfg.sim_steps),
+            sense_noise=rcfg.sense_noise, seed=int(rcfg.seed or 0),
+            capture_radius=0.2 if cap is None else float(cap), **kw)
 
     # ---- derived ---------------------------------------------------------------------------
     @property
@@ -121,7 +169,7 @@ class QuadSimConfig:
 
     @property
     def act_dim(self) -> int:
-        return 4
+        return 2 if self.env_mode == "fork" else 4      # quadrotor_control.py:74-86 (CustomPidControl) vs :37-49
 
     @property
     def dt(self) -> float:
@@ -143,9 +191,12 @@ class QuadSimConfig:
             mode = "o_mix"
         if mode not in SCENARIOS:
             raise ValueError(f"quads_mode {self.quads_mode!r} is not available on the device "
-                             f"(supported: static_same_goal; with obstacles: mix, o_random, o_static_same_goal)")
+                             f"(supported: static_same_goal, dynamic_repulsive (fork mode); with obstacles: mix, "
+                             f"o_random, o_static_same_goal)")
         if self.use_obstacles != mode.startswith("o_"):
             raise ValueError(f"quads_mode {self.quads_mode!r} inconsistent with use_obstacles={self.use_obstacles}")
+        if (mode == "dynamic_repulsive") != (self.env_mode == "fork"):
+            raise ValueError("dynamic_repulsive is the fork-mode scenario (env_mode='fork') and the only one it supports")
         return SCENARIOS[mode]
 
     def to_c(self) -> QsConfigC:
@@ -153,10 +204,21 @@ class QuadSimConfig:
             raise ValueError(f"num_agents must be in [1, {QS_MAX_AGENTS}]")
         if self.num_envs < 1:
             raise ValueError("num_envs must be >= 1")
+        if self.env_mode not in ENV_MODES:
+            raise ValueError(f"env_mode {self.env_mode!r} not supported")
         if self.obs_repr not in OBS_REPR:
             raise ValueError(f"obs_repr {self.obs_repr!r} not supported")
         if self.neighbor_obs_type not in NEIGHBOR_OBS:
             raise ValueError(f"neighbor_obs_type {self.neighbor_obs_type!r} not supported")
+        is_fork = self.env_mode == "fork"
+        if (self.obs_repr in FORK_OBS_REPR) != is_fork:
+            raise ValueError(f"obs_repr {self.obs_repr!r} does not belong to env_mode {self.env_mode!r}")
+        if is_fork and self.neighbor_obs_type not in FORK_NEIGHBOR_OBS:
+            raise ValueError(f"neighbor_obs_type {self.neighbor_obs_type!r} is not a fork-mode type")
+        if not is_fork and self.neighbor_obs_type in ("dist_angle", "dist_sangle"):
+            raise ValueError(f"neighbor_obs_type {self.neighbor_obs_type!r} needs env_mode='fork'")
+        if is_fork and self.use_obstacles:
+            raise ValueError("the fork env has its obstacle path commented out (quadrotor_multi_rewards.py:106-119)")
         rew = dict(DEFAULT_REW_COEFF)
         unknown = set(self.rew_coeff) - set(rew) - {"action_change", "yaw", "rot", "attitude", "vel"}
         if unknown:
@@ -165,10 +227,13 @@ class QuadSimConfig:
         q = quad_model.crazyflie_constants(self.geometry, self.motor, self.dt)
         c = QsConfigC()
         c.api_version = QS_API_VERSION
+        c.env_mode = ENV_MODES[self.env_mode]
         c.num_envs, c.num_agents = self.num_envs, self.num_agents
         c.scenario = self.scenario_id()
         c.obs_repr = OBS_REPR[self.obs_repr]
         c.neighbor_obs_type = NEIGHBOR_OBS[self.neighbor_obs_type] if self.visible > 0 else 0
+        if is_fork and self.fork.substeps < 1:
+            raise ValueError("fork.substeps must be >= 1")
         c.neighbor_visible_num = self.visible
         c.use_obstacles = int(self.use_obstacles)
         c.use_downwash = int(self.use_downwash)
@@ -215,4 +280,17 @@ class QuadSimConfig:
         c.obst_size = self.obst_size
         c.sdf_resolution = 0.1                                    # obstacles/obstacles.py:13
         c.approach_goal_metric = 0.5                              # scenarios/base.py:35
+        f, fp = c.fork, self.fork
+        f.substeps = fp.substeps
+        for n in ("capture_radius", "rew_existence", "rew_captor", "rew_helper", "max_angular_rate", "chaser_speed",
+                  "evader_v_max", "evader_dt", "evader_arena", "spawn_ring", "evader_r_min", "evader_r_span",
+                  "rate_out_scale"):
+            setattr(f, n, float(getattr(fp, n)))
+        for i, row in enumerate(fp.pid_table()):
+            f.pid[i][:] = row
+        mx = fp.model.mixer()
+        for i in range(4):
+            f.mixer[i][:] = [float(v) for v in mx[i]]
+        f.ctrl_mass, f.ctrl_g, f.ctrl_kf = fp.model.mass, fp.model.g, fp.model.kf
+        f.ctrl_min_rpm, f.ctrl_max_rpm = fp.model.min_rpm, fp.model.max_rpm
         return c

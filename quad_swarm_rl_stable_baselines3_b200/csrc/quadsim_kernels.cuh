@@ -15,6 +15,9 @@
 #include "../../include/quadsim.h"
 
 #define QS_FULL 0xffffffffu
+#ifndef QS_STEP_MINBLOCKS
+#define QS_STEP_MINBLOCKS 4      // resident 128-thread blocks per SM the step kernel is compiled for (register cap 65536/(128*n))
+#endif
 #define QS_PI_F 3.14159265358979323846f
 
 namespace qs {
@@ -302,15 +305,6 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
     q.v[0] = kd * q.v[0] + dt * ax; q.v[1] = kd * q.v[1] + dt * ay; q.v[2] = kd * q.v[2] + dt * az;
 }
 
-// rot2quat branches for trace <= 0 (sensor_noise.py:44-62)
-__device__ __noinline__ void rot2quat_rare(const float *R, float &qw, float &qx, float &qy, float &qz)
-{
-    float S;
-    if (R[0] > R[4] && R[0] > R[8]) { S = sqrtf(1.0f + R[0] - R[4] - R[8]) * 2.f; qw = (R[7] - R[5]) / S; qx = 0.25f * S; qy = (R[1] + R[3]) / S; qz = (R[2] + R[6]) / S; }
-    else if (R[4] > R[8]) { S = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2.f; qw = (R[2] - R[6]) / S; qx = (R[1] + R[3]) / S; qy = 0.25f * S; qz = (R[5] + R[7]) / S; }
-    else { S = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2.f; qw = (R[3] - R[1]) / S; qx = (R[2] + R[6]) / S; qy = (R[5] + R[7]) / S; qz = 0.25f * S; }
-}
-
 // ----------------------------------------------------------------------------------------------------------------
 // a9  self observation: SensorNoise.add_noise_numba + state_xyz_vxyz_R_omega* (sensor_noise.py:172-261, get_state.py:226-292)
 // ----------------------------------------------------------------------------------------------------------------
@@ -329,8 +323,17 @@ __device__ __forceinline__ void self_obs(const DevConst &c, const Rng &g, int si
         // R -> quaternion -> R round trip (sensor_noise.py:34-63, 205-210; quad_utils.py:162-168), zero rotation noise
         const float *R = q.R;
         float tr = R[0] + R[4] + R[8], qw, qx, qy, qz, S;
-        if (tr > 0.f) { S = sqrtf(tr + 1.0f) * 2.f; float iS = 1.0f / S; qw = 0.25f * S; qx = (R[7] - R[5]) * iS; qy = (R[2] - R[6]) * iS; qz = (R[3] - R[1]) * iS; }
-        else rot2quat_rare(R, qw, qx, qy, qz);                            // tilted past ~120 deg: out of line
+        // one sqrt + one reciprocal shared by the four rot2quat branches (sensor_noise.py:34-63)
+        const bool b0 = tr > 0.f, b1 = !b0 && (R[0] > R[4] && R[0] > R[8]), b2 = !b0 && !b1 && (R[4] > R[8]);
+        const float arg = b0 ? tr : (b1 ? R[0] - R[4] - R[8] : (b2 ? R[4] - R[0] - R[8] : R[8] - R[0] - R[4]));
+        S = sqrtf(arg + 1.0f) * 2.f;
+        const float iS = 1.0f / S, big = 0.25f * S;
+        const float a76 = (R[7] - R[5]) * iS, a26 = (R[2] - R[6]) * iS, a31 = (R[3] - R[1]) * iS;
+        const float s13 = (R[1] + R[3]) * iS, s26 = (R[2] + R[6]) * iS, s57 = (R[5] + R[7]) * iS;
+        qw = b0 ? big : (b1 ? a76 : (b2 ? a26 : a31));
+        qx = b0 ? a76 : (b1 ? big : (b2 ? s13 : s26));
+        qy = b0 ? a26 : (b1 ? s13 : (b2 ? big : s57));
+        qz = b0 ? a31 : (b1 ? s26 : (b2 ? s57 : big));
         o[6] = 1.0f - 2.f * qy * qy - 2.f * qz * qz; o[7] = 2.f * qx * qy - 2.f * qz * qw; o[8] = 2.f * qx * qz + 2.f * qy * qw;
         o[9] = 2.f * qx * qy + 2.f * qz * qw; o[10] = 1.0f - 2.f * qx * qx - 2.f * qz * qz; o[11] = 2.f * qy * qz - 2.f * qx * qw;
         o[12] = 2.f * qx * qz - 2.f * qy * qw; o[13] = 2.f * qy * qz + 2.f * qx * qw; o[14] = 1.0f - 2.f * qx * qx - 2.f * qy * qy;
@@ -370,7 +373,7 @@ __device__ __forceinline__ void compute_new_omega(const float *u4, float magn_sc
 }
 
 // perform_collision_between_drones, collisions/quadrotors.py:9-59.  Inputs are drone i ("1") and drone j ("2").
-__device__ __noinline__ void pair_impulse(const Rng &g, int i, int j, const float *p1, const float *p2, float *v1, float *v2,
+__device__ __noinline__ void pair_impulse(const Rng g, int i, int j, const float *p1, const float *p2, float *v1, float *v2,
                                           float *w1, float *w2)
 {
     float n0 = p1[0] - p2[0], n1 = p1[1] - p2[1], n2 = p1[2] - p2[2];
@@ -406,12 +409,13 @@ __device__ __noinline__ void pair_impulse(const Rng &g, int i, int j, const floa
 }
 
 // perform_collision_with_obstacle, collisions/obstacles.py:9-50
-__device__ __noinline__ void obstacle_impulse(const DevConst &c, const Rng &g, int drone, Drone &q, float ox, float oy)
+__device__ __noinline__ void obstacle_impulse(const DevConst &c, const Rng g, int drone, const float *p, float *v, float *w,
+                                              float ox, float oy)
 {
-    float n0 = q.p[0] - ox, n1 = q.p[1] - oy;
+    float n0 = p[0] - ox, n1 = p[1] - oy;
     float nm = sqrtf(n0 * n0 + n1 * n1), den = (nm == 0.0f) ? nm + 1e-5f : nm;
     n0 /= den; n1 /= den;
-    float vm = norm3f(q.v[0], q.v[1], q.v[2]);
+    float vm = norm3f(v[0], v[1], v[2]);
     float nv[3] = { vm * n0, vm * n1, 0.f }, noise[3] = { 0.f, 0.f, 0.f };
     for (int att = 0; att < 3; ++att) {
         float x[4], y[4];
@@ -420,42 +424,42 @@ __device__ __noinline__ void obstacle_impulse(const DevConst &c, const Rng &g, i
         float t[3] = { 0.1f * x[0] + 0.05f * x[3], 0.1f * x[1] + 0.05f * y[0], 0.1f * x[2] + 0.05f * y[1] };
         if ((nv[0] + t[0]) * n0 + (nv[1] + t[1]) * n1 > 0.f) { noise[0] = t[0]; noise[1] = t[1]; noise[2] = t[2]; break; }
     }
-    float dz = q.p[2] - 0.5f * c.room_h;
-    float d3 = norm3f(q.p[0] - ox, q.p[1] - oy, dz);
-    float shift[3] = { nv[0] - q.v[0] + noise[0], nv[1] - q.v[1] + noise[1], nv[2] - q.v[2] + noise[2] };
+    float dz = p[2] - 0.5f * c.room_h;
+    float d3 = norm3f(p[0] - ox, p[1] - oy, dz);
+    float shift[3] = { nv[0] - v[0] + noise[0], nv[1] - v[1] + noise[1], nv[2] - v[2] + noise[2] };
     float u[4], t[4];
     rng_u4(g, SITE_OBST, drone, 0, 6, u);                             // idx 24..27
     rng_u4(g, SITE_OBST, drone, 0, 7, t);                             // idx 28..31
     float decay = (d3 < c.obst_rad) ? 1.0f : 0.2f + 0.6f * u[0];
-    compute_new_vel(vm, q.v, shift, decay);
-    float u4[4] = { u[1], u[2], u[3], t[0] }, w[3];
-    compute_new_omega(u4, 1.0f, w);
-    q.w[0] += w[0]; q.w[1] += w[1]; q.w[2] += w[2];
+    compute_new_vel(vm, v, shift, decay);
+    float u4[4] = { u[1], u[2], u[3], t[0] }, dw[3];
+    compute_new_omega(u4, 1.0f, dw);
+    w[0] += dw[0]; w[1] += dw[1]; w[2] += dw[2];
 }
 
 // perform_collision_with_wall / _ceiling, collisions/room.py:6-45, 91-113
-__device__ __noinline__ void room_impulse(const DevConst &c, const Rng &g, int drone, Drone &q, bool is_wall)
+__device__ __noinline__ void room_impulse(const DevConst &c, const Rng g, int drone, int flags, float *v, float *w, bool is_wall)
 {
     int site = is_wall ? SITE_WALL : SITE_CEILING;
     float u[12];
     rng_u4(g, site, drone, 0, 0, u); rng_u4(g, site, drone, 0, 1, u + 4); rng_u4(g, site, drone, 0, 2, u + 8);
-    float sp = norm3f(q.v[0], q.v[1], q.v[2]);
+    float sp = norm3f(v[0], v[1], v[2]);
     float lo = 0.2f * sp, hi = 0.8f * sp;
     float real = clampf(lo + (hi - lo) * u[0], 0.1f, 6.0f);
     float d0 = -1.f + 2.f * u[1], d1 = -1.f + 2.f * u[2], d2;
     int k;
     if (is_wall) {
-        if (q.flags & F_AT_XLO) d0 = 0.1f + 0.9f * u[4]; else if (q.flags & F_AT_XHI) d0 = -1.0f + 0.9f * u[4];
-        if (q.flags & F_AT_YLO) d1 = 0.1f + 0.9f * u[5]; else if (q.flags & F_AT_YHI) d1 = -1.0f + 0.9f * u[5];
+        if (flags & F_AT_XLO) d0 = 0.1f + 0.9f * u[4]; else if (flags & F_AT_XHI) d0 = -1.0f + 0.9f * u[4];
+        if (flags & F_AT_YLO) d1 = 0.1f + 0.9f * u[5]; else if (flags & F_AT_YHI) d1 = -1.0f + 0.9f * u[5];
         k = 6;
     } else k = 4;
     d2 = -1.0f + 0.5f * u[k];
     float dm = norm3f(d0, d1, d2) + 1e-5f;
-    q.v[0] = real * (d0 / dm); q.v[1] = real * (d1 / dm); q.v[2] = real * (d2 / dm);
+    v[0] = real * (d0 / dm); v[1] = real * (d1 / dm); v[2] = real * (d2 / dm);
     float w0 = -1.f + 2.f * u[k + 1], w1 = -1.f + 2.f * u[k + 2], w2 = -1.f + 2.f * u[k + 3];
     float wm = norm3f(w0, w1, w2) + 1e-5f;
     float omax = 20.f * QS_PI_F, mag = 0.5f * omax + 0.5f * omax * u[k + 4];
-    q.w[0] += w0 / wm * mag; q.w[1] += w1 / wm * mag; q.w[2] += w2 / wm * mag;
+    w[0] += w0 / wm * mag; w[1] += w1 / wm * mag; w[2] += w2 / wm * mag;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -484,7 +488,7 @@ __device__ __forceinline__ void choice_fy(const Rng &g, int aux, int n, int k, u
 // obst_generation_given_density (quadrotor_multi.py:405-426) + Scenario_o_random / o_static_same_goal .reset
 // (scenarios/obstacles/o_random.py:26-52, o_static_same_goal.py:27-48, o_base.py:69-81,124-153).
 // Every lane of the group evaluates it redundantly (same keys -> same values); lane `drone` keeps its own spawn/goal.
-__device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rng &g, int drone, bool leader, float2 *obst_xy,
+__device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rng g, int drone, bool leader, float2 *obst_xy,
                                                      float *spawn, float *goal, int &scenario_now)
 {
     const int L = c.obst_L, W = c.obst_W, M = c.M, K = c.K;
@@ -537,14 +541,15 @@ __device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rn
 }
 
 // QuadrotorSingle._reset, quadrotor_single.py:401-469
-__device__ __noinline__ void drone_reset(const DevConst &c, const Rng &g, int drone, const float *spawn, Drone &q)
+// out = { x, y, z, cos(yaw), sin(yaw) }
+__device__ __noinline__ void drone_reset(const DevConst &c, const Rng g, int drone, const float *spawn, float *out)
 {
     float u[4];
     rng_u4(g, SITE_SPAWN, drone, 0, 0, u);
-    q.p[0] = (-c.spawn_box + 2.0f * c.spawn_box * u[0]) + spawn[0];
-    q.p[1] = (-c.spawn_box + 2.0f * c.spawn_box * u[1]) + spawn[1];
-    q.p[2] = fmaxf((-c.spawn_box + 2.0f * c.spawn_box * u[2]) + spawn[2], c.spawn_min_z);
-    float hx = -q.p[0], hy = -q.p[1], hn = sqrtf(hx * hx + hy * hy);
+    float px = (-c.spawn_box + 2.0f * c.spawn_box * u[0]) + spawn[0];
+    float py = (-c.spawn_box + 2.0f * c.spawn_box * u[1]) + spawn[1];
+    float pz = fmaxf((-c.spawn_box + 2.0f * c.spawn_box * u[2]) + spawn[2], c.spawn_min_z);
+    float hx = -px, hy = -py, hn = sqrtf(hx * hx + hy * hy);
     if (!(hn < 0.00001f)) { hx /= hn; hy /= hn; }
     float cy, sy;
     unit_dir(hx, hy, cy, sy);                                           // fallback: face the origin
@@ -560,11 +565,7 @@ __device__ __noinline__ void drone_reset(const DevConst &c, const Rng &g, int dr
             }
         }
     }
-    set_yaw(q.R, cy, sy);
-    q.v[0] = q.v[1] = q.v[2] = 0.f; q.w[0] = q.w[1] = q.w[2] = 0.f;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) { q.rd[m] = 0.f; q.cd[m] = 0.f; }
-    q.flags = 0; q.colmask = 0u;
+    out[0] = px; out[1] = py; out[2] = pz; out[3] = cy; out[4] = sy;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -662,15 +663,24 @@ template <int KG>
 __device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P, const Rng &g, int env, int d, bool valid, Drone &q,
                                             int &scenario_now)
 {
-    float spawn[3];
+    float spawn[3], goal[3], out[5];
     if (c.use_obstacles) {
-        obstacle_scenario_reset(c, g, d, valid && d == 0, P.obst_xy + (size_t)env * QS_MAX_OBSTACLES, spawn, q.goal, scenario_now);
+        int scen = 0;
+        obstacle_scenario_reset(c, g, d, valid && d == 0, P.obst_xy + (size_t)env * QS_MAX_OBSTACLES, spawn, goal, scen);
+        scenario_now = scen;
     } else {
-        q.goal[0] = 0.f; q.goal[1] = 0.f; q.goal[2] = 2.0f;               // static_same_goal: formation size 0 (scenarios/utils.py:30)
+        goal[0] = 0.f; goal[1] = 0.f; goal[2] = 2.0f;                     // static_same_goal: formation size 0 (scenarios/utils.py:30)
         spawn[0] = 0.f; spawn[1] = 0.f; spawn[2] = 2.0f;
         scenario_now = QS_SCENARIO_STATIC_SAME_GOAL;
     }
-    drone_reset(c, g, d, spawn, q);
+    drone_reset(c, g, d, spawn, out);
+    q.goal[0] = goal[0]; q.goal[1] = goal[1]; q.goal[2] = goal[2];
+    q.p[0] = out[0]; q.p[1] = out[1]; q.p[2] = out[2];
+    set_yaw(q.R, out[3], out[4]);
+    q.v[0] = q.v[1] = q.v[2] = 0.f; q.w[0] = q.w[1] = q.w[2] = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { q.rd[m] = 0.f; q.cd[m] = 0.f; }
+    q.flags = 0; q.colmask = 0u;
 }
 
 // coalesced copy of the warp's observation tile (rows contiguous in global memory) out of shared memory
@@ -689,7 +699,7 @@ __device__ __forceinline__ void warp_store_tile(const float *tile, float *dst, i
 // The step kernel: QuadrotorEnvMulti.step (quadrotor_multi.py:521-842) for every env, one launch.
 // ----------------------------------------------------------------------------------------------------------------
 template <int KG>
-__global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
+__global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
                                                    const float4 *__restrict__ actions, float *__restrict__ obs,
                                                    float *__restrict__ rew, uint8_t *__restrict__ done, float *__restrict__ term_obs)
 {
@@ -720,9 +730,11 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevCo
         if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
         g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
     }
+    float4 ring = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
         load_drone(P, gi, q);
         act = __ldcs(actions + gi);
+        ring = P.plane[PL_DIST_RING][gi];                               // issued with the state loads: one exposed HBM latency per thread
     } else {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { q.p[a] = 1.0e6f * (float)(lane + 1); q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
@@ -840,7 +852,6 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevCo
     // distance_to_goal log: reached-goal flag from the mean of the last 5 entries, and the 1/3/5 s windows (:651-655, 762-767)
     if (valid) {
         float dlog = c.dt * dist;                                      // -rewraw_pos
-        float4 ring = P.plane[PL_DIST_RING][gi];
         if (tick >= 5 && !(q.flags & F_REACHED)) {
             float m5 = (ring.x + ring.y + ring.z + ring.w + dlog) / 5.0f;
             float metric = (c.use_obstacles && scen_now == QS_SCENARIO_O_STATIC_SAME_GOAL) ? 1.0f : c.approach_metric;
@@ -918,12 +929,23 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevCo
             flag = true;
         }
         if (c.use_obstacles && obst_ballot) {
-            if (obst_new) { float2 xy = P.obst_xy[(size_t)env * QS_MAX_OBSTACLES + obst_hit]; obstacle_impulse(c, g, d, q, xy.x, xy.y); }
+            if (obst_new) {
+                float2 xy = P.obst_xy[(size_t)env * QS_MAX_OBSTACLES + obst_hit];
+                float tp[3] = { q.p[0], q.p[1], q.p[2] }, tv[3] = { q.v[0], q.v[1], q.v[2] }, tw[3] = { q.w[0], q.w[1], q.w[2] };
+                obstacle_impulse(c, g, d, tp, tv, tw, xy.x, xy.y);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { q.v[a] = tv[a]; q.w[a] = tw[a]; }
+            }
             flag = true;
         }
         if (wall_ballot | ceil_ballot) {
-            if (new_wall) room_impulse(c, g, d, q, true);
-            if (new_ceil) room_impulse(c, g, d, q, false);
+            if (new_wall || new_ceil) {
+                float tv[3] = { q.v[0], q.v[1], q.v[2] }, tw[3] = { q.w[0], q.w[1], q.w[2] };
+                if (new_wall) room_impulse(c, g, d, q.flags, tv, tw, true);
+                if (new_ceil) room_impulse(c, g, d, q.flags, tv, tw, false);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { q.v[a] = tv[a]; q.w[a] = tw[a]; }
+            }
             flag = true;
         }
     }

@@ -123,6 +123,97 @@ def gen_traces():
               f"draws N={len(out['tn'])} U={len(out['tu'])} C={len(out['tc'])} -> {os.path.getsize(path) // 1024} KiB")
 
 
+# fork env (quadrotor_multi_rewards.py) traces: name -> (QuadrotorEnvConfig overrides, VecEnv steps, capture-radius schedule)
+FORK_TRACES = {
+    # sb_train.py defaults: 4 chasers, dist_angle neighbours, capture radius 3.0 -> frequent immediate captures + timeouts
+    "fork_k4": dict(env=dict(num_agents=4, episode_duration=1.6), steps=110, radius={40: 1.0, 80: 2.6}),
+    # BASELINE configs[0]: single quadrotor
+    "fork_k1": dict(env=dict(num_agents=1, episode_duration=1.0, initial_capture_radius=2.4), steps=60, radius={}),
+    # sangle reprs, 3 nearest of 7 neighbours
+    "fork_k8_sangle": dict(env=dict(num_agents=8, episode_duration=0.8, initial_capture_radius=2.2,
+                                    obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot",
+                                    neighbor_obs_type="dist_sangle", neighbor_visible_num=3), steps=50, radius={}),
+}
+FORK_STATE_KEYS = STATE_KEYS + ("pid", "angle", "ang_vel", "evader")
+
+
+def gen_fork_traces():
+    """The env sb_train.py trains on, driven the way SubprocVecEnvCustom's worker drives it
+    (swarm_rl/env_wrappers/subproc_vec_env_custom.py:35-52): step, and on any(done) keep the terminal observation and reset."""
+    os.environ["NUMBA_DISABLE_JIT"] = "1"
+    import io
+    import contextlib
+    import numpy as np
+    import ref_harness as rh
+
+    tape = rh.Tape(seed=4321)
+    rh.install_tape(tape)
+    for name, spec in FORK_TRACES.items():
+        K = spec["env"]["num_agents"]
+        with contextlib.redirect_stdout(io.StringIO()):
+            env = rh.make_fork_env(tape=tape, **spec["env"])
+        rs = np.random.RandomState(sum(map(ord, name)))
+        rec = {k: [] for k in ("actions", "obs", "rew", "done", "term", "success", "radius", "tn", "tu", "n_tn", "n_tu", "tick")}
+        snaps = {k: [] for k in FORK_STATE_KEYS}
+
+        def push_tape(m):
+            k, v = tape.since(m)
+            assert not (k == 2).any()
+            for key, kind in (("tn", 0), ("tu", 1)):
+                vals = v[k == kind]
+                rec[key].append(vals)
+                rec["n_" + key].append(len(vals))
+
+        def push_snap():
+            sn = rh.fork_snapshot(env)
+            for k in FORK_STATE_KEYS:
+                snaps[k].append(sn[k])
+            rec["tick"].append(int(sn["tick"][0]))
+
+        m = tape.mark()
+        with contextlib.redirect_stdout(io.StringIO()):
+            obs, _ = env.reset()
+        push_tape(m)
+        push_snap()
+        rec["obs"].append(np.array(obs, dtype=np.float64))
+        n_done = n_succ = 0
+        for s in range(spec["steps"]):
+            if s in spec["radius"]:
+                env.set_capture_radius(spec["radius"][s])
+            rec["radius"].append(float(env.capture_radius))
+            a = rs.uniform(-1.0, 1.0, (K, 2))
+            m = tape.mark()
+            with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+                obs, rew, done, infos = env.step(a)
+                term = np.array(obs, dtype=np.float64)
+                succ = -1
+                if any(done):
+                    obs, info = env.reset()
+                    succ = int(info["success"])
+                    n_done += 1
+                    n_succ += succ
+            push_tape(m)
+            push_snap()
+            rec["actions"].append(a)
+            rec["obs"].append(np.array(obs, dtype=np.float64))
+            rec["rew"].append(np.array(rew, dtype=np.float64))
+            rec["done"].append(np.array(done, dtype=bool))
+            rec["term"].append(term)
+            rec["success"].append(succ)
+        out = dict(actions=np.array(rec["actions"]), obs=np.array(rec["obs"]), rew=np.array(rec["rew"]),
+                   done=np.array(rec["done"]), term=np.array(rec["term"]), success=np.array(rec["success"]),
+                   radius=np.array(rec["radius"]), tick=np.array(rec["tick"]),
+                   tn=np.concatenate(rec["tn"]), tu=np.concatenate(rec["tu"]),
+                   n_tn=np.array(rec["n_tn"]), n_tu=np.array(rec["n_tu"]))
+        for k in FORK_STATE_KEYS:
+            out["s_" + k] = np.array(snaps[k])
+        out["env_kwargs"] = np.array(repr(spec["env"]))
+        path = os.path.join(HERE, f"trace_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: steps={spec['steps']} dones={n_done} captures={n_succ} draws N={len(out['tn'])} U={len(out['tu'])} "
+              f"-> {os.path.getsize(path) // 1024} KiB")
+
+
 def gen_dyn_jit():
     """JIT ON: QuadrotorDynamics.step (quadrotor_dynamics.py:215-221) on one drone, thrust noise off."""
     import numpy as np
@@ -182,8 +273,11 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which == "traces":
         gen_traces()
+    elif which == "fork":
+        gen_fork_traces()
     elif which == "dyn":
         gen_dyn_jit()
     else:   # separate interpreters: NUMBA_DISABLE_JIT must be decided before numba is imported
         subprocess.check_call([sys.executable, __file__, "dyn"])
         subprocess.check_call([sys.executable, __file__, "traces"])
+        subprocess.check_call([sys.executable, __file__, "fork"])

@@ -151,3 +151,89 @@ def test_env_trace(golden_dir, name):
     assert n_done >= 1
     if name in ("smallroom_k8", "crowd_k16", "cfg3_obst_k8"):
         assert n_impulse >= 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fork mode (quadrotor_multi_rewards.py: PID pre-controller, 8 control steps per call, capture task)
+# ------------------------------------------------------------------------------------------------------------------
+FORK_TRACE_NAMES = ["fork_k4", "fork_k1", "fork_k8_sangle"]
+
+
+def fork_cfg_from_kwargs(kw):
+    kw = dict(kw)
+    m = dict(num_agents=kw.pop("num_agents"), ep_time=kw.pop("episode_duration", 30.0))
+    if "initial_capture_radius" in kw:
+        m["capture_radius"] = kw.pop("initial_capture_radius")
+    m.update(kw)          # obs_repr / neighbor_obs_type / neighbor_visible_num carry the reference's names
+    return QuadSimConfig.fork_default(num_envs=1, **m)
+
+
+def test_fork_constants_match_survey_known_answers():
+    """mixer allocation and controller inertia of the reference."""
+    from quad_swarm_rl_stable_baselines3_b200.fork_model import ForkParams
+    p = ForkParams()
+    s = 0.7071067811865476
+    np.testing.assert_allclose(p.model.mixer(), [[-s, -s, -1, 1], [s, s, -1, 1], [s, -s, 1, 1], [-s, s, 1, 1]], atol=1e-12)
+    np.testing.assert_allclose(p.model.inertia_diag(), [1.48072512e-05, 1.48072512e-05, 2.95725024e-05], rtol=1e-8)
+
+
+@pytest.mark.parametrize("name", FORK_TRACE_NAMES)
+def test_fork_env_trace(golden_dir, name):
+    """QuadrotorEnvMulti.step (fork) + the VecEnv worker's auto-reset, every draw taped.  The full state (dynamics,
+    12 PIDs, heading, evader) is re-synchronised to the reference before every call; the 8 control sub-steps inside a
+    call, the episode bookkeeping and the capture-radius schedule free-run."""
+    g = np.load(os.path.join(golden_dir, f"trace_{name}.npz"))
+    cfg = fork_cfg_from_kwargs(ast.literal_eval(str(g["env_kwargs"])))
+    K = cfg.num_agents
+    o = OracleEnv(cfg)
+    assert o.D == g["obs"].shape[2] and o.A == 2
+    on, ou_ = np.cumsum(np.r_[0, g["n_tn"]]), np.cumsum(np.r_[0, g["n_tu"]])
+
+    def tape(i):
+        o.set_tape(g["tn"][on[i]:on[i + 1]], g["tu"][ou_[i]:ou_[i + 1]], None)
+
+    def check(i, what):
+        assert o.tape_pos()[:2] == (g["n_tn"][i], g["n_tu"][i]), (what, o.tape_pos(), g["n_tn"][i], g["n_tu"][i])
+        st, fs = o.get_state(), o.get_fork_state()
+        for k in PHYS:
+            np.testing.assert_allclose(st[k].reshape(K, -1), g["s_" + k][i].reshape(K, -1), rtol=0, atol=2e-8, err_msg=f"{what} {k}")
+        np.testing.assert_allclose(st["goal"], g["s_goal"][i], atol=1e-12, err_msg=f"{what} goal")
+        np.testing.assert_allclose(fs["evader"], g["s_evader"][i], atol=1e-12, err_msg=f"{what} evader")
+        np.testing.assert_allclose(fs["heading"][:, 0], g["s_angle"][i], atol=1e-12, err_msg=f"{what} angle")
+        np.testing.assert_allclose(fs["heading"][:, 1], g["s_ang_vel"][i], atol=1e-12, err_msg=f"{what} ang_vel")
+        np.testing.assert_allclose(fs["pid"], g["s_pid"][i], rtol=1e-7, atol=1e-9, err_msg=f"{what} pid")
+        assert st["tick"] == g["tick"][i], what
+
+    def force(i):
+        st = o.get_state()
+        fl = st["flags"] & ~0xF
+        for bit, key in enumerate(("on_floor", "crashed_floor", "crashed_wall", "crashed_ceiling")):
+            fl |= g["s_" + key][i].astype(np.int32) << bit
+        o.set_state(flags=fl, goal=g["s_goal"][i], **{k: g["s_" + k][i] for k in PHYS})
+        o.set_fork_state(pid=g["s_pid"][i], heading=np.stack([g["s_angle"][i], g["s_ang_vel"][i]], axis=1), evader=g["s_evader"][i])
+
+    # the very first reset starts from the constructor state of the reference: drones at the origin, evader at (0, 0)
+    tape(0)
+    o.set_state(pos=np.zeros((K, 3)))
+    obs = o.reset()
+    check(0, "reset")
+    np.testing.assert_allclose(obs, g["obs"][0], rtol=0, atol=1e-8)
+    n_done = n_succ = 0
+    for s in range(g["actions"].shape[0]):
+        force(s)
+        o.set_param(8, float(g["radius"][s]))                    # QS_PARAM_CAPTURE_RADIUS
+        tape(s + 1)
+        obs, rew, done, term = o.step(g["actions"][s], want_terminal=True)
+        check(s + 1, f"step {s}")
+        np.testing.assert_allclose(rew, g["rew"][s], rtol=0, atol=1e-9, err_msg=f"step {s} reward")
+        assert np.array_equal(done, g["done"][s]), f"step {s} done"
+        np.testing.assert_allclose(obs, g["obs"][s + 1], rtol=0, atol=2e-7, err_msg=f"step {s} obs")
+        if done.any():
+            np.testing.assert_allclose(term, g["term"][s], rtol=0, atol=2e-7, err_msg=f"step {s} terminal obs")
+            assert o.last_reset_success == bool(g["success"][s]), f"step {s} reset_info['success']"
+            n_done += 1
+            n_succ += int(g["success"][s])
+        else:
+            assert o.last_reset_success is None and g["success"][s] == -1
+    assert n_done >= 3 and n_succ >= 1
+    assert o.stats()["episodes"] == n_done and o.stats()["episodes_success"] == n_succ
