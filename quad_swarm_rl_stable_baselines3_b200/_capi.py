@@ -64,9 +64,9 @@ def lib():
     L.qs_launch_count.argtypes = [vp]
     L.qs_launch_count.restype = C.c_int64
     L.qs_reset.argtypes = [vp, vp, vp, vp]
-    L.qs_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.qs_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.qs_reset_host.argtypes = [vp, vp, vp]
-    L.qs_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.qs_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.qs_get_state.argtypes = [vp, C.POINTER(QsStateViewC), vp]
     L.qs_set_state.argtypes = [vp, C.POINTER(QsStateViewC), vp]
     L.qs_set_param.argtypes = [vp, i32, C.c_double]

@@ -8,7 +8,7 @@
 #include <cstring>
 #include <string>
 
-#include "quadsim_kernels.cuh"
+#include "fork_kernels.cuh"
 
 using namespace qs;
 
@@ -16,6 +16,10 @@ struct qs_env {
     qs_config cfg;
     DevConst dc;
     DevPtrs dp;
+    ForkConst fc;
+    ForkPtrs fp;
+    bool fork;
+    int A;                  // action dim
     int device;
     int KG;                 // lanes per env
     int block;              // threads per block
@@ -24,8 +28,8 @@ struct qs_env {
     void *slab;             // one allocation for all device state
     size_t slab_bytes;
     // pinned host staging + device io buffers for the *_host entry points
-    float *h_act, *h_obs, *h_rew; uint8_t *h_done;
-    float *d_act, *d_obs, *d_rew; uint8_t *d_done;
+    float *h_act, *h_obs, *h_rew, *h_term; uint8_t *h_done, *h_succ;
+    float *d_act, *d_obs, *d_rew, *d_term; uint8_t *d_done, *d_succ;
     long long launches;
     std::string err;
 };
@@ -54,8 +58,14 @@ static void fill_const(const qs_config &c, DevConst &d)
     d.use_downwash = c.use_downwash; d.apply_force = c.apply_collision_force; d.sense_noise = c.sense_noise;
     d.ep_len = c.ep_len; d.sim_steps = c.sim_steps; d.svd_period = c.svd_period;
     d.obst_L = c.obst_area_len; d.obst_W = c.obst_area_wid; d.M = c.num_obstacles;
-    d.S = c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR ? 19 : (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_WALL ? 24 : 18);
-    d.D = d.S + (c.neighbor_obs_type == QS_NEIGHBOR_POS_VEL ? 6 * c.neighbor_visible_num : 0) + (c.use_obstacles ? 9 : 0);
+    if (c.env_mode == QS_MODE_FORK) {
+        d.S = c.obs_repr == QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_SANGLE_ANGLEDOT ? 7 : 6;
+        int W = c.neighbor_obs_type == QS_NEIGHBOR_DIST_ANGLE ? 2 : (c.neighbor_obs_type == QS_NEIGHBOR_DIST_SANGLE ? 3 : 0);
+        d.D = d.S + W * c.neighbor_visible_num;
+    } else {
+        d.S = c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR ? 19 : (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_WALL ? 24 : 18);
+        d.D = d.S + (c.neighbor_obs_type == QS_NEIGHBOR_POS_VEL ? 6 * c.neighbor_visible_num : 0) + (c.use_obstacles ? 9 : 0);
+    }
     d.key0 = (uint32_t)c.seed; d.key1 = (uint32_t)(c.seed >> 32);
     d.env_id_offset = c.env_id_offset;
     d.dt = (float)c.dt;
@@ -84,8 +94,41 @@ static void fill_const(const qs_config &c, DevConst &d)
     d.control_dt = (float)(1.0 / control_freq);                            // quadrotor_multi.py:91
 }
 
+static void fill_fork(const qs_config &c, ForkConst &f)
+{
+    memset(&f, 0, sizeof(f));
+    const qs_fork_config &s = c.fork;
+    f.substeps = s.substeps;
+    f.capture_radius = (float)s.capture_radius; f.rew_existence = (float)s.rew_existence; f.rew_captor = (float)s.rew_captor;
+    f.rew_helper = (float)s.rew_helper; f.max_angular_rate = (float)s.max_angular_rate; f.chaser_speed = (float)s.chaser_speed;
+    f.ev_vmax = (float)s.evader_v_max; f.ev_dt = (float)s.evader_dt; f.ev_arena = (float)s.evader_arena;
+    f.spawn_ring = (float)s.spawn_ring; f.ev_rmin = (float)s.evader_r_min; f.ev_rspan = (float)s.evader_r_span;
+    for (int i = 0; i < 12; ++i) for (int k = 0; k < 5; ++k) f.pid[i][k] = (float)s.pid[i][k];
+    f.rate_scale = (float)s.rate_out_scale;
+    for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) f.mixer[i][k] = (float)s.mixer[i][k];
+    f.mass = (float)s.ctrl_mass; f.g = (float)s.ctrl_g; f.inv_kf4 = (float)(1.0 / (s.ctrl_kf * 4.0));
+    f.min_rpm = (float)s.ctrl_min_rpm; f.inv_rpm_span = (float)(1.0 / (s.ctrl_max_rpm - s.ctrl_min_rpm));
+    f.half_len = (float)(c.room_dims[0] / 2.0);
+}
+
 static int validate(const qs_config *c, std::string &why)
 {
+    if (c->env_mode == QS_MODE_FORK) {
+        if (c->api_version != QS_API_VERSION) { why = "api_version mismatch"; return 0; }
+        if (c->num_envs < 1) { why = "num_envs < 1"; return 0; }
+        if (c->num_agents < 1 || c->num_agents > QS_MAX_AGENTS) { why = "num_agents out of [1, 32]"; return 0; }
+        if (c->scenario != QS_SCENARIO_DYNAMIC_REPULSIVE) { why = "fork mode supports quads_mode dynamic_repulsive only"; return 0; }
+        if (c->obs_repr < QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_ANGLE_ANGLEDOT || c->obs_repr > QS_OBS_AW_AWDOT_DIST_DISTDOT_ANGLE_ANGLEDOT) { why = "fork mode needs a fork obs_repr"; return 0; }
+        if (c->neighbor_obs_type != QS_NEIGHBOR_NONE && c->neighbor_obs_type != QS_NEIGHBOR_DIST_ANGLE && c->neighbor_obs_type != QS_NEIGHBOR_DIST_SANGLE) { why = "fork mode needs a fork neighbor_obs_type"; return 0; }
+        if (c->neighbor_visible_num < 0 || c->neighbor_visible_num > c->num_agents - 1) { why = "neighbor_visible_num out of range"; return 0; }
+        if (c->use_obstacles || c->use_downwash || c->apply_collision_force) { why = "fork mode: obstacles / downwash / collision forces are off in the reference (quadrotor_multi_rewards.py:106-119,203) and not built"; return 0; }
+        if (c->fork.substeps < 1 || c->fork.substeps > 64) { why = "fork.substeps out of [1, 64]"; return 0; }
+        if (c->sim_steps < 1 || c->sim_steps > 16 || !(c->dt > 0) || c->svd_period < 1 || c->ep_len < 1) { why = "bad sim_steps / dt / svd_period / ep_len"; return 0; }
+        if (!(c->mass > 0) || !(c->inertia[0] > 0) || !(c->inertia[1] > 0) || !(c->inertia[2] > 0)) { why = "bad mass / inertia"; return 0; }
+        return 1;
+    }
+    if (c->env_mode != QS_MODE_UPSTREAM) { why = "unknown env_mode"; return 0; }
+    if (c->scenario == QS_SCENARIO_DYNAMIC_REPULSIVE) { why = "dynamic_repulsive needs env_mode fork"; return 0; }
     if (c->api_version != QS_API_VERSION) { why = "api_version mismatch"; return 0; }
     if (c->num_envs < 1) { why = "num_envs < 1"; return 0; }
     if (c->num_agents < 1 || c->num_agents > QS_MAX_AGENTS) { why = "num_agents out of [1, 32]"; return 0; }
@@ -144,9 +187,13 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
 
     qs_env *e = new qs_env();
     e->cfg = *cfg; e->device = device; e->launches = 0;
-    e->h_act = e->h_obs = e->h_rew = nullptr; e->h_done = nullptr;
-    e->d_act = e->d_obs = e->d_rew = nullptr; e->d_done = nullptr;
+    e->h_act = e->h_obs = e->h_rew = e->h_term = nullptr; e->h_done = e->h_succ = nullptr;
+    e->d_act = e->d_obs = e->d_rew = e->d_term = nullptr; e->d_done = e->d_succ = nullptr;
     fill_const(*cfg, e->dc);
+    e->fork = cfg->env_mode == QS_MODE_FORK;
+    e->A = e->fork ? 2 : 4;
+    fill_fork(*cfg, e->fc);
+    memset(&e->fp, 0, sizeof(e->fp));
     const int N = cfg->num_envs, K = cfg->num_agents;
     e->KG = pow2_at_least(K);
     const long long lanes = (long long)N * e->KG;
@@ -173,6 +220,12 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     size_t o_ecnt = off; off += align((size_t)N * EC_COUNT * sizeof(int));
     size_t o_obst = off; off += align((size_t)N * QS_MAX_OBSTACLES * sizeof(float2));
     size_t o_stats = off; off += align(sizeof(qs_stats));
+    size_t fplane_off[FP_COUNT] = {0}, o_evader = 0, o_fflags = 0;
+    if (e->fork) {
+        for (int p = 0; p < FP_COUNT; ++p) { fplane_off[p] = off; off += align(nd * sizeof(float4)); }
+        o_evader = off; off += align((size_t)N * sizeof(float2));
+        o_fflags = off; off += align((size_t)N * sizeof(int));
+    }
     e->slab_bytes = off;
     r = cudaMalloc(&e->slab, off);
     if (r != cudaSuccess) { delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: cudaMalloc: ") + cudaGetErrorString(r)); }
@@ -181,6 +234,10 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     for (int p = 0; p < PL_COUNT; ++p) e->dp.plane[p] = (float4 *)(b + plane_off[p]);
     e->dp.tick = (int *)(b + o_tick); e->dp.svd_ctr = (int *)(b + o_svd); e->dp.step_ctr = (uint32_t *)(b + o_step);
     e->dp.ecnt = (int *)(b + o_ecnt); e->dp.obst_xy = (float2 *)(b + o_obst); e->dp.stats = (qs_stats *)(b + o_stats);
+    if (e->fork) {
+        for (int p = 0; p < FP_COUNT; ++p) e->fp.plane[p] = (float4 *)(b + fplane_off[p]);
+        e->fp.evader = (float2 *)(b + o_evader); e->fp.flags = (int *)(b + o_fflags);
+    }
     // identity rotations so that an un-reset env is still a valid state
     {
         StateView v; memset(&v, 0, sizeof(v));
@@ -190,11 +247,12 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
         for (size_t i = 0; i < nd; ++i) for (int a = 0; a < 9; ++a) h[9 * i + a] = (a % 4 == 0) ? 1.f : 0.f;
         cudaMemcpy(rot, h, nd * 9 * sizeof(float), cudaMemcpyHostToDevice);
         v.rot = rot;
-        state_io_kernel<<<(int)((nd + 127) / 128), 128>>>(e->dc, e->dp, v, 1);
+        state_io_kernel<<<(int)((nd + 127) / 128), 128>>>(e->dc, e->dp, e->fp, v, 1);
         cudaDeviceSynchronize();
         cudaFree(rot); free(h);
     }
-    QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, step_kernel<KG>); set_smem_attr(e->smem_bytes, reset_kernel<KG>));
+    if (e->fork) { QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, fork_step_kernel<KG>); set_smem_attr(e->smem_bytes, fork_reset_kernel<KG>)); }
+    else { QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, step_kernel<KG>); set_smem_attr(e->smem_bytes, reset_kernel<KG>)); }
     r = cudaGetLastError();
     if (r != cudaSuccess) { cudaFree(e->slab); delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: ") + cudaGetErrorString(r)); }
     *out = e;
@@ -210,6 +268,10 @@ int qs_destroy(qs_env *e)
     if (e->h_obs) cudaFreeHost(e->h_obs);
     if (e->h_rew) cudaFreeHost(e->h_rew);
     if (e->h_done) cudaFreeHost(e->h_done);
+    if (e->h_term) cudaFreeHost(e->h_term);
+    if (e->h_succ) cudaFreeHost(e->h_succ);
+    if (e->d_term) cudaFree(e->d_term);
+    if (e->d_succ) cudaFree(e->d_succ);
     if (e->d_act) cudaFree(e->d_act);
     if (e->d_obs) cudaFree(e->d_obs);
     if (e->d_rew) cudaFree(e->d_rew);
@@ -221,25 +283,31 @@ int qs_destroy(qs_env *e)
 int qs_num_envs(const qs_env *e) { return e ? e->cfg.num_envs : QS_ERR_NULL; }
 int qs_num_agents(const qs_env *e) { return e ? e->cfg.num_agents : QS_ERR_NULL; }
 int qs_obs_dim(const qs_env *e) { return e ? e->dc.D : QS_ERR_NULL; }
-int qs_act_dim(const qs_env *e) { return e ? 4 : QS_ERR_NULL; }
+int qs_act_dim(const qs_env *e) { return e ? e->A : QS_ERR_NULL; }
 int64_t qs_launch_count(const qs_env *e) { return e ? e->launches : 0; }
 
 int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
 {
     if (!e || !obs) return fail(e, QS_ERR_NULL, "qs_reset: null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    QS_DISPATCH_KG(e->KG, (reset_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs)));
+    if (e->fork) { QS_DISPATCH_KG(e->KG, (fork_reset_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->fc, e->dp, e->fp, env_mask, obs))); }
+    else { QS_DISPATCH_KG(e->KG, (reset_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs))); }
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
 }
 
-int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *done, float *terminal_obs, void *stream)
+int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *done, float *terminal_obs, uint8_t *reset_success,
+            void *stream)
 {
     if (!e || !actions || !obs || !rew || !done) return fail(e, QS_ERR_NULL, "qs_step: null argument");
     if (((size_t)actions & 15) != 0) return fail(e, QS_ERR_SHAPE, "qs_step: actions must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    QS_DISPATCH_KG(e->KG, (step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs)));
+    if (e->fork) {
+        QS_DISPATCH_KG(e->KG, (fork_step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->fc, e->dp, e->fp, (const float2 *)actions, obs, rew, done, terminal_obs, reset_success)));
+    } else {
+        QS_DISPATCH_KG(e->KG, (step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success)));
+    }
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
@@ -249,11 +317,11 @@ static int ensure_host_buffers(qs_env *e)
 {
     if (e->h_act) return QS_OK;
     const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
-    QS_CUDA(e, cudaMallocHost(&e->h_act, nd * 4 * sizeof(float)));
+    QS_CUDA(e, cudaMallocHost(&e->h_act, nd * e->A * sizeof(float)));
     QS_CUDA(e, cudaMallocHost(&e->h_obs, nd * D * sizeof(float)));
     QS_CUDA(e, cudaMallocHost(&e->h_rew, nd * sizeof(float)));
     QS_CUDA(e, cudaMallocHost(&e->h_done, nd));
-    QS_CUDA(e, cudaMalloc(&e->d_act, nd * 4 * sizeof(float)));
+    QS_CUDA(e, cudaMalloc(&e->d_act, nd * e->A * sizeof(float)));
     QS_CUDA(e, cudaMalloc(&e->d_obs, nd * D * sizeof(float)));
     QS_CUDA(e, cudaMalloc(&e->d_rew, nd * sizeof(float)));
     QS_CUDA(e, cudaMalloc(&e->d_done, nd));
@@ -285,26 +353,52 @@ int qs_reset_host(qs_env *e, float *obs_host, void *stream)
     return QS_OK;
 }
 
-int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *rew_host, uint8_t *done_host, void *stream)
+int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *rew_host, uint8_t *done_host,
+                 float *terminal_obs_host, uint8_t *reset_success_host, void *stream)
 {
     if (!e || !actions_host || !obs_host || !rew_host || !done_host) return fail(e, QS_ERR_NULL, "qs_step_host: null argument");
     int rc = ensure_host_buffers(e);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
+    const size_t N = (size_t)e->cfg.num_envs, nd = N * e->cfg.num_agents, D = (size_t)e->dc.D, A = (size_t)e->A;
+    if (terminal_obs_host && !e->d_term) {
+        QS_CUDA(e, cudaMalloc(&e->d_term, nd * D * sizeof(float)));
+        QS_CUDA(e, cudaMemsetAsync(e->d_term, 0, nd * D * sizeof(float), s));
+        QS_CUDA(e, cudaMallocHost(&e->h_term, nd * D * sizeof(float)));
+    }
+    if (reset_success_host && !e->d_succ) {
+        QS_CUDA(e, cudaMalloc(&e->d_succ, N));
+        QS_CUDA(e, cudaMemsetAsync(e->d_succ, 0, N, s));
+        QS_CUDA(e, cudaMallocHost(&e->h_succ, N));
+    }
     // page-locked caller buffers are DMA'd directly; pageable ones are staged through the handle's pinned buffers
     const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rew_host), pd = is_pinned(done_host);
-    if (!pa) memcpy(e->h_act, actions_host, nd * 4 * sizeof(float));
-    QS_CUDA(e, cudaMemcpyAsync(e->d_act, pa ? actions_host : e->h_act, nd * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = qs_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, nullptr, stream);
+    const bool pt = terminal_obs_host && is_pinned(terminal_obs_host), ps = reset_success_host && is_pinned(reset_success_host);
+    if (!pa) memcpy(e->h_act, actions_host, nd * A * sizeof(float));
+    QS_CUDA(e, cudaMemcpyAsync(e->d_act, pa ? actions_host : e->h_act, nd * A * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = qs_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, terminal_obs_host ? e->d_term : nullptr,
+                 reset_success_host ? e->d_succ : nullptr, stream);
     if (rc) return rc;
     QS_CUDA(e, cudaMemcpyAsync(pr ? rew_host : e->h_rew, e->d_rew, nd * sizeof(float), cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaMemcpyAsync(pd ? done_host : e->h_done, e->d_done, nd, cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaMemcpyAsync(po ? obs_host : e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reset_success_host) QS_CUDA(e, cudaMemcpyAsync(ps ? reset_success_host : e->h_succ, e->d_succ, N, cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaStreamSynchronize(s));
     if (!po) memcpy(obs_host, e->h_obs, nd * D * sizeof(float));
     if (!pr) memcpy(rew_host, e->h_rew, nd * sizeof(float));
     if (!pd) memcpy(done_host, e->h_done, nd);
+    if (reset_success_host && !ps) memcpy(reset_success_host, e->h_succ, N);
+    if (terminal_obs_host) {
+        // terminal observations are only needed for envs that finished (rare): copy them after looking at `done`
+        const uint8_t *dn = pd ? done_host : e->h_done;
+        bool any = false;
+        for (size_t i = 0; i < nd && !any; i += (size_t)e->cfg.num_agents) any = dn[i] != 0;
+        if (any) {
+            QS_CUDA(e, cudaMemcpyAsync(pt ? terminal_obs_host : e->h_term, e->d_term, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+            QS_CUDA(e, cudaStreamSynchronize(s));
+            if (!pt) memcpy(terminal_obs_host, e->h_term, nd * D * sizeof(float));
+        }
+    }
     return QS_OK;
 }
 
@@ -315,8 +409,9 @@ static int state_io(qs_env *e, const qs_state_view *view, void *stream, int set)
     v.pos = view->pos; v.vel = view->vel; v.rot = view->rot; v.omega = view->omega; v.rot_damp = view->rot_damp;
     v.cmds_damp = view->cmds_damp; v.ou = view->ou; v.goal = view->goal; v.flags = view->flags; v.col_mask = view->col_mask;
     v.tick = view->tick; v.svd_ctr = view->svd_ctr; v.step_ctr = view->step_ctr; v.obst_xy = view->obst_xy;
+    v.pid = e->fork ? view->pid : nullptr; v.heading = e->fork ? view->heading : nullptr; v.evader = e->fork ? view->evader : nullptr;
     const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents;
-    state_io_kernel<<<(int)((nd + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->dc, e->dp, v, set);
+    state_io_kernel<<<(int)((nd + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->dc, e->dp, e->fp, v, set);
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
@@ -336,9 +431,11 @@ int qs_set_param(qs_env *e, int key, double value)
         case QS_PARAM_REW_QUADCOL_BIN: e->cfg.rew_quadcol_bin = value; break;
         case QS_PARAM_REW_QUADCOL_BIN_SMOOTH_MAX: e->cfg.rew_quadcol_bin_smooth_max = value; break;
         case QS_PARAM_REW_QUADCOL_BIN_OBST: e->cfg.rew_quadcol_bin_obst = value; break;
+        case QS_PARAM_CAPTURE_RADIUS: e->cfg.fork.capture_radius = value; break;
         default: return fail(e, QS_ERR_BAD_CONFIG, "qs_set_param: unknown key");
     }
     fill_const(e->cfg, e->dc);
+    fill_fork(e->cfg, e->fc);
     return QS_OK;
 }
 

@@ -701,7 +701,8 @@ __device__ __forceinline__ void warp_store_tile(const float *tile, float *dst, i
 template <int KG>
 __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
                                                    const float4 *__restrict__ actions, float *__restrict__ obs,
-                                                   float *__restrict__ rew, uint8_t *__restrict__ done, float *__restrict__ term_obs)
+                                                   float *__restrict__ rew, uint8_t *__restrict__ done, float *__restrict__ term_obs,
+                                                   uint8_t *__restrict__ reset_success)
 {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
@@ -1018,6 +1019,7 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
                     atomicAdd((unsigned long long *)&st->agents_deadlock, (unsigned long long)__popc(b_dead));
                     atomicAdd((unsigned long long *)&st->agents_collided, (unsigned long long)__popc(b_col));
                     if (bad_ballot) atomicAdd((unsigned long long *)&st->nonfinite_resets, 1ull);
+                    if (reset_success != nullptr) reset_success[env] = 0;   // upstream reset() reports no success flag
                     atomicAdd(&st->distance_to_goal_1s, (double)m1);
                     atomicAdd(&st->distance_to_goal_3s, (double)m3);
                     atomicAdd(&st->distance_to_goal_5s, (double)m5);
@@ -1133,9 +1135,18 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
 struct StateView {
     float *pos, *vel, *rot, *omega, *rot_damp, *cmds_damp, *ou, *goal;
     int *flags; uint32_t *col_mask; int *tick, *svd_ctr; uint32_t *step_ctr; float *obst_xy;
+    float *pid, *heading, *evader;      // fork mode
 };
 
-__global__ void state_io_kernel(DevConst c, DevPtrs P, StateView v, int set)
+// fork-mode planes (fork_kernels.cuh): 6 float4 planes of PID state + (angle, ang_vel, -, -); per env evader + flags
+enum { FP_PID0 = 0, FP_HEADING = 6, FP_COUNT = 7 };
+struct ForkPtrs {
+    float4 *plane[FP_COUNT];   // each [N*K]
+    float2 *evader;            // [N]
+    int *flags;                // [N]
+};
+
+__global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, int set)
 {
     int gi = blockIdx.x * blockDim.x + threadIdx.x;
     int nd = c.N * c.K;
@@ -1166,6 +1177,22 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, StateView v, int set)
             if (v.flags) v.flags[gi] = q.flags;
             if (v.col_mask) v.col_mask[gi] = q.colmask;
         }
+    }
+    if (gi < nd && F.plane[0] != nullptr) {
+        if (v.pid) {
+            for (int k = 0; k < 6; ++k) {
+                if (set) F.plane[FP_PID0 + k][gi] = make_float4(v.pid[24 * gi + 4 * k], v.pid[24 * gi + 4 * k + 1], v.pid[24 * gi + 4 * k + 2], v.pid[24 * gi + 4 * k + 3]);
+                else { float4 x = F.plane[FP_PID0 + k][gi]; v.pid[24 * gi + 4 * k] = x.x; v.pid[24 * gi + 4 * k + 1] = x.y; v.pid[24 * gi + 4 * k + 2] = x.z; v.pid[24 * gi + 4 * k + 3] = x.w; }
+            }
+        }
+        if (v.heading) {
+            if (set) F.plane[FP_HEADING][gi] = make_float4(v.heading[2 * gi], v.heading[2 * gi + 1], 0.f, 0.f);
+            else { float4 x = F.plane[FP_HEADING][gi]; v.heading[2 * gi] = x.x; v.heading[2 * gi + 1] = x.y; }
+        }
+    }
+    if (gi < c.N && F.evader != nullptr && v.evader) {
+        if (set) F.evader[gi] = make_float2(v.evader[2 * gi], v.evader[2 * gi + 1]);
+        else { float2 x = F.evader[gi]; v.evader[2 * gi] = x.x; v.evader[2 * gi + 1] = x.y; }
     }
     if (gi < c.N) {
         if (set) {

@@ -20,6 +20,7 @@ _STATE_SHAPES = {"pos": (3, torch.float32), "vel": (3, torch.float32), "rot": (9
                  "omega": (3, torch.float32), "rot_damp": (4, torch.float32), "cmds_damp": (4, torch.float32),
                  "ou": (4, torch.float32), "goal": (3, torch.float32), "flags": (1, torch.int32),
                  "col_mask": (1, torch.int32)}
+_FORK_SHAPES = {"pid": (24, torch.float32), "heading": (2, torch.float32)}     # fork mode only
 _ENV_FIELDS = {"tick": torch.int32, "svd_ctr": torch.int32, "step_ctr": torch.int32}
 
 
@@ -49,7 +50,9 @@ class QuadSwarmSim:
         self.rew = torch.zeros((n,), dtype=torch.float32, device=dev)
         self._done_u8 = torch.zeros((n,), dtype=torch.uint8, device=dev)
         self.terminal_obs = torch.zeros((n, self.D), dtype=torch.float32, device=dev)
+        self.reset_success = torch.zeros((self.N,), dtype=torch.uint8, device=dev)   # reset_info["success"] of envs that just finished
         self.want_terminal_obs = True
+        self.is_fork = cfg.env_mode == "fork"
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -89,7 +92,9 @@ class QuadSwarmSim:
         return self.obs
 
     def step(self, actions: torch.Tensor):
-        """One control step for all envs.  actions: CUDA float32 [N*K, 4].  Returns (obs, rew, done) CUDA tensors."""
+        """One step for all envs (upstream mode: one control step; fork mode: `fork.substeps` control steps, like the
+        reference's step()).  actions: CUDA float32 [N*K, A].  Returns (obs, rew, done) CUDA tensors; `self.terminal_obs`
+        and `self.reset_success` hold the finished envs' last observation / reset_info["success"]."""
         if actions.device != self.device or actions.dtype != torch.float32:
             raise ValueError("actions must be a float32 tensor on the simulator's device (use step_host for numpy)")
         if actions.numel() != self.N * self.K * self.A:
@@ -100,7 +105,7 @@ class QuadSwarmSim:
         with torch.cuda.device(self.device):
             rc = self._lib.qs_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(self.obs.data_ptr()),
                                    C.c_void_p(self.rew.data_ptr()), C.c_void_p(self._done_u8.data_ptr()), tp,
-                                   self._stream())
+                                   C.c_void_p(self.reset_success.data_ptr()), self._stream())
         _capi.check(self._h, rc, "qs_step")
         return self.obs, self.rew, self.done
 
@@ -112,15 +117,21 @@ class QuadSwarmSim:
         _capi.check(self._h, rc, "qs_reset_host")
         return out
 
-    def step_host(self, actions: np.ndarray, out=None):
+    def step_host(self, actions: np.ndarray, out=None, terminal_obs: Optional[np.ndarray] = None,
+                  reset_success: Optional[np.ndarray] = None):
+        """Host-buffer step.  `out` = (obs, rew, done_u8) numpy arrays to fill (pinned ones are DMA'd directly);
+        `terminal_obs` [N*K, D] float32 / `reset_success` [N] uint8 are filled for envs that finished."""
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.N * self.K, self.A)
         if out is None:
             out = (np.empty((self.N * self.K, self.D), dtype=np.float32), np.empty(self.N * self.K, dtype=np.float32),
                    np.empty(self.N * self.K, dtype=np.uint8))
         obs, rew, done = out
+        tp = None if terminal_obs is None else terminal_obs.ctypes.data_as(C.c_void_p)
+        sp = None if reset_success is None else reset_success.ctypes.data_as(C.c_void_p)
         with torch.cuda.device(self.device):
             rc = self._lib.qs_step_host(self._h, a.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p),
-                                        rew.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p), self._stream())
+                                        rew.ctypes.data_as(C.c_void_p), done.ctypes.data_as(C.c_void_p), tp, sp,
+                                        self._stream())
         _capi.check(self._h, rc, "qs_step_host")
         return obs, rew, done.view(np.bool_)
 
@@ -134,16 +145,20 @@ class QuadSwarmSim:
 
     def get_state(self, fields=None) -> Dict[str, torch.Tensor]:
         n = self.N * self.K
-        names = list(fields) if fields is not None else list(_STATE_SHAPES) + list(_ENV_FIELDS) + ["obst_xy"]
+        names = list(fields) if fields is not None else (list(_STATE_SHAPES) + list(_ENV_FIELDS) + ["obst_xy"] +
+                                                         (list(_FORK_SHAPES) + ["evader"] if self.is_fork else []))
+        shapes = dict(_STATE_SHAPES, **_FORK_SHAPES)
         out = {}
         for name in names:
-            if name in _STATE_SHAPES:
-                w, dt = _STATE_SHAPES[name]
+            if name in shapes:
+                w, dt = shapes[name]
                 out[name] = torch.zeros((n, w) if w > 1 else (n,), dtype=dt, device=self.device)
             elif name in _ENV_FIELDS:
                 out[name] = torch.zeros((self.N,), dtype=_ENV_FIELDS[name], device=self.device)
             elif name == "obst_xy":
                 out[name] = torch.zeros((self.N, 64, 2), dtype=torch.float32, device=self.device)
+            elif name == "evader":
+                out[name] = torch.zeros((self.N, 2), dtype=torch.float32, device=self.device)
             else:
                 raise KeyError(name)
         v = self._view(out)
@@ -156,11 +171,12 @@ class QuadSwarmSim:
     def set_state(self, **fields):
         n = self.N * self.K
         keep = {}
+        shapes = dict(_STATE_SHAPES, **_FORK_SHAPES)
         for name, val in fields.items():
             if val is None:
                 continue
-            if name in _STATE_SHAPES:
-                w, dt = _STATE_SHAPES[name]
+            if name in shapes:
+                w, dt = shapes[name]
                 t = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val)
                 if name == "col_mask":
                     t = t.to(torch.int64).to(torch.int32) if t.dtype != torch.int32 else t
@@ -174,6 +190,9 @@ class QuadSwarmSim:
                 t = t.reshape(self.N, -1, 2)
                 full[:, :t.shape[1]] = t
                 keep[name] = full
+            elif name == "evader":
+                t = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val)
+                keep[name] = t.to(device=self.device, dtype=torch.float32).reshape(self.N, 2).contiguous()
             else:
                 raise KeyError(name)
         v = self._view(keep)
@@ -189,6 +208,10 @@ class QuadSwarmSim:
             if k not in PARAM_KEYS:
                 raise KeyError(k)
             _capi.check(self._h, self._lib.qs_set_param(self._h, PARAM_KEYS[k], float(v)), "qs_set_param")
+
+    def set_capture_radius(self, value: float):
+        """QuadrotorEnvMulti.set_capture_radius (quadrotor_multi_rewards.py:210-211), all envs of this handle."""
+        _capi.check(self._h, self._lib.qs_set_param(self._h, PARAM_KEYS["capture_radius"], float(value)), "qs_set_param")
 
     def episode_stats(self, reset: bool = False) -> Dict[str, float]:
         s = QsStatsC()

@@ -30,7 +30,7 @@ def test_header_symbols_exported(lib):
 def test_struct_layouts(lib):
     assert lib.qs_config_size() == C.sizeof(QsConfigC)
     assert lib.qs_stats_size() == C.sizeof(QsStatsC)
-    assert lib.qs_api_version() == 1
+    assert lib.qs_api_version() == 2
 
 
 def test_create_without_gpu_fails_loudly(lib):
@@ -73,3 +73,18 @@ def test_config_derivations():
     cc = c.to_c()
     assert abs(cc.collision_hitbox_radius * cc.arm - 0.09192388155425119) < 1e-15
     assert cc.svd_period == 100
+
+
+def test_fork_config_validation():
+    """fork-mode configuration: the reference's QuadrotorEnvConfig defaults and what the device rejects."""
+    c = QuadSimConfig.fork_default(num_envs=3)
+    assert (c.num_agents, c.obs_dim, c.act_dim, c.ep_len) == (4, 6 + 2 * 3, 2, 3000)     # global_cfg.py:63-71, 30 s @ 100 Hz
+    cc = c.to_c()
+    assert cc.env_mode == 1 and cc.scenario == 4 and cc.fork.substeps == 8 and cc.apply_collision_force == 0
+    assert abs(cc.fork.pid[2][4] - 2.0) < 1e-12 and cc.fork.pid[9][3] == -1.0          # z anti-windup 2.0; rate PIDs unsaturated
+    with pytest.raises(ValueError):
+        QuadSimConfig(env_mode="fork").to_c()                  # upstream obs_repr in fork mode
+    with pytest.raises(ValueError):
+        QuadSimConfig(quads_mode="dynamic_repulsive").to_c()   # fork scenario in upstream mode
+    with pytest.raises(ValueError):
+        QuadSimConfig.fork_default(use_obstacles=True).to_c()
