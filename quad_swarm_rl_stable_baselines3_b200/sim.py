@@ -213,9 +213,15 @@ class QuadSwarmSim:
         """QuadrotorEnvMulti.set_capture_radius (quadrotor_multi_rewards.py:210-211), all envs of this handle."""
         _capi.check(self._h, self._lib.qs_set_param(self._h, PARAM_KEYS["capture_radius"], float(value)), "qs_set_param")
 
-    def episode_stats(self, reset: bool = False) -> Dict[str, float]:
+    def episode_stats(self, reset: bool = False, reduce: bool = False) -> Dict[str, float]:
+        """Sums of the per-episode `episode_extra_stats` over the episodes finished since the last reset=True call.
+        reduce=True additionally sums over all ranks (one small NCCL all-reduce; the only collective of the simulator)."""
         s = QsStatsC()
         with torch.cuda.device(self.device):
             rc = self._lib.qs_episode_stats(self._h, C.byref(s), int(reset), self._stream())
         _capi.check(self._h, rc, "qs_episode_stats")
-        return s.as_dict()
+        out = s.as_dict()
+        if reduce:
+            from .sharding import all_reduce_stats
+            out = all_reduce_stats(out, device=self.device)
+        return out

@@ -1,0 +1,54 @@
+"""Test helper: the CPU oracle behind QuadSwarmSim's host interface, so the host-side logic (VecEnv facade, sharding,
+stat reduction) can be exercised on a box without a GPU.  TEST INFRASTRUCTURE ONLY."""
+import numpy as np
+
+from oracle import OracleEnv
+from quad_swarm_rl_stable_baselines3_b200.config import PARAM_KEYS
+
+
+class OracleSim:
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.N, self.K, self.D, self.A = cfg.num_envs, cfg.num_agents, cfg.obs_dim, cfg.act_dim
+        self.envs = [OracleEnv(cfg, i) for i in range(self.N)]      # gid = cfg.env_id_offset + i inside qo_create
+        self.closed = False
+
+    def reset_host(self):
+        return np.concatenate([o.reset() for o in self.envs]).astype(np.float32)
+
+    def step_host(self, actions, out=None, terminal_obs=None, reset_success=None):
+        a = np.asarray(actions, dtype=np.float64).reshape(self.N, self.K, self.A)
+        if out is None:
+            out = (np.empty((self.N * self.K, self.D), np.float32), np.empty(self.N * self.K, np.float32),
+                   np.empty(self.N * self.K, np.uint8))
+        obs, rew, done = out
+        K = self.K
+        for e, o in enumerate(self.envs):
+            r = o.step(a[e], want_terminal=True)
+            sl = slice(e * K, (e + 1) * K)
+            obs[sl], rew[sl], done[sl] = r[0], r[1], r[2]
+            if r[2].any():
+                if terminal_obs is not None:
+                    terminal_obs[sl] = r[3]
+                if reset_success is not None:
+                    reset_success[e] = int(bool(o.last_reset_success))
+        return obs, rew, done.view(np.bool_)
+
+    def set_capture_radius(self, v):
+        for o in self.envs:
+            o.set_param(PARAM_KEYS["capture_radius"], float(v))
+
+    def set_rew_coeff(self, **kw):
+        for o in self.envs:
+            for k, v in kw.items():
+                o.set_param(PARAM_KEYS[k], float(v))
+
+    def episode_stats(self, reset=False):
+        tot = {}
+        for o in self.envs:
+            for k, v in o.stats().items():
+                tot[k] = tot.get(k, 0) + v
+        return tot
+
+    def close(self):
+        self.closed = True
