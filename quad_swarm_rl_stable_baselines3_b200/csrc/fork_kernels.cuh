@@ -134,11 +134,9 @@ __device__ __forceinline__ void fork_self_obs(const DevConst &c, const Rng &g, i
 {
     float p0 = q.p[0], p1 = q.p[1], v0 = q.v[0], v1 = q.v[1];
     if (c.sense_noise) {
-        float n[4], m[4];
-        rng_n4(g, site, drone, 0, 0, n);
-        rng_n4(g, site, drone, 0, 1, m);
-        p0 += c.s_pos * n[0]; p1 += c.s_pos * n[1];
-        v0 += c.s_vel * n[3]; v1 += c.s_vel * m[0];
+        const float4 n = rng_n4v(g, site, drone, 0, 0), m = rng_n4v(g, site, drone, 0, 1);
+        p0 += c.s_pos * n.x; p1 += c.s_pos * n.y;
+        v0 += c.s_vel * n.w; v1 += c.s_vel * m.x;
     }
     const float dt = c.dt, inv_dt = 1.0f / c.dt;
     float rx = q.goal[0] - p0, ry = q.goal[1] - p1;
@@ -289,9 +287,10 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         const int time_remain = c.ep_len - tick;
         // ---- QuadrotorSingle._step, quadrotor_single_rewards.py:418-457
         if (valid) {
-            float cmd[4], n[4];
+            float cmd[4];
             fork_controller(c, f, q, pid, angle, ang_vel, act.x, cmd);
-            rng_n4(g, SITE_OU, d, 0, 0, n);
+            const float4 nv = rng_n4v(g, SITE_OU, d, 0, 0);
+            const float n[4] = { nv.x, nv.y, nv.z, nv.w };
 #pragma unroll
             for (int m = 0; m < 4; ++m) q.ou[m] = q.ou[m] + (c.ou_theta * (0.0f - q.ou[m]) + c.ou_sigma * n[m]);
             for (int s = 0; s < c.sim_steps; ++s) {

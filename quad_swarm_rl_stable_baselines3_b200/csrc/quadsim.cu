@@ -92,6 +92,7 @@ static void fill_const(const qs_config &c, DevConst &d)
     d.grace_steps = (float)(1.5 * control_freq);                           // quadrotor_multi.py:156
     d.final_grace_steps = (float)(5.0 * control_freq);                     // quadrotor_multi.py:160
     d.control_dt = (float)(1.0 / control_freq);                            // quadrotor_multi.py:91
+    d.small_angle = (std::sqrt(3.0) * c.omega_max * c.dt * 0.5 <= 0.25) ? 1 : 0;
 }
 
 static void fill_fork(const qs_config &c, ForkConst &f)

@@ -28,6 +28,7 @@ namespace qs {
 struct DevConst {
     int N, K, scenario, obs_repr, nbr_type, V, use_obstacles, use_downwash, apply_force, sense_noise;
     int ep_len, sim_steps, svd_period, obst_L, obst_W, M, D, S;   // D obs dim, S self-obs dim
+    int small_angle;                                              // sqrt(3) * omega_max * dt / 2 <= 0.25 rad
     uint32_t key0, key1;
     long long env_id_offset;
     float dt, hx, hy, hz, room_l, room_w, room_h, gravity, mass, inv_mass;
@@ -125,6 +126,21 @@ __device__ __forceinline__ void rng_n4(const Rng &g, int site, int drone, int au
     box_muller(r.z, r.w, n[2], n[3]);
 }
 
+// One Philox block -> 4 standard normals, out of line: the hot path draws 4 blocks per drone-step and four inlined
+// copies (~115 instructions each) do not fit the instruction-cache budget of the step kernel.
+__device__ __noinline__ float4 rng_normal4(uint32_t gid, uint32_t step, uint32_t c2, uint32_t block, uint32_t k0, uint32_t k1)
+{
+    uint4 r = philox4x32_10(gid, step, c2, block, k0, k1);
+    float4 n;
+    box_muller(r.x, r.y, n.x, n.y);
+    box_muller(r.z, r.w, n.z, n.w);
+    return n;
+}
+__device__ __forceinline__ float4 rng_n4v(const Rng &g, int site, int drone, int aux, int block)
+{
+    return rng_normal4(g.gid, g.step, (uint32_t)site | ((uint32_t)drone << 8) | ((uint32_t)aux << 16), (uint32_t)block, g.k0, g.k1);
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // per-drone register state
 // ----------------------------------------------------------------------------------------------------------------
@@ -220,7 +236,12 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
     if (wn != 0.0f) {
         float inv = 1.0f / wn, kx = wx * inv, ky = wy * inv, kz = wz * inv;
         float ang = wn * dt, s, ch;
-        sincosf(0.5f * ang, &s, &ch);
+        if (c.small_angle) {
+            // |omega| <= sqrt(3) omega_max, so x = ang/2 <= 0.25 rad: degree-9/8 Taylor, truncation < 3e-12
+            float x = 0.5f * ang, x2 = x * x;
+            s = x * (1.0f + x2 * (-1.0f / 6.0f + x2 * (1.0f / 120.0f + x2 * (-1.0f / 5040.0f + x2 * (1.0f / 362880.0f)))));
+            ch = 1.0f + x2 * (-0.5f + x2 * (1.0f / 24.0f + x2 * (-1.0f / 720.0f + x2 * (1.0f / 40320.0f))));
+        } else sincosf(0.5f * ang, &s, &ch);
         float sn = 2.0f * s * ch, oc = 2.0f * s * s;               // sin(ang), 1 - cos(ang) without cancellation
         // dR = I + sn*K + oc*K^2,  K^2 = k k^T - I
         float d00 = 1.f + oc * (kx * kx - 1.f), d01 = -sn * kz + oc * kx * ky, d02 = sn * ky + oc * kx * kz;
@@ -236,7 +257,7 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
 #pragma unroll
         for (int j = 0; j < 9; ++j) q.R[j] = n[j];
     }
-    if (do_svd) polar_orthonormalise(q.R);                           // :554-558
+    if (__builtin_expect(do_svd, 0)) polar_orthonormalise(q.R);                           // :554-558
     // omega (:562-567)
     {
         float i0 = c.inertia[0] * q.w[0], i1 = c.inertia[1] * q.w[1], i2 = c.inertia[2] * q.w[2];
@@ -312,14 +333,10 @@ __device__ __forceinline__ void self_obs(const DevConst &c, const Rng &g, int si
 {
     float p0 = q.p[0], p1 = q.p[1], p2 = q.p[2], v0 = q.v[0], v1 = q.v[1], v2 = q.v[2], w0 = q.w[0], w1 = q.w[1], w2 = q.w[2];
     if (c.sense_noise) {
-        float n[4], m[4], l0, l1;
-        rng_n4(g, site, drone, 0, 0, n);
-        rng_n4(g, site, drone, 0, 1, m);
-        uint4 r = rng_block(g, site, drone, 0, 2);
-        box_muller(r.x, r.y, l0, l1);
-        p0 += c.s_pos * n[0]; p1 += c.s_pos * n[1]; p2 += c.s_pos * n[2];
-        v0 += c.s_vel * n[3]; v1 += c.s_vel * m[0]; v2 += c.s_vel * m[1];
-        w0 += c.s_gyro * m[2]; w1 += c.s_gyro * m[3]; w2 += c.s_gyro * l0;
+        const float4 n = rng_n4v(g, site, drone, 0, 0), m = rng_n4v(g, site, drone, 0, 1), l = rng_n4v(g, site, drone, 0, 2);
+        p0 += c.s_pos * n.x; p1 += c.s_pos * n.y; p2 += c.s_pos * n.z;
+        v0 += c.s_vel * n.w; v1 += c.s_vel * m.x; v2 += c.s_vel * m.y;
+        w0 += c.s_gyro * m.z; w1 += c.s_gyro * m.w; w2 += c.s_gyro * l.x;
         // R -> quaternion -> R round trip (sensor_noise.py:34-63, 205-210; quad_utils.py:162-168), zero rotation noise
         const float *R = q.R;
         float tr = R[0] + R[4] + R[8], qw, qx, qy, qz, S;
@@ -614,13 +631,31 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const DevPtrs 
                     rank[b] += b_first ? 0 : 1;
                 }
             if (valid) {
+                if (KG <= 8) {
+                    // ranks packed 4 bits per candidate so that the row writes can be a rolled loop: the unrolled form is
+                    // 8 x 30 instructions of code executed once each, and the hot path must stay inside the 32 KB L1.5 I-cache
+                    uint32_t pk = 0u;
 #pragma unroll
-                for (int j = 0; j < KG; ++j) {
-                    if (rank[j] < c.V && met[j] < INF) {
-                        float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
-                        float *r = o + c.S + 6 * rank[j];
-                        r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
-                        r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                    for (int j = 0; j < KG; ++j) pk |= (uint32_t)((met[j] < INF) ? rank[j] : 15) << (4 * j);
+#pragma unroll 1
+                    for (int j = 0; j < KG; ++j) {
+                        const int rk = (int)((pk >> (4 * j)) & 15u);
+                        if (rk < c.V) {
+                            float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                            float *r = o + c.S + 6 * rk;
+                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                            r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < KG; ++j) {
+                        if (rank[j] < c.V && met[j] < INF) {
+                            float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                            float *r = o + c.S + 6 * rank[j];
+                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                            r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                        }
                     }
                 }
             }
@@ -731,11 +766,12 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
         if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
         g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
     }
-    float4 ring = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ring = make_float4(0.f, 0.f, 0.f, 0.f), sums = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
         load_drone(P, gi, q);
         act = __ldcs(actions + gi);
         ring = P.plane[PL_DIST_RING][gi];                               // issued with the state loads: one exposed HBM latency per thread
+        if (c.ep_len - tick < 500) sums = P.plane[PL_DIST_SUMS][gi];    // last-5-s window (:762-767): needed late, fetched early
     } else {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { q.p[a] = 1.0e6f * (float)(lane + 1); q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
@@ -752,8 +788,8 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
 #pragma unroll
     for (int m = 0; m < 4; ++m) cmd[m] = 0.5f * (clampf(a4[m], -1.0f, 1.0f) + 1.0f);
     if (valid) {
-        float n[4];
-        rng_n4(g, SITE_OU, d, 0, 0, n);                                // OUNoiseNumba.noise, numba_utils.py:101-105
+        const float4 nv = rng_n4v(g, SITE_OU, d, 0, 0);                // OUNoiseNumba.noise, numba_utils.py:101-105
+        const float n[4] = { nv.x, nv.y, nv.z, nv.w };
 #pragma unroll
         for (int m = 0; m < 4; ++m) q.ou[m] = q.ou[m] + (c.ou_theta * (0.0f - q.ou[m]) + c.ou_sigma * n[m]);
         for (int s = 0; s < c.sim_steps; ++s) {
@@ -790,7 +826,7 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
         __syncwarp(gmask);
         // pre-filter on the squared distance (slightly widened), exact `<=` tests on the rounded distance only for near pairs
         const float thr_far = fmaxf(c.thr_col, c.thr_fall), fall2 = thr_far * thr_far * 1.0001f;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < KG; ++j) {
             float4 o4 = stage[2 * (base + j)];
             float dx = q.p[0] - o4.x, dy = q.p[1] - o4.y, dz = q.p[2] - o4.z;
@@ -860,8 +896,7 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
         }
         P.plane[PL_DIST_RING][gi] = make_float4(ring.y, ring.z, ring.w, dlog);
         int steps_left = c.ep_len + 1 - tick;
-        if (steps_left < 500) {
-            float4 sums = P.plane[PL_DIST_SUMS][gi];
+        if (steps_left < 500) {                                         // == the prefetch condition (tick was incremented since)
             if (steps_left < 100) sums.x += dlog;
             if (steps_left < 300) sums.y += dlog;
             sums.z += dlog;
@@ -905,7 +940,7 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
         flag = (__ballot_sync(QS_FULL, hit) & gmask) != 0u;
     }
     if (c.apply_force) {
-        if (pair_ballot) {
+        if (__builtin_expect(pair_ballot != 0u, 0)) {
             // new pairs in (i, j) lexicographic order; a drone in two pairs is updated twice (:674-677)
             for (int i = 0; i < c.K - 1; ++i) {
                 uint32_t rowi = __shfl_sync(gmask, new_pairs, base + i) & ~((2u << i) - 1u);   // j > i
@@ -929,7 +964,7 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
             }
             flag = true;
         }
-        if (c.use_obstacles && obst_ballot) {
+        if (__builtin_expect(c.use_obstacles && obst_ballot, 0)) {
             if (obst_new) {
                 float2 xy = P.obst_xy[(size_t)env * QS_MAX_OBSTACLES + obst_hit];
                 float tp[3] = { q.p[0], q.p[1], q.p[2] }, tv[3] = { q.v[0], q.v[1], q.v[2] }, tw[3] = { q.w[0], q.w[1], q.w[2] };
@@ -939,7 +974,7 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
             }
             flag = true;
         }
-        if (wall_ballot | ceil_ballot) {
+        if (__builtin_expect((wall_ballot | ceil_ballot) != 0u, 0)) {
             if (new_wall || new_ceil) {
                 float tv[3] = { q.v[0], q.v[1], q.v[2] }, tw[3] = { q.w[0], q.w[1], q.w[2] };
                 if (new_wall) room_impulse(c, g, d, q.flags, tv, tw, true);
@@ -975,7 +1010,7 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
 
     // ---- 7. dones (:739-838): episode stats, then the env resets itself and returns the new episode's first observation
     const uint32_t done_ballot = __ballot_sync(QS_FULL, all_done && valid);
-    if (done_ballot) {
+    if (__builtin_expect(done_ballot != 0u, 0)) {
         __syncwarp();
         if (term_obs != nullptr) {
             // terminal observation of the finished episode (rows of envs that go on are left untouched)
