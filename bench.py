@@ -121,7 +121,7 @@ def cpu_port_throughput(envs, agents, budget_s, threads):
     t0 = time.perf_counter()
     b.step(acts[3]); b.step(acts[4])
     per = (time.perf_counter() - t0) / 2
-    n = int(max(5, min(5000, budget_s / max(per, 1e-6))))
+    n = int(max(5, min(20000, budget_s / max(per, 1e-6))))
     t0 = time.perf_counter()
     for i in range(n):
         b.step(acts[i % 8])
@@ -206,12 +206,12 @@ def main():
     sim, act_pool = make(n_envs)
 
     # ---- device-resident path: value.  K back-to-back steps, one CUDA-event pair on the launching stream ---------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # nvidia-smi takes ~1 s to deliver its first sample: start it before the warm-up
     for i in range(args.warmup):
         sim.step(act_pool[i % POOL])
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = sim.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -225,8 +225,8 @@ def main():
     launches = sim.launch_count - l0
     clocks = None
     if rank == 0:
-        if wall_s < 1.5:      # keep the GPU under the same load a little longer so that nvidia-smi samples it
-            t_end = time.perf_counter() + 1.5
+        if wall_s < 3.0:      # keep the GPU under the same load a little longer so that nvidia-smi samples it
+            t_end = time.perf_counter() + 3.0
             j = 0
             while time.perf_counter() < t_end:
                 sim.step(act_pool[j % POOL]); j += 1
