@@ -25,6 +25,9 @@ struct qs_env {
     int block;              // threads per block
     int grid;
     size_t smem_bytes;
+    bool persist;           // upstream step kernel as a persistent, TMA-prefetched warp-tile loop (large batches)
+    int grid_persist;
+    size_t smem_persist;
     void *slab;             // one allocation for all device state
     size_t slab_bytes;
     // pinned host staging + device io buffers for the *_host entry points
@@ -252,8 +255,26 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
         cudaDeviceSynchronize();
         cudaFree(rot); free(h);
     }
+    e->persist = false; e->grid_persist = 0; e->smem_persist = 0;
     if (e->fork) { QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, fork_step_kernel<KG>); set_smem_attr(e->smem_bytes, fork_reset_kernel<KG>)); }
-    else { QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, step_kernel<KG>); set_smem_attr(e->smem_bytes, reset_kernel<KG>)); }
+    else {
+        QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, step_kernel<KG, false>); set_smem_attr(e->smem_bytes, reset_kernel<KG>));
+        // persistent form: worth it once the batch is several waves of resident blocks
+        const size_t tiles_floats = (((size_t)warps * 256 + (size_t)warps * rows_per_warp * e->dc.D) + 3) & ~(size_t)3;
+        e->smem_persist = tiles_floats * sizeof(float) + (size_t)warps * PF_SLOTS * 32 * sizeof(float4) + (size_t)warps * sizeof(uint64_t);
+        int per_sm = 0;
+        if (e->smem_persist <= 227 * 1024) {
+            QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_persist, step_kernel<KG, true>);
+                           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KG, true>, e->block, e->smem_persist));
+        }
+        // Measured (profiles/README.md): hiding the start-of-tile HBM latency does not pay on this kernel -- with 16 resident
+        // warps per SM the other warps already cover it (88.3 us plain vs 90.1 us persistent at 65536 envs) -- so the
+        // persistent form is opt-in (QS_PERSIST=1); it is kept bitwise-tested against the plain form.
+        const char *pe = getenv("QS_PERSIST");
+        const bool want = pe ? atoi(pe) != 0 : false;
+        if (per_sm > 0 && want) { e->persist = true; e->grid_persist = (e->grid < per_sm * sms) ? e->grid : per_sm * sms; }
+        if (const char *pb = getenv("QS_PERSIST_BLOCKS")) { int v = atoi(pb); if (v >= 1 && v < e->grid_persist) e->grid_persist = v; }   // tests: force looping
+    }
     r = cudaGetLastError();
     if (r != cudaSuccess) { cudaFree(e->slab); delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: ") + cudaGetErrorString(r)); }
     *out = e;
@@ -307,7 +328,11 @@ int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *do
     if (e->fork) {
         QS_DISPATCH_KG(e->KG, (fork_step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->fc, e->dp, e->fp, (const float2 *)actions, obs, rew, done, terminal_obs, reset_success)));
     } else {
-        QS_DISPATCH_KG(e->KG, (step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success)));
+        if (e->persist) {
+            QS_DISPATCH_KG(e->KG, (step_kernel<KG, true><<<e->grid_persist, e->block, e->smem_persist, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success)));
+        } else {
+            QS_DISPATCH_KG(e->KG, (step_kernel<KG, false><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success)));
+        }
     }
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());

@@ -16,7 +16,10 @@
 
 #define QS_FULL 0xffffffffu
 #ifndef QS_STEP_MINBLOCKS
-#define QS_STEP_MINBLOCKS 4      // resident 128-thread blocks per SM the step kernel is compiled for (register cap 65536/(128*n))
+#define QS_STEP_MINBLOCKS 4      // resident blocks per SM the step kernel is compiled for (register cap 65536/(threads*n))
+#endif
+#ifndef QS_STEP_MAXTHREADS
+#define QS_STEP_MAXTHREADS 128
 #endif
 #define QS_PI_F 3.14159265358979323846f
 
@@ -155,6 +158,22 @@ __device__ __forceinline__ void load_drone(const DevPtrs &P, int gi, Drone &q)
     float4 a = P.plane[PL_POS_VX][gi], b = P.plane[PL_V_W][gi], c = P.plane[PL_W_R0][gi], d = P.plane[PL_R1][gi],
            e = P.plane[PL_R2_FLAGS][gi], f = P.plane[PL_ROT_DAMP][gi], g = P.plane[PL_CMDS_DAMP][gi],
            h = P.plane[PL_OU][gi], k = P.plane[PL_GOAL][gi];
+    q.p[0] = a.x; q.p[1] = a.y; q.p[2] = a.z; q.v[0] = a.w; q.v[1] = b.x; q.v[2] = b.y;
+    q.w[0] = b.z; q.w[1] = b.w; q.w[2] = c.x;
+    q.R[0] = c.y; q.R[1] = c.z; q.R[2] = c.w; q.R[3] = d.x; q.R[4] = d.y; q.R[5] = d.z; q.R[6] = d.w; q.R[7] = e.x; q.R[8] = e.y;
+    q.flags = __float_as_int(e.z); q.colmask = __float_as_uint(e.w);
+    q.rd[0] = f.x; q.rd[1] = f.y; q.rd[2] = f.z; q.rd[3] = f.w;
+    q.cd[0] = g.x; q.cd[1] = g.y; q.cd[2] = g.z; q.cd[3] = g.w;
+    q.ou[0] = h.x; q.ou[1] = h.y; q.ou[2] = h.z; q.ou[3] = h.w;
+    q.goal[0] = k.x; q.goal[1] = k.y; q.goal[2] = k.z;
+}
+
+// same unpacking out of a warp's prefetch buffer (slot s holds rows of plane s)
+__device__ __forceinline__ void load_drone_smem(const float4 *pf, int row, Drone &q)
+{
+    float4 a = pf[PL_POS_VX * 32 + row], b = pf[PL_V_W * 32 + row], c = pf[PL_W_R0 * 32 + row], d = pf[PL_R1 * 32 + row],
+           e = pf[PL_R2_FLAGS * 32 + row], f = pf[PL_ROT_DAMP * 32 + row], g = pf[PL_CMDS_DAMP * 32 + row],
+           h = pf[PL_OU * 32 + row], k = pf[PL_GOAL * 32 + row];
     q.p[0] = a.x; q.p[1] = a.y; q.p[2] = a.z; q.v[0] = a.w; q.v[1] = b.x; q.v[2] = b.y;
     q.w[0] = b.z; q.w[1] = b.w; q.w[2] = c.x;
     q.R[0] = c.y; q.R[1] = c.z; q.R[2] = c.w; q.R[3] = d.x; q.R[4] = d.y; q.R[5] = d.z; q.R[6] = d.w; q.R[7] = e.x; q.R[8] = e.y;
@@ -733,46 +752,137 @@ __device__ __forceinline__ void warp_store_tile(const float *tile, float *dst, i
 // ----------------------------------------------------------------------------------------------------------------
 // The step kernel: QuadrotorEnvMulti.step (quadrotor_multi.py:521-842) for every env, one launch.
 // ----------------------------------------------------------------------------------------------------------------
-template <int KG>
-__global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
+// PERSIST = false: one warp-tile (32 lanes = 32/KG envs) per warp, state read straight from HBM.
+// PERSIST = true : grid = resident blocks only; every warp loops over warp-tiles and the 12 x 512 B of per-drone input of
+//                  its NEXT tile (9 state planes, distance ring + windows, actions) are fetched by TMA bulk copies
+//                  (cp.async.bulk -> shared memory, completion on a per-warp mbarrier) while the current tile is being
+//                  computed, so the one exposed HBM latency at the top of the kernel (12 % of the stall samples of the
+//                  non-persistent form, profiles/README.md) is paid once per warp instead of once per tile.
+enum { PF_SLOTS = 12, PF_RING = 9, PF_SUMS = 10, PF_ACT = 11 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QS_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QS_DONE;\n"
+        "bra QS_WAIT;\n"
+        "QS_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// lane 0 of a warp: fetch the inputs of warp-tile `wt` (rows gi0 .. gi0+cnt-1 of every plane) into the warp's buffer
+__device__ __forceinline__ void prefetch_tile(const DevPtrs &P, const float4 *actions, float4 *pf, uint64_t *bar, int gi0, int cnt)
+{
+    const uint32_t bytes = (uint32_t)cnt * 16u;
+    mbar_expect_tx(bar, bytes * PF_SLOTS);
+#pragma unroll
+    for (int s = 0; s < PL_COUNT; ++s) tma_load_1d(pf + s * 32, P.plane[s] + gi0, bytes, bar);    // PL_* order == slot order
+    tma_load_1d(pf + PF_ACT * 32, actions + gi0, bytes, bar);
+}
+
+template <int KG, bool PERSIST>
+__global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
                                                    const float4 *__restrict__ actions, float *__restrict__ obs,
                                                    float *__restrict__ rew, uint8_t *__restrict__ done, float *__restrict__ term_obs,
                                                    uint8_t *__restrict__ reset_success)
 {
     extern __shared__ __align__(16) float smem[];
-    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int env = tid / KG, d = tid % KG;
-    const bool valid = env < c.N && d < c.K;
-    const int gi = env * c.K + d;
+    const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
+    const int d = lane % KG;
     const uint32_t gmask = group_mask<KG>(lane);
     const int base = lane & ~(KG - 1);
     constexpr int GPW = 32 / KG;                                        // env groups per warp
     const int rows_per_warp = GPW * c.K;
     float4 *stage = reinterpret_cast<float4 *>(smem) + (size_t)warp_in_block * 64;          // 32 lanes x 2 float4
-    float *tile = smem + (size_t)(blockDim.x >> 5) * 256 + (size_t)warp_in_block * rows_per_warp * c.D;   // this warp's obs rows
+    float *tile = smem + (size_t)warps_per_block * 256 + (size_t)warp_in_block * rows_per_warp * c.D;   // this warp's obs rows
     const int row = (lane / KG) * c.K + d;
     float *orow = tile + (size_t)row * c.D;
-    const int warp_env0 = (tid - lane) / KG;                            // first env of this warp
-    const int warp_rows = max(0, min(GPW, c.N - warp_env0)) * c.K;      // valid rows of this warp
+    const int n_wt = (c.N + GPW - 1) / GPW;                             // warp-tiles
+    const int wt_stride = PERSIST ? (int)gridDim.x * warps_per_block : n_wt;
+    // prefetch buffer + mbarrier of this warp (PERSIST only); the obs tiles end at a multiple of 16 bytes
+    const size_t pf_off = ((size_t)warps_per_block * 256 + (size_t)warps_per_block * rows_per_warp * c.D + 3) & ~(size_t)3;
+    float4 *pf = reinterpret_cast<float4 *>(smem + pf_off) + (size_t)warp_in_block * PF_SLOTS * 32;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pf_off + (size_t)warps_per_block * PF_SLOTS * 32 * 4) + warp_in_block;
+    uint32_t phase = 0u;
+    int wt = (int)blockIdx.x * warps_per_block + warp_in_block;
+    int nx_tick = 0, nx_svd = 0;
+    uint32_t nx_step = 0u;
+    if (PERSIST) {
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+        if (wt < n_wt) {
+            if (lane == 0) prefetch_tile(P, actions, pf, bar, wt * GPW * c.K, max(0, min(GPW, c.N - wt * GPW)) * c.K);
+            const int e0 = wt * GPW + lane / KG;
+            if (e0 < c.N) { nx_tick = P.tick[e0]; nx_svd = P.svd_ctr[e0]; nx_step = P.step_ctr[e0]; }
+        }
+    }
+    for (; wt < n_wt; wt += wt_stride) {
+    const int warp_env0 = wt * GPW;                                     // first env of this warp-tile
+    const int env = warp_env0 + lane / KG;
+    const bool valid = env < c.N && d < c.K;
+    const int gi = env * c.K + d;
+    const int warp_rows = max(0, min(GPW, c.N - warp_env0)) * c.K;      // valid rows of this warp-tile
 
     Drone q;
     float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
     int tick = 0, svd = 0;
     Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
     int scen_now = 0;
-    if (env < c.N) {                                                    // env-level scalars: every lane of the group
-        tick = P.tick[env]; svd = P.svd_ctr[env];
-        if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
-        g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
-    }
     float4 ring = make_float4(0.f, 0.f, 0.f, 0.f), sums = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-        load_drone(P, gi, q);
-        act = __ldcs(actions + gi);
-        ring = P.plane[PL_DIST_RING][gi];                               // issued with the state loads: one exposed HBM latency per thread
-        if (c.ep_len - tick < 500) sums = P.plane[PL_DIST_SUMS][gi];    // last-5-s window (:762-767): needed late, fetched early
+    if (PERSIST) {
+        tick = nx_tick; svd = nx_svd; g.step = nx_step;
+        if (env < c.N) {
+            if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
+            g.gid = (uint32_t)(c.env_id_offset + env);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        if (valid) {
+            load_drone_smem(pf, row, q);
+            act = pf[PF_ACT * 32 + row];
+            ring = pf[PF_RING * 32 + row];
+            sums = pf[PF_SUMS * 32 + row];
+        }
+        __syncwarp();                                                   // every lane has read the buffer: refill it for the next tile
+        const int wn = wt + wt_stride;
+        if (wn < n_wt) {
+            if (lane == 0) prefetch_tile(P, actions, pf, bar, wn * GPW * c.K, max(0, min(GPW, c.N - wn * GPW)) * c.K);
+            const int e1 = wn * GPW + lane / KG;
+            if (e1 < c.N) { nx_tick = P.tick[e1]; nx_svd = P.svd_ctr[e1]; nx_step = P.step_ctr[e1]; }
+        }
     } else {
+        if (env < c.N) {                                                // env-level scalars: every lane of the group
+            tick = P.tick[env]; svd = P.svd_ctr[env];
+            if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
+            g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
+        }
+        if (valid) {
+            load_drone(P, gi, q);
+            act = __ldcs(actions + gi);
+            ring = P.plane[PL_DIST_RING][gi];                           // issued with the state loads: one exposed HBM latency per thread
+            if (c.ep_len - tick < 500) sums = P.plane[PL_DIST_SUMS][gi];    // last-5-s window (:762-767): needed late, fetched early
+        }
+    }
+    if (!valid) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { q.p[a] = 1.0e6f * (float)(lane + 1); q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
 #pragma unroll
@@ -1092,6 +1202,8 @@ __global__ void __launch_bounds__(128, QS_STEP_MINBLOCKS) step_kernel(const __gr
     }
     __syncwarp();
     if (warp_rows > 0) warp_store_tile(tile, obs + (size_t)warp_env0 * c.K * c.D, warp_rows * c.D, lane);
+    __syncwarp();                                                       // the tile and the exchange buffer are reused by the next warp-tile
+    }   // warp-tile loop
 }
 
 // ----------------------------------------------------------------------------------------------------------------
