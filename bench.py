@@ -160,7 +160,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU, help="override for size sweeps (not the bench line)")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--skip-small", action="store_true", help="skip the 4096-env cfg2 point")
+    ap.add_argument("--skip-small", action="store_true", help="skip the secondary points (4096-env cfg2, cfg3 obstacles)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg3 = obstacle scenario as the timed workload (profiling aid; the bench line is cfg2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -190,8 +192,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def make(n_envs):
-        cfg = QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, seed=0, env_id_offset=rank * n_envs)
+    def cfg3_config(n_envs):
+        # BASELINE.json configs[2]: 8x8 m obstacle area, density 0.2 -> 12 obstacles of 0.6 m, SDF obs, downwash, 2 neighbours, obs 40
+        return QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, quads_mode="mix", use_obstacles=True, use_downwash=True,
+                             obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2, seed=0, env_id_offset=rank * n_envs)
+
+    def make(n_envs, workload="cfg2"):
+        cfg = (cfg3_config(n_envs) if workload == "cfg3" else
+               QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, seed=0, env_id_offset=rank * n_envs))
         sim = QuadSwarmSim(cfg, device=dev)
         sim.want_terminal_obs = False
         gen = torch.Generator(device=dev)
@@ -203,7 +211,7 @@ def main():
     POOL = 8
     n_envs = args.envs_per_gpu
     nd = n_envs * AGENTS
-    sim, act_pool = make(n_envs)
+    sim, act_pool = make(n_envs, args.workload)
 
     # ---- device-resident path: value.  K back-to-back steps, one CUDA-event pair on the launching stream ---------
     sampler = ClockSampler(local_rank)
@@ -274,13 +282,27 @@ def main():
         small_ms = sum(a.elapsed_time(b) for a, b in ev) / ns
         d_small = sim2.D
         del sim2, pool2, flush_buf
+        # configs[2] (obstacle scenario), same 65536 envs per GPU, back-to-back steps
+        sim3, pool3 = make(n_envs, "cfg3")
+        for i in range(20):
+            sim3.step(pool3[i % POOL])
+        ns3 = min(args.steps, 300)
+        barrier()
+        e0.record(stream)
+        for i in range(ns3):
+            sim3.step(pool3[i % POOL])
+        e1.record(stream)
+        barrier()
+        cfg3_ms = e0.elapsed_time(e1) / ns3
+        del sim3, pool3
     else:
         d_small = 54
+        cfg3_ms = 0.0
 
-    t = torch.tensor([total_ms, e2e_ms, small_ms or 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, small_ms or 0.0, cfg3_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, small_ms_max = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_ms, small_ms_max, cfg3_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -321,6 +343,12 @@ def main():
                                  "l2": "flushed between timed steps (256 MiB write), per-step CUDA events",
                                  "roofline_frac": ach2 / peak,
                                  "note": "32768 threads = 0.43 waves of 148 SMs: bounded by one thread's latency chain, not by HBM"}
+            line["cfg3_obstacles"] = {"workload": "configs[2]: 65536 envs x 8 quads per GPU, 12 obstacles, SDF obs, downwash, obs 40",
+                                      "ms_per_step": cfg3_ms, "value": world * nd / (cfg3_ms * 1e-3), "unit": "drone-steps/s",
+                                      "roofline_frac": 453.0 * nd / (cfg3_ms * 1e-3) / 1e9 / peak,
+                                      "algorithmic_bytes_per_drone_step": 453.0}
+        if args.workload != "cfg2":
+            line["config"]["workload"] = "PROFILING AID, not the bench line: " + args.workload
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -20,6 +20,7 @@ struct qs_env {
     ForkPtrs fp;
     bool fork;
     int A;                  // action dim
+    int feat;               // upstream step kernel specialisation (bit 0 obstacles, bit 1 downwash)
     int device;
     int KG;                 // lanes per env
     int block;              // threads per block
@@ -170,6 +171,15 @@ static void set_smem_attr(size_t bytes, void (*kernel)(Args...))
         default: { constexpr int KG = 32; CALL; } break; \
     }
 
+// compile-time feature set of the upstream step kernel: bit 0 obstacles, bit 1 downwash
+#define QS_DISPATCH_FEAT(FEATv, CALL)              \
+    switch (FEATv) {                               \
+        case 0: { constexpr int FEAT = 0; CALL; } break; \
+        case 1: { constexpr int FEAT = 1; CALL; } break; \
+        case 2: { constexpr int FEAT = 2; CALL; } break; \
+        default: { constexpr int FEAT = 3; CALL; } break; \
+    }
+
 extern "C" {
 
 size_t qs_config_size(void) { return sizeof(qs_config); }
@@ -196,6 +206,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     fill_const(*cfg, e->dc);
     e->fork = cfg->env_mode == QS_MODE_FORK;
     e->A = e->fork ? 2 : 4;
+    e->feat = (cfg->use_obstacles ? 1 : 0) | ((cfg->use_downwash && cfg->num_agents > 1) ? 2 : 0);
     fill_fork(*cfg, e->fc);
     memset(&e->fp, 0, sizeof(e->fp));
     const int N = cfg->num_envs, K = cfg->num_agents;
@@ -210,7 +221,10 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     e->grid = (int)((lanes + e->block - 1) / e->block);
     const int warps = e->block / 32 > 0 ? e->block / 32 : 1;
     const int rows_per_warp = (32 / e->KG) * K;
-    e->smem_bytes = (size_t)warps * 256 * sizeof(float) + (size_t)warps * rows_per_warp * e->dc.D * sizeof(float);
+    // exchange buffers + observation tiles (+ the staged obstacle centres of the upstream step kernel)
+    const size_t tiles_floats = (((size_t)warps * 256 + (size_t)warps * rows_per_warp * e->dc.D) + 3) & ~(size_t)3;
+    const size_t obst_floats = (cfg->use_obstacles ? (size_t)warps * (32 / e->KG) * cfg->num_obstacles * 2 : 0);
+    e->smem_bytes = (tiles_floats + obst_floats) * sizeof(float);
     if (e->smem_bytes > 200 * 1024) { delete e; return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: observation tile does not fit in shared memory"); }
 
     // one slab: planes, per-env scalars, obstacle centres, stats
@@ -258,14 +272,15 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     e->persist = false; e->grid_persist = 0; e->smem_persist = 0;
     if (e->fork) { QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, fork_step_kernel<KG>); set_smem_attr(e->smem_bytes, fork_reset_kernel<KG>)); }
     else {
-        QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, step_kernel<KG, false>); set_smem_attr(e->smem_bytes, reset_kernel<KG>));
+        QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, set_smem_attr(e->smem_bytes, step_kernel<KG, false, FEAT>)));
+        QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, reset_kernel<KG, false>); set_smem_attr(e->smem_bytes, reset_kernel<KG, true>));
         // persistent form: worth it once the batch is several waves of resident blocks
-        const size_t tiles_floats = (((size_t)warps * 256 + (size_t)warps * rows_per_warp * e->dc.D) + 3) & ~(size_t)3;
-        e->smem_persist = tiles_floats * sizeof(float) + (size_t)warps * PF_SLOTS * 32 * sizeof(float4) + (size_t)warps * sizeof(uint64_t);
+        const size_t pf_floats = (tiles_floats + obst_floats + 3) & ~(size_t)3;
+        e->smem_persist = pf_floats * sizeof(float) + (size_t)warps * PF_SLOTS * 32 * sizeof(float4) + (size_t)warps * sizeof(uint64_t);
         int per_sm = 0;
         if (e->smem_persist <= 227 * 1024) {
-            QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_persist, step_kernel<KG, true>);
-                           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KG, true>, e->block, e->smem_persist));
+            QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, set_smem_attr(e->smem_persist, step_kernel<KG, true, FEAT>);
+                           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KG, true, FEAT>, e->block, e->smem_persist)));
         }
         // Measured (profiles/README.md): hiding the start-of-tile HBM latency does not pay on this kernel -- with 16 resident
         // warps per SM the other warps already cover it (88.3 us plain vs 90.1 us persistent at 65536 envs) -- so the
@@ -313,7 +328,8 @@ int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
     if (!e || !obs) return fail(e, QS_ERR_NULL, "qs_reset: null argument");
     cudaStream_t s = (cudaStream_t)stream;
     if (e->fork) { QS_DISPATCH_KG(e->KG, (fork_reset_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->fc, e->dp, e->fp, env_mask, obs))); }
-    else { QS_DISPATCH_KG(e->KG, (reset_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs))); }
+    else if (e->cfg.use_obstacles) { QS_DISPATCH_KG(e->KG, (reset_kernel<KG, true><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs))); }
+    else { QS_DISPATCH_KG(e->KG, (reset_kernel<KG, false><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs))); }
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
@@ -329,9 +345,9 @@ int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *do
         QS_DISPATCH_KG(e->KG, (fork_step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->fc, e->dp, e->fp, (const float2 *)actions, obs, rew, done, terminal_obs, reset_success)));
     } else {
         if (e->persist) {
-            QS_DISPATCH_KG(e->KG, (step_kernel<KG, true><<<e->grid_persist, e->block, e->smem_persist, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success)));
+            QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, (step_kernel<KG, true, FEAT><<<e->grid_persist, e->block, e->smem_persist, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success))));
         } else {
-            QS_DISPATCH_KG(e->KG, (step_kernel<KG, false><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success)));
+            QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, (step_kernel<KG, false, FEAT><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success))));
         }
     }
     e->launches += 1;

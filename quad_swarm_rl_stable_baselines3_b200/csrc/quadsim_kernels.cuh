@@ -614,8 +614,9 @@ __device__ __forceinline__ uint32_t group_mask(int lane) { return (KG == 32) ? Q
 // vs: the velocity snapshot the reference's `self.vel` holds (stale at reset, quadrotor_multi.py:477).
 // `stage` is this warp's 32 x 2 float4 exchange buffer: every lane publishes (pos, vs), the group syncs, and each lane
 // reads its K-1 neighbours as broadcast 16-byte shared-memory loads.
-template <int KG>
-__device__ __forceinline__ void group_obs_tail(const DevConst &c, const DevPtrs &P, int env, int d, int lane, uint32_t gmask, bool valid,
+// `ob`: the env's obstacle centres (the warp's shared-memory copy in the step path, global memory right after a reset)
+template <int KG, bool OBST>
+__device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *ob, int d, int lane, uint32_t gmask, bool valid,
                                                const Drone &q, const float *vs, float *o, float4 *stage)
 {
     const int base = lane & ~(KG - 1);
@@ -689,9 +690,8 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const DevPtrs 
             }
         }
     }
-    if (c.use_obstacles && valid) {
+    if (OBST && valid) {
         // a14: get_surround_sdfs, obstacles/utils.py:5-27 (min over obstacles commutes with sqrt)
-        const float2 *ob = P.obst_xy + (size_t)env * QS_MAX_OBSTACLES;
         float gx[3] = { q.p[0] - c.sdf_res, q.p[0], q.p[0] + c.sdf_res }, gy[3] = { q.p[1] - c.sdf_res, q.p[1], q.p[1] + c.sdf_res };
         float md[9];
 #pragma unroll
@@ -713,12 +713,12 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const DevPtrs 
 }
 
 // Reset of one environment (QuadrotorEnvMulti.reset, quadrotor_multi.py:440-519), executed by the env's lane group.
-template <int KG>
+template <int KG, bool OBST>
 __device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P, const Rng &g, int env, int d, bool valid, Drone &q,
                                             int &scenario_now)
 {
     float spawn[3], goal[3], out[5];
-    if (c.use_obstacles) {
+    if (OBST) {
         int scen = 0;
         obstacle_scenario_reset(c, g, d, valid && d == 0, P.obst_xy + (size_t)env * QS_MAX_OBSTACLES, spawn, goal, scen);
         scenario_now = scen;
@@ -799,13 +799,17 @@ __device__ __forceinline__ void prefetch_tile(const DevPtrs &P, const float4 *ac
     tma_load_1d(pf + PF_ACT * 32, actions + gi0, bytes, bar);
 }
 
-template <int KG, bool PERSIST>
+// FEAT: compile-time feature set (bit 0 obstacles, bit 1 downwash).  The big optional passes are specialised away instead of
+// being skipped at run time: a cfg2 launch then carries none of their code or registers (an "uber-kernel" with run-time
+// flags cost the plain 8-quad swarm 9 % when the obstacle / downwash code was reshaped).
+template <int KG, bool PERSIST, int FEAT>
 __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
                                                    const float4 *__restrict__ actions, float *__restrict__ obs,
                                                    float *__restrict__ rew, uint8_t *__restrict__ done, float *__restrict__ term_obs,
                                                    uint8_t *__restrict__ reset_success)
 {
     extern __shared__ __align__(16) float smem[];
+    constexpr bool OBST = (FEAT & 1) != 0, DOWNWASH = (FEAT & 2) != 0;
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     const int d = lane % KG;
     const uint32_t gmask = group_mask<KG>(lane);
@@ -818,8 +822,14 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     float *orow = tile + (size_t)row * c.D;
     const int n_wt = (c.N + GPW - 1) / GPW;                             // warp-tiles
     const int wt_stride = PERSIST ? (int)gridDim.x * warps_per_block : n_wt;
-    // prefetch buffer + mbarrier of this warp (PERSIST only); the obs tiles end at a multiple of 16 bytes
-    const size_t pf_off = ((size_t)warps_per_block * 256 + (size_t)warps_per_block * rows_per_warp * c.D + 3) & ~(size_t)3;
+    // obstacle centres of this warp-tile's envs (GPW x M float2), staged once per tile: the hit test and the SDF read each of
+    // them K times, and the serial `first hit wins` loop would otherwise chain M dependent global loads
+    const size_t ob_off = ((size_t)warps_per_block * 256 + (size_t)warps_per_block * rows_per_warp * c.D + 3) & ~(size_t)3;
+    const int ob_per_warp = OBST ? GPW * c.M : 0;
+    float2 *ob_sm = reinterpret_cast<float2 *>(smem + ob_off) + (size_t)warp_in_block * ob_per_warp;
+    const float2 *ob_env = ob_sm + (lane / KG) * c.M;
+    // prefetch buffer + mbarrier of this warp (PERSIST only), 16-byte aligned
+    const size_t pf_off = (ob_off + (size_t)warps_per_block * ob_per_warp * 2 + 3) & ~(size_t)3;
     float4 *pf = reinterpret_cast<float4 *>(smem + pf_off) + (size_t)warp_in_block * PF_SLOTS * 32;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pf_off + (size_t)warps_per_block * PF_SLOTS * 32 * 4) + warp_in_block;
     uint32_t phase = 0u;
@@ -851,7 +861,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     if (PERSIST) {
         tick = nx_tick; svd = nx_svd; g.step = nx_step;
         if (env < c.N) {
-            if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
+            if (OBST) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
             g.gid = (uint32_t)(c.env_id_offset + env);
         }
         mbar_wait(bar, phase);
@@ -872,7 +882,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     } else {
         if (env < c.N) {                                                // env-level scalars: every lane of the group
             tick = P.tick[env]; svd = P.svd_ctr[env];
-            if (c.use_obstacles) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
+            if (OBST) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
             g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
         }
         if (valid) {
@@ -890,6 +900,13 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 #pragma unroll
         for (int a = 0; a < 4; ++a) { q.rd[a] = q.cd[a] = q.ou[a] = 0.f; }
         q.flags = 0; q.colmask = 0;
+    }
+    if (OBST) {
+        for (int k = lane; k < ob_per_warp; k += 32) {
+            const int e = k / c.M, m = k - e * c.M;
+            ob_sm[k] = (warp_env0 + e < c.N) ? P.obst_xy[(size_t)(warp_env0 + e) * QS_MAX_OBSTACLES + m] : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
     }
 
     // ---- per-drone: RawControl.step -> QuadrotorDynamics.step (quadrotor_control.py:53-57, quadrotor_dynamics.py:215-221)
@@ -961,12 +978,11 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     // ---- 1.2 obstacles (obstacles/utils.py:31-43, quadrotor_multi.py:571-597)
     int obst_hit = -1;
     bool obst_new = false;
-    if (c.use_obstacles) {
+    if (OBST) {
         if (valid) {
-            const float2 *ob = P.obst_xy + (size_t)env * QS_MAX_OBSTACLES;
             const float obst2 = c.thr_obst * c.thr_obst * 1.0001f;
             for (int m = 0; m < c.M; ++m) {
-                float2 xy = ob[m];
+                float2 xy = ob_env[m];
                 float dx = q.p[0] - xy.x, dy = q.p[1] - xy.y, d2 = dx * dx + dy * dy;
                 if (d2 <= obst2 && __fsqrt_rn(d2) <= c.thr_obst) { obst_hit = m; break; }
             }
@@ -994,14 +1010,14 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     // ---- 2. rewards (quadrotor_multi.py:610-655)
     reward += c.rew_col * ((unique_any_nonzero && is_unique) ? -1.0f : 0.0f);
     reward += -1.0f * (c.control_dt * prox);
-    if (c.use_obstacles) reward += c.rew_col_obst * (obst_new ? -1.0f : 0.0f);
+    if (OBST) reward += c.rew_col_obst * (obst_new ? -1.0f : 0.0f);
 
     // distance_to_goal log: reached-goal flag from the mean of the last 5 entries, and the 1/3/5 s windows (:651-655, 762-767)
     if (valid) {
         float dlog = c.dt * dist;                                      // -rewraw_pos
         if (tick >= 5 && !(q.flags & F_REACHED)) {
             float m5 = (ring.x + ring.y + ring.z + ring.w + dlog) / 5.0f;
-            float metric = (c.use_obstacles && scen_now == QS_SCENARIO_O_STATIC_SAME_GOAL) ? 1.0f : c.approach_metric;
+            float metric = (OBST && scen_now == QS_SCENARIO_O_STATIC_SAME_GOAL) ? 1.0f : c.approach_metric;
             if (m5 / c.dt < metric) q.flags |= F_REACHED;
         }
         P.plane[PL_DIST_RING][gi] = make_float4(ring.y, ring.z, ring.w, dlog);
@@ -1016,28 +1032,31 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 
     // ---- 3. impulses (quadrotor_multi.py:659-698): rare, group-divergent
     bool flag = false;
-    if (c.use_downwash && KG > 1) {
+    if (DOWNWASH && KG > 1) {
         // perform_downwash, aerodynamics/downwash.py:4-66: lane j accumulates the pushes of every source i in index order
         float ua = 0.f, uw = 0.f;
         if (valid) { float u[4]; rng_u4(g, SITE_DOWNWASH, d, 0xFF, 0, u); ua = u[0]; uw = u[1]; }
-        const float zx0 = q.R[2], zy0 = q.R[5], zz0 = q.R[8], px0 = q.p[0], py0 = q.p[1], pz0 = q.p[2];
+        const float px0 = q.p[0], py0 = q.p[1], pz0 = q.p[2];
+        // every drone publishes (pos, a-jitter) and (body z axis, w-jitter); sources are read back as broadcast 16-byte loads
+        __syncwarp(gmask);
+        stage[2 * lane] = make_float4(px0, py0, pz0, ua);
+        stage[2 * lane + 1] = make_float4(q.R[2], q.R[5], q.R[8], uw);
+        __syncwarp(gmask);
         bool hit = false;
-#pragma unroll
-        for (int i = 0; i < KG; ++i) {
-            float px = __shfl_sync(gmask, px0, base + i), py = __shfl_sync(gmask, py0, base + i), pz = __shfl_sync(gmask, pz0, base + i);
-            float zx = __shfl_sync(gmask, zx0, base + i), zy = __shfl_sync(gmask, zy0, base + i), zz = __shfl_sync(gmask, zz0, base + i);
-            float sa = __shfl_sync(gmask, ua, base + i), sw = __shfl_sync(gmask, uw, base + i);
-            if (i < c.K && i != d && valid) {
-                float rx = px0 - px, ry = py0 - py, rz = pz0 - pz;
+#pragma unroll 1
+        for (int i = 0; i < c.K; ++i) {
+            const float4 sp = stage[2 * (base + i)], sz = stage[2 * (base + i) + 1];
+            if (i != d && valid) {
+                float rx = px0 - sp.x, ry = py0 - sp.y, rz = pz0 - sp.z;
                 float dd = norm3f(rx, ry, rz);
-                float relz = rx * zx + ry * zy + rz * zz;
+                float relz = rx * sz.x + ry * sz.y + rz * sz.z;
                 float rxy = sqrtf(dd * dd - relz * relz);
                 if (-0.7f < relz && relz < 0.f && rxy < 0.1f) {
-                    float acc = fmaxf(1e-6f, (6.0f / 17.0f) * (-10.0f * dd + 7.0f) + (-0.1f + 0.2f * sa));
-                    float ow = fmaxf(1e-6f, 0.3f * (dd - 1.0f) * (dd - 1.0f) + (-0.01f + 0.02f * sw));
+                    float acc = fmaxf(1e-6f, (6.0f / 17.0f) * (-10.0f * dd + 7.0f) + (-0.1f + 0.2f * sp.w));
+                    float ow = fmaxf(1e-6f, 0.3f * (dd - 1.0f) * (dd - 1.0f) + (-0.01f + 0.02f * sz.w));
                     float u[4], t[4];
                     rng_u4(g, SITE_DOWNWASH, i, d, 0, u); rng_u4(g, SITE_DOWNWASH, i, d, 1, t);
-                    float nx = zx + (-0.1f + 0.2f * u[0]), ny = zy + (-0.1f + 0.2f * u[1]), nz = zz + (-0.1f + 0.2f * u[2]);
+                    float nx = sz.x + (-0.1f + 0.2f * u[0]), ny = sz.y + (-0.1f + 0.2f * u[1]), nz = sz.z + (-0.1f + 0.2f * u[2]);
                     float nm = norm3f(nx, ny, nz), den = (nm == 0.f) ? nm + 1e-6f : nm;
                     float wx = -1.f + 2.f * u[3], wy = -1.f + 2.f * t[0], wz = -1.f + 2.f * t[1];
                     float wm = norm3f(wx, wy, wz), wden = (wm == 0.f) ? wm + 1e-6f : wm;
@@ -1074,7 +1093,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             }
             flag = true;
         }
-        if (__builtin_expect(c.use_obstacles && obst_ballot, 0)) {
+        if (__builtin_expect(OBST && obst_ballot, 0)) {
             if (obst_new) {
                 float2 xy = P.obst_xy[(size_t)env * QS_MAX_OBSTACLES + obst_hit];
                 float tp[3] = { q.p[0], q.p[1], q.p[2] }, tv[3] = { q.v[0], q.v[1], q.v[2] }, tw[3] = { q.w[0], q.w[1], q.w[2] };
@@ -1115,7 +1134,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     // ---- 5. observations (:703-720).  Self obs carries fresh sensor noise if any impulse fired (:711-712)
     float vs[3] = { q.v[0], q.v[1], q.v[2] };                          // self.vel snapshot, :705-709
     if (valid) self_obs(c, g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d, q, orow);
-    group_obs_tail<KG>(c, P, env, d, lane, gmask, valid, q, vs, orow, stage);
+    group_obs_tail<KG, OBST>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
     if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }
 
     // ---- 7. dones (:739-838): episode stats, then the env resets itself and returns the new episode's first observation
@@ -1176,7 +1195,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
                 for (int m = 0; m < 4; ++m) q.ou[m] = isfinite(q.ou[m]) ? q.ou[m] : 0.f;
                 if (!isfinite(vs[0] + vs[1] + vs[2])) { vs[0] = vs[1] = vs[2] = 0.f; }
             }
-            group_reset<KG>(c, P, g, env, d, valid, q, scen);
+            group_reset<KG, OBST>(c, P, g, env, d, valid, q, scen);
             tick = 0;
             if (valid) {
                 if (d == 0) {
@@ -1190,7 +1209,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             __threadfence_block();                                      // obstacle centres written by the leader lane
             __syncwarp(gmask);
             if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
-            group_obs_tail<KG>(c, P, env, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
+            group_obs_tail<KG, OBST>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
         }
         __syncwarp();
     }
@@ -1209,7 +1228,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 // ----------------------------------------------------------------------------------------------------------------
 // explicit reset (QuadrotorEnvMulti.reset through VecEnv.reset)
 // ----------------------------------------------------------------------------------------------------------------
-template <int KG>
+template <int KG, bool OBST>
 __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
                                                     const uint8_t *__restrict__ env_mask, float *__restrict__ obs)
 {
@@ -1246,7 +1265,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
     }
     int scen = 0;
     if (valid) {
-        group_reset<KG>(c, P, g, env, d, true, q, scen);
+        group_reset<KG, OBST>(c, P, g, env, d, true, q, scen);
         if (d == 0) {
             int *ec = P.ecnt + env * EC_COUNT;
 #pragma unroll
@@ -1261,7 +1280,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
     __threadfence_block();
     __syncwarp();
     if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
-    group_obs_tail<KG>(c, P, env, d, lane, gmask, valid, q, vs, orow, stage);
+    group_obs_tail<KG, OBST>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);
     __syncwarp();
     // rows of envs that were not reset stay untouched: per-row masked copy
     const int warp_env0 = (tid - lane) / KG;
