@@ -25,17 +25,40 @@ EXPORTS = ("qs_config_size", "qs_stats_size", "qs_api_version", "qs_last_error",
            "qs_reset_host", "qs_step_host", "qs_get_state", "qs_set_state", "qs_set_param", "qs_episode_stats")
 
 
+KG_VALUES = (1, 2, 4, 8, 16, 32)
+
+
 def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, "quadsim.cu")]
-    deps = srcs + [os.path.join(CSRC, "quadsim_kernels.cuh"), os.path.join(os.path.dirname(_PKG), "include", "quadsim.h")]
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU).  One translation unit per
+    lane-group width (kernels_kg.cu, -DQS_KG=n) plus the host API (quadsim.cu), compiled in parallel, then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    root = os.path.dirname(_PKG)
+    deps = [os.path.join(CSRC, f) for f in ("quadsim.cu", "kernels_kg.cu", "quadsim_kernels.cuh", "fork_kernels.cuh", "launch.h")]
+    deps.append(os.path.join(root, "include", "quadsim.h"))
     if not force and out is None and os.path.exists(LIB_PATH) and all(
             (not os.path.exists(d)) or os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
     target = out or LIB_PATH
-    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + srcs
-    subprocess.check_call(cmd)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objdir = os.path.join(root, "build", "obj" if out is None else "obj_" + os.path.basename(out))
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    jobs = [([nvcc] + flags + ["-c", os.path.join(CSRC, "quadsim.cu"), "-o", os.path.join(objdir, "quadsim.o")])]
+    for kg in KG_VALUES:
+        jobs.append([nvcc] + flags + [f"-DQS_KG={kg}", "-c", os.path.join(CSRC, "kernels_kg.cu"), "-o", os.path.join(objdir, f"kernels_kg{kg}.o")])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            import sys
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise subprocess.CalledProcessError(r.returncode, cmd)
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        list(ex.map(run, jobs))
+    objs = [j[-1] for j in jobs]
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target] + objs)
     return target
 
 

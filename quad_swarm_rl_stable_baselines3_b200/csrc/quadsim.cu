@@ -8,7 +8,92 @@
 #include <cstring>
 #include <string>
 
-#include "fork_kernels.cuh"
+#include "launch.h"
+
+namespace qs {
+
+// ----------------------------------------------------------------------------------------------------------------
+// kernels that do not depend on the lane-group width live in this translation unit
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, int set)
+{
+    int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    int nd = c.N * c.K;
+    if (gi < nd) {
+        Drone q;
+        load_drone(P, gi, q);
+        if (set) {
+            if (v.pos) for (int a = 0; a < 3; ++a) q.p[a] = v.pos[3 * gi + a];
+            if (v.vel) for (int a = 0; a < 3; ++a) q.v[a] = v.vel[3 * gi + a];
+            if (v.omega) for (int a = 0; a < 3; ++a) q.w[a] = v.omega[3 * gi + a];
+            if (v.rot) for (int a = 0; a < 9; ++a) q.R[a] = v.rot[9 * gi + a];
+            if (v.rot_damp) for (int a = 0; a < 4; ++a) q.rd[a] = v.rot_damp[4 * gi + a];
+            if (v.cmds_damp) for (int a = 0; a < 4; ++a) q.cd[a] = v.cmds_damp[4 * gi + a];
+            if (v.ou) for (int a = 0; a < 4; ++a) q.ou[a] = v.ou[4 * gi + a];
+            if (v.goal) for (int a = 0; a < 3; ++a) q.goal[a] = v.goal[3 * gi + a];
+            if (v.flags) q.flags = v.flags[gi];
+            if (v.col_mask) q.colmask = v.col_mask[gi];
+            store_drone(P, gi, q, true);
+        } else {
+            if (v.pos) for (int a = 0; a < 3; ++a) v.pos[3 * gi + a] = q.p[a];
+            if (v.vel) for (int a = 0; a < 3; ++a) v.vel[3 * gi + a] = q.v[a];
+            if (v.omega) for (int a = 0; a < 3; ++a) v.omega[3 * gi + a] = q.w[a];
+            if (v.rot) for (int a = 0; a < 9; ++a) v.rot[9 * gi + a] = q.R[a];
+            if (v.rot_damp) for (int a = 0; a < 4; ++a) v.rot_damp[4 * gi + a] = q.rd[a];
+            if (v.cmds_damp) for (int a = 0; a < 4; ++a) v.cmds_damp[4 * gi + a] = q.cd[a];
+            if (v.ou) for (int a = 0; a < 4; ++a) v.ou[4 * gi + a] = q.ou[a];
+            if (v.goal) for (int a = 0; a < 3; ++a) v.goal[3 * gi + a] = q.goal[a];
+            if (v.flags) v.flags[gi] = q.flags;
+            if (v.col_mask) v.col_mask[gi] = q.colmask;
+        }
+    }
+    if (gi < nd && F.plane[0] != nullptr) {
+        if (v.pid) {
+            for (int k = 0; k < 6; ++k) {
+                if (set) F.plane[FP_PID0 + k][gi] = make_float4(v.pid[24 * gi + 4 * k], v.pid[24 * gi + 4 * k + 1], v.pid[24 * gi + 4 * k + 2], v.pid[24 * gi + 4 * k + 3]);
+                else { float4 x = F.plane[FP_PID0 + k][gi]; v.pid[24 * gi + 4 * k] = x.x; v.pid[24 * gi + 4 * k + 1] = x.y; v.pid[24 * gi + 4 * k + 2] = x.z; v.pid[24 * gi + 4 * k + 3] = x.w; }
+            }
+        }
+        if (v.heading) {
+            if (set) F.plane[FP_HEADING][gi] = make_float4(v.heading[2 * gi], v.heading[2 * gi + 1], 0.f, 0.f);
+            else { float4 x = F.plane[FP_HEADING][gi]; v.heading[2 * gi] = x.x; v.heading[2 * gi + 1] = x.y; }
+        }
+    }
+    if (gi < c.N && F.evader != nullptr && v.evader) {
+        if (set) F.evader[gi] = make_float2(v.evader[2 * gi], v.evader[2 * gi + 1]);
+        else { float2 x = F.evader[gi]; v.evader[2 * gi] = x.x; v.evader[2 * gi + 1] = x.y; }
+    }
+    if (gi < c.N) {
+        if (set) {
+            if (v.tick) P.tick[gi] = v.tick[gi];
+            if (v.svd_ctr) P.svd_ctr[gi] = v.svd_ctr[gi];
+            if (v.step_ctr) P.step_ctr[gi] = v.step_ctr[gi];
+        } else {
+            if (v.tick) v.tick[gi] = P.tick[gi];
+            if (v.svd_ctr) v.svd_ctr[gi] = P.svd_ctr[gi];
+            if (v.step_ctr) v.step_ctr[gi] = P.step_ctr[gi];
+        }
+    }
+    if (v.obst_xy) {
+        int tot = c.N * QS_MAX_OBSTACLES;
+        for (int k = gi; k < tot; k += gridDim.x * blockDim.x) {
+            if (set) P.obst_xy[k] = make_float2(v.obst_xy[2 * k], v.obst_xy[2 * k + 1]);
+            else { float2 xy = P.obst_xy[k]; v.obst_xy[2 * k] = xy.x; v.obst_xy[2 * k + 1] = xy.y; }
+        }
+    }
+}
+
+// raw generator probe used by the tests to pin the RNG contract bit-for-bit against the oracle
+__global__ void philox_probe_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out, float *fout)
+{
+    uint4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+    fout[0] = u23(r.x); fout[1] = u23(r.y);
+    box_muller(r.x, r.y, fout[2], fout[3]);
+    box_muller(r.z, r.w, fout[4], fout[5]);
+}
+
+}  // namespace qs
 
 using namespace qs;
 
@@ -152,33 +237,17 @@ static int validate(const qs_config *c, std::string &why)
     return 1;
 }
 
-template <typename... Args>
-static void set_smem_attr(size_t bytes, void (*kernel)(Args...))
+static const KgLaunchers &launchers(int KG)
 {
-    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    // the kernels stream their state (no L1 reuse): give the whole unified L1/shared array to shared memory so that the
-    // observation tiles never limit the number of resident blocks
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    switch (KG) {
+        case 1: return launchers_kg1();
+        case 2: return launchers_kg2();
+        case 4: return launchers_kg4();
+        case 8: return launchers_kg8();
+        case 16: return launchers_kg16();
+        default: return launchers_kg32();
+    }
 }
-
-#define QS_DISPATCH_KG(KGv, CALL)                 \
-    switch (KGv) {                                \
-        case 1: { constexpr int KG = 1; CALL; } break;   \
-        case 2: { constexpr int KG = 2; CALL; } break;   \
-        case 4: { constexpr int KG = 4; CALL; } break;   \
-        case 8: { constexpr int KG = 8; CALL; } break;   \
-        case 16: { constexpr int KG = 16; CALL; } break; \
-        default: { constexpr int KG = 32; CALL; } break; \
-    }
-
-// compile-time feature set of the upstream step kernel: bit 0 obstacles, bit 1 downwash
-#define QS_DISPATCH_FEAT(FEATv, CALL)              \
-    switch (FEATv) {                               \
-        case 0: { constexpr int FEAT = 0; CALL; } break; \
-        case 1: { constexpr int FEAT = 1; CALL; } break; \
-        case 2: { constexpr int FEAT = 2; CALL; } break; \
-        default: { constexpr int FEAT = 3; CALL; } break; \
-    }
 
 extern "C" {
 
@@ -270,24 +339,17 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
         cudaFree(rot); free(h);
     }
     e->persist = false; e->grid_persist = 0; e->smem_persist = 0;
-    if (e->fork) { QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, fork_step_kernel<KG>); set_smem_attr(e->smem_bytes, fork_reset_kernel<KG>)); }
-    else {
-        QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, set_smem_attr(e->smem_bytes, step_kernel<KG, false, FEAT>)));
-        QS_DISPATCH_KG(e->KG, set_smem_attr(e->smem_bytes, reset_kernel<KG, false>); set_smem_attr(e->smem_bytes, reset_kernel<KG, true>));
-        // persistent form: worth it once the batch is several waves of resident blocks
+    {
         const size_t pf_floats = (tiles_floats + obst_floats + 3) & ~(size_t)3;
-        e->smem_persist = pf_floats * sizeof(float) + (size_t)warps * PF_SLOTS * 32 * sizeof(float4) + (size_t)warps * sizeof(uint64_t);
+        if (!e->fork) e->smem_persist = pf_floats * sizeof(float) + (size_t)warps * PF_SLOTS * 32 * sizeof(float4) + (size_t)warps * sizeof(uint64_t);
         int per_sm = 0;
-        if (e->smem_persist <= 227 * 1024) {
-            QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, set_smem_attr(e->smem_persist, step_kernel<KG, true, FEAT>);
-                           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<KG, true, FEAT>, e->block, e->smem_persist)));
-        }
+        launchers(e->KG).prepare(e->feat, e->smem_bytes, e->smem_persist, e->block, &per_sm, e->fork);
         // Measured (profiles/README.md): hiding the start-of-tile HBM latency does not pay on this kernel -- with 16 resident
         // warps per SM the other warps already cover it (88.3 us plain vs 90.1 us persistent at 65536 envs) -- so the
         // persistent form is opt-in (QS_PERSIST=1); it is kept bitwise-tested against the plain form.
         const char *pe = getenv("QS_PERSIST");
         const bool want = pe ? atoi(pe) != 0 : false;
-        if (per_sm > 0 && want) { e->persist = true; e->grid_persist = (e->grid < per_sm * sms) ? e->grid : per_sm * sms; }
+        if (!e->fork && per_sm > 0 && want) { e->persist = true; e->grid_persist = (e->grid < per_sm * sms) ? e->grid : per_sm * sms; }
         if (const char *pb = getenv("QS_PERSIST_BLOCKS")) { int v = atoi(pb); if (v >= 1 && v < e->grid_persist) e->grid_persist = v; }   // tests: force looping
     }
     r = cudaGetLastError();
@@ -327,9 +389,9 @@ int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
 {
     if (!e || !obs) return fail(e, QS_ERR_NULL, "qs_reset: null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->fork) { QS_DISPATCH_KG(e->KG, (fork_reset_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->fc, e->dp, e->fp, env_mask, obs))); }
-    else if (e->cfg.use_obstacles) { QS_DISPATCH_KG(e->KG, (reset_kernel<KG, true><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs))); }
-    else { QS_DISPATCH_KG(e->KG, (reset_kernel<KG, false><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, env_mask, obs))); }
+    const LaunchShape shape = { e->grid, e->block, e->smem_bytes };
+    if (e->fork) launchers(e->KG).fork_reset(shape, s, e->dc, e->fc, e->dp, e->fp, env_mask, obs);
+    else launchers(e->KG).reset(e->cfg.use_obstacles != 0, shape, s, e->dc, e->dp, env_mask, obs);
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
@@ -342,13 +404,14 @@ int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *do
     if (((size_t)actions & 15) != 0) return fail(e, QS_ERR_SHAPE, "qs_step: actions must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     if (e->fork) {
-        QS_DISPATCH_KG(e->KG, (fork_step_kernel<KG><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->fc, e->dp, e->fp, (const float2 *)actions, obs, rew, done, terminal_obs, reset_success)));
+        launchers(e->KG).fork_step({ e->grid, e->block, e->smem_bytes }, s, e->dc, e->fc, e->dp, e->fp, (const float2 *)actions, obs, rew,
+                                   done, terminal_obs, reset_success);
+    } else if (e->persist) {
+        launchers(e->KG).step(true, e->feat, { e->grid_persist, e->block, e->smem_persist }, s, e->dc, e->dp, (const float4 *)actions, obs,
+                              rew, done, terminal_obs, reset_success);
     } else {
-        if (e->persist) {
-            QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, (step_kernel<KG, true, FEAT><<<e->grid_persist, e->block, e->smem_persist, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success))));
-        } else {
-            QS_DISPATCH_KG(e->KG, QS_DISPATCH_FEAT(e->feat, (step_kernel<KG, false, FEAT><<<e->grid, e->block, e->smem_bytes, s>>>(e->dc, e->dp, (const float4 *)actions, obs, rew, done, terminal_obs, reset_success))));
-        }
+        launchers(e->KG).step(false, e->feat, { e->grid, e->block, e->smem_bytes }, s, e->dc, e->dp, (const float4 *)actions, obs, rew, done,
+                              terminal_obs, reset_success);
     }
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());

@@ -131,7 +131,7 @@ __device__ __forceinline__ void rng_n4(const Rng &g, int site, int drone, int au
 
 // One Philox block -> 4 standard normals, out of line: the hot path draws 4 blocks per drone-step and four inlined
 // copies (~115 instructions each) do not fit the instruction-cache budget of the step kernel.
-__device__ __noinline__ float4 rng_normal4(uint32_t gid, uint32_t step, uint32_t c2, uint32_t block, uint32_t k0, uint32_t k1)
+static __device__ __noinline__ float4 rng_normal4(uint32_t gid, uint32_t step, uint32_t c2, uint32_t block, uint32_t k0, uint32_t k1)
 {
     uint4 r = philox4x32_10(gid, step, c2, block, k0, k1);
     float4 n;
@@ -409,7 +409,7 @@ __device__ __forceinline__ void compute_new_omega(const float *u4, float magn_sc
 }
 
 // perform_collision_between_drones, collisions/quadrotors.py:9-59.  Inputs are drone i ("1") and drone j ("2").
-__device__ __noinline__ void pair_impulse(const Rng g, int i, int j, const float *p1, const float *p2, float *v1, float *v2,
+static __device__ __noinline__ void pair_impulse(const Rng g, int i, int j, const float *p1, const float *p2, float *v1, float *v2,
                                           float *w1, float *w2)
 {
     float n0 = p1[0] - p2[0], n1 = p1[1] - p2[1], n2 = p1[2] - p2[2];
@@ -445,7 +445,7 @@ __device__ __noinline__ void pair_impulse(const Rng g, int i, int j, const float
 }
 
 // perform_collision_with_obstacle, collisions/obstacles.py:9-50
-__device__ __noinline__ void obstacle_impulse(const DevConst &c, const Rng g, int drone, const float *p, float *v, float *w,
+static __device__ __noinline__ void obstacle_impulse(const DevConst &c, const Rng g, int drone, const float *p, float *v, float *w,
                                               float ox, float oy)
 {
     float n0 = p[0] - ox, n1 = p[1] - oy;
@@ -474,7 +474,7 @@ __device__ __noinline__ void obstacle_impulse(const DevConst &c, const Rng g, in
 }
 
 // perform_collision_with_wall / _ceiling, collisions/room.py:6-45, 91-113
-__device__ __noinline__ void room_impulse(const DevConst &c, const Rng g, int drone, int flags, float *v, float *w, bool is_wall)
+static __device__ __noinline__ void room_impulse(const DevConst &c, const Rng g, int drone, int flags, float *v, float *w, bool is_wall)
 {
     int site = is_wall ? SITE_WALL : SITE_CEILING;
     float u[12];
@@ -524,7 +524,7 @@ __device__ __forceinline__ void choice_fy(const Rng &g, int aux, int n, int k, u
 // obst_generation_given_density (quadrotor_multi.py:405-426) + Scenario_o_random / o_static_same_goal .reset
 // (scenarios/obstacles/o_random.py:26-52, o_static_same_goal.py:27-48, o_base.py:69-81,124-153).
 // Every lane of the group evaluates it redundantly (same keys -> same values); lane `drone` keeps its own spawn/goal.
-__device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rng g, int drone, bool leader, float2 *obst_xy,
+static __device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rng g, int drone, bool leader, float2 *obst_xy,
                                                      float *spawn, float *goal, int &scenario_now)
 {
     const int L = c.obst_L, W = c.obst_W, M = c.M, K = c.K;
@@ -578,7 +578,7 @@ __device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rn
 
 // QuadrotorSingle._reset, quadrotor_single.py:401-469
 // out = { x, y, z, cos(yaw), sin(yaw) }
-__device__ __noinline__ void drone_reset(const DevConst &c, const Rng g, int drone, const float *spawn, float *out)
+static __device__ __noinline__ void drone_reset(const DevConst &c, const Rng g, int drone, const float *spawn, float *out)
 {
     float u[4];
     rng_u4(g, SITE_SPAWN, drone, 0, 0, u);
@@ -615,7 +615,35 @@ __device__ __forceinline__ uint32_t group_mask(int lane) { return (KG == 32) ? Q
 // `stage` is this warp's 32 x 2 float4 exchange buffer: every lane publishes (pos, vs), the group syncs, and each lane
 // reads its K-1 neighbours as broadcast 16-byte shared-memory loads.
 // `ob`: the env's obstacle centres (the warp's shared-memory copy in the step path, global memory right after a reset)
-template <int KG, bool OBST>
+// a14 in one pass over the env's obstacles: the 3x3 SDF patch (get_surround_sdfs, obstacles/utils.py:5-27; the min over
+// obstacles commutes with the sqrt) and the first obstacle the drone touches (collision_detection, obstacles/utils.py:31-43:
+// 2-D distance <= arm + size/2, lowest index wins) -- the centre cell of the patch IS that distance.
+__device__ __forceinline__ void obstacle_sdf_and_hit(const DevConst &c, const float2 *ob, float px, float py, float *r, int &hit)
+{
+    const float gx[3] = { px - c.sdf_res, px, px + c.sdf_res }, gy[3] = { py - c.sdf_res, py, py + c.sdf_res };
+    const float obst2 = c.thr_obst * c.thr_obst * 1.0001f;
+    float md[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) md[a] = 10000.0f;                       // (100)^2
+    hit = -1;
+    for (int m = 0; m < c.M; ++m) {
+        const float2 xy = ob[m];
+        float dx2[3], dy2[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { float dx = gx[a] - xy.x, dy = gy[a] - xy.y; dx2[a] = dx * dx; dy2[a] = dy * dy; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) md[a * 3 + b] = fminf(md[a * 3 + b], dx2[a] + dy2[b]);
+        const float d2 = dx2[1] + dy2[1];
+        if (d2 <= obst2 && hit < 0 && __fsqrt_rn(d2) <= c.thr_obst) hit = m;
+    }
+#pragma unroll
+    for (int a = 0; a < 9; ++a) r[a] = sqrtf(md[a]) - c.obst_rad;
+}
+
+// SDF = false: the caller already wrote the SDF patch of these positions (step path: together with the hit test)
+template <int KG, bool OBST, bool SDF>
 __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *ob, int d, int lane, uint32_t gmask, bool valid,
                                                const Drone &q, const float *vs, float *o, float4 *stage)
 {
@@ -690,25 +718,9 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
             }
         }
     }
-    if (OBST && valid) {
-        // a14: get_surround_sdfs, obstacles/utils.py:5-27 (min over obstacles commutes with sqrt)
-        float gx[3] = { q.p[0] - c.sdf_res, q.p[0], q.p[0] + c.sdf_res }, gy[3] = { q.p[1] - c.sdf_res, q.p[1], q.p[1] + c.sdf_res };
-        float md[9];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) md[a] = 10000.0f;                   // (100)^2
-        for (int m = 0; m < c.M; ++m) {
-            float2 xy = ob[m];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    float dx = gx[a] - xy.x, dy = gy[b] - xy.y;
-                    md[a * 3 + b] = fminf(md[a * 3 + b], dx * dx + dy * dy);
-                }
-        }
-        float *r = o + c.S + ((c.nbr_type == QS_NEIGHBOR_POS_VEL) ? 6 * c.V : 0);
-#pragma unroll
-        for (int a = 0; a < 9; ++a) r[a] = sqrtf(md[a]) - c.obst_rad;
+    if (OBST && SDF && valid) {
+        int hit;
+        obstacle_sdf_and_hit(c, ob, q.p[0], q.p[1], o + c.S + ((c.nbr_type == QS_NEIGHBOR_POS_VEL) ? 6 * c.V : 0), hit);
     }
 }
 
@@ -979,14 +991,9 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     int obst_hit = -1;
     bool obst_new = false;
     if (OBST) {
-        if (valid) {
-            const float obst2 = c.thr_obst * c.thr_obst * 1.0001f;
-            for (int m = 0; m < c.M; ++m) {
-                float2 xy = ob_env[m];
-                float dx = q.p[0] - xy.x, dy = q.p[1] - xy.y, d2 = dx * dx + dy * dy;
-                if (d2 <= obst2 && __fsqrt_rn(d2) <= c.thr_obst) { obst_hit = m; break; }
-            }
-        }
+        // positions are final for this step (impulses only touch vel / omega), so the SDF patch of the observation is
+        // produced here in the same pass as the hit test and goes straight into the warp's observation tile
+        if (valid) obstacle_sdf_and_hit(c, ob_env, q.p[0], q.p[1], orow + c.S + ((c.nbr_type == QS_NEIGHBOR_POS_VEL) ? 6 * c.V : 0), obst_hit);
         obst_new = (obst_hit >= 0) && !(q.flags & F_PREV_OBST);
         q.flags = (obst_hit >= 0) ? (q.flags | F_PREV_OBST) : (q.flags & ~F_PREV_OBST);
     }
@@ -1034,26 +1041,29 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     bool flag = false;
     if (DOWNWASH && KG > 1) {
         // perform_downwash, aerodynamics/downwash.py:4-66: lane j accumulates the pushes of every source i in index order
-        float ua = 0.f, uw = 0.f;
-        if (valid) { float u[4]; rng_u4(g, SITE_DOWNWASH, d, 0xFF, 0, u); ua = u[0]; uw = u[1]; }
         const float px0 = q.p[0], py0 = q.p[1], pz0 = q.p[2];
-        // every drone publishes (pos, a-jitter) and (body z axis, w-jitter); sources are read back as broadcast 16-byte loads
+        // every drone publishes its position and body z axis; sources are read back as broadcast 16-byte loads
         __syncwarp(gmask);
-        stage[2 * lane] = make_float4(px0, py0, pz0, ua);
-        stage[2 * lane + 1] = make_float4(q.R[2], q.R[5], q.R[8], uw);
+        stage[2 * lane] = make_float4(px0, py0, pz0, 0.f);
+        stage[2 * lane + 1] = make_float4(q.R[2], q.R[5], q.R[8], 0.f);
         __syncwarp(gmask);
         bool hit = false;
 #pragma unroll 1
         for (int i = 0; i < c.K; ++i) {
-            const float4 sp = stage[2 * (base + i)], sz = stage[2 * (base + i) + 1];
-            if (i != d && valid) {
-                float rx = px0 - sp.x, ry = py0 - sp.y, rz = pz0 - sp.z;
-                float dd = norm3f(rx, ry, rz);
+            const float4 sp = stage[2 * (base + i)];
+            float rx = px0 - sp.x, ry = py0 - sp.y, rz = pz0 - sp.z;
+            float d2 = rx * rx + ry * ry + rz * rz;
+            // inside the wake cylinder (|relz| < 0.7, rxy < 0.1) means d^2 < 0.5: everything else is skipped on d^2 alone
+            if (i != d && valid && d2 < 0.51f) {
+                const float4 sz = stage[2 * (base + i) + 1];
+                float dd = sqrtf(d2);
                 float relz = rx * sz.x + ry * sz.y + rz * sz.z;
                 float rxy = sqrtf(dd * dd - relz * relz);
                 if (-0.7f < relz && relz < 0.f && rxy < 0.1f) {
-                    float acc = fmaxf(1e-6f, (6.0f / 17.0f) * (-10.0f * dd + 7.0f) + (-0.1f + 0.2f * sp.w));
-                    float ow = fmaxf(1e-6f, 0.3f * (dd - 1.0f) * (dd - 1.0f) + (-0.01f + 0.02f * sz.w));
+                    float su[4];
+                    rng_u4(g, SITE_DOWNWASH, i, 0xFF, 0, su);            // the source's own (a, w) jitter: same counter on every target
+                    float acc = fmaxf(1e-6f, (6.0f / 17.0f) * (-10.0f * dd + 7.0f) + (-0.1f + 0.2f * su[0]));
+                    float ow = fmaxf(1e-6f, 0.3f * (dd - 1.0f) * (dd - 1.0f) + (-0.01f + 0.02f * su[1]));
                     float u[4], t[4];
                     rng_u4(g, SITE_DOWNWASH, i, d, 0, u); rng_u4(g, SITE_DOWNWASH, i, d, 1, t);
                     float nx = sz.x + (-0.1f + 0.2f * u[0]), ny = sz.y + (-0.1f + 0.2f * u[1]), nz = sz.z + (-0.1f + 0.2f * u[2]);
@@ -1134,7 +1144,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     // ---- 5. observations (:703-720).  Self obs carries fresh sensor noise if any impulse fired (:711-712)
     float vs[3] = { q.v[0], q.v[1], q.v[2] };                          // self.vel snapshot, :705-709
     if (valid) self_obs(c, g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d, q, orow);
-    group_obs_tail<KG, OBST>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
+    group_obs_tail<KG, OBST, false>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
     if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }
 
     // ---- 7. dones (:739-838): episode stats, then the env resets itself and returns the new episode's first observation
@@ -1209,7 +1219,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             __threadfence_block();                                      // obstacle centres written by the leader lane
             __syncwarp(gmask);
             if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
-            group_obs_tail<KG, OBST>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
+            group_obs_tail<KG, OBST, true>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
         }
         __syncwarp();
     }
@@ -1280,7 +1290,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
     __threadfence_block();
     __syncwarp();
     if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
-    group_obs_tail<KG, OBST>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);
+    group_obs_tail<KG, OBST, true>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);
     __syncwarp();
     // rows of envs that were not reset stay untouched: per-row masked copy
     const int warp_env0 = (tid - lane) / KG;
@@ -1311,83 +1321,5 @@ struct ForkPtrs {
     float2 *evader;            // [N]
     int *flags;                // [N]
 };
-
-__global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, int set)
-{
-    int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    int nd = c.N * c.K;
-    if (gi < nd) {
-        Drone q;
-        load_drone(P, gi, q);
-        if (set) {
-            if (v.pos) for (int a = 0; a < 3; ++a) q.p[a] = v.pos[3 * gi + a];
-            if (v.vel) for (int a = 0; a < 3; ++a) q.v[a] = v.vel[3 * gi + a];
-            if (v.omega) for (int a = 0; a < 3; ++a) q.w[a] = v.omega[3 * gi + a];
-            if (v.rot) for (int a = 0; a < 9; ++a) q.R[a] = v.rot[9 * gi + a];
-            if (v.rot_damp) for (int a = 0; a < 4; ++a) q.rd[a] = v.rot_damp[4 * gi + a];
-            if (v.cmds_damp) for (int a = 0; a < 4; ++a) q.cd[a] = v.cmds_damp[4 * gi + a];
-            if (v.ou) for (int a = 0; a < 4; ++a) q.ou[a] = v.ou[4 * gi + a];
-            if (v.goal) for (int a = 0; a < 3; ++a) q.goal[a] = v.goal[3 * gi + a];
-            if (v.flags) q.flags = v.flags[gi];
-            if (v.col_mask) q.colmask = v.col_mask[gi];
-            store_drone(P, gi, q, true);
-        } else {
-            if (v.pos) for (int a = 0; a < 3; ++a) v.pos[3 * gi + a] = q.p[a];
-            if (v.vel) for (int a = 0; a < 3; ++a) v.vel[3 * gi + a] = q.v[a];
-            if (v.omega) for (int a = 0; a < 3; ++a) v.omega[3 * gi + a] = q.w[a];
-            if (v.rot) for (int a = 0; a < 9; ++a) v.rot[9 * gi + a] = q.R[a];
-            if (v.rot_damp) for (int a = 0; a < 4; ++a) v.rot_damp[4 * gi + a] = q.rd[a];
-            if (v.cmds_damp) for (int a = 0; a < 4; ++a) v.cmds_damp[4 * gi + a] = q.cd[a];
-            if (v.ou) for (int a = 0; a < 4; ++a) v.ou[4 * gi + a] = q.ou[a];
-            if (v.goal) for (int a = 0; a < 3; ++a) v.goal[3 * gi + a] = q.goal[a];
-            if (v.flags) v.flags[gi] = q.flags;
-            if (v.col_mask) v.col_mask[gi] = q.colmask;
-        }
-    }
-    if (gi < nd && F.plane[0] != nullptr) {
-        if (v.pid) {
-            for (int k = 0; k < 6; ++k) {
-                if (set) F.plane[FP_PID0 + k][gi] = make_float4(v.pid[24 * gi + 4 * k], v.pid[24 * gi + 4 * k + 1], v.pid[24 * gi + 4 * k + 2], v.pid[24 * gi + 4 * k + 3]);
-                else { float4 x = F.plane[FP_PID0 + k][gi]; v.pid[24 * gi + 4 * k] = x.x; v.pid[24 * gi + 4 * k + 1] = x.y; v.pid[24 * gi + 4 * k + 2] = x.z; v.pid[24 * gi + 4 * k + 3] = x.w; }
-            }
-        }
-        if (v.heading) {
-            if (set) F.plane[FP_HEADING][gi] = make_float4(v.heading[2 * gi], v.heading[2 * gi + 1], 0.f, 0.f);
-            else { float4 x = F.plane[FP_HEADING][gi]; v.heading[2 * gi] = x.x; v.heading[2 * gi + 1] = x.y; }
-        }
-    }
-    if (gi < c.N && F.evader != nullptr && v.evader) {
-        if (set) F.evader[gi] = make_float2(v.evader[2 * gi], v.evader[2 * gi + 1]);
-        else { float2 x = F.evader[gi]; v.evader[2 * gi] = x.x; v.evader[2 * gi + 1] = x.y; }
-    }
-    if (gi < c.N) {
-        if (set) {
-            if (v.tick) P.tick[gi] = v.tick[gi];
-            if (v.svd_ctr) P.svd_ctr[gi] = v.svd_ctr[gi];
-            if (v.step_ctr) P.step_ctr[gi] = v.step_ctr[gi];
-        } else {
-            if (v.tick) v.tick[gi] = P.tick[gi];
-            if (v.svd_ctr) v.svd_ctr[gi] = P.svd_ctr[gi];
-            if (v.step_ctr) v.step_ctr[gi] = P.step_ctr[gi];
-        }
-    }
-    if (v.obst_xy) {
-        int tot = c.N * QS_MAX_OBSTACLES;
-        for (int k = gi; k < tot; k += gridDim.x * blockDim.x) {
-            if (set) P.obst_xy[k] = make_float2(v.obst_xy[2 * k], v.obst_xy[2 * k + 1]);
-            else { float2 xy = P.obst_xy[k]; v.obst_xy[2 * k] = xy.x; v.obst_xy[2 * k + 1] = xy.y; }
-        }
-    }
-}
-
-// raw generator probe used by the tests to pin the RNG contract bit-for-bit against the oracle
-__global__ void philox_probe_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out, float *fout)
-{
-    uint4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
-    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
-    fout[0] = u23(r.x); fout[1] = u23(r.y);
-    box_muller(r.x, r.y, fout[2], fout[3]);
-    box_muller(r.z, r.w, fout[4], fout[5]);
-}
 
 }  // namespace qs
