@@ -76,7 +76,11 @@ enum { QS_OBS_XYZ_VXYZ_R_OMEGA = 0, QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR = 1, QS_OBS_XY
 enum { QS_NEIGHBOR_NONE = 0, QS_NEIGHBOR_POS_VEL = 1,
        /* fork types (quadrotor_multi_rewards.py:326-358), QS_MODE_FORK only */
        QS_NEIGHBOR_DIST_ANGLE = 2,      /* [|dp|, bearing - heading] */
-       QS_NEIGHBOR_DIST_SANGLE = 3 };   /* [|dp|, cos, sin of the relative bearing] */
+       QS_NEIGHBOR_DIST_SANGLE = 3,     /* [|dp|, cos, sin of the relative bearing] */
+       QS_NEIGHBOR_DIST_ANGLE_HEADING = 4,    /* + heading_j - heading_i wrapped (:372-376) */
+       QS_NEIGHBOR_DIST_SANGLE_SHEADING = 5,  /* + cos, sin of the relative heading (:377-382) */
+       QS_NEIGHBOR_NDIST_NSANGLE = 6 };       /* camera model: [noisy dist clipped to 0..10, cos, sin of the noisy bearing]
+                                                 (simulate_camera_measurement_vect, quadrotor_multi_rewards.py:238-324,338-347,370-371) */
 
 /* noise source: counter-based Philox on the device (production) */
 enum { QS_SENSE_NOISE_NONE = 0, QS_SENSE_NOISE_DEFAULT = 1 };
@@ -115,6 +119,14 @@ typedef struct qs_fork_config {
     double ctrl_kf;               /* 1.25e-9 */
     double ctrl_min_rpm;          /* 1170 */
     double ctrl_max_rpm;          /* 13000 */
+    /* camera model of the ndist / nsangle neighbour observations (swarm_rl/global_cfg.py:12-17) */
+    double cam_focal_length;      /* focal_length_cam 0.035 m */
+    double cam_target_size;       /* neighbour_size_cam 0.2 m */
+    double cam_pixel_noise;       /* pixel_noise_cam (std, px); sb_train.py:136 sets 0 */
+    double cam_fov_deg;           /* 70  (quadrotor_multi_rewards.py:286) */
+    double cam_resolution;        /* 640 (:287) */
+    int32_t cam_num;              /* n_cameras 3 */
+    int32_t reserved2;
 } qs_fork_config;
 
 /*

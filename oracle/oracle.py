@@ -175,7 +175,7 @@ class OracleEnv:
             lib().qo_set_obstacles(self.h, _dp(xy), xy.shape[0])
 
     def get_fork_state(self):
-        pid, heading, evader, fl = np.zeros((self.K, 24)), np.zeros((self.K, 2)), np.zeros(2), (C.c_int32 * 2)()
+        pid, heading, evader, fl = np.zeros((self.K, 24)), np.zeros((self.K, 3)), np.zeros(2), (C.c_int32 * 2)()
         lib().qo_get_fork_state(self.h, _dp(pid), _dp(heading), _dp(evader), fl)
         return dict(pid=pid, heading=heading, evader=evader, episode_success=bool(fl[0]), chasers_placed=bool(fl[1]))
 

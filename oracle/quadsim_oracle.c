@@ -31,7 +31,7 @@
 /* RNG sites (DESIGN.md "RNG contract") */
 enum { SITE_OU = 0, SITE_SENSOR = 1, SITE_SENSOR_IMPULSE = 2, SITE_SENSOR_RESET = 3, SITE_FLOOR_YAW = 4,
        SITE_PAIR = 5, SITE_OBST = 6, SITE_WALL = 7, SITE_CEILING = 8, SITE_DOWNWASH = 9,
-       SITE_SPAWN = 10, SITE_SCENARIO = 11 };
+       SITE_SPAWN = 10, SITE_SCENARIO = 11, SITE_CAMERA = 12 };
 
 typedef struct {
     double pos[3], vel[3], rot[9], omega[3];
@@ -63,6 +63,8 @@ typedef struct qo_env {
     int scenario_now;                   /* QS_SCENARIO_O_RANDOM / O_STATIC_SAME_GOAL / STATIC_SAME_GOAL */
     double evader[2];                   /* fork mode: Scenario_dynamic_repulsive.pos */
     int episode_success;                /* fork mode: quadrotor_multi_rewards.py:757,625-627 */
+    double snap_heading[QS_MAX_AGENTS]; /* fork mode: self.heading, refreshed in step only (stale in the reset-time neighbour obs) */
+    double cam_n1[QS_MAX_AGENTS], cam_n2[QS_MAX_AGENTS];   /* camera pixel-noise normals of the current neighbour pass */
     int chasers_placed;                 /* fork mode: 0 until the first reset has given the dynamics a position; the evader's very
                                            first step ignores the chasers (`hasattr(env.dynamics, "pos")`, dynamic_repulsive.py:44) */
     double approach_metric;
@@ -931,12 +933,12 @@ void qo_step(qo_env *e, const double *actions, double *obs, double *rew, uint8_t
     if (is_fork(e)) fork_env_step(e, actions, obs, rew, done, terminal_obs, reset_success);
     else { env_step(e, actions, obs, rew, done, terminal_obs); if (reset_success && done[0]) *reset_success = 0; }
 }
-/* fork-mode state: pid [K,24], heading [K,2] = (angle, angular_velocity), evader [2] */
+/* fork-mode state: pid [K,24], heading [K,3] = (angle, angular_velocity, self.heading snapshot), evader [2] */
 void qo_get_fork_state(const qo_env *e, double *pid, double *heading, double *evader, int32_t *env_flags /* [2]: episode_success, chasers_placed */)
 {
     for (int i = 0; i < e->K; ++i) {
         if (pid) memcpy(pid + 24 * i, e->d[i].pid, sizeof(double) * 24);
-        if (heading) { heading[2 * i] = e->d[i].angle; heading[2 * i + 1] = e->d[i].ang_vel; }
+        if (heading) { heading[3 * i] = e->d[i].angle; heading[3 * i + 1] = e->d[i].ang_vel; heading[3 * i + 2] = e->snap_heading[i]; }
     }
     if (evader) { evader[0] = e->evader[0]; evader[1] = e->evader[1]; }
     if (env_flags) { env_flags[0] = e->episode_success; env_flags[1] = e->chasers_placed; }
@@ -946,7 +948,7 @@ void qo_set_fork_state(qo_env *e, const double *pid, const double *heading, cons
     if (env_flags) { e->episode_success = env_flags[0]; e->chasers_placed = env_flags[1]; }
     for (int i = 0; i < e->K; ++i) {
         if (pid) memcpy(e->d[i].pid, pid + 24 * i, sizeof(double) * 24);
-        if (heading) { e->d[i].angle = heading[2 * i]; e->d[i].ang_vel = heading[2 * i + 1]; }
+        if (heading) { e->d[i].angle = heading[3 * i]; e->d[i].ang_vel = heading[3 * i + 1]; e->snap_heading[i] = heading[3 * i + 2]; }
     }
     if (evader) { e->evader[0] = evader[0]; e->evader[1] = evader[1]; }
 }

@@ -335,4 +335,5 @@ def fork_snapshot(env):
     s["angle"] = np.array([e.pre_controller.angle for e in env.envs], dtype=np.float64)
     s["ang_vel"] = np.array([e.pre_controller.angular_velocity for e in env.envs], dtype=np.float64)
     s["evader"] = np.array(env.scenario.pos, dtype=np.float64)
+    s["heading"] = np.array(env.heading, dtype=np.float64)                 # refreshed in step only (quadrotor_multi_rewards.py:647)
     return s

@@ -25,9 +25,11 @@ OBS_REPR_DIM = {"xyz_vxyz_R_omega": 18, "xyz_vxyz_R_omega_floor": 19, "xyz_vxyz_
                 "cdist_cdistdot_dist_distdot_angle_angledot": 6, "cdist_cdistdot_dist_distdot_sangle_angledot": 7,
                 "aw_awdot_dist_distdot_angle_angledot": 6}
 FORK_OBS_REPR = {k for k, v in OBS_REPR.items() if v >= 3}
-NEIGHBOR_OBS = {"none": 0, "pos_vel": 1, "dist_angle": 2, "dist_sangle": 3}
-NEIGHBOR_OBS_DIM = {"none": 0, "pos_vel": 6, "dist_angle": 2, "dist_sangle": 3}                      # quad_utils.py:40-58
-FORK_NEIGHBOR_OBS = {"none", "dist_angle", "dist_sangle"}
+NEIGHBOR_OBS = {"none": 0, "pos_vel": 1, "dist_angle": 2, "dist_sangle": 3, "dist_angle_heading": 4,
+                "dist_sangle_sheading": 5, "ndist_nsangle": 6}
+NEIGHBOR_OBS_DIM = {"none": 0, "pos_vel": 6, "dist_angle": 2, "dist_sangle": 3, "dist_angle_heading": 3,      # quad_utils.py:40-58
+                    "dist_sangle_sheading": 5, "ndist_nsangle": 3}
+FORK_NEIGHBOR_OBS = {"none", "dist_angle", "dist_sangle", "dist_angle_heading", "dist_sangle_sheading", "ndist_nsangle"}
 PARAM_KEYS = {"pos": 0, "effort": 1, "crash": 2, "orient": 3, "spin": 4,
               "quadcol_bin": 5, "quadcol_bin_smooth_max": 6, "quadcol_bin_obst": 7, "capture_radius": 8}
 
@@ -39,7 +41,9 @@ class QsForkConfigC(C.Structure):
         "evader_v_max", "evader_dt", "evader_arena", "spawn_ring", "evader_r_min", "evader_r_span")] + [
         ("pid", (C.c_double * 5) * 12), ("rate_out_scale", C.c_double), ("mixer", (C.c_double * 4) * 4),
         ("ctrl_mass", C.c_double), ("ctrl_g", C.c_double), ("ctrl_kf", C.c_double), ("ctrl_min_rpm", C.c_double),
-        ("ctrl_max_rpm", C.c_double)]
+        ("ctrl_max_rpm", C.c_double), ("cam_focal_length", C.c_double), ("cam_target_size", C.c_double),
+        ("cam_pixel_noise", C.c_double), ("cam_fov_deg", C.c_double), ("cam_resolution", C.c_double),
+        ("cam_num", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class QsConfigC(C.Structure):
@@ -133,10 +137,15 @@ class QuadSimConfig:
                     neighbor_visible_num=-1, room_dims=(15.0, 15.0, 3.0), ep_time=30.0,
                     apply_collision_force=False)                  # quadrotor_multi_rewards.py:203
         capture_radius = kw.pop("capture_radius", None)
+        camera = kw.pop("camera", None)
         base.update(kw)
         cfg = cls(**base)
         if capture_radius is not None:
             cfg.fork.capture_radius = float(capture_radius)
+        for k, v in (camera or {}).items():          # cam_focal_length / cam_target_size / cam_pixel_noise / cam_num
+            if not hasattr(cfg.fork, k):
+                raise KeyError(k)
+            setattr(cfg.fork, k, v)
         return cfg
 
     @classmethod
@@ -150,7 +159,9 @@ class QuadSimConfig:
             collision_hitbox_radius=rcfg.collision_hitbox_radius, collision_falloff_radius=rcfg.collision_falloff_radius,
             use_downwash=bool(rcfg.use_downwash), sim_freq=float(rcfg.sim_freq), sim_steps=int(rcfg.sim_steps),
             sense_noise=rcfg.sense_noise, seed=int(rcfg.seed or 0),
-            capture_radius=0.2 if cap is None else float(cap), **kw)
+            capture_radius=0.2 if cap is None else float(cap),
+            camera=dict(cam_focal_length=float(rcfg.focal_length_cam), cam_target_size=float(rcfg.neighbour_size_cam),
+                        cam_pixel_noise=float(rcfg.pixel_noise_cam), cam_num=int(rcfg.n_cameras)), **kw)
 
     # ---- derived ---------------------------------------------------------------------------
     @property
@@ -215,7 +226,7 @@ class QuadSimConfig:
             raise ValueError(f"obs_repr {self.obs_repr!r} does not belong to env_mode {self.env_mode!r}")
         if is_fork and self.neighbor_obs_type not in FORK_NEIGHBOR_OBS:
             raise ValueError(f"neighbor_obs_type {self.neighbor_obs_type!r} is not a fork-mode type")
-        if not is_fork and self.neighbor_obs_type in ("dist_angle", "dist_sangle"):
+        if not is_fork and self.neighbor_obs_type in FORK_NEIGHBOR_OBS - {"none"}:
             raise ValueError(f"neighbor_obs_type {self.neighbor_obs_type!r} needs env_mode='fork'")
         if is_fork and self.use_obstacles:
             raise ValueError("the fork env has its obstacle path commented out (quadrotor_multi_rewards.py:106-119)")
@@ -293,4 +304,6 @@ class QuadSimConfig:
             f.mixer[i][:] = [float(v) for v in mx[i]]
         f.ctrl_mass, f.ctrl_g, f.ctrl_kf = fp.model.mass, fp.model.g, fp.model.kf
         f.ctrl_min_rpm, f.ctrl_max_rpm = fp.model.min_rpm, fp.model.max_rpm
+        f.cam_focal_length, f.cam_target_size, f.cam_pixel_noise = fp.cam_focal_length, fp.cam_target_size, fp.cam_pixel_noise
+        f.cam_fov_deg, f.cam_resolution, f.cam_num = fp.cam_fov_deg, fp.cam_resolution, int(fp.cam_num)
         return c

@@ -75,6 +75,12 @@ class ForkParams:
     evader_r_min: float = 2.0               # :79
     evader_r_span: float = 3.0
     rate_out_scale: float = 800.0           # RateController.py:84-86
+    cam_focal_length: float = 0.035         # swarm_rl/global_cfg.py:13-17
+    cam_num: int = 3
+    cam_target_size: float = 0.2            # neighbour_size_cam
+    cam_pixel_noise: float = 3.0
+    cam_fov_deg: float = 70.0               # quadrotor_multi_rewards.py:286-287
+    cam_resolution: float = 640.0
     model: ControllerModel = field(default_factory=ControllerModel)
 
     def pid_table(self) -> List[List[float]]:

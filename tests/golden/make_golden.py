@@ -133,8 +133,21 @@ FORK_TRACES = {
     "fork_k8_sangle": dict(env=dict(num_agents=8, episode_duration=0.8, initial_capture_radius=2.2,
                                     obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot",
                                     neighbor_obs_type="dist_sangle", neighbor_visible_num=3), steps=50, radius={}),
+    # the author's current sweep (sb_train.py:122-137): camera-model neighbour observations, here with pixel noise on
+    "fork_k4_cam": dict(env=dict(num_agents=4, episode_duration=0.8, initial_capture_radius=2.4,
+                                 obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot", neighbor_obs_type="ndist_nsangle"),
+                        steps=40, radius={}),
+    # camera model + ranking (2 nearest of 5): the ranking pass draws its own pixel noise
+    "fork_k6_cam_v2": dict(env=dict(num_agents=6, episode_duration=0.8, initial_capture_radius=2.2, pixel_noise_cam=1.0,
+                                    n_cameras=4, neighbor_obs_type="ndist_nsangle", neighbor_visible_num=2), steps=30, radius={}),
+    # relative-heading neighbour types
+    "fork_k4_heading": dict(env=dict(num_agents=4, episode_duration=0.8, initial_capture_radius=2.4,
+                                     neighbor_obs_type="dist_angle_heading"), steps=40, radius={}),
+    "fork_k5_sheading_v3": dict(env=dict(num_agents=5, episode_duration=0.8, initial_capture_radius=2.2,
+                                         obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot",
+                                         neighbor_obs_type="dist_sangle_sheading", neighbor_visible_num=3), steps=30, radius={}),
 }
-FORK_STATE_KEYS = STATE_KEYS + ("pid", "angle", "ang_vel", "evader")
+FORK_STATE_KEYS = STATE_KEYS + ("pid", "angle", "ang_vel", "evader", "heading")
 
 
 def gen_fork_traces():
