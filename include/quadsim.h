@@ -216,7 +216,8 @@ typedef struct qs_state_view {
     float *obst_xy;      /* [N, QS_MAX_OBSTACLES, 2] obstacle centres (first num_obstacles valid) */
     /* fork mode (NULL / ignored otherwise) */
     float *pid;          /* [N*K,24] (last_error, integral) of the 12 PIDs in cascade order */
-    float *heading;      /* [N*K,2]  pre_controller.angle, pre_controller.angular_velocity */
+    float *heading;      /* [N*K,3]  pre_controller.angle, pre_controller.angular_velocity, env.heading snapshot
+                                     (refreshed in step only, quadrotor_multi_rewards.py:647) */
     float *evader;       /* [N,2]    Scenario_dynamic_repulsive.pos */
 } qs_state_view;
 

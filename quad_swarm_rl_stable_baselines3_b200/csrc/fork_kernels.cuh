@@ -21,6 +21,10 @@ struct ForkConst {
     float ev_vmax, ev_dt, ev_arena, spawn_ring, ev_rmin, ev_rspan;
     float pid[12][5];
     float rate_scale, mixer[4][4], mass, g, inv_kf4, min_rpm, inv_rpm_span, half_len;
+    // camera model (simulate_camera_measurement_vect, quadrotor_multi_rewards.py:278-324)
+    float cam_r, cam_noise_tan;      // target radius; pixel-noise std already scaled to tan units: noise_px * w / (resolution * f)
+    float cam_seg, cam_inv_seg;      // 2 pi / n_cameras and its inverse
+    int cam_num;
 };
 
 enum { FF_SUCCESS = 1, FF_PLACED = 2 };               // per-env fork flags (ForkPtrs::flags); planes: quadsim_kernels.cuh
@@ -154,45 +158,121 @@ __device__ __forceinline__ void fork_self_obs(const DevConst &c, const Rng &g, i
     else { o[4] = rel_angle; o[5] = adot; }
 }
 
+// simulate_camera_measurement_vect (quadrotor_multi_rewards.py:278-324): the two tangent rays from the camera to a disc of
+// radius r around the neighbour, seen by the best of n cameras, plus pixel noise.  The reference intersects the disc with the
+// circle whose diameter is [camera, centre]; with c2 = c/2 and r2 = d = |c|/2 its `a` is exactly r^2 / (2 d), which is what is
+// evaluated here (the literal r1^2 - r2^2 + d^2 cancels catastrophically in fp32).  NaN (target closer than its radius) -> 0.
+__device__ __forceinline__ void camera_measure(const ForkConst &f, float rx, float ry, float global_angle, float n1, float n2,
+                                               float &dist, float &angle_rel)
+{
+    float sg, cg;
+    sincosf(global_angle, &sg, &cg);
+    const float px = cg * rx + sg * ry, py = -sg * rx + cg * ry;         // R(-global_angle) rel_pos
+    const float two_pi = 6.283185307179586f;
+    float ao = atan2f(py, px);
+    ao = ao - two_pi * floorf(ao / two_pi);                             // python %
+    int cam_idx = (int)rintf(ao * f.cam_inv_seg) % f.cam_num;           // np.round: half to even
+    const float cam = (float)cam_idx * f.cam_seg;
+    float sc, cc;
+    sincosf(cam, &sc, &cc);
+    const float cx = cc * px + sc * py, cy = -sc * px + cc * py;
+    const float r = f.cam_r;
+    const float d = 0.5f * sqrtf(cx * cx + cy * cy);
+    const float a = r * r / (2.0f * d);
+    const float h = sqrtf(r * r - a * a);
+    const float ux = -0.5f * cx / d, uy = -0.5f * cy / d;               // (c2 - c1) / d
+    const float mx = cx + a * ux, my = cy + a * uy;
+    const float x1x = mx - h * uy, x1y = my + h * ux, x2x = mx + h * uy, x2y = my - h * ux;
+    const float t1 = x1y / x1x + f.cam_noise_tan * n1, t2 = x2y / x2x + f.cam_noise_tan * n2;   // u / f
+    const float a1 = atanf(t1), a2 = atanf(t2);
+    float l = r / sinf(0.5f * fabsf(a1 - a2));
+    float ar = wrap_pi(0.5f * (a1 + a2) + cam);
+    dist = isnan(l) ? 0.f : l;
+    angle_rel = isnan(ar) ? 0.f : ar;
+}
+
+__device__ __forceinline__ int fork_nbr_width(int type)
+{
+    return (type == QS_NEIGHBOR_DIST_ANGLE) ? 2 : ((type == QS_NEIGHBOR_DIST_SANGLE || type == QS_NEIGHBOR_DIST_ANGLE_HEADING ||
+            type == QS_NEIGHBOR_NDIST_NSANGLE) ? 3 : ((type == QS_NEIGHBOR_DIST_SANGLE_SHEADING) ? 5 : 0));
+}
+
+// one feature row of get_rel_pos_vel_item (quadrotor_multi_rewards.py:326-420) for neighbour j (position + heading snapshot `nb`).
+// call 0: rows of the observation; call 1: the evaluation neighborhood_indices makes for the ranking (own camera noise).
+__device__ __forceinline__ void fork_nbr_row(const DevConst &c, const ForkConst &f, const Rng &g, int d, int j, int call, const Drone &q,
+                                             float angle, float hsnap, float4 nb, float *row)
+{
+    const float dx = nb.x - q.p[0], dy = nb.y - q.p[1], dz = nb.z - q.p[2];
+    const float dist = norm3f(dx, dy, dz);
+    row[0] = dist; row[1] = 0.f; row[2] = 0.f; row[3] = 0.f; row[4] = 0.f;
+    if (c.nbr_type == QS_NEIGHBOR_NDIST_NSANGLE) {
+        const float4 n = rng_n4v(g, SITE_CAMERA, d, j, call);
+        float nd, na;
+        camera_measure(f, dx, dy, angle, n.x, n.y, nd, na);
+        row[0] = clampf(nd, 0.f, 10.f);
+        sincosf(na, &row[2], &row[1]);
+        return;
+    }
+    const float ang = wrap_pi(atan2f(dy, dx) - angle);
+    const float hd = wrap_pi(nb.w - hsnap);
+    if (c.nbr_type == QS_NEIGHBOR_DIST_ANGLE) row[1] = ang;
+    else if (c.nbr_type == QS_NEIGHBOR_DIST_ANGLE_HEADING) { row[1] = ang; row[2] = hd; }
+    else {
+        sincosf(ang, &row[2], &row[1]);
+        if (c.nbr_type == QS_NEIGHBOR_DIST_SANGLE_SHEADING) sincosf(hd, &row[4], &row[3]);
+    }
+}
+
 // get_rel_pos_vel_item / neighborhood_indices / extend_obs_space, quadrotor_multi_rewards.py:326-476
 template <int KG>
-__device__ __forceinline__ void fork_neighbor_obs(const DevConst &c, const ForkConst &f, int d, int lane, uint32_t gmask, bool valid,
-                                                  const Drone &q, float angle, float *o, float4 *stage)
+__device__ __forceinline__ void fork_neighbor_obs(const DevConst &c, const ForkConst &f, const Rng &g, int d, int lane, uint32_t gmask,
+                                                  bool valid, const Drone &q, float angle, float hsnap, float *o, float4 *stage)
 {
-    const int W = (c.nbr_type == QS_NEIGHBOR_DIST_ANGLE) ? 2 : ((c.nbr_type == QS_NEIGHBOR_DIST_SANGLE) ? 3 : 0);
+    const int W = fork_nbr_width(c.nbr_type);
     if (W == 0 || c.V <= 0 || KG == 1) return;
     const int base = lane & ~(KG - 1);
     __syncwarp(gmask);
-    stage[2 * lane] = make_float4(q.p[0], q.p[1], q.p[2], 0.f);
+    stage[2 * lane] = make_float4(q.p[0], q.p[1], q.p[2], hsnap);
     __syncwarp(gmask);
-    const float INF = __int_as_float(0x7f800000);
-    float f0[KG], f1[KG], f2[KG], met[KG];
-#pragma unroll
-    for (int j = 0; j < KG; ++j) {
-        float4 a = stage[2 * (base + j)];
-        float dx = a.x - q.p[0], dy = a.y - q.p[1], dz = a.z - q.p[2];
-        float dist = norm3f(dx, dy, dz);
-        float ang = wrap_pi(atan2f(dy, dx) - angle);
-        f0[j] = dist;
-        if (W == 2) { f1[j] = ang; f2[j] = 0.f; } else { sincosf(ang, &f2[j], &f1[j]); }
-        float ss = f0[j] * f0[j] + f1[j] * f1[j] + f2[j] * f2[j];
-        met[j] = (j < c.K && j != d) ? fmaxf(ss, 1.0e-4f) : INF;     // squared metric: same order as norm(row), max(., 0.01)
-    }
     if (!valid) return;
+    const float INF = __int_as_float(0x7f800000);
+    float met[KG];
+    const bool ranked = c.V < c.K - 1;
+    if (ranked) {
+#pragma unroll 1
+        for (int j = 0; j < KG; ++j) {
+            float row[5], m = INF;
+            if (j < c.K && j != d) {
+                fork_nbr_row(c, f, g, d, j, 1, q, angle, hsnap, stage[2 * (base + j)], row);
+                m = fmaxf(row[0] * row[0] + row[1] * row[1] + row[2] * row[2] + row[3] * row[3] + row[4] * row[4], 1.0e-4f);   // squared metric: same order
+            }
 #pragma unroll
-    for (int j = 0; j < KG; ++j) {
-        if (!(met[j] < INF)) continue;
+            for (int k = 0; k < KG; ++k) if (k == j) met[k] = m;
+        }
+    }
+#pragma unroll 1
+    for (int j = 0; j < c.K; ++j) {
+        if (j == d) continue;
         int slot;
-        if (c.V < c.K - 1) {
+        if (ranked) {
+            float mj = INF;
+#pragma unroll
+            for (int k = 0; k < KG; ++k) if (k == j) mj = met[k];
             slot = 0;                                                  // stable rank among the candidates
 #pragma unroll
-            for (int k = 0; k < KG; ++k) slot += (met[k] < met[j] || (met[k] == met[j] && k < j)) ? 1 : 0;
+            for (int k = 0; k < KG; ++k) slot += (met[k] < mj || (met[k] == mj && k < j)) ? 1 : 0;
         } else slot = j - (j > d ? 1 : 0);                             // all others in index order
         if (slot < c.V) {
+            float row[5];
+            fork_nbr_row(c, f, g, d, j, 0, q, angle, hsnap, stage[2 * (base + j)], row);
             float *r = o + W * slot;
-            r[0] = clampf(f0[j], -f.half_len, f.half_len);
-            if (W == 2) r[1] = clampf(f1[j], -QS_PI_F, QS_PI_F);
-            else { r[1] = clampf(f1[j], -1.f, 1.f); r[2] = clampf(f2[j], -1.f, 1.f); }
+            r[0] = clampf(row[0], -f.half_len, f.half_len);
+            if (c.nbr_type == QS_NEIGHBOR_DIST_ANGLE || c.nbr_type == QS_NEIGHBOR_DIST_ANGLE_HEADING) {
+                r[1] = clampf(row[1], -QS_PI_F, QS_PI_F);
+                if (W == 3) r[2] = clampf(row[2], -QS_PI_F, QS_PI_F);
+            } else {
+                for (int k = 1; k < W; ++k) r[k] = clampf(row[k], -1.f, 1.f);
+            }
         }
     }
 }
@@ -250,7 +330,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
     const int warp_rows = max(0, min(GPW, c.N - warp_env0)) * c.K;
 
     Drone q;
-    float pid[24], angle = 0.f, ang_vel = 0.f, ex = 1.f, ey = 0.f;
+    float pid[24], angle = 0.f, ang_vel = 0.f, hsnap = 0.f, ex = 1.f, ey = 0.f;
     float2 act = make_float2(0.f, 0.f);
     int tick = 0, svd = 0, fflags = 0;
     Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
@@ -265,7 +345,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         act = actions[gi];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { float4 v = F.plane[FP_PID0 + k][gi]; pid[4 * k] = v.x; pid[4 * k + 1] = v.y; pid[4 * k + 2] = v.z; pid[4 * k + 3] = v.w; }
-        float4 h = F.plane[FP_HEADING][gi]; angle = h.x; ang_vel = h.y;
+        float4 h = F.plane[FP_HEADING][gi]; angle = h.x; ang_vel = h.y; hsnap = h.z;
     } else {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { q.p[a] = 1.0e6f * (float)(lane + 1); q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
@@ -289,6 +369,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         if (valid) {
             float cmd[4];
             fork_controller(c, f, q, pid, angle, ang_vel, act.x, cmd);
+            hsnap = angle;                                               // self.heading[i] = pre_controller.angle (:647)
             const float4 nv = rng_n4v(g, SITE_OU, d, 0, 0);
             const float n[4] = { nv.x, nv.y, nv.z, nv.w };
 #pragma unroll
@@ -355,7 +436,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         if (sub + 1 < f.substeps) g.step += 1u;                          // next control step -> next RNG counter
     }
     // ---- neighbour observations once, after the sub-steps (:990-991)
-    fork_neighbor_obs<KG>(c, f, d, lane, gmask, valid, q, angle, orow + c.S, stage);
+    fork_neighbor_obs<KG>(c, f, g, d, lane, gmask, valid, q, angle, hsnap, orow + c.S, stage);
     if (valid) { rew[gi] = reward; done[gi] = any_done ? 1 : 0; }
 
     __syncwarp();
@@ -432,14 +513,14 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         tick = 0;
         fflags = FF_PLACED;
         if (valid) fork_self_obs(c, g, SITE_SENSOR_RESET, d, q, angle, ang_vel, orow);
-        fork_neighbor_obs<KG>(c, f, d, lane, gmask, valid, q, angle, orow + c.S, stage);
+        fork_neighbor_obs<KG>(c, f, g, d, lane, gmask, valid, q, angle, hsnap, orow + c.S, stage);   // self.heading is NOT refreshed by reset()
     }
     // ---- write back
     if (valid) {
         store_drone(P, gi, q, true);
 #pragma unroll
         for (int k = 0; k < 6; ++k) F.plane[FP_PID0 + k][gi] = make_float4(pid[4 * k], pid[4 * k + 1], pid[4 * k + 2], pid[4 * k + 3]);
-        F.plane[FP_HEADING][gi] = make_float4(angle, ang_vel, 0.f, 0.f);
+        F.plane[FP_HEADING][gi] = make_float4(angle, ang_vel, hsnap, 0.f);
     }
     if (env_ok && d == 0) {
         P.tick[env] = tick; P.svd_ctr[env] = svd; P.step_ctr[env] = g.step + 1u;
@@ -472,7 +553,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
     float *orow = tile + (size_t)row * c.D;
 
     Drone q;
-    float angle = 0.f, ang_vel = 0.f, ex = 1.f, ey = 0.f;
+    float angle = 0.f, ang_vel = 0.f, hsnap = 0.f, ex = 1.f, ey = 0.f;
     int fflags = 0;
     Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
 #pragma unroll
@@ -483,7 +564,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
     for (int a = 0; a < 4; ++a) { q.rd[a] = q.cd[a] = q.ou[a] = 0.f; }
     q.flags = 0; q.colmask = 0;
     if (env_ok) { g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env]; fflags = F.flags[env]; }
-    if (env_ok && d < c.K) { load_drone(P, gi, q); float4 h = F.plane[FP_HEADING][gi]; ang_vel = h.y; }
+    if (env_ok && d < c.K) { load_drone(P, gi, q); float4 h = F.plane[FP_HEADING][gi]; ang_vel = h.y; hsnap = h.z; }
     float u[4], t[4];
     rng_u4(g, SITE_SCENARIO, 0xFF, 7, d >> 1, u);
     float sa_ = u[(2 * d) & 3] - 0.5f, sb_ = u[(2 * d + 1) & 3] - 0.5f, sn_ = sqrtf(sa_ * sa_ + sb_ * sb_);
@@ -507,7 +588,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
     q.flags = 0; q.colmask = 0u;
     if (valid) {
         store_drone(P, gi, q, true);
-        F.plane[FP_HEADING][gi] = make_float4(angle, ang_vel, 0.f, 0.f);
+        F.plane[FP_HEADING][gi] = make_float4(angle, ang_vel, hsnap, 0.f);
         fork_self_obs(c, g, SITE_SENSOR_RESET, d, q, angle, ang_vel, orow);
     }
     if (sel && d == 0) {
@@ -517,7 +598,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
         P.tick[env] = 0; P.step_ctr[env] = g.step + 1u;
         F.evader[env] = make_float2(ex, ey); F.flags[env] = FF_PLACED;
     }
-    fork_neighbor_obs<KG>(c, f, d, lane, gmask, valid, q, angle, orow + c.S, stage);
+    fork_neighbor_obs<KG>(c, f, g, d, lane, gmask, valid, q, angle, hsnap, orow + c.S, stage);
     __syncwarp();
     const int warp_env0 = (tid - lane) / KG;
     const int warp_rows = max(0, min(GPW, c.N - warp_env0)) * c.K;

@@ -55,8 +55,8 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, 
             }
         }
         if (v.heading) {
-            if (set) F.plane[FP_HEADING][gi] = make_float4(v.heading[2 * gi], v.heading[2 * gi + 1], 0.f, 0.f);
-            else { float4 x = F.plane[FP_HEADING][gi]; v.heading[2 * gi] = x.x; v.heading[2 * gi + 1] = x.y; }
+            if (set) F.plane[FP_HEADING][gi] = make_float4(v.heading[3 * gi], v.heading[3 * gi + 1], v.heading[3 * gi + 2], 0.f);
+            else { float4 x = F.plane[FP_HEADING][gi]; v.heading[3 * gi] = x.x; v.heading[3 * gi + 1] = x.y; v.heading[3 * gi + 2] = x.z; }
         }
     }
     if (gi < c.N && F.evader != nullptr && v.evader) {
@@ -149,7 +149,13 @@ static void fill_const(const qs_config &c, DevConst &d)
     d.obst_L = c.obst_area_len; d.obst_W = c.obst_area_wid; d.M = c.num_obstacles;
     if (c.env_mode == QS_MODE_FORK) {
         d.S = c.obs_repr == QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_SANGLE_ANGLEDOT ? 7 : 6;
-        int W = c.neighbor_obs_type == QS_NEIGHBOR_DIST_ANGLE ? 2 : (c.neighbor_obs_type == QS_NEIGHBOR_DIST_SANGLE ? 3 : 0);
+        int W = 0;
+        switch (c.neighbor_obs_type) {
+            case QS_NEIGHBOR_DIST_ANGLE: W = 2; break;
+            case QS_NEIGHBOR_DIST_SANGLE: case QS_NEIGHBOR_DIST_ANGLE_HEADING: case QS_NEIGHBOR_NDIST_NSANGLE: W = 3; break;
+            case QS_NEIGHBOR_DIST_SANGLE_SHEADING: W = 5; break;
+            default: break;
+        }
         d.D = d.S + W * c.neighbor_visible_num;
     } else {
         d.S = c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR ? 19 : (c.obs_repr == QS_OBS_XYZ_VXYZ_R_OMEGA_WALL ? 24 : 18);
@@ -199,6 +205,13 @@ static void fill_fork(const qs_config &c, ForkConst &f)
     f.mass = (float)s.ctrl_mass; f.g = (float)s.ctrl_g; f.inv_kf4 = (float)(1.0 / (s.ctrl_kf * 4.0));
     f.min_rpm = (float)s.ctrl_min_rpm; f.inv_rpm_span = (float)(1.0 / (s.ctrl_max_rpm - s.ctrl_min_rpm));
     f.half_len = (float)(c.room_dims[0] / 2.0);
+    const double PI = 3.14159265358979323846;
+    const double w = 2.0 * std::tan((s.cam_fov_deg / 2.0) * PI / 180.0) * s.cam_focal_length;      // sensor width, :289
+    f.cam_r = (float)(s.cam_target_size / 2.0);
+    // u_px = u * res / w + noise  ->  u / f = (x_y / x_x) + noise * w / (res * f)
+    f.cam_noise_tan = (s.cam_resolution > 0 && s.cam_focal_length > 0) ? (float)(s.cam_pixel_noise * w / (s.cam_resolution * s.cam_focal_length)) : 0.f;
+    f.cam_num = s.cam_num > 0 ? s.cam_num : 1;
+    f.cam_seg = (float)(2.0 * PI / f.cam_num); f.cam_inv_seg = (float)(f.cam_num / (2.0 * PI));
 }
 
 static int validate(const qs_config *c, std::string &why)
@@ -209,7 +222,8 @@ static int validate(const qs_config *c, std::string &why)
         if (c->num_agents < 1 || c->num_agents > QS_MAX_AGENTS) { why = "num_agents out of [1, 32]"; return 0; }
         if (c->scenario != QS_SCENARIO_DYNAMIC_REPULSIVE) { why = "fork mode supports quads_mode dynamic_repulsive only"; return 0; }
         if (c->obs_repr < QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_ANGLE_ANGLEDOT || c->obs_repr > QS_OBS_AW_AWDOT_DIST_DISTDOT_ANGLE_ANGLEDOT) { why = "fork mode needs a fork obs_repr"; return 0; }
-        if (c->neighbor_obs_type != QS_NEIGHBOR_NONE && c->neighbor_obs_type != QS_NEIGHBOR_DIST_ANGLE && c->neighbor_obs_type != QS_NEIGHBOR_DIST_SANGLE) { why = "fork mode needs a fork neighbor_obs_type"; return 0; }
+        if (c->neighbor_obs_type != QS_NEIGHBOR_NONE && (c->neighbor_obs_type < QS_NEIGHBOR_DIST_ANGLE || c->neighbor_obs_type > QS_NEIGHBOR_NDIST_NSANGLE)) { why = "fork mode needs a fork neighbor_obs_type"; return 0; }
+        if (c->neighbor_obs_type == QS_NEIGHBOR_NDIST_NSANGLE && (c->fork.cam_num < 1 || !(c->fork.cam_focal_length > 0) || !(c->fork.cam_target_size > 0))) { why = "bad camera parameters"; return 0; }
         if (c->neighbor_visible_num < 0 || c->neighbor_visible_num > c->num_agents - 1) { why = "neighbor_visible_num out of range"; return 0; }
         if (c->use_obstacles || c->use_downwash || c->apply_collision_force) { why = "fork mode: obstacles / downwash / collision forces are off in the reference (quadrotor_multi_rewards.py:106-119,203) and not built"; return 0; }
         if (c->fork.substeps < 1 || c->fork.substeps > 64) { why = "fork.substeps out of [1, 64]"; return 0; }

@@ -69,7 +69,7 @@ enum { F_ON_FLOOR = 1, F_CR_FLOOR = 2, F_CR_WALL = 4, F_CR_CEIL = 8, F_PREV_WALL
 // RNG sites: DESIGN.md "RNG contract" (identical table in oracle/quadsim_oracle.c)
 enum { SITE_OU = 0, SITE_SENSOR = 1, SITE_SENSOR_IMPULSE = 2, SITE_SENSOR_RESET = 3, SITE_FLOOR_YAW = 4,
        SITE_PAIR = 5, SITE_OBST = 6, SITE_WALL = 7, SITE_CEILING = 8, SITE_DOWNWASH = 9, SITE_SPAWN = 10,
-       SITE_SCENARIO = 11 };
+       SITE_SCENARIO = 11, SITE_CAMERA = 12 };
 
 
 // ----------------------------------------------------------------------------------------------------------------

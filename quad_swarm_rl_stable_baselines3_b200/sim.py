@@ -20,7 +20,7 @@ _STATE_SHAPES = {"pos": (3, torch.float32), "vel": (3, torch.float32), "rot": (9
                  "omega": (3, torch.float32), "rot_damp": (4, torch.float32), "cmds_damp": (4, torch.float32),
                  "ou": (4, torch.float32), "goal": (3, torch.float32), "flags": (1, torch.int32),
                  "col_mask": (1, torch.int32)}
-_FORK_SHAPES = {"pid": (24, torch.float32), "heading": (2, torch.float32)}     # fork mode only
+_FORK_SHAPES = {"pid": (24, torch.float32), "heading": (3, torch.float32)}     # fork mode only: (angle, ang_vel, heading snapshot)
 _ENV_FIELDS = {"tick": torch.int32, "svd_ctr": torch.int32, "step_ctr": torch.int32}
 
 

@@ -28,6 +28,14 @@ FORK_CONFIGS = {
                            obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot", neighbor_obs_type="dist_sangle",
                            neighbor_visible_num=3),
     "fork_k3_aw": dict(num_envs=11, num_agents=3, ep_time=0.4, capture_radius=0.3, obs_repr="aw_awdot_dist_distdot_angle_angledot"),
+    # sb_train.py:122-137 (the author's current sweep): camera-model neighbour observations; pixel noise on here
+    "fork_k4_cam": dict(num_envs=24, num_agents=4, ep_time=0.4, capture_radius=2.4, neighbor_obs_type="ndist_nsangle",
+                        obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot"),
+    "fork_k6_cam_v2": dict(num_envs=12, num_agents=6, ep_time=0.4, capture_radius=2.2, neighbor_obs_type="ndist_nsangle",
+                           neighbor_visible_num=2, camera=dict(cam_pixel_noise=1.0, cam_num=4)),
+    "fork_k4_heading": dict(num_envs=16, num_agents=4, ep_time=0.4, capture_radius=2.4, neighbor_obs_type="dist_angle_heading"),
+    "fork_k5_sheading_v3": dict(num_envs=10, num_agents=5, ep_time=0.4, capture_radius=2.2, neighbor_obs_type="dist_sangle_sheading",
+                                neighbor_visible_num=3, obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot"),
 }
 
 
@@ -54,6 +62,8 @@ def ranking_tie(cfg, o):
         return False
     pos = o.get_state()["pos"]
     ang = o.get_fork_state()["heading"][:, 0]
+    hsn = o.get_fork_state()["heading"][:, 2]
+    return_camera = False
     for i in range(K):
         mets = []
         for j in range(K):
@@ -62,10 +72,21 @@ def ranking_tie(cfg, o):
             d = pos[j] - pos[i]
             dist = np.linalg.norm(d)
             a = (np.arctan2(d[1], d[0]) - ang[i] + np.pi) % (2 * np.pi) - np.pi
-            row = [dist, a] if cfg.neighbor_obs_type == "dist_angle" else [dist, np.cos(a), np.sin(a)]
+            hd = (hsn[j] - hsn[i] + np.pi) % (2 * np.pi) - np.pi
+            t = cfg.neighbor_obs_type
+            if t == "ndist_nsangle":
+                return_camera = True
+                row = [min(dist, 10.0), 1.0]         # |(l, cos, sin)| = sqrt(l^2 + 1); l ~ dist up to the pixel noise
+            else:
+                row = {"dist_angle": [dist, a], "dist_sangle": [dist, np.cos(a), np.sin(a)],
+                       "dist_angle_heading": [dist, a, hd],
+                       "dist_sangle_sheading": [dist, np.cos(a), np.sin(a), np.cos(hd), np.sin(hd)]}[t]
             mets.append(max(np.linalg.norm(row), 0.01))
         mets = np.sort(mets)
-        if np.any(np.diff(mets) < 2e-6 * mets[1:]):
+        # camera rows carry pixel noise (amplified ~dist^2/(r f) px) and the disc degenerates below its radius: only call
+        # the ranking decided when the candidates are clearly separated
+        tol = 5e-3 if return_camera else 2e-6
+        if np.any(np.diff(mets) < tol * mets[1:]):
             return True
     return False
 
@@ -95,8 +116,10 @@ def test_fork_reset_parity(name):
     np.testing.assert_allclose(st["evader"], np.stack([o.get_fork_state()["evader"] for o in oracles]), atol=2e-6)
     np.testing.assert_allclose(st["heading"], np.concatenate([o.get_fork_state()["heading"] for o in oracles]), atol=2e-6)
     K = cfg.num_agents
+    S = 7 if "sangle" in cfg.obs_repr else 6
+    np.testing.assert_allclose(obs[:, :S], ref[:, :S], atol=5e-5)                      # self block: always
     ok = np.repeat([not ranking_tie(cfg, o) for o in oracles], K)
-    assert ok.sum() >= len(ok) // 2
+    assert ok.sum() >= len(ok) // 2 or cfg.neighbor_obs_type == "ndist_nsangle"       # (camera rows of mm-apart drones: all ties)
     np.testing.assert_allclose(obs[ok], ref[ok], atol=5e-4)      # bearings between drones millimetres apart, see test_fork_step_parity
     # second reset: the evader's first step now sees the chasers (dynamic_repulsive.py:44)
     obs = sim.reset().cpu().numpy()
@@ -105,7 +128,8 @@ def test_fork_reset_parity(name):
     np.testing.assert_allclose(obs[ok], ref[ok], atol=5e-4)
 
 
-@pytest.mark.parametrize("name,steps", [("fork_k4", 60), ("fork_k1", 40), ("fork_k8_sangle", 40), ("fork_k3_aw", 40)])
+@pytest.mark.parametrize("name,steps", [("fork_k4", 60), ("fork_k1", 40), ("fork_k8_sangle", 40), ("fork_k3_aw", 40),
+                                        ("fork_k4_cam", 40), ("fork_k6_cam_v2", 40), ("fork_k4_heading", 40), ("fork_k5_sheading_v3", 40)])
 def test_fork_step_parity(name, steps):
     import torch
     cfg, sim, oracles = make_pair(name)
@@ -114,13 +138,22 @@ def test_fork_step_parity(name, steps):
     for o in oracles:
         o.reset()
     rs = np.random.RandomState(11)
-    worst = dict(pos=0.0, vel=0.0, rot=0.0, omega=0.0, pid=0.0, obs=0.0)
+    worst = dict(pos=0.0, vel=0.0, rot=0.0, omega=0.0, pid=0.0, obs=0.0, nbr=0.0)
     n_done = n_succ = n_tie = n_rank_tie = 0
     for s in range(steps):
         if s == steps // 2:
             sim.set_capture_radius(0.9)
             for o in oracles:
                 o.set_param(8, 0.9)
+        if name.endswith(("_v2", "_v3")):
+            # fewer than K-1 neighbours visible: spread the chasers of freshly reset envs over metres (they respawn within
+            # millimetres of each other, where every ranking metric ties) so that the ranking is actually decided
+            stt = sim.get_state(["tick", "pos"])
+            fresh = np.repeat(stt["tick"].cpu().numpy() == 0, K)
+            if fresh.any():
+                pos = stt["pos"].cpu().numpy()
+                pos[fresh, :2] = rs.uniform(-3.0, 3.0, (int(fresh.sum()), 2))
+                sim.set_state(pos=pos)
         push_state(sim, oracles, cfg)
         a = rs.uniform(-1.0, 1.0, (N * K, 2)).astype(np.float32)
         obs, rew, done = sim.step(torch.from_numpy(a).cuda())
@@ -147,7 +180,10 @@ def test_fork_step_parity(name, steps):
                 # chasers respawn on a ring of radius U(0, 0.5): neighbour bearings atan2(dy, dx) of drones a few mm apart
                 # amplify the fp32 rounding of the positions (1e-8 m) by 1/distance
                 S = 7 if "sangle" in cfg.obs_repr else 6
-                cols = slice(0, S) if ranking_tie(cfg, o) else slice(0, D)
+                pp = o.get_state()["pos"]
+                dmin = min([np.linalg.norm(pp[a] - pp[b]) for a in range(K) for b in range(a + 1, K)], default=1.0)
+                # bearing error ~ 1e-8 m / distance: compare the neighbour block only when the respawn ring is not degenerate
+                cols = slice(0, S) if (ranking_tie(cfg, o) or dmin < 2e-3) else slice(0, D)
                 np.testing.assert_allclose(obs[sl][:, cols], r_obs[:, cols], atol=5e-4, err_msg=f"step {s} env {e} reset obs")
                 continue
             for k, floor in (("pos", 1.0), ("vel", 1.0), ("rot", 1.0), ("omega", 1.0)):
@@ -156,13 +192,18 @@ def test_fork_step_parity(name, steps):
             S = 7 if "sangle" in cfg.obs_repr else 6
             cols = slice(0, S) if ranking_tie(cfg, o) else slice(0, D)
             n_rank_tie += cols.stop != D
-            worst["obs"] = max(worst["obs"], relerr(obs[sl][:, cols], r_obs[:, cols], 1.0))
+            worst["obs"] = max(worst["obs"], relerr(obs[sl][:, :S], r_obs[:, :S], 1.0))
+            worst["nbr"] = max(worst["nbr"], relerr(obs[sl][:, cols], r_obs[:, cols], 1.0))
             assert st["tick"][e] == os_["tick"], (s, e)
             np.testing.assert_allclose(st["evader"][e], fs["evader"], atol=5e-6)
     print(f"\n[{name}] worst rel err after one call (8 control steps): {worst}  dones={n_done} captures={n_succ} ties={n_tie} ranking-tie env-steps={n_rank_tie}")
     assert n_done >= 3 and n_tie <= 2
     assert max(worst[k] for k in ("pos", "vel", "rot", "omega")) <= 8e-5
     assert worst["obs"] <= 2e-4
+    # neighbour block.  The camera model measures distance as l = r / sin(alpha / 2) from the angle alpha between two tangent
+    # rays (r = 0.1 m): dl = l^2 / (2 r) d(alpha), i.e. fp32 round-off of the ray slopes (4e-7) becomes 2e-3 m at l = 10 m --
+    # three orders of magnitude below what one pixel of the model's own noise does there (3 m).
+    assert worst["nbr"] <= (5e-3 if cfg.neighbor_obs_type == "ndist_nsangle" else 2e-4)
     gs, osum = sim.episode_stats(), [o.stats() for o in oracles]
     if n_tie == 0:
         for k in ("episodes", "episodes_success", "num_collisions", "num_collisions_with_floor", "num_collisions_with_wall"):
