@@ -667,42 +667,62 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                 float ss = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5;
                 met[j] = (j < c.K && j != d) ? fmaxf(ss, 1.0e-4f) : INF;
             }
-            int rank[KG];
-#pragma unroll
-            for (int j = 0; j < KG; ++j) rank[j] = 0;
-#pragma unroll
-            for (int a = 0; a < KG; ++a)
-#pragma unroll
-                for (int b = a + 1; b < KG; ++b) {
-                    bool b_first = met[b] < met[a];
-                    rank[a] += b_first ? 1 : 0;
-                    rank[b] += b_first ? 0 : 1;
-                }
-            if (valid) {
-                if (KG <= 8) {
-                    // ranks packed 4 bits per candidate so that the row writes can be a rolled loop: the unrolled form is
-                    // 8 x 30 instructions of code executed once each, and the hot path must stay inside the 32 KB L1.5 I-cache
-                    uint32_t pk = 0u;
-#pragma unroll
-                    for (int j = 0; j < KG; ++j) pk |= (uint32_t)((met[j] < INF) ? rank[j] : 15) << (4 * j);
+            if (KG >= 16 && c.V * 3 < 2 * (KG - 1)) {
+                // few rows out of many candidates (6 of 31): V rounds of first-minimum selection cost ~3 KG instructions
+                // each, the all-pairs rank count below ~2 KG (KG - 1).  Wide groups only: the 8-lane kernels keep a single
+                // selection path (their hot code has to stay inside the instruction cache).
 #pragma unroll 1
-                    for (int j = 0; j < KG; ++j) {
-                        const int rk = (int)((pk >> (4 * j)) & 15u);
-                        if (rk < c.V) {
-                            float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
-                            float *r = o + c.S + 6 * rk;
-                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
-                            r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
-                        }
-                    }
-                } else {
+                for (int sidx = 0; sidx < c.V; ++sidx) {
+                    float best = INF; int jb = 0;
 #pragma unroll
-                    for (int j = 0; j < KG; ++j) {
-                        if (rank[j] < c.V && met[j] < INF) {
-                            float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
-                            float *r = o + c.S + 6 * rank[j];
-                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
-                            r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                    for (int j = 0; j < KG; ++j) if (met[j] < best) { best = met[j]; jb = j; }
+#pragma unroll
+                    for (int j = 0; j < KG; ++j) met[j] = (j == jb) ? INF : met[j];
+                    if (valid) {
+                        float4 a = stage[2 * (base + jb)], b = stage[2 * (base + jb) + 1];
+                        float *r = o + c.S + 6 * sidx;
+                        r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                        r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                    }
+                }
+            } else {
+                int rank[KG];
+    #pragma unroll
+                for (int j = 0; j < KG; ++j) rank[j] = 0;
+    #pragma unroll
+                for (int a = 0; a < KG; ++a)
+    #pragma unroll
+                    for (int b = a + 1; b < KG; ++b) {
+                        bool b_first = met[b] < met[a];
+                        rank[a] += b_first ? 1 : 0;
+                        rank[b] += b_first ? 0 : 1;
+                    }
+                if (valid) {
+                    if (KG <= 8) {
+                        // ranks packed 4 bits per candidate so that the row writes can be a rolled loop: the unrolled form is
+                        // 8 x 30 instructions of code executed once each, and the hot path must stay inside the 32 KB L1.5 I-cache
+                        uint32_t pk = 0u;
+    #pragma unroll
+                        for (int j = 0; j < KG; ++j) pk |= (uint32_t)((met[j] < INF) ? rank[j] : 15) << (4 * j);
+    #pragma unroll 1
+                        for (int j = 0; j < KG; ++j) {
+                            const int rk = (int)((pk >> (4 * j)) & 15u);
+                            if (rk < c.V) {
+                                float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                                float *r = o + c.S + 6 * rk;
+                                r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                                r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                            }
+                        }
+                    } else {
+    #pragma unroll
+                        for (int j = 0; j < KG; ++j) {
+                            if (rank[j] < c.V && met[j] < INF) {
+                                float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                                float *r = o + c.S + 6 * rank[j];
+                                r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                                r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                            }
                         }
                     }
                 }
