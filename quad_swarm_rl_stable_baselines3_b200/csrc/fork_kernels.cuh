@@ -29,14 +29,15 @@ struct ForkConst {
 
 enum { FF_SUCCESS = 1, FF_PLACED = 2 };               // per-env fork flags (ForkPtrs::flags); planes: quadsim_kernels.cuh
 
-// _pid_update_numba, Controller/Pid.py:7-26
+// _pid_update_numba, Controller/Pid.py:7-26.  Branch-free: the host stores a disabled saturation as +inf and a disabled
+// anti-windup limit as -1 (the open interval (-aw, aw) is then empty), so 12 PIDs x 8 sub-steps cost no branches.
 __device__ __forceinline__ float pid_update(float &last, float &integ, const float *p, float err, float inv_dt, float dt)
 {
     float diff = (err - last) * inv_dt;
     last = err;
     float out = p[0] * err + p[1] * diff + p[2] * integ;
-    if (p[3] > 0.f) out = fminf(fmaxf(out, -p[3]), p[3]);
-    if (p[4] > 0.f && -p[4] < out && out < p[4]) integ += err * dt;
+    out = fminf(fmaxf(out, -p[3]), p[3]);
+    integ = (-p[4] < out && out < p[4]) ? integ + err * dt : integ;
     return out;
 }
 
@@ -110,10 +111,9 @@ __device__ __forceinline__ void fork_controller(const DevConst &c, const ForkCon
 #pragma unroll
     for (int k = 0; k < 4; ++k) m[k] = f.mixer[k][0] * g0 + f.mixer[k][1] * g1 + f.mixer[k][2] * g2 + f.mixer[k][3] * throttle;
     float mn = fminf(fminf(m[0], m[1]), fminf(m[2], m[3]));
-    if (mn < 0.f) {
+    const float lift = fmaxf(-mn, 0.f);                                  // if mn < 0: motors += |mn|
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m[k] += fabsf(mn);
-    }
+    for (int k = 0; k < 4; ++k) m[k] += lift;
     float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
     if (mx > 1.0f) {
         if (throttle > 1e-2f) {

@@ -199,7 +199,11 @@ static void fill_fork(const qs_config &c, ForkConst &f)
     f.rew_helper = (float)s.rew_helper; f.max_angular_rate = (float)s.max_angular_rate; f.chaser_speed = (float)s.chaser_speed;
     f.ev_vmax = (float)s.evader_v_max; f.ev_dt = (float)s.evader_dt; f.ev_arena = (float)s.evader_arena;
     f.spawn_ring = (float)s.spawn_ring; f.ev_rmin = (float)s.evader_r_min; f.ev_rspan = (float)s.evader_r_span;
-    for (int i = 0; i < 12; ++i) for (int k = 0; k < 5; ++k) f.pid[i][k] = (float)s.pid[i][k];
+    for (int i = 0; i < 12; ++i) {
+        for (int k = 0; k < 3; ++k) f.pid[i][k] = (float)s.pid[i][k];
+        f.pid[i][3] = s.pid[i][3] > 0 ? (float)s.pid[i][3] : INFINITY;      // saturation disabled -> +inf (branch-free clamp)
+        f.pid[i][4] = s.pid[i][4] > 0 ? (float)s.pid[i][4] : -1.0f;         // anti-windup disabled -> empty interval
+    }
     f.rate_scale = (float)s.rate_out_scale;
     for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) f.mixer[i][k] = (float)s.mixer[i][k];
     f.mass = (float)s.ctrl_mass; f.g = (float)s.ctrl_g; f.inv_kf4 = (float)(1.0 / (s.ctrl_kf * 4.0));
