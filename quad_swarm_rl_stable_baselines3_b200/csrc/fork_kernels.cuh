@@ -285,9 +285,18 @@ __device__ __forceinline__ float group_sum(float v, uint32_t gmask)
     return v;
 }
 
-// Scenario_dynamic_repulsive.step, scenarios/dynamic_repulsive.py:41-64 (every lane of the group ends with the same evader)
+// Scenario_dynamic_repulsive.step, scenarios/dynamic_repulsive.py:41-64: (fx, fy) = sum over the chasers of r / |r|^2
+__device__ __forceinline__ void evader_advance(const ForkConst &f, float fx, float fy, float &ex, float &ey)
+{
+    float de = sqrtf(ex * ex + ey * ey);
+    float iden = 1.0f / (de * fmaxf(f.ev_arena - de, 0.1f));
+    float vx = fx - ex * iden, vy = fy - ey * iden;
+    float vs = sqrtf(vx * vx + vy * vy), k = fminf(vs, f.ev_vmax) / vs * f.ev_dt;
+    ex += vx * k; ey += vy * k;
+}
+// every lane of the group ends with the same evader; `mask` must name converged lanes (callers pass the full warp)
 template <int KG>
-__device__ __forceinline__ void evader_step(const ForkConst &f, const Drone &q, bool valid, bool placed, uint32_t gmask, float &ex, float &ey)
+__device__ __forceinline__ void evader_step(const ForkConst &f, const Drone &q, bool valid, bool placed, uint32_t mask, float &ex, float &ey)
 {
     float fx = 0.f, fy = 0.f;
     if (valid && placed) {
@@ -295,12 +304,8 @@ __device__ __forceinline__ void evader_step(const ForkConst &f, const Drone &q, 
         float id2 = 1.0f / (rx * rx + ry * ry);
         fx = rx * id2; fy = ry * id2;
     }
-    fx = group_sum<KG>(fx, gmask); fy = group_sum<KG>(fy, gmask);
-    float de = sqrtf(ex * ex + ey * ey);
-    float iden = 1.0f / (de * fmaxf(f.ev_arena - de, 0.1f));
-    float vx = fx - ex * iden, vy = fy - ey * iden;
-    float vs = sqrtf(vx * vx + vy * vy), k = fminf(vs, f.ev_vmax) / vs * f.ev_dt;
-    ex += vx * k; ey += vy * k;
+    fx = group_sum<KG>(fx, mask); fy = group_sum<KG>(fy, mask);
+    evader_advance(f, fx, fy, ex, ey);
 }
 
 // The fork step kernel.
@@ -363,10 +368,16 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
     for (int k = 0; k < EC_COUNT; ++k) ec[k] = 0;                       // this launch's increments (leader lane)
     float reward = 0.f;
     bool any_done = false, bad_any = false;
+    // The sub-step loop is WARP-uniform: env groups that finish early (capture / timeout) idle under a predicate instead of
+    // leaving the loop, so every collective below runs once per warp on the full mask.  (Group-masked collectives inside a
+    // group-divergent loop are serialised per group by the compiler: 8 passes per warp for K = 4 -- that was 14 % of the
+    // stall samples of the first version, profiles/r1_v4_fork_step_kernel_ncu_full.json.)
+    bool grp_done = false;
     for (int sub = 0; sub < f.substeps; ++sub) {
+        const bool gact = !grp_done, lact = valid && gact;
         const int time_remain = c.ep_len - tick;
         // ---- QuadrotorSingle._step, quadrotor_single_rewards.py:418-457
-        if (valid) {
+        if (lact) {
             float cmd[4];
             fork_controller(c, f, q, pid, angle, ang_vel, act.x, cmd);
             hsnap = angle;                                               // self.heading[i] = pre_controller.angle (:647)
@@ -380,63 +391,70 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
                 if (fire) svd = 0;
                 dynamics_substep(c, g, d, q, cmd, s, fire);
             }
-        } else {
+        } else if (gact) {
             for (int s = 0; s < c.sim_steps; ++s) { svd += 1; if (svd >= c.svd_period) svd = 0; }
         }
-        tick += 1;
+        if (gact) tick += 1;
         const bool timeout = tick > c.ep_len;
         float chk = q.p[0] + q.p[1] + q.p[2] + q.v[0] + q.v[1] + q.v[2] + q.w[0] + q.w[1] + q.w[2] + q.R[0] + q.R[4] + q.R[8] + pid[0] + pid[12] + pid[18];
-        const bool bad = valid && !isfinite(chk);
-        bad_any = (__ballot_sync(gmask, bad) & gmask) != 0u;
+        const bool bad = lact && !isfinite(chk);
+        const bool bad_now = (__ballot_sync(QS_FULL, bad) & gmask) != 0u;
         // ---- drone-drone collision bookkeeping (counters only: rewards and impulses are off in the fork, :775-786,818)
         uint32_t rowmask = 0u;
         if (KG > 1) {
-            __syncwarp(gmask);
+            __syncwarp();
             stage[2 * lane] = make_float4(q.p[0], q.p[1], q.p[2], 0.f);
-            __syncwarp(gmask);
+            __syncwarp();
             const float col2 = c.thr_col * c.thr_col * 1.0001f;
 #pragma unroll
             for (int j = 0; j < KG; ++j) {
                 float4 o4 = stage[2 * (base + j)];
                 float dx = q.p[0] - o4.x, dy = q.p[1] - o4.y, dz = q.p[2] - o4.z, d2 = dx * dx + dy * dy + dz * dz;
-                if ((j != d) && (j < c.K) && valid && d2 <= col2 && __fsqrt_rn(d2) <= c.thr_col) rowmask |= 1u << j;
+                if ((j != d) && (j < c.K) && lact && d2 <= col2 && __fsqrt_rn(d2) <= c.thr_col) rowmask |= 1u << j;
             }
         }
-        const bool is_unique = (rowmask != 0u) && (q.colmask == 0u);
-        const int col_tick = __popc(__ballot_sync(gmask, is_unique) & gmask) >> 1;
+        const bool is_unique = lact && (rowmask != 0u) && (q.colmask == 0u);
+        const int col_tick = __popc(__ballot_sync(QS_FULL, is_unique) & gmask) >> 1;
         const bool settled = (float)tick >= c.grace_steps;
-        if (col_tick > 0 && settled && is_unique) q.flags |= F_COL_AGENT;
-        q.colmask = rowmask;
         // ---- room bookkeeping (:715-721, 760-764)
         const bool new_wall = (q.flags & F_CR_WALL) && !(q.flags & F_PREV_WALL);
         const bool new_ceil = (q.flags & F_CR_CEIL) && !(q.flags & F_PREV_CEIL);
         const bool cr_floor = (q.flags & F_CR_FLOOR) != 0;
         const bool new_room = (cr_floor || new_wall || new_ceil) && !(q.flags & F_PREV_ROOM);
-        q.flags = (q.flags & ~(F_PREV_WALL | F_PREV_CEIL | F_PREV_ROOM)) | (new_wall ? F_PREV_WALL : 0) | (new_ceil ? F_PREV_CEIL : 0) |
-                  (new_room ? F_PREV_ROOM : 0);
-        const uint32_t wall_b = __ballot_sync(gmask, new_wall && valid) & gmask, ceil_b = __ballot_sync(gmask, new_ceil && valid) & gmask;
-        const uint32_t floor_b = __ballot_sync(gmask, cr_floor && valid) & gmask, room_b = __ballot_sync(gmask, new_room && valid) & gmask;
-        ec[EC_COL] += col_tick;
-        if (settled) { ec[EC_COL_SETTLE] += col_tick; ec[EC_ROOM] += __popc(room_b); ec[EC_FLOOR] += __popc(floor_b); ec[EC_WALL] += __popc(wall_b); ec[EC_CEIL] += __popc(ceil_b); }
-        if ((float)time_remain <= c.final_grace_steps) ec[EC_COL_FINAL] += col_tick;
+        const uint32_t wall_b = __ballot_sync(QS_FULL, new_wall && lact) & gmask, ceil_b = __ballot_sync(QS_FULL, new_ceil && lact) & gmask;
+        const uint32_t floor_b = __ballot_sync(QS_FULL, cr_floor && lact) & gmask, room_b = __ballot_sync(QS_FULL, new_room && lact) & gmask;
         // ---- capture reward (:733-758): distance to envs[0].goal = the evader before this sub-step's scenario.step
-        const float gx = ex, gy = ey;
-        const float rdx = gx - q.p[0], rdy = gy - q.p[1], rd = __fsqrt_rn(rdx * rdx + rdy * rdy);
-        const bool cap = valid && (f.capture_radius > rd);
-        const bool any_cap = (__ballot_sync(gmask, cap) & gmask) != 0u;
-        reward = f.rew_existence;                                        // the list is rebuilt every sub-step (:634)
-        if (any_cap) { reward += cap ? f.rew_captor : 0.f; reward += (f.capture_radius < rd) ? f.rew_helper : 0.f; fflags |= FF_SUCCESS; }
-        any_done = any_cap || timeout || bad_any;
-        // ---- self observation of the last executed sub-step (goal = evader before scenario.step)
-        if (valid && (any_done || sub == f.substeps - 1)) fork_self_obs(c, g, SITE_SENSOR, d, q, angle, ang_vel, orow);
-        // ---- scenario.step (:848)
-        evader_step<KG>(f, q, valid, (fflags & FF_PLACED) != 0, gmask, ex, ey);
-        q.goal[0] = ex; q.goal[1] = ey; q.goal[2] = 2.0f;
-        if (any_done) break;
-        if (sub + 1 < f.substeps) g.step += 1u;                          // next control step -> next RNG counter
+        const float rdx = ex - q.p[0], rdy = ey - q.p[1], rd = __fsqrt_rn(rdx * rdx + rdy * rdy);
+        const bool cap = lact && (f.capture_radius > rd);
+        const bool any_cap = (__ballot_sync(QS_FULL, cap) & gmask) != 0u;
+        // the evader's push from the chasers of this group (scenario.step, :848) -- reduced on the full mask as well
+        float efx = 0.f, efy = 0.f;
+        if (lact && (fflags & FF_PLACED)) { const float id2 = 1.0f / (rdx * rdx + rdy * rdy); efx = rdx * id2; efy = rdy * id2; }
+        efx = group_sum<KG>(efx, QS_FULL); efy = group_sum<KG>(efy, QS_FULL);
+        if (gact) {
+            if (col_tick > 0 && settled && is_unique) q.flags |= F_COL_AGENT;
+            q.colmask = rowmask;
+            q.flags = (q.flags & ~(F_PREV_WALL | F_PREV_CEIL | F_PREV_ROOM)) | (new_wall ? F_PREV_WALL : 0) | (new_ceil ? F_PREV_CEIL : 0) |
+                      (new_room ? F_PREV_ROOM : 0);
+            ec[EC_COL] += col_tick;
+            if (settled) { ec[EC_COL_SETTLE] += col_tick; ec[EC_ROOM] += __popc(room_b); ec[EC_FLOOR] += __popc(floor_b); ec[EC_WALL] += __popc(wall_b); ec[EC_CEIL] += __popc(ceil_b); }
+            if ((float)time_remain <= c.final_grace_steps) ec[EC_COL_FINAL] += col_tick;
+            reward = f.rew_existence;                                    // the list is rebuilt every sub-step (:634)
+            if (any_cap) { reward += cap ? f.rew_captor : 0.f; reward += (f.capture_radius < rd) ? f.rew_helper : 0.f; fflags |= FF_SUCCESS; }
+            bad_any = bad_now;
+            any_done = any_cap || timeout || bad_now;
+            // ---- self observation of the last executed sub-step (goal = evader before scenario.step)
+            if (valid && (any_done || sub == f.substeps - 1)) fork_self_obs(c, g, SITE_SENSOR, d, q, angle, ang_vel, orow);
+            // ---- scenario.step (:848)
+            evader_advance(f, efx, efy, ex, ey);
+            q.goal[0] = ex; q.goal[1] = ey; q.goal[2] = 2.0f;
+            grp_done = any_done;
+            if (!any_done && sub + 1 < f.substeps) g.step += 1u;         // next control step -> next RNG counter
+        }
+        if (__all_sync(QS_FULL, grp_done)) break;                        // warp-uniform exit
     }
     // ---- neighbour observations once, after the sub-steps (:990-991)
-    fork_neighbor_obs<KG>(c, f, g, d, lane, gmask, valid, q, angle, hsnap, orow + c.S, stage);
+    fork_neighbor_obs<KG>(c, f, g, d, lane, QS_FULL, valid, q, angle, hsnap, orow + c.S, stage);
     if (valid) { rew[gi] = reward; done[gi] = any_done ? 1 : 0; }
 
     __syncwarp();
