@@ -78,7 +78,9 @@ def make_spaces(cfg: QuadSimConfig):
         "rxyz": ([-v for v in room], room), "rvxyz": ([-2 * vmax] * 3, [2 * vmax] * 3), "octmap": ([-10.0] * 9, [10.0] * 9),
     }
     names = cfg.obs_repr.split("_")
-    nb = {"pos_vel": ["rxyz", "rvxyz"], "dist_angle": ["dist", "angle"], "dist_sangle": ["dist", "sangle"], "none": []}
+    nb = {"pos_vel": ["rxyz", "rvxyz"], "dist_angle": ["dist", "angle"], "dist_sangle": ["dist", "sangle"],
+          "dist_angle_heading": ["dist", "angle", "angle"], "dist_sangle_sheading": ["dist", "sangle", "sangle"],
+          "ndist_nsangle": ["dist", "sangle"], "none": []}            # quadrotor_single_rewards.py:368-393
     names = names + nb[cfg.neighbor_obs_type] * cfg.visible
     if cfg.use_obstacles:
         names.append("octmap")
