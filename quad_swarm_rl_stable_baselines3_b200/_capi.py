@@ -39,6 +39,8 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, de
             (not os.path.exists(d)) or os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     target = out or LIB_PATH
+    if os.path.exists(target):
+        os.remove(target)          # a failed rebuild must not leave a stale library behind
     nvcc = os.environ.get("NVCC", "nvcc")
     objdir = os.path.join(root, "build", "obj" if out is None else "obj_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)

@@ -93,6 +93,16 @@ __global__ void philox_probe_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint3
     box_muller(r.z, r.w, fout[4], fout[5]);
 }
 
+// every rotation starts as the identity so that an env that was never reset is still a valid state
+__global__ void init_identity_kernel(DevPtrs P, int nd)
+{
+    int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= nd) return;
+    P.plane[PL_W_R0][gi] = make_float4(0.f, 1.f, 0.f, 0.f);      // omega.z, R00 R01 R02
+    P.plane[PL_R1][gi] = make_float4(0.f, 1.f, 0.f, 0.f);        // R10 R11 R12 R20
+    P.plane[PL_R2_FLAGS][gi] = make_float4(0.f, 1.f, 0.f, 0.f);  // R21 R22 flags colmask
+}
+
 }  // namespace qs
 
 using namespace qs;
@@ -120,6 +130,7 @@ struct qs_env {
     float *h_act, *h_obs, *h_rew, *h_term; uint8_t *h_done, *h_succ;
     float *d_act, *d_obs, *d_rew, *d_term; uint8_t *d_done, *d_succ;
     long long launches;
+    bool host_ready;        // staging buffers of the *_host entry points are allocated
     std::string err;
 };
 
@@ -136,6 +147,17 @@ static int fail(qs_env *e, int code, const std::string &msg)
         cudaError_t _r = (call);                                                                       \
         if (_r != cudaSuccess) return fail(e, QS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); \
     } while (0)
+
+// makes `device` current for the scope of an entry point and restores the caller's device afterwards
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 static int pow2_at_least(int k) { int p = 1; while (p < k) p <<= 1; return p; }
 
@@ -220,6 +242,7 @@ static void fill_fork(const qs_config &c, ForkConst &f)
 
 static int validate(const qs_config *c, std::string &why)
 {
+    if (c->num_envs >= 1 && c->num_agents >= 1 && (long long)c->num_envs * 32 > (1ll << 30)) { why = "num_envs too large for 32-bit lane indices (<= 2^25)"; return 0; }
     if (c->env_mode == QS_MODE_FORK) {
         if (c->api_version != QS_API_VERSION) { why = "api_version mismatch"; return 0; }
         if (c->num_envs < 1) { why = "num_envs < 1"; return 0; }
@@ -267,6 +290,43 @@ static const KgLaunchers &launchers(int KG)
     }
 }
 
+static void free_host_buffers(qs_env *e)
+{
+    if (e->h_act) cudaFreeHost(e->h_act);
+    if (e->h_obs) cudaFreeHost(e->h_obs);
+    if (e->h_rew) cudaFreeHost(e->h_rew);
+    if (e->h_done) cudaFreeHost(e->h_done);
+    if (e->d_act) cudaFree(e->d_act);
+    if (e->d_obs) cudaFree(e->d_obs);
+    if (e->d_rew) cudaFree(e->d_rew);
+    if (e->d_done) cudaFree(e->d_done);
+    e->h_act = e->h_obs = e->h_rew = nullptr; e->h_done = nullptr;
+    e->d_act = e->d_obs = e->d_rew = nullptr; e->d_done = nullptr;
+    e->host_ready = false;
+}
+
+// staging buffers of the *_host entry points, allocated on first use (all or nothing)
+static int ensure_host_buffers(qs_env *e)
+{
+    if (e->host_ready) return QS_OK;
+    const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
+    cudaError_t r = cudaSuccess;
+    if (r == cudaSuccess) r = cudaMallocHost(&e->h_act, nd * e->A * sizeof(float));
+    if (r == cudaSuccess) r = cudaMallocHost(&e->h_obs, nd * D * sizeof(float));
+    if (r == cudaSuccess) r = cudaMallocHost(&e->h_rew, nd * sizeof(float));
+    if (r == cudaSuccess) r = cudaMallocHost(&e->h_done, nd);
+    if (r == cudaSuccess) r = cudaMalloc(&e->d_act, nd * e->A * sizeof(float));
+    if (r == cudaSuccess) r = cudaMalloc(&e->d_obs, nd * D * sizeof(float));
+    if (r == cudaSuccess) r = cudaMalloc(&e->d_rew, nd * sizeof(float));
+    if (r == cudaSuccess) r = cudaMalloc(&e->d_done, nd);
+    if (r != cudaSuccess) {
+        free_host_buffers(e);
+        return fail(e, QS_ERR_CUDA, std::string("host staging buffers: ") + cudaGetErrorString(r));
+    }
+    e->host_ready = true;
+    return QS_OK;
+}
+
 extern "C" {
 
 size_t qs_config_size(void) { return sizeof(qs_config); }
@@ -284,10 +344,10 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     cudaError_t r = cudaGetDeviceCount(&ndev);
     if (r != cudaSuccess || ndev == 0) return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: no CUDA device (") + cudaGetErrorString(r) + ")");
     if (device < 0 || device >= ndev) return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: bad device index");
-    QS_CUDA(nullptr, cudaSetDevice(device));
+    DeviceGuard guard(device);
 
     qs_env *e = new qs_env();
-    e->cfg = *cfg; e->device = device; e->launches = 0;
+    e->cfg = *cfg; e->device = device; e->launches = 0; e->host_ready = false;
     e->h_act = e->h_obs = e->h_rew = e->h_term = nullptr; e->h_done = e->h_succ = nullptr;
     e->d_act = e->d_obs = e->d_rew = e->d_term = nullptr; e->d_done = e->d_succ = nullptr;
     fill_const(*cfg, e->dc);
@@ -323,7 +383,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     size_t o_svd = off; off += align((size_t)N * sizeof(int));
     size_t o_step = off; off += align((size_t)N * sizeof(uint32_t));
     size_t o_ecnt = off; off += align((size_t)N * EC_COUNT * sizeof(int));
-    size_t o_obst = off; off += align((size_t)N * QS_MAX_OBSTACLES * sizeof(float2));
+    size_t o_obst = off; off += align((cfg->use_obstacles ? (size_t)N * QS_MAX_OBSTACLES : 1) * sizeof(float2));
     size_t o_stats = off; off += align(sizeof(qs_stats));
     size_t fplane_off[FP_COUNT] = {0}, o_evader = 0, o_fflags = 0;
     if (e->fork) {
@@ -334,7 +394,8 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     e->slab_bytes = off;
     r = cudaMalloc(&e->slab, off);
     if (r != cudaSuccess) { delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: cudaMalloc: ") + cudaGetErrorString(r)); }
-    cudaMemset(e->slab, 0, off);
+    r = cudaMemset(e->slab, 0, off);
+    if (r != cudaSuccess) { cudaFree(e->slab); delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: cudaMemset: ") + cudaGetErrorString(r)); }
     char *b = (char *)e->slab;
     for (int p = 0; p < PL_COUNT; ++p) e->dp.plane[p] = (float4 *)(b + plane_off[p]);
     e->dp.tick = (int *)(b + o_tick); e->dp.svd_ctr = (int *)(b + o_svd); e->dp.step_ctr = (uint32_t *)(b + o_step);
@@ -343,19 +404,9 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
         for (int p = 0; p < FP_COUNT; ++p) e->fp.plane[p] = (float4 *)(b + fplane_off[p]);
         e->fp.evader = (float2 *)(b + o_evader); e->fp.flags = (int *)(b + o_fflags);
     }
-    // identity rotations so that an un-reset env is still a valid state
-    {
-        StateView v; memset(&v, 0, sizeof(v));
-        float *rot = nullptr;
-        cudaMalloc(&rot, nd * 9 * sizeof(float));
-        float *h = (float *)malloc(nd * 9 * sizeof(float));
-        for (size_t i = 0; i < nd; ++i) for (int a = 0; a < 9; ++a) h[9 * i + a] = (a % 4 == 0) ? 1.f : 0.f;
-        cudaMemcpy(rot, h, nd * 9 * sizeof(float), cudaMemcpyHostToDevice);
-        v.rot = rot;
-        state_io_kernel<<<(int)((nd + 127) / 128), 128>>>(e->dc, e->dp, e->fp, v, 1);
-        cudaDeviceSynchronize();
-        cudaFree(rot); free(h);
-    }
+    init_identity_kernel<<<(int)((nd + 127) / 128), 128>>>(e->dp, (int)nd);
+    r = cudaDeviceSynchronize();
+    if (r != cudaSuccess) { cudaFree(e->slab); delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: state init: ") + cudaGetErrorString(r)); }
     e->persist = false; e->grid_persist = 0; e->smem_persist = 0;
     {
         const size_t pf_floats = (tiles_floats + obst_floats + 3) & ~(size_t)3;
@@ -379,20 +430,13 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
 int qs_destroy(qs_env *e)
 {
     if (!e) return QS_ERR_NULL;
-    cudaSetDevice(e->device);
+    DeviceGuard guard(e->device);
     cudaFree(e->slab);
-    if (e->h_act) cudaFreeHost(e->h_act);
-    if (e->h_obs) cudaFreeHost(e->h_obs);
-    if (e->h_rew) cudaFreeHost(e->h_rew);
-    if (e->h_done) cudaFreeHost(e->h_done);
+    free_host_buffers(e);
     if (e->h_term) cudaFreeHost(e->h_term);
     if (e->h_succ) cudaFreeHost(e->h_succ);
     if (e->d_term) cudaFree(e->d_term);
     if (e->d_succ) cudaFree(e->d_succ);
-    if (e->d_act) cudaFree(e->d_act);
-    if (e->d_obs) cudaFree(e->d_obs);
-    if (e->d_rew) cudaFree(e->d_rew);
-    if (e->d_done) cudaFree(e->d_done);
     delete e;
     return QS_OK;
 }
@@ -406,6 +450,7 @@ int64_t qs_launch_count(const qs_env *e) { return e ? e->launches : 0; }
 int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
 {
     if (!e || !obs) return fail(e, QS_ERR_NULL, "qs_reset: null argument");
+    DeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     const LaunchShape shape = { e->grid, e->block, e->smem_bytes };
     if (e->fork) launchers(e->KG).fork_reset(shape, s, e->dc, e->fc, e->dp, e->fp, env_mask, obs);
@@ -420,6 +465,7 @@ int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *do
 {
     if (!e || !actions || !obs || !rew || !done) return fail(e, QS_ERR_NULL, "qs_step: null argument");
     if (((size_t)actions & 15) != 0) return fail(e, QS_ERR_SHAPE, "qs_step: actions must be 16-byte aligned");
+    DeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (e->fork) {
         launchers(e->KG).fork_step({ e->grid, e->block, e->smem_bytes }, s, e->dc, e->fc, e->dp, e->fp, (const float2 *)actions, obs, rew,
@@ -436,21 +482,6 @@ int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *do
     return QS_OK;
 }
 
-static int ensure_host_buffers(qs_env *e)
-{
-    if (e->h_act) return QS_OK;
-    const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents, D = (size_t)e->dc.D;
-    QS_CUDA(e, cudaMallocHost(&e->h_act, nd * e->A * sizeof(float)));
-    QS_CUDA(e, cudaMallocHost(&e->h_obs, nd * D * sizeof(float)));
-    QS_CUDA(e, cudaMallocHost(&e->h_rew, nd * sizeof(float)));
-    QS_CUDA(e, cudaMallocHost(&e->h_done, nd));
-    QS_CUDA(e, cudaMalloc(&e->d_act, nd * e->A * sizeof(float)));
-    QS_CUDA(e, cudaMalloc(&e->d_obs, nd * D * sizeof(float)));
-    QS_CUDA(e, cudaMalloc(&e->d_rew, nd * sizeof(float)));
-    QS_CUDA(e, cudaMalloc(&e->d_done, nd));
-    return QS_OK;
-}
-
 // true if `p` is page-locked host memory the copy engines can reach directly (cudaHostAlloc / cudaHostRegister /
 // torch pin_memory); pageable buffers go through the handle's pinned staging area instead.
 static bool is_pinned(const void *p)
@@ -463,6 +494,7 @@ static bool is_pinned(const void *p)
 int qs_reset_host(qs_env *e, float *obs_host, void *stream)
 {
     if (!e || !obs_host) return fail(e, QS_ERR_NULL, "qs_reset_host: null argument");
+    DeviceGuard guard(e->device);
     int rc = ensure_host_buffers(e);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -480,6 +512,7 @@ int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *r
                  float *terminal_obs_host, uint8_t *reset_success_host, void *stream)
 {
     if (!e || !actions_host || !obs_host || !rew_host || !done_host) return fail(e, QS_ERR_NULL, "qs_step_host: null argument");
+    DeviceGuard guard(e->device);
     int rc = ensure_host_buffers(e);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -528,10 +561,12 @@ int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *r
 static int state_io(qs_env *e, const qs_state_view *view, void *stream, int set)
 {
     if (!e || !view) return fail(e, QS_ERR_NULL, "qs_get/set_state: null argument");
+    DeviceGuard guard(e->device);
     StateView v;
     v.pos = view->pos; v.vel = view->vel; v.rot = view->rot; v.omega = view->omega; v.rot_damp = view->rot_damp;
     v.cmds_damp = view->cmds_damp; v.ou = view->ou; v.goal = view->goal; v.flags = view->flags; v.col_mask = view->col_mask;
-    v.tick = view->tick; v.svd_ctr = view->svd_ctr; v.step_ctr = view->step_ctr; v.obst_xy = view->obst_xy;
+    v.tick = view->tick; v.svd_ctr = view->svd_ctr; v.step_ctr = view->step_ctr;
+    v.obst_xy = e->cfg.use_obstacles ? view->obst_xy : nullptr;      // obstacle storage exists only with use_obstacles
     v.pid = e->fork ? view->pid : nullptr; v.heading = e->fork ? view->heading : nullptr; v.evader = e->fork ? view->evader : nullptr;
     const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents;
     state_io_kernel<<<(int)((nd + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->dc, e->dp, e->fp, v, set);
@@ -565,6 +600,7 @@ int qs_set_param(qs_env *e, int key, double value)
 int qs_episode_stats(qs_env *e, qs_stats *out, int reset, void *stream)
 {
     if (!e || !out) return fail(e, QS_ERR_NULL, "qs_episode_stats: null argument");
+    DeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     QS_CUDA(e, cudaMemcpyAsync(out, e->dp.stats, sizeof(qs_stats), cudaMemcpyDeviceToHost, s));
     if (reset) QS_CUDA(e, cudaMemsetAsync(e->dp.stats, 0, sizeof(qs_stats), s));
