@@ -63,7 +63,7 @@ def gen_traces():
         env = rh.make_upstream_env(tape=tape, **spec["env"])
         rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
         rec = {k: [] for k in ("actions", "obs", "rew", "done", "tn", "tu", "tc", "n_tn", "n_tu", "n_tc", "tick",
-                               "obst_xy", "scenario")}
+                               "obst_xy", "scenario", "ep_stats", "ep_step")}
         snaps = {k: [] for k in STATE_KEYS}
 
         def push_tape(m):
@@ -104,11 +104,27 @@ def gen_traces():
             rec["rew"].append(np.array(rew, dtype=np.float64))
             rec["done"].append(np.array(done, dtype=bool))
             events["done"] += int(any(done))
+            if any(done):
+                # infos[i]['episode_extra_stats'] of the finished episode (quadrotor_multi.py:739-831), summed over agents where
+                # the value is per agent -> the aggregate qs_stats keeps
+                es = [inf["episode_extra_stats"] for inf in infos]
+                e0 = es[0]
+                rec["ep_step"].append(s)
+                rec["ep_stats"].append([
+                    e0["num_collisions"], e0["num_collisions_after_settle"], e0["num_collisions_final_5_s"],
+                    e0["num_collisions_with_room"], e0["num_collisions_with_floor"], e0["num_collisions_with_wall"],
+                    e0["num_collisions_with_ceiling"], e0.get("num_collisions_obst_quad", 0),
+                    e0.get("num_collisions_obst_quad_after_settle", 0),
+                    round(e0["metric/agent_success_rate"] * K), round(e0["metric/agent_deadlock_rate"] * K),
+                    round(e0["metric/agent_col_rate"] * K),
+                    sum(x["distance_to_goal_1s"] for x in es), sum(x["distance_to_goal_3s"] for x in es),
+                    sum(x["distance_to_goal_5s"] for x in es)])
         out = dict(
             actions=np.array(rec["actions"]), obs=np.array(rec["obs"]), rew=np.array(rec["rew"]),
             done=np.array(rec["done"]), tick=np.array(rec["tick"]),
             tn=np.concatenate(rec["tn"]), tu=np.concatenate(rec["tu"]), tc=np.concatenate(rec["tc"]),
             n_tn=np.array(rec["n_tn"]), n_tu=np.array(rec["n_tu"]), n_tc=np.array(rec["n_tc"]),
+            ep_step=np.array(rec["ep_step"], dtype=np.int64), ep_stats=np.array(rec["ep_stats"], dtype=np.float64),
         )
         for k in STATE_KEYS:
             out["s_" + k] = np.array(snaps[k])

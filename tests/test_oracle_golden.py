@@ -132,6 +132,12 @@ def test_env_trace(golden_dir, name):
     check_state(0, "reset")
     n_done = n_impulse = 0
     T = g["actions"].shape[0]
+    ep_rows = {int(st_): row for st_, row in zip(g["ep_step"], g["ep_stats"])} if "ep_step" in g.files else {}
+    STAT_KEYS = ("num_collisions", "num_collisions_after_settle", "num_collisions_final_5s", "num_collisions_with_room",
+                 "num_collisions_with_floor", "num_collisions_with_wall", "num_collisions_with_ceiling",
+                 "num_collisions_obst_quad", "num_collisions_obst_quad_after_settle", "agents_success", "agents_deadlock",
+                 "agents_collided", "distance_to_goal_1s", "distance_to_goal_3s", "distance_to_goal_5s")
+    prev_stats = o.stats()
     for s in range(T):
         # teacher forcing of the physical state only
         st = o.get_state()
@@ -148,7 +154,16 @@ def test_env_trace(golden_dir, name):
         np.testing.assert_allclose(obs, g["obs"][s + 1], rtol=0, atol=1e-8, err_msg=f"step {s} obs")
         n_done += int(done.any())
         n_impulse += o.diag()["impulse_flag"]
+        if done.any() and ep_rows:
+            # infos[i]['episode_extra_stats'] of the reference (quadrotor_multi.py:739-831) vs what this episode added to qs_stats
+            cur = o.stats()
+            delta = np.array([cur[k] - prev_stats[k] for k in STAT_KEYS], dtype=np.float64)
+            np.testing.assert_allclose(delta[:12], ep_rows[s][:12], rtol=0, atol=0, err_msg=f"step {s} episode counters")
+            np.testing.assert_allclose(delta[12:], ep_rows[s][12:], rtol=1e-9, atol=1e-9, err_msg=f"step {s} distance_to_goal windows")
+            assert cur["episodes"] - prev_stats["episodes"] == 1
+            prev_stats = cur
     assert n_done >= 1
+    assert not ep_rows or len(ep_rows) == n_done
     if name in ("smallroom_k8", "crowd_k16", "cfg3_obst_k8"):
         assert n_impulse >= 1
 
