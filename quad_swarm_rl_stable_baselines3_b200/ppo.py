@@ -1,0 +1,260 @@
+"""Device-resident PPO over the CUDA simulator: rollout storage, GAE and minibatching never leave HBM.
+
+What it replaces: `stable_baselines3.PPO(...).learn()` as driven by `swarm_rl/sb_train.py:54-99` -- SB3's
+`collect_rollouts` / `RolloutBuffer` are numpy-based, so every env step costs a D2H of the observations and an H2D of the
+actions; at the simulator's throughput that host round trip is the only bottleneck left.  Here the policy reads
+`QuadSwarmSim.step`'s CUDA tensors directly and the rollout is a set of preallocated CUDA tensors.
+
+The policy mirrors the reference's `ActorCriticPolicyCustomSeparateWeights` (swarm_rl/models/ActorCriticPolicyCustom.py:284-556)
+with a `QuadMultiEncoder` per tower (swarm_rl/models/quad_multi_model.py:250-354): self-observation MLP, neighbour encoder
+('mlp' or deep-sets 'mean_embed'), optional obstacle MLP, tanh feed-forward to 2*rnn_size; separate actor and critic weights;
+state-independent log-std diagonal Gaussian (log_std_init 0, no squashing), xavier-uniform initialisation.  The dense layers
+are plain PyTorch (cuBLAS): nothing here is a hand-written kernel, and nothing of SB3's arithmetic is pinned by a reference
+test (SB3 is not installed in the build image) -- "parity unpinned" for this file; the GAE recursion is tested against a
+numpy restatement of SB3's `RolloutBuffer.compute_returns_and_advantage`.
+
+Multi-GPU: one process per GPU, each with its own env shard (sharding.py); the only collectives are the gradient all-reduce
+per minibatch (one flat NCCL buffer) and the episode-stat all-reduce per rollout.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .config import NEIGHBOR_OBS_DIM, OBS_REPR_DIM, QuadSimConfig
+
+
+def _mlp(sizes, act=nn.Tanh):
+    layers = []
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        layers += [nn.Linear(a, b), act()]
+    return nn.Sequential(*layers)
+
+
+class QuadEncoder(nn.Module):
+    """One tower: QuadMultiEncoder (quad_multi_model.py:250-354)."""
+
+    def __init__(self, cfg: QuadSimConfig, hidden: int = 256, neighbor_hidden: int = 256, neighbor_encoder: str = "mean_embed"):
+        super().__init__()
+        self.S = OBS_REPR_DIM[cfg.obs_repr]
+        self.V = cfg.visible
+        self.W = NEIGHBOR_OBS_DIM[cfg.neighbor_obs_type] if self.V > 0 else 0
+        self.O = 9 if cfg.use_obstacles else 0
+        self.kind = neighbor_encoder if self.V > 0 else "none"
+        self.self_encoder = _mlp([self.S, hidden, hidden])
+        out = hidden
+        if self.kind == "mlp":                       # QuadNeighborhoodEncoderMlp (:104-122)
+            self.neighbor = _mlp([self.W * self.V, neighbor_hidden, neighbor_hidden, neighbor_hidden])
+            out += neighbor_hidden
+        elif self.kind == "mean_embed":              # QuadNeighborhoodEncoderDeepsets (:16-41): phi([self, nbr]) averaged over neighbours
+            self.neighbor = _mlp([self.S + self.W, neighbor_hidden, neighbor_hidden])
+            out += neighbor_hidden
+        elif self.kind != "none":
+            raise NotImplementedError(f"neighbor_encoder {neighbor_encoder!r} (available: mlp, mean_embed)")
+        if self.O:
+            self.obstacle = _mlp([self.O, hidden, hidden])
+            out += hidden
+        self.feed_forward = nn.Sequential(nn.Linear(out, 2 * hidden), nn.Tanh())
+        self.out_size = 2 * hidden
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        s = obs[:, :self.S]
+        parts = [self.self_encoder(s)]
+        if self.kind == "mlp":
+            parts.append(self.neighbor(obs[:, self.S:self.S + self.W * self.V]))
+        elif self.kind == "mean_embed":
+            nb = obs[:, self.S:self.S + self.W * self.V].reshape(-1, self.V, self.W)
+            x = torch.cat([s.unsqueeze(1).expand(-1, self.V, -1), nb], dim=2)
+            parts.append(self.neighbor(x.reshape(-1, self.S + self.W)).reshape(-1, self.V, self.neighbor[-2].out_features).mean(dim=1))
+        if self.O:
+            parts.append(self.obstacle(obs[:, self.S + self.W * self.V:]))
+        return self.feed_forward(torch.cat(parts, dim=1))
+
+
+class QuadActorCritic(nn.Module):
+    """Separate actor / critic towers + diagonal Gaussian head (ActorCriticPolicyCustom.py:284-556)."""
+
+    def __init__(self, cfg: QuadSimConfig, hidden: int = 256, neighbor_hidden: int = 256, neighbor_encoder: str = "mean_embed",
+                 log_std_init: float = 0.0):
+        super().__init__()
+        self.actor = QuadEncoder(cfg, hidden, neighbor_hidden, neighbor_encoder)
+        self.critic = QuadEncoder(cfg, hidden, neighbor_hidden, neighbor_encoder)
+        self.action_net = nn.Linear(self.actor.out_size, cfg.act_dim)
+        self.value_net = nn.Linear(self.critic.out_size, 1)
+        self.log_std = nn.Parameter(torch.full((cfg.act_dim,), float(log_std_init)))
+        for m in self.modules():                                  # :176-182, 405-411
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight, gain=1.0)
+                nn.init.zeros_(m.bias)
+
+    def dist(self, obs):
+        mean = self.action_net(self.actor(obs))
+        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean))
+
+    def value(self, obs):
+        return self.value_net(self.critic(obs)).squeeze(-1)
+
+    @torch.no_grad()
+    def act(self, obs):
+        d = self.dist(obs)
+        a = d.sample()
+        return a, d.log_prob(a).sum(-1), self.value(obs)
+
+    def evaluate(self, obs, actions):
+        d = self.dist(obs)
+        return d.log_prob(actions).sum(-1), d.entropy().sum(-1), self.value(obs)
+
+
+def compute_gae(rewards, values, dones, last_values, gamma: float, lam: float):
+    """SB3 `RolloutBuffer.compute_returns_and_advantage`: rewards/values/dones [T, n]; dones[t] marks the transition
+    produced by step t (the env auto-reset after it), last_values [n] = V(s_T).  Returns (advantages, returns), [T, n]."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(last_values)
+    for t in reversed(range(T)):
+        nonterminal = 1.0 - dones[t].to(rewards.dtype)
+        next_v = last_values if t == T - 1 else values[t + 1]
+        delta = rewards[t] + gamma * next_v * nonterminal - values[t]
+        last = delta + gamma * lam * nonterminal * last
+        adv[t] = last
+    return adv, adv + values
+
+
+@dataclass
+class PPOConfig:
+    n_steps: int = 128          # env.step calls per rollout (sb_train.py:58 uses 512 with 13 envs)
+    batch_size: int = 32768     # minibatch rows
+    n_epochs: int = 4           # sb_train.py:60 uses 10
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    ent_coef: float = 0.0
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    learning_rate: float = 1e-4     # global_cfg.py:29
+    normalize_advantage: bool = True
+    hidden: int = 256
+    neighbor_hidden: int = 256
+    neighbor_encoder: str = "mean_embed"
+    autocast_bf16: bool = False     # bf16 autocast for the dense layers (tensor cores); the simulator stays fp32
+
+
+class DevicePPO:
+    def __init__(self, sim, cfg: QuadSimConfig, ppo: Optional[PPOConfig] = None, seed: int = 0):
+        self.sim, self.cfg, self.p = sim, cfg, ppo or PPOConfig()
+        self.device = torch.device(sim.device)
+        torch.manual_seed(seed)                                   # same initial weights on every rank
+        self.policy = QuadActorCritic(cfg, self.p.hidden, self.p.neighbor_hidden, self.p.neighbor_encoder).to(self.device)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.p.learning_rate, eps=1e-5)
+        n, T, D, A = cfg.num_envs * cfg.num_agents, self.p.n_steps, cfg.obs_dim, cfg.act_dim
+        dev = self.device
+        self.obs_buf = torch.empty((T, n, D), device=dev)
+        self.act_buf = torch.empty((T, n, A), device=dev)
+        self.logp_buf = torch.empty((T, n), device=dev)
+        self.val_buf = torch.empty((T, n), device=dev)
+        self.rew_buf = torch.empty((T, n), device=dev)
+        self.done_buf = torch.empty((T, n), dtype=torch.bool, device=dev)
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self._flat = None
+        self.obs = sim.reset().clone()
+        self.total_agent_steps = 0
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def _autocast(self):
+        return torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.p.autocast_bf16)
+
+    # ---- rollout: policy inference and env stepping, all on the device ---------------------------------------------
+    @torch.no_grad()
+    def collect(self) -> Dict[str, float]:
+        p = self.p
+        t0 = time.perf_counter()
+        for t in range(p.n_steps):
+            with self._autocast():
+                a, logp, v = self.policy.act(self.obs)
+            self.obs_buf[t].copy_(self.obs)
+            self.act_buf[t].copy_(a); self.logp_buf[t].copy_(logp.float()); self.val_buf[t].copy_(v.float())
+            obs, rew, done = self.sim.step(a.float().contiguous())       # the env clips the action itself (RawControl.step)
+            self.rew_buf[t].copy_(rew); self.done_buf[t].copy_(done)
+            self.obs.copy_(obs)                                          # sim.obs aliases a buffer that the next step overwrites
+        with self._autocast():
+            last_v = self.policy.value(self.obs).float()
+        self.adv, self.ret = compute_gae(self.rew_buf, self.val_buf, self.done_buf, last_v, p.gamma, p.gae_lambda)
+        self._sync()
+        n = self.obs.shape[0]
+        self.total_agent_steps += n * p.n_steps * self.world
+        return {"rollout_s": time.perf_counter() - t0, "mean_reward": float(self.rew_buf.mean()),
+                "done_frac": float(self.done_buf.float().mean())}
+
+    def _allreduce_grads(self):
+        if self.world == 1:
+            return
+        params = [q for q in self.policy.parameters() if q.grad is not None]
+        if self._flat is None:
+            self._flat = torch.empty(sum(q.numel() for q in params), device=self.device)
+        off = 0
+        for q in params:
+            self._flat[off:off + q.numel()].copy_(q.grad.reshape(-1)); off += q.numel()
+        torch.distributed.all_reduce(self._flat)                  # NCCL over NVLink: the gradient all-reduce
+        self._flat.div_(self.world)
+        off = 0
+        for q in params:
+            q.grad.copy_(self._flat[off:off + q.numel()].view_as(q.grad)); off += q.numel()
+
+    # ---- PPO update: minibatches gathered on the device ------------------------------------------------------------
+    def update(self) -> Dict[str, float]:
+        p = self.p
+        t0 = time.perf_counter()
+        T, n = self.rew_buf.shape
+        total = T * n
+        obs = self.obs_buf.view(total, -1); act = self.act_buf.view(total, -1)
+        logp_old = self.logp_buf.view(total); adv = self.adv.reshape(total); ret = self.ret.reshape(total)
+        stats = dict(pg=0.0, vf=0.0, ent=0.0, kl=0.0, clip_frac=0.0)
+        nb = 0
+        for _ in range(p.n_epochs):
+            perm = torch.randperm(total, device=self.device)
+            for s in range(0, total, p.batch_size):
+                idx = perm[s:s + p.batch_size]
+                a_mb = adv[idx]
+                if p.normalize_advantage and a_mb.numel() > 1:
+                    a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
+                with self._autocast():
+                    logp, ent, v = self.policy.evaluate(obs[idx], act[idx])
+                logp, ent, v = logp.float(), ent.float(), v.float()
+                ratio = (logp - logp_old[idx]).exp()
+                pg = -torch.min(a_mb * ratio, a_mb * ratio.clamp(1 - p.clip_range, 1 + p.clip_range)).mean()
+                vf = torch.nn.functional.mse_loss(v, ret[idx])
+                loss = pg + p.vf_coef * vf - p.ent_coef * ent.mean()
+                self.opt.zero_grad(set_to_none=False)
+                loss.backward()
+                self._allreduce_grads()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), p.max_grad_norm)
+                self.opt.step()
+                with torch.no_grad():
+                    stats["pg"] += float(pg); stats["vf"] += float(vf); stats["ent"] += float(ent.mean())
+                    stats["kl"] += float((logp_old[idx] - logp).mean()); stats["clip_frac"] += float(((ratio - 1).abs() > p.clip_range).float().mean())
+                nb += 1
+        self._sync()
+        out = {k: v / max(nb, 1) for k, v in stats.items()}
+        out["update_s"] = time.perf_counter() - t0
+        out["minibatches"] = nb
+        return out
+
+    def learn(self, iterations: int, log=None):
+        hist = []
+        for it in range(iterations):
+            r = self.collect()
+            u = self.update()
+            es = self.sim.episode_stats(reset=True, reduce=self.world > 1)      # the episode-stat all-reduce
+            row = dict(iteration=it, agent_steps=self.total_agent_steps, episodes=es["episodes"], **r, **u)
+            hist.append(row)
+            if log:
+                log(row)
+        return hist
