@@ -295,14 +295,33 @@ def main():
         barrier()
         cfg3_ms = e0.elapsed_time(e1) / ns3
         del sim3, pool3
+        # configs[0] family: the fork env sb_train.py trains on (4 chasers, PID pre-controller, 8 control steps per call)
+        fcfg = QuadSimConfig.fork_default(num_envs=n_envs, seed=0, env_id_offset=rank * n_envs)
+        simf = QuadSwarmSim(fcfg, device=dev)
+        simf.want_terminal_obs = False
+        poolf = (torch.rand((POOL, n_envs * fcfg.num_agents, 2), device=dev) * 2.0 - 1.0).contiguous()
+        simf.reset()
+        for i in range(10):
+            simf.step(poolf[i % POOL])
+        nsf = min(args.steps, 100)
+        barrier()
+        e0.record(stream)
+        for i in range(nsf):
+            simf.step(poolf[i % POOL])
+        e1.record(stream)
+        barrier()
+        fork_ms = e0.elapsed_time(e1) / nsf
+        fork_agents, fork_sub = fcfg.num_agents, fcfg.fork.substeps
+        del simf, poolf
     else:
         d_small = 54
-        cfg3_ms = 0.0
+        cfg3_ms = fork_ms = 0.0
+        fork_agents, fork_sub = 4, 8
 
-    t = torch.tensor([total_ms, e2e_ms, small_ms or 0.0, cfg3_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, small_ms or 0.0, cfg3_ms, fork_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, small_ms_max, cfg3_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    total_ms, e2e_ms, small_ms_max, cfg3_ms, fork_ms = (float(v) for v in t)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -347,6 +366,10 @@ def main():
                                       "ms_per_step": cfg3_ms, "value": world * nd / (cfg3_ms * 1e-3), "unit": "drone-steps/s",
                                       "roofline_frac": 453.0 * nd / (cfg3_ms * 1e-3) / 1e9 / peak,
                                       "algorithmic_bytes_per_drone_step": 453.0}
+            line["fork_k4"] = {"workload": "fork env of sb_train.py: 65536 envs x 4 chasers per GPU, dynamic_repulsive, one call = 8 control steps",
+                               "ms_per_call": fork_ms, "value": world * n_envs * fork_agents * fork_sub / (fork_ms * 1e-3),
+                               "unit": "drone-steps/s (control steps)",
+                               "agent_steps_per_s": world * n_envs * fork_agents / (fork_ms * 1e-3)}
         if args.workload != "cfg2":
             line["config"]["workload"] = "PROFILING AID, not the bench line: " + args.workload
         print(json.dumps(line), flush=True)
