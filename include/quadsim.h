@@ -58,7 +58,32 @@ enum { QS_SCENARIO_STATIC_SAME_GOAL = 0,      /* scenarios/static_same_goal.py *
        QS_SCENARIO_O_MIX = 1,                 /* scenarios/mix.py with obstacles: o_random | o_static_same_goal per episode */
        QS_SCENARIO_O_RANDOM = 2,              /* scenarios/obstacles/o_random.py */
        QS_SCENARIO_O_STATIC_SAME_GOAL = 3,    /* scenarios/obstacles/o_static_same_goal.py */
-       QS_SCENARIO_DYNAMIC_REPULSIVE = 4 };   /* scenarios/dynamic_repulsive.py (fork mode: pursuit of a repelled evader) */
+       QS_SCENARIO_DYNAMIC_REPULSIVE = 4,     /* scenarios/dynamic_repulsive.py (fork mode: pursuit of a repelled evader) */
+       /* formation scenarios of the upstream env (scenarios/base.py:42-173, one of 8 formations per episode) */
+       QS_SCENARIO_STATIC_DIFF_GOAL = 5,      /* scenarios/static_diff_goal.py */
+       QS_SCENARIO_DYNAMIC_SAME_GOAL = 6,     /* scenarios/dynamic_same_goal.py: a new common goal every 4-6 s */
+       QS_SCENARIO_DYNAMIC_DIFF_GOAL = 7,     /* scenarios/dynamic_diff_goal.py: a new formation + centre every 4-6 s */
+       QS_SCENARIO_SWAP_GOALS = 8,            /* scenarios/swap_goals.py: goals reshuffled every 4-6 s */
+       QS_SCENARIO_DYNAMIC_FORMATIONS = 9,    /* scenarios/dynamic_formations.py: formation size breathing every step */
+       QS_SCENARIO_MIX = 10,                  /* scenarios/mix.py without obstacles: one of the 9 (K = 1: 5) modes per episode */
+       QS_SCENARIO_EP_LISSAJOUS3D = 11,       /* scenarios/ep_lissajous3D.py: common goal integrating a Lissajous velocity */
+       QS_SCENARIO_EP_RAND_BEZIER = 12,       /* scenarios/ep_rand_bezier.py: common goal along random quadratic Bezier arcs */
+       QS_SCENARIO_SWARM_VS_SWARM = 13 };     /* scenarios/swarm_vs_swarm.py: two half-swarms exchanging formation centres */
+
+/* per-env state of the formation scenarios (the reference's QuadrotorScenario object, scenarios/base.py:9-35), as a row of
+ * QS_SC_COUNT floats in qs_state_view.scenario.  Integers are stored as exactly representable floats. */
+enum { QS_SC_SCENARIO = 0,    /* the scenario of the current episode (differs from qs_config.scenario under mix) */
+       QS_SC_FORMATION = 1,   /* index into QUADS_FORMATION_LIST, scenarios/utils.py:25-26 */
+       QS_SC_SIZE = 2,        /* formation_size */
+       QS_SC_LAYER_DIST = 3,
+       QS_SC_HIGHEST = 4,     /* highest_formation_size */
+       QS_SC_LOWEST = 5,      /* lowest_formation_size */
+       QS_SC_CENTER = 6,      /* formation_center xyz (6..8) */
+       QS_SC_CTL_STEPS = 9,   /* control_step_for_sec: goals change when tick % this == 0 */
+       QS_SC_INCREASE = 10,   /* dynamic_formations: growing (1) or shrinking (0) */
+       QS_SC_SPEED = 11,      /* dynamic_formations: control_speed */
+       QS_SC_AUX = 12,        /* 12..20: swarm_vs_swarm goal_center_1, goal_center_2 | ep_rand_bezier control points P0 P1 P2 */
+       QS_SC_COUNT = 24 };
 
 /* env_mode: which of the reference's two live env variants the handle reproduces */
 enum { QS_MODE_UPSTREAM = 0,   /* gym_art/quadrotor_multi/quadrotor_multi.py + quadrotor_single.py (RawControl, 4 motor thrusts) */
@@ -153,6 +178,10 @@ typedef struct qs_config {
     int32_t obst_area_wid;        /* int(obst_spawn_area[1]) */
     int32_t num_obstacles;        /* int(density * area), quadrotor_multi.py:138 */
     int32_t env_mode;             /* QS_MODE_* */
+    int32_t cube_dim[3];          /* cube formation: int(np.power(n, 1/3)) for n = K, K/2, K - K/2 (scenarios/base.py:101-102); evaluated
+                                     on the host with numpy like the reference, because the last-ulp rounding of that power decides
+                                     e.g. int(27 ** (1/3)) == 2 */
+    int32_t reserved0;
     uint64_t seed;                /* Philox key */
     int64_t env_id_offset;        /* global id of local env 0 (multi-GPU sharding keeps streams G-independent) */
 
@@ -214,6 +243,7 @@ typedef struct qs_state_view {
     int32_t *svd_ctr;    /* [N]     sub-steps since the last re-orthonormalisation */
     uint32_t *step_ctr;  /* [N]     control steps since creation (RNG counter) */
     float *obst_xy;      /* [N, QS_MAX_OBSTACLES, 2] obstacle centres (first num_obstacles valid) */
+    float *scenario;     /* [N, QS_SC_COUNT] formation-scenario state (QS_SC_*); only for the formation scenarios */
     /* fork mode (NULL / ignored otherwise) */
     float *pid;          /* [N*K,24] (last_error, integral) of the 12 PIDs in cascade order */
     float *heading;      /* [N*K,3]  pre_controller.angle, pre_controller.angular_velocity, env.heading snapshot

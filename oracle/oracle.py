@@ -17,7 +17,7 @@ _ROOT = os.path.dirname(_HERE)
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from quad_swarm_rl_stable_baselines3_b200.config import QsConfigC, QsStatsC, QuadSimConfig  # noqa: E402
+from quad_swarm_rl_stable_baselines3_b200.config import QsConfigC, QsStatsC, QuadSimConfig, cube_floor_dim  # noqa: E402
 
 _LIB = None
 
@@ -26,9 +26,8 @@ def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libquadsim_oracle.so")
     src = os.path.join(_HERE, "quadsim_oracle.c")
     hdr = os.path.join(_ROOT, "include", "quadsim.h")
-    if force or not os.path.exists(so) or (
-            os.path.exists(src) and os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libquadsim_oracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.exists(src):      # make tracks the .c / .inc / header dependencies; without sources keep the prebuilt library
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []) + ["libquadsim_oracle.so"], stdout=subprocess.DEVNULL)
     return so
 
 
@@ -51,6 +50,9 @@ def lib():
         L.qo_dynamics_only.argtypes = [C.c_void_p, C.c_int, dp]
         L.qo_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 11
         L.qo_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+        L.qo_get_scenario.argtypes = [C.c_void_p, dp]
+        L.qo_set_scenario.argtypes = [C.c_void_p, dp]
+        L.qo_generate_goals.argtypes = [C.c_int, C.c_double, C.c_int, dp, C.c_double, C.c_int, dp]
         L.qo_set_obstacles.argtypes = [C.c_void_p, dp, C.c_int]
         L.qo_get_obstacles.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int)]
         L.qo_get_stats.argtypes = [C.c_void_p, C.POINTER(QsStatsC)]
@@ -174,6 +176,16 @@ class OracleEnv:
             xy = np.ascontiguousarray(kw["obst_xy"], dtype=np.float64).reshape(-1, 2)
             lib().qo_set_obstacles(self.h, _dp(xy), xy.shape[0])
 
+    def get_scenario(self):
+        """QS_SC_* row (include/quadsim.h) of the formation-scenario state."""
+        o = np.zeros(24)
+        lib().qo_get_scenario(self.h, _dp(o))
+        return o
+
+    def set_scenario(self, row):
+        a = np.ascontiguousarray(row, dtype=np.float64).reshape(24)
+        lib().qo_set_scenario(self.h, _dp(a))
+
     def get_fork_state(self):
         pid, heading, evader, fl = np.zeros((self.K, 24)), np.zeros((self.K, 3)), np.zeros(2), (C.c_int32 * 2)()
         lib().qo_get_fork_state(self.h, _dp(pid), _dp(heading), _dp(evader), fl)
@@ -203,6 +215,14 @@ class OracleEnv:
 
     def set_param(self, key: int, value: float):
         lib().qo_set_param(self.h, key, value)
+
+
+def generate_goals(formation: int, size: float, n: int, center, layer_dist: float) -> np.ndarray:
+    """QuadrotorScenario.generate_goals of the oracle for formation index `formation` (QUADS_FORMATION_LIST order)."""
+    out = np.zeros((max(n, 3) + 1, 3))
+    c = np.ascontiguousarray(center, dtype=np.float64)
+    rows = lib().qo_generate_goals(formation, float(size), int(n), _dp(c), float(layer_dist), cube_floor_dim(int(n)), _dp(out))
+    return out[:rows].copy()
 
 
 class OracleBatch:

@@ -49,8 +49,21 @@ typedef struct {
     double pid[24], angle, ang_vel;
 } qo_drone;
 
+/* formation scenarios (scenario_oracle.inc): the state of the reference's QuadrotorScenario object */
+typedef struct {
+    int formation, per_layer;           /* index into QUADS_FORMATION_LIST; num_agents_per_layer */
+    double size, lowest, highest, layer_dist, center[3];
+    int ctl_steps;                      /* control_step_for_sec */
+    int increase; double speed;         /* dynamic_formations */
+    double c1[3], c2[3];                /* swarm_vs_swarm goal centres */
+    double bez[3][3];                   /* ep_rand_bezier control points */
+    double goals[2 * QS_MAX_AGENTS + 6][3];
+    int n_goals, n1_rows;
+} qo_scen;
+
 typedef struct qo_env {
     qs_config c;
+    qo_scen sc;
     int K;
     uint32_t gid;
     qo_drone d[QS_MAX_AGENTS];
@@ -684,6 +697,8 @@ static void obstacle_scenario_reset(qo_env *e)
     }
 }
 
+#include "scenario_oracle.inc"
+
 /* QuadrotorSingle._reset, quadrotor_single.py:401-469 */
 static void drone_reset(qo_env *e, int i)
 {
@@ -713,12 +728,10 @@ static void env_reset(qo_env *e, double *obs)
     int K = e->K;
     if (c->use_obstacles) obstacle_scenario_reset(e);
     else {
-        /* Scenario_static_same_goal / QuadrotorScenario.reset (scenarios/base.py:144-156): formation index,
-         * formation size U(0,0), layer dist U(0,0), shuffle of K identical goals -> 3 + (K-1) unit draws, no effect */
-        burn_u(e, 3 + (K - 1));
-        for (int i = 0; i < K; ++i) { e->d[i].goal[0] = 0; e->d[i].goal[1] = 0; e->d[i].goal[2] = 2.0; memcpy(e->d[i].spawn_point, e->d[i].goal, sizeof(double) * 3); }
-        e->approach_metric = c->approach_goal_metric;
-        e->scenario_now = QS_SCENARIO_STATIC_SAME_GOAL;
+        /* scenario.reset() then goal / spawn_point = scenario.goals[i] (quadrotor_multi.py:459,467-472).  static_same_goal draws
+         * 3 + (K-1) unit values that cannot change its K identical goals */
+        formation_scenario_reset(e);
+        for (int i = 0; i < K; ++i) { memcpy(e->d[i].goal, e->sc.goals[i], sizeof(double) * 3); memcpy(e->d[i].spawn_point, e->d[i].goal, sizeof(double) * 3); }
     }
     int D = obs_dim(c), S = self_obs_dim(c), NB = (c->neighbor_obs_type == QS_NEIGHBOR_POS_VEL) ? 6 * c->neighbor_visible_num : 0;
     for (int i = 0; i < K; ++i) {
@@ -864,6 +877,10 @@ static void env_step(qo_env *e, const double *actions, double *obs, double *rew,
     for (int i = 0; i < K; ++i) e->d[i].col_mask = row[i];       /* :568 */
     e->last_impulse_flag = flag;
 
+    /* 4. scenario.step(), :701 -- goals may move; the self observations computed above keep the old goal unless an impulse
+     * forces their recomputation below */
+    if (!c->use_obstacles) formation_scenario_step(e);
+
     /* 5. observations, :703-720 */
     for (int i = 0; i < K; ++i) memcpy(e->snap_vel[i], e->d[i].vel, sizeof(double) * 3);
     if (flag) for (int i = 0; i < K; ++i) self_obs(e, i, SITE_SENSOR_IMPULSE, obs + (size_t)i * D);   /* :711-712, fresh noise */
@@ -993,7 +1010,7 @@ void qo_set_state(qo_env *e, const double *pos, const double *vel, const double 
         if (rot_damp) memcpy(q->rot_damp, rot_damp + 4 * i, 32);
         if (cmds_damp) memcpy(q->cmds_damp, cmds_damp + 4 * i, 32);
         if (ou) memcpy(q->ou, ou + 4 * i, 32);
-        if (goal) memcpy(q->goal, goal + 3 * i, 24);
+        if (goal) { memcpy(q->goal, goal + 3 * i, 24); memcpy(e->sc.goals[i], goal + 3 * i, 24); }
         if (flags) {
             q->on_floor = flags[i] & 1; q->crashed_floor = (flags[i] >> 1) & 1; q->crashed_wall = (flags[i] >> 2) & 1;
             q->crashed_ceiling = (flags[i] >> 3) & 1; q->prev_new_wall = (flags[i] >> 4) & 1; q->prev_new_ceiling = (flags[i] >> 5) & 1;
@@ -1002,6 +1019,39 @@ void qo_set_state(qo_env *e, const double *pos, const double *vel, const double 
         if (col_mask) q->col_mask = col_mask[i];
     }
     if (tick_svd_step) { e->tick = tick_svd_step[0]; e->svd_ctr = tick_svd_step[1]; e->step_ctr = (uint32_t)tick_svd_step[2]; }
+}
+
+/* formation-scenario state in the flat layout of qs_state_view.scenario (include/quadsim.h, QS_SC_*) */
+void qo_get_scenario(const qo_env *e, double *o)
+{
+    const qo_scen *s = &e->sc;
+    memset(o, 0, sizeof(double) * QS_SC_COUNT);
+    o[QS_SC_SCENARIO] = e->scenario_now; o[QS_SC_FORMATION] = s->formation; o[QS_SC_SIZE] = s->size; o[QS_SC_LAYER_DIST] = s->layer_dist;
+    o[QS_SC_HIGHEST] = s->highest; o[QS_SC_LOWEST] = s->lowest;
+    for (int a = 0; a < 3; ++a) o[QS_SC_CENTER + a] = s->center[a];
+    o[QS_SC_CTL_STEPS] = s->ctl_steps; o[QS_SC_INCREASE] = s->increase; o[QS_SC_SPEED] = s->speed;
+    if (e->scenario_now == QS_SCENARIO_EP_RAND_BEZIER) for (int k = 0; k < 9; ++k) o[QS_SC_AUX + k] = s->bez[k / 3][k % 3];
+    else for (int a = 0; a < 3; ++a) { o[QS_SC_AUX + a] = s->c1[a]; o[QS_SC_AUX + 3 + a] = s->c2[a]; }
+}
+void qo_set_scenario(qo_env *e, const double *o)
+{
+    qo_scen *s = &e->sc;
+    e->scenario_now = (int)o[QS_SC_SCENARIO]; s->formation = (int)o[QS_SC_FORMATION]; s->size = o[QS_SC_SIZE]; s->layer_dist = o[QS_SC_LAYER_DIST];
+    s->highest = o[QS_SC_HIGHEST]; s->lowest = o[QS_SC_LOWEST];
+    s->per_layer = (s->formation >= QF_GRID_H && s->formation <= QF_GRID_YZ) ? 50 : 8;
+    for (int a = 0; a < 3; ++a) s->center[a] = o[QS_SC_CENTER + a];
+    s->ctl_steps = (int)o[QS_SC_CTL_STEPS]; s->increase = (int)o[QS_SC_INCREASE]; s->speed = o[QS_SC_SPEED];
+    if (e->scenario_now == QS_SCENARIO_EP_RAND_BEZIER) for (int k = 0; k < 9; ++k) s->bez[k / 3][k % 3] = o[QS_SC_AUX + k];
+    else for (int a = 0; a < 3; ++a) { s->c1[a] = o[QS_SC_AUX + a]; s->c2[a] = o[QS_SC_AUX + 3 + a]; }
+}
+/* QuadrotorScenario.generate_goals on its own (formation fixture of tests/golden/formations.npz) */
+int qo_generate_goals(int formation, double size, int n, const double *center, double layer_dist, int cube_dim, double *out)
+{
+    qo_scen s;
+    memset(&s, 0, sizeof(s));
+    s.formation = formation; s.size = size;
+    s.per_layer = (formation >= QF_GRID_H && formation <= QF_GRID_YZ) ? 50 : 8;
+    return scen_generate_goals(&s, n, center, layer_dist, (double (*)[3])out, cube_dim);
 }
 
 void qo_set_obstacles(qo_env *e, const double *xy, int n) { e->n_obst = n; for (int m = 0; m < n; ++m) { e->obst_xy[m][0] = xy[2 * m]; e->obst_xy[m][1] = xy[2 * m + 1]; } }

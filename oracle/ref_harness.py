@@ -72,7 +72,28 @@ def install_stubs():
     sys.modules["gymnasium.utils"] = utils
     sys.modules["gymnasium.utils.seeding"] = seeding
 
-    sys.modules["bezier"] = types.ModuleType("bezier")
+    # `bezier` is not installed here.  ep_rand_bezier.py only needs Curve(nodes, degree=2).evaluate_multi(pts); the stub
+    # evaluates the curve the package documents, B(s) = sum_k C(n,k) (1-s)^(n-k) s^k P_k, so the scenario code itself runs
+    # unmodified.
+    bz = types.ModuleType("bezier")
+
+    class Curve:
+        def __init__(self, nodes, degree):
+            self.nodes = np.asarray(nodes, dtype=np.float64)
+            self.degree = int(degree)
+            assert self.nodes.shape[1] == self.degree + 1
+
+        def evaluate_multi(self, s_vals):
+            from math import comb
+            s = np.asarray(s_vals, dtype=np.float64)
+            n = self.degree
+            out = np.zeros((self.nodes.shape[0], len(s)))
+            for k in range(n + 1):
+                out += comb(n, k) * ((1.0 - s) ** (n - k)) * (s ** k) * self.nodes[:, k:k + 1]
+            return out
+
+    bz.Curve = Curve
+    sys.modules["bezier"] = bz
 
     sf = types.ModuleType("sample_factory")
     sfu = types.ModuleType("sample_factory.utils")
@@ -149,6 +170,14 @@ class Tape:
     def rand_fn(self, *shape):
         return self.rand(shape if shape else None)
 
+    def randint(self, low, high=None, size=None):
+        # legacy np.random.randint(low, high): one taped uniform, low + floor(u * (high - low)) on the truncated bounds
+        if high is None:
+            low, high = 0, low
+        assert size is None
+        low, high = int(low), int(high)
+        return low + int(np.floor(self.rand() * (high - low)))
+
     def choice(self, a, size=None, replace=True, p=None):
         assert not replace and p is None
         pop = np.arange(a) if np.isscalar(a) else np.asarray(list(a))
@@ -193,6 +222,7 @@ def install_tape(tape):
     nr.randn = tape.randn_fn
     nr.rand = tape.rand_fn
     nr.choice = tape.choice
+    nr.randint = tape.randint
     import numba as nb
     nb.random = types.SimpleNamespace(uniform=tape.uniform)
     import gym_art.quadrotor_multi.sensor_noise as sn

@@ -16,7 +16,12 @@ QS_API_VERSION = 2
 QS_MAX_AGENTS = 32
 QS_MAX_OBSTACLES = 64
 
-SCENARIOS = {"static_same_goal": 0, "o_mix": 1, "o_random": 2, "o_static_same_goal": 3, "dynamic_repulsive": 4}
+SCENARIOS = {"static_same_goal": 0, "o_mix": 1, "o_random": 2, "o_static_same_goal": 3, "dynamic_repulsive": 4,
+             "static_diff_goal": 5, "dynamic_same_goal": 6, "dynamic_diff_goal": 7, "swap_goals": 8, "dynamic_formations": 9,
+             "mix": 10, "ep_lissajous3D": 11, "ep_rand_bezier": 12, "swarm_vs_swarm": 13}
+FORMATION_SCENARIOS = ("static_same_goal", "static_diff_goal", "dynamic_same_goal", "dynamic_diff_goal", "swap_goals",
+                       "dynamic_formations", "mix", "ep_lissajous3D", "ep_rand_bezier", "swarm_vs_swarm")
+QS_SC_COUNT = 24       # floats per env of formation-scenario state (include/quadsim.h QS_SC_*)
 ENV_MODES = {"upstream": 0, "fork": 1}
 OBS_REPR = {"xyz_vxyz_R_omega": 0, "xyz_vxyz_R_omega_floor": 1, "xyz_vxyz_R_omega_wall": 2,
             "cdist_cdistdot_dist_distdot_angle_angledot": 3, "cdist_cdistdot_dist_distdot_sangle_angledot": 4,
@@ -32,6 +37,12 @@ NEIGHBOR_OBS_DIM = {"none": 0, "pos_vel": 6, "dist_angle": 2, "dist_sangle": 3, 
 FORK_NEIGHBOR_OBS = {"none", "dist_angle", "dist_sangle", "dist_angle_heading", "dist_sangle_sheading", "ndist_nsangle"}
 PARAM_KEYS = {"pos": 0, "effort": 1, "crash": 2, "orient": 3, "spin": 4,
               "quadcol_bin": 5, "quadcol_bin_smooth_max": 6, "quadcol_bin_obst": 7, "capture_radius": 8}
+
+
+def cube_floor_dim(n: int) -> int:
+    """floor_dim_size of the cube formation exactly as the reference evaluates it (scenarios/base.py:101-102)."""
+    import numpy as np
+    return int(np.power(n, 1.0 / 3)) if n > 0 else 1
 
 
 class QsForkConfigC(C.Structure):
@@ -54,7 +65,7 @@ class QsConfigC(C.Structure):
         ("use_obstacles", C.c_int32), ("use_downwash", C.c_int32), ("apply_collision_force", C.c_int32),
         ("sense_noise", C.c_int32), ("ep_len", C.c_int32), ("sim_steps", C.c_int32), ("svd_period", C.c_int32),
         ("obst_area_len", C.c_int32), ("obst_area_wid", C.c_int32), ("num_obstacles", C.c_int32),
-        ("env_mode", C.c_int32),
+        ("env_mode", C.c_int32), ("cube_dim", C.c_int32 * 3), ("reserved0", C.c_int32),
         ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
         ("dt", C.c_double), ("room_dims", C.c_double * 3), ("gravity", C.c_double),
         ("mass", C.c_double), ("inertia", C.c_double * 3), ("thrust_max", C.c_double * 4),
@@ -89,7 +100,7 @@ class QsStatsC(C.Structure):
 class QsStateViewC(C.Structure):
     """Binary mirror of `struct qs_state_view`: raw device addresses."""
     FIELDS = ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou", "goal", "flags", "col_mask",
-              "tick", "svd_ctr", "step_ctr", "obst_xy", "pid", "heading", "evader")
+              "tick", "svd_ctr", "step_ctr", "obst_xy", "scenario", "pid", "heading", "evader")
     _fields_ = [(n, C.c_void_p) for n in FIELDS]
 
 
@@ -201,13 +212,22 @@ class QuadSimConfig:
         if self.use_obstacles and mode == "mix":
             mode = "o_mix"
         if mode not in SCENARIOS:
-            raise ValueError(f"quads_mode {self.quads_mode!r} is not available on the device "
-                             f"(supported: static_same_goal, dynamic_repulsive (fork mode); with obstacles: mix, "
-                             f"o_random, o_static_same_goal)")
+            raise ValueError(f"quads_mode {self.quads_mode!r} is not available on the device (supported without obstacles: "
+                             f"{', '.join(FORMATION_SCENARIOS)}; with obstacles: mix, o_random, o_static_same_goal; "
+                             f"fork mode: dynamic_repulsive)")
         if self.use_obstacles != mode.startswith("o_"):
             raise ValueError(f"quads_mode {self.quads_mode!r} inconsistent with use_obstacles={self.use_obstacles}")
         if (mode == "dynamic_repulsive") != (self.env_mode == "fork"):
             raise ValueError("dynamic_repulsive is the fork-mode scenario (env_mode='fork') and the only one it supports")
+        K = self.num_agents
+        # a sphere of fewer than 3 drones still has 3 goal rows in the reference (scenarios/utils.py:77-80); scenarios that
+        # permute stored rows need every row to belong to a drone
+        if mode == "swap_goals" and K < 3:
+            raise ValueError("swap_goals needs num_agents >= 3 on the device")
+        if mode == "swarm_vs_swarm" and K < 2:
+            raise ValueError("swarm_vs_swarm needs num_agents >= 2")             # scenarios/utils.py:10
+        if mode == "mix" and K == 2:
+            raise ValueError("mix needs num_agents == 1 or >= 3 on the device (it contains swap_goals)")
         return SCENARIOS[mode]
 
     def to_c(self) -> QsConfigC:
@@ -241,6 +261,9 @@ class QuadSimConfig:
         c.env_mode = ENV_MODES[self.env_mode]
         c.num_envs, c.num_agents = self.num_envs, self.num_agents
         c.scenario = self.scenario_id()
+        K = self.num_agents
+        for i, n in enumerate((K, K // 2, K - K // 2)):
+            c.cube_dim[i] = cube_floor_dim(n)
         c.obs_repr = OBS_REPR[self.obs_repr]
         c.neighbor_obs_type = NEIGHBOR_OBS[self.neighbor_obs_type] if self.visible > 0 else 0
         if is_fork and self.fork.substeps < 1:

@@ -51,19 +51,89 @@ TRACES = {
 }
 
 
-def gen_traces():
+# Formation scenarios.  Sensor noise off and float32 observations keep the files small: the state, goal and
+# reward traces stay float64 and pin the arithmetic; the scenario object's own state is recorded next to them.
+_SC = dict(sense_noise=None, neighbor_visible_num=2)
+SCENARIO_TRACES = {
+    # every formation over many short episodes: circle / sphere / grid / cube goal layouts, spawn at the shuffled goals
+    "scen_static_diff_k8": dict(env=dict(num_agents=8, quads_mode="static_diff_goal", ep_time=0.12, **_SC), steps=420, act="hover"),
+    # 12 drones: two circle layers, 3x4 grid, cube with floor dimension 2
+    "scen_static_diff_k12": dict(env=dict(num_agents=12, quads_mode="static_diff_goal", ep_time=0.08, **_SC), steps=150, act="hover"),
+    # goal teleports every 4-6 s
+    "scen_dyn_same_k3": dict(env=dict(num_agents=3, quads_mode="dynamic_same_goal", ep_time=6.3, **_SC), steps=680, act="hover"),
+    "scen_dyn_diff_k4": dict(env=dict(num_agents=4, quads_mode="dynamic_diff_goal", ep_time=6.3, **_SC), steps=680, act="hover"),
+    "scen_swap_k3": dict(env=dict(num_agents=3, quads_mode="swap_goals", ep_time=6.3, **_SC), steps=680, act="hover"),
+    "scen_swarm_k6": dict(env=dict(num_agents=6, quads_mode="swarm_vs_swarm", ep_time=6.3, **_SC), steps=680, act="hover"),
+    # halves of 2 drones: a sphere of fewer than 3 drones still yields 3 goal rows (scenarios/utils.py:77-80)
+    "scen_swarm_k4": dict(env=dict(num_agents=4, quads_mode="swarm_vs_swarm", ep_time=0.08, **_SC), steps=260, act="hover"),
+    # formation size breathing every step, direction flips at +-highest_formation_size
+    "scen_dynform_k5": dict(env=dict(num_agents=5, quads_mode="dynamic_formations", ep_time=4.0, **_SC), steps=900, act="hover"),
+    "scen_lissajous_k3": dict(env=dict(num_agents=3, quads_mode="ep_lissajous3D", ep_time=1.0, **_SC), steps=230, act="hover"),
+    # quadratic Bezier arcs resampled at tick 1 and every 5 s (rejection loop on the room bounds)
+    "scen_bezier_k3": dict(env=dict(num_agents=3, quads_mode="ep_rand_bezier", ep_time=5.4, **_SC), steps=600, act="hover"),
+    # the upstream training recipe --quads_mode=mix: a fresh scenario object per episode
+    "scen_mix_k4": dict(env=dict(num_agents=4, quads_mode="mix", ep_time=0.25, **_SC), steps=1000, act="hover"),
+    "scen_mix_k1": dict(env=dict(num_agents=1, quads_mode="mix", ep_time=0.2, sense_noise=None, neighbor_visible_num=0,
+                                 neighbor_obs_type="none"), steps=400, act="hover"),
+}
+FORMATIONS = ("circle_horizontal", "circle_vertical_xz", "circle_vertical_yz", "sphere", "grid_horizontal",
+              "grid_vertical_xz", "grid_vertical_yz", "cube")
+
+
+def scenario_row(env):
+    """The live scenario object's state in the QS_SC_* layout of include/quadsim.h (+ its class name)."""
+    import numpy as np
+    sc = env.scenario.scenario if hasattr(env.scenario, "scenario") and env.scenario.scenario is not None else env.scenario
+    row = np.zeros(24)
+    row[1] = FORMATIONS.index(sc.formation)
+    row[2], row[3], row[4], row[5] = sc.formation_size, sc.layer_dist, sc.highest_formation_size, sc.lowest_formation_size
+    row[6:9] = sc.formation_center
+    row[9] = getattr(sc, "control_step_for_sec", 0)
+    row[10] = float(getattr(sc, "increase_formation_size", 0))
+    row[11] = getattr(sc, "control_speed", 0.0)
+    if getattr(sc, "goal_center_1", None) is not None:
+        row[12:15], row[15:18] = sc.goal_center_1, sc.goal_center_2
+    return sc.__class__.__name__[len("Scenario_"):], row
+
+
+def gen_formations():
+    """QuadrotorScenario.generate_goals of the reference for every formation x swarm size (scenarios/base.py:42-116)."""
+    os.environ["NUMBA_DISABLE_JIT"] = "1"
+    import numpy as np
+    import ref_harness as rh
+    rh.install_stubs()
+    from gym_art.quadrotor_multi.scenarios.base import QuadrotorScenario
+    out, index = {}, []
+    rs = np.random.RandomState(5)
+    for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 17, 24, 27, 32):
+        for fi, form in enumerate(FORMATIONS):
+            sc = QuadrotorScenario("static_diff_goal", envs=[], num_agents=n, room_dims=(10, 10, 10), rng=np.random.default_rng(0))
+            sc.formation = form
+            sc.num_agents_per_layer = 50 if form.startswith("grid") else 8
+            sc.formation_size = float(rs.uniform(-0.5, 1.5))
+            center, layer = rs.uniform(-2, 2, 3) + np.array([0, 0, 3.0]), float(rs.uniform(0.1, 0.6))
+            goals = np.array(sc.generate_goals(num_agents=n, formation_center=center, layer_dist=layer), dtype=np.float64)
+            index.append([n, fi, sc.formation_size, layer, *center, goals.shape[0]])
+            out[f"g{len(index) - 1}"] = goals
+    out["index"] = np.array(index)
+    path = os.path.join(HERE, "formations.npz")
+    np.savez_compressed(path, **out)
+    print("formations:", len(index), "cases ->", os.path.getsize(path) // 1024, "KiB")
+
+
+def gen_traces(traces=None, tape_seed=1234, compact=False):
     os.environ["NUMBA_DISABLE_JIT"] = "1"
     import numpy as np
     import ref_harness as rh
 
-    tape = rh.Tape(seed=1234)
+    tape = rh.Tape(seed=tape_seed)
     rh.install_tape(tape)
-    for name, spec in TRACES.items():
+    for name, spec in (TRACES if traces is None else traces).items():
         K = spec["env"]["num_agents"]
         env = rh.make_upstream_env(tape=tape, **spec["env"])
         rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
         rec = {k: [] for k in ("actions", "obs", "rew", "done", "tn", "tu", "tc", "n_tn", "n_tu", "n_tc", "tick",
-                               "obst_xy", "scenario", "ep_stats", "ep_step")}
+                               "obst_xy", "scenario", "ep_stats", "ep_step", "sc_row")}
         snaps = {k: [] for k in STATE_KEYS}
 
         def push_tape(m):
@@ -81,6 +151,10 @@ def gen_traces():
             if env.use_obstacles:
                 rec["obst_xy"].append(np.array(env.obstacles.pos_arr)[:, :2].copy())
                 rec["scenario"].append(env.scenario.scenario.__class__.__name__)
+            elif compact:
+                nm, row = scenario_row(env)
+                rec["scenario"].append(nm)
+                rec["sc_row"].append(row)
 
         m = tape.mark()
         obs, _ = env.reset()
@@ -95,6 +169,8 @@ def gen_traces():
                 a = rs.uniform(-0.2, 1.3, (K, 4))
             else:                                # near hover, small differential -> long free flight, collisions
                 a = 0.05 + rs.uniform(-0.15, 0.15, (K, 4))
+            if compact:
+                a = a.astype(np.float32).astype(np.float64)
             m = tape.mark()
             obs, rew, done, infos = env.step(a)
             push_tape(m)
@@ -131,11 +207,22 @@ def gen_traces():
         if env.use_obstacles:
             out["obst_xy"] = np.array(rec["obst_xy"])
             out["scenario"] = np.array(rec["scenario"])
+        if compact:
+            out["scenario"] = np.array(rec["scenario"])
+            out["sc_row"] = np.array(rec["sc_row"])
+            out["obs"] = out["obs"].astype(np.float32)
+            out["actions"] = out["actions"].astype(np.float32)
+            for k in ("on_floor", "crashed_floor", "crashed_wall", "crashed_ceiling"):
+                out["s_" + k] = np.packbits(out["s_" + k], axis=None)
+            out["flag_shape"] = np.array(np.array(snaps["on_floor"]).shape)
+            goal_moves = int((np.abs(np.diff(out["s_goal"], axis=0)).max(axis=(1, 2)) > 0).sum())
+            print(f"    scenarios={sorted(set(rec['scenario']))} formations={sorted(set(int(r[1]) for r in rec['sc_row']))} "
+                  f"steps with goal changes={goal_moves}")
         out["env_kwargs"] = np.array(repr(spec["env"]))
         path = os.path.join(HERE, f"trace_{name}.npz")
         np.savez_compressed(path, **out)
-        print(f"{name}: steps={spec['steps']} dones={events['done']} floor={int(out['s_on_floor'].any(axis=1).sum())} "
-              f"wall={int(out['s_crashed_wall'].sum())} ceil={int(out['s_crashed_ceiling'].sum())} "
+        print(f"{name}: steps={spec['steps']} dones={events['done']} floor={int(np.array(snaps['on_floor']).any(axis=1).sum())} "
+              f"wall={int(np.array(snaps['crashed_wall']).sum())} ceil={int(np.array(snaps['crashed_ceiling']).sum())} "
               f"draws N={len(out['tn'])} U={len(out['tu'])} C={len(out['tc'])} -> {os.path.getsize(path) // 1024} KiB")
 
 
@@ -302,6 +389,10 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which == "traces":
         gen_traces()
+    elif which == "scenarios":
+        gen_formations()
+        only = sys.argv[2:]
+        gen_traces({k: v for k, v in SCENARIO_TRACES.items() if not only or k in only}, tape_seed=2468, compact=True)
     elif which == "fork":
         gen_fork_traces()
     elif which == "dyn":
@@ -310,3 +401,4 @@ if __name__ == "__main__":
         subprocess.check_call([sys.executable, __file__, "dyn"])
         subprocess.check_call([sys.executable, __file__, "traces"])
         subprocess.check_call([sys.executable, __file__, "fork"])
+        subprocess.check_call([sys.executable, __file__, "scenarios"])

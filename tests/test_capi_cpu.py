@@ -67,7 +67,7 @@ def test_config_derivations():
     with pytest.raises(ValueError):
         QuadSimConfig(num_agents=4, neighbor_visible_num=6).to_c()
     with pytest.raises(ValueError):
-        QuadSimConfig(quads_mode="swap_goals").to_c()
+        QuadSimConfig(quads_mode="run_away").to_c()                  # not a scenario the device runs
     with pytest.raises(AssertionError):
         QuadSimConfig(rew_coeff=dict(typo=1.0)).to_c()
     cc = c.to_c()

@@ -93,14 +93,45 @@ def test_dynamics_jit_on(golden_dir):
 
 
 TRACE_NAMES = ["cfg2_k8", "smallroom_k8", "crowd_k16", "cfg3_obst_k8", "cfg4_k32", "nonoise_k4"]
+# formation scenarios: compact fixtures -- float32 observations / actions, bit-packed flags, and the
+# reference scenario object's own state per step (QS_SC_* row)
+SCENARIO_TRACE_NAMES = ["scen_static_diff_k8", "scen_static_diff_k12", "scen_dyn_same_k3", "scen_dyn_diff_k4", "scen_swap_k3",
+                        "scen_swarm_k6", "scen_swarm_k4", "scen_dynform_k5", "scen_lissajous_k3", "scen_bezier_k3",
+                        "scen_mix_k4", "scen_mix_k1"]
+SCENARIO_IDS = {"static_same_goal": 0, "static_diff_goal": 5, "dynamic_same_goal": 6, "dynamic_diff_goal": 7, "swap_goals": 8,
+                "dynamic_formations": 9, "ep_lissajous3D": 11, "ep_rand_bezier": 12, "swarm_vs_swarm": 13}
 
 
-@pytest.mark.parametrize("name", TRACE_NAMES)
+def load_trace(golden_dir, name):
+    g = dict(np.load(os.path.join(golden_dir, f"trace_{name}.npz")))
+    if "flag_shape" in g:
+        shape = tuple(int(v) for v in g["flag_shape"])
+        for k in ("on_floor", "crashed_floor", "crashed_wall", "crashed_ceiling"):
+            g["s_" + k] = np.unpackbits(g["s_" + k])[:int(np.prod(shape))].reshape(shape).astype(bool)
+        g["actions"] = g["actions"].astype(np.float64)
+    return g
+
+
+def test_formation_goals(golden_dir):
+    """QuadrotorScenario.generate_goals (scenarios/base.py:42-116) for all 8 formations x 16 swarm sizes, incl. the quirks:
+    a sphere of n < 3 drones has 3 rows, int(27 ** (1/3)) == 2, the cube's x uses formation_center[2]."""
+    from oracle import generate_goals
+    g = np.load(os.path.join(golden_dir, "formations.npz"))
+    for i, (n, fi, size, layer, cx, cy, cz, rows) in enumerate(g["index"]):
+        mine = generate_goals(int(fi), size, int(n), [cx, cy, cz], layer)
+        assert mine.shape[0] == int(rows), (n, fi)
+        np.testing.assert_allclose(mine, g[f"g{i}"], rtol=0, atol=1e-12, err_msg=f"n={n} formation={fi}")
+
+
+@pytest.mark.parametrize("name", TRACE_NAMES + SCENARIO_TRACE_NAMES)
 def test_env_trace(golden_dir, name):
     """QuadrotorEnvMulti.reset/step traces (JIT off, every draw taped): the oracle replays the reference's own draws.
     The physical state is re-synchronised to the reference before every step (teacher forcing; contact dynamics are
     chaotic), while collision / room / episode bookkeeping free-runs across the whole trace."""
-    g = np.load(os.path.join(golden_dir, f"trace_{name}.npz"))
+    g = load_trace(golden_dir, name)
+    files = tuple(g.keys())
+    compact = "sc_row" in g
+    obs_tol = 2e-6 if compact else 1e-9          # compact fixtures keep observations in float32
     kw = ast.literal_eval(str(g["env_kwargs"]))
     cfg = cfg_from_kwargs(kw)
     K = cfg.num_agents
@@ -122,17 +153,23 @@ def test_env_trace(golden_dir, name):
         for bit, key in enumerate(("on_floor", "crashed_floor", "crashed_wall", "crashed_ceiling")):
             assert np.array_equal((st["flags"] >> bit) & 1, g["s_" + key][i].astype(np.int32)), (what, key)
         assert st["tick"] == g["tick"][i], what
-        if "obst_xy" in g.files:
+        if "obst_xy" in files:
             np.testing.assert_allclose(st["obst_xy"], g["obst_xy"][i], atol=1e-12, err_msg=f"{what} obstacles")
+        if compact:
+            # the scenario object itself: which scenario this episode runs, formation, sizes, centre, timers
+            row, ref = o.get_scenario(), g["sc_row"][i]
+            assert int(row[0]) == SCENARIO_IDS[str(g["scenario"][i])], (what, row[0], g["scenario"][i])
+            n_cmp = 18 if str(g["scenario"][i]) == "swarm_vs_swarm" else 12
+            np.testing.assert_allclose(row[1:n_cmp], ref[1:n_cmp], rtol=0, atol=1e-12, err_msg=f"{what} scenario state")
 
     tape(0)
     obs = o.reset()
     check_tape(0, "reset")
-    np.testing.assert_allclose(obs, g["obs"][0], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(obs, g["obs"][0], rtol=0, atol=obs_tol)
     check_state(0, "reset")
     n_done = n_impulse = 0
     T = g["actions"].shape[0]
-    ep_rows = {int(st_): row for st_, row in zip(g["ep_step"], g["ep_stats"])} if "ep_step" in g.files else {}
+    ep_rows = {int(st_): row for st_, row in zip(g["ep_step"], g["ep_stats"])} if "ep_step" in files else {}
     STAT_KEYS = ("num_collisions", "num_collisions_after_settle", "num_collisions_final_5s", "num_collisions_with_room",
                  "num_collisions_with_floor", "num_collisions_with_wall", "num_collisions_with_ceiling",
                  "num_collisions_obst_quad", "num_collisions_obst_quad_after_settle", "agents_success", "agents_deadlock",
@@ -151,7 +188,7 @@ def test_env_trace(golden_dir, name):
         check_state(s + 1, f"step {s}")
         np.testing.assert_allclose(rew, g["rew"][s], rtol=0, atol=1e-9, err_msg=f"step {s} reward")
         assert np.array_equal(done, g["done"][s]), f"step {s} done"
-        np.testing.assert_allclose(obs, g["obs"][s + 1], rtol=0, atol=1e-8, err_msg=f"step {s} obs")
+        np.testing.assert_allclose(obs, g["obs"][s + 1], rtol=0, atol=max(obs_tol, 1e-8), err_msg=f"step {s} obs")
         n_done += int(done.any())
         n_impulse += o.diag()["impulse_flag"]
         if done.any() and ep_rows:
