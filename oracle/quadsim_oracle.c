@@ -1041,6 +1041,7 @@ void qo_set_scenario(qo_env *e, const double *o)
     s->per_layer = (s->formation >= QF_GRID_H && s->formation <= QF_GRID_YZ) ? 50 : 8;
     for (int a = 0; a < 3; ++a) s->center[a] = o[QS_SC_CENTER + a];
     s->ctl_steps = (int)o[QS_SC_CTL_STEPS]; s->increase = (int)o[QS_SC_INCREASE]; s->speed = o[QS_SC_SPEED];
+    s->n_goals = e->K;                                          /* swap_goals permutes the K rows the drones hold */
     if (e->scenario_now == QS_SCENARIO_EP_RAND_BEZIER) for (int k = 0; k < 9; ++k) s->bez[k / 3][k % 3] = o[QS_SC_AUX + k];
     else for (int a = 0; a < 3; ++a) { s->c1[a] = o[QS_SC_AUX + a]; s->c2[a] = o[QS_SC_AUX + 3 + a]; }
 }

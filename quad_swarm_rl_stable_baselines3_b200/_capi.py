@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, de
     lane-group width (kernels_kg.cu, -DQS_KG=n) plus the host API (quadsim.cu), compiled in parallel, then linked."""
     from concurrent.futures import ThreadPoolExecutor
     root = os.path.dirname(_PKG)
-    deps = [os.path.join(CSRC, f) for f in ("quadsim.cu", "kernels_kg.cu", "quadsim_kernels.cuh", "fork_kernels.cuh", "launch.h")]
+    deps = [os.path.join(CSRC, f) for f in ("quadsim.cu", "kernels_kg.cu", "quadsim_kernels.cuh", "fork_kernels.cuh", "scenario_kernels.cuh", "launch.h")]
     deps.append(os.path.join(root, "include", "quadsim.h"))
     if not force and out is None and os.path.exists(LIB_PATH) and all(
             (not os.path.exists(d)) or os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):

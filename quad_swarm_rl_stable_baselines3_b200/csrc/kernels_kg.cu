@@ -19,7 +19,18 @@ void set_attr(size_t bytes, void (*kernel)(Args...))
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+// feature sets of the upstream step kernel: bit 0 obstacles, bit 1 downwash, bit 2 formation scenarios (never with obstacles)
 #define QS_FEAT_SWITCH(FEATv, CALL)                       \
+    switch (FEATv) {                                      \
+        case 0: { constexpr int FEAT = 0; CALL; } break;  \
+        case 1: { constexpr int FEAT = 1; CALL; } break;  \
+        case 2: { constexpr int FEAT = 2; CALL; } break;  \
+        case 3: { constexpr int FEAT = 3; CALL; } break;  \
+        case 4: { constexpr int FEAT = 4; CALL; } break;  \
+        default: { constexpr int FEAT = 6; CALL; } break; \
+    }
+// the persistent form exists for the feature sets without formation scenarios
+#define QS_FEAT_SWITCH_PERSIST(FEATv, CALL)               \
     switch (FEATv) {                                      \
         case 0: { constexpr int FEAT = 0; CALL; } break;  \
         case 1: { constexpr int FEAT = 1; CALL; } break;  \
@@ -36,10 +47,11 @@ void prepare(int feat, size_t smem_plain, size_t smem_persist, int block, int *p
         return;
     }
     QS_FEAT_SWITCH(feat, set_attr(smem_plain, step_kernel<KG, false, FEAT>));
-    set_attr(smem_plain, reset_kernel<KG, false>);
-    set_attr(smem_plain, reset_kernel<KG, true>);
-    if (smem_persist > 0 && smem_persist <= 227 * 1024) {
-        QS_FEAT_SWITCH(feat, set_attr(smem_persist, step_kernel<KG, true, FEAT>);
+    set_attr(smem_plain, reset_kernel<KG, false, false>);
+    set_attr(smem_plain, reset_kernel<KG, true, false>);
+    set_attr(smem_plain, reset_kernel<KG, false, true>);
+    if (feat < 4 && smem_persist > 0 && smem_persist <= 227 * 1024) {
+        QS_FEAT_SWITCH_PERSIST(feat, set_attr(smem_persist, step_kernel<KG, true, FEAT>);
                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(persist_blocks_per_sm, step_kernel<KG, true, FEAT>, block, smem_persist));
     }
 }
@@ -47,17 +59,18 @@ void prepare(int feat, size_t smem_plain, size_t smem_persist, int block, int *p
 void step(bool persist, int feat, LaunchShape s, cudaStream_t st, const DevConst &c, const DevPtrs &P, const float4 *actions, float *obs,
           float *rew, uint8_t *done, float *term_obs, uint8_t *reset_success)
 {
-    if (persist) {
-        QS_FEAT_SWITCH(feat, (step_kernel<KG, true, FEAT><<<s.grid, s.block, s.smem, st>>>(c, P, actions, obs, rew, done, term_obs, reset_success)));
+    if (persist && feat < 4) {
+        QS_FEAT_SWITCH_PERSIST(feat, (step_kernel<KG, true, FEAT><<<s.grid, s.block, s.smem, st>>>(c, P, actions, obs, rew, done, term_obs, reset_success)));
     } else {
         QS_FEAT_SWITCH(feat, (step_kernel<KG, false, FEAT><<<s.grid, s.block, s.smem, st>>>(c, P, actions, obs, rew, done, term_obs, reset_success)));
     }
 }
 
-void reset(bool obst, LaunchShape s, cudaStream_t st, const DevConst &c, const DevPtrs &P, const uint8_t *mask, float *obs)
+void reset(int feat, LaunchShape s, cudaStream_t st, const DevConst &c, const DevPtrs &P, const uint8_t *mask, float *obs)
 {
-    if (obst) reset_kernel<KG, true><<<s.grid, s.block, s.smem, st>>>(c, P, mask, obs);
-    else reset_kernel<KG, false><<<s.grid, s.block, s.smem, st>>>(c, P, mask, obs);
+    if (feat & 1) reset_kernel<KG, true, false><<<s.grid, s.block, s.smem, st>>>(c, P, mask, obs);
+    else if (feat & 4) reset_kernel<KG, false, true><<<s.grid, s.block, s.smem, st>>>(c, P, mask, obs);
+    else reset_kernel<KG, false, false><<<s.grid, s.block, s.smem, st>>>(c, P, mask, obs);
 }
 
 void fork_step(LaunchShape s, cudaStream_t st, const DevConst &c, const ForkConst &f, const DevPtrs &P, const ForkPtrs &F,

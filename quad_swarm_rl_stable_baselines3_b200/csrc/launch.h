@@ -18,7 +18,7 @@ struct KgLaunchers {
     void (*prepare)(int feat, size_t smem_plain, size_t smem_persist, int block, int *persist_blocks_per_sm, bool fork);
     void (*step)(bool persist, int feat, LaunchShape s, cudaStream_t st, const DevConst &c, const DevPtrs &P, const float4 *actions,
                  float *obs, float *rew, uint8_t *done, float *term_obs, uint8_t *reset_success);
-    void (*reset)(bool obst, LaunchShape s, cudaStream_t st, const DevConst &c, const DevPtrs &P, const uint8_t *mask, float *obs);
+    void (*reset)(int feat, LaunchShape s, cudaStream_t st, const DevConst &c, const DevPtrs &P, const uint8_t *mask, float *obs);
     void (*fork_step)(LaunchShape s, cudaStream_t st, const DevConst &c, const ForkConst &f, const DevPtrs &P, const ForkPtrs &F,
                       const float2 *actions, float *obs, float *rew, uint8_t *done, float *term_obs, uint8_t *reset_success);
     void (*fork_reset)(LaunchShape s, cudaStream_t st, const DevConst &c, const ForkConst &f, const DevPtrs &P, const ForkPtrs &F,

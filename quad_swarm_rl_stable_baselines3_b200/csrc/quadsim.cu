@@ -74,6 +74,14 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, 
             if (v.step_ctr) v.step_ctr[gi] = P.step_ctr[gi];
         }
     }
+    if (v.scenario && P.scen) {
+        int tot = c.N * QS_SC_COUNT;
+        float *rows = reinterpret_cast<float *>(P.scen);
+        for (int k = gi; k < tot; k += gridDim.x * blockDim.x) {
+            if (set) rows[k] = v.scenario[k];
+            else v.scenario[k] = rows[k];
+        }
+    }
     if (v.obst_xy) {
         int tot = c.N * QS_MAX_OBSTACLES;
         for (int k = gi; k < tot; k += gridDim.x * blockDim.x) {
@@ -115,7 +123,7 @@ struct qs_env {
     ForkPtrs fp;
     bool fork;
     int A;                  // action dim
-    int feat;               // upstream step kernel specialisation (bit 0 obstacles, bit 1 downwash)
+    int feat;               // upstream step kernel specialisation (bit 0 obstacles, bit 1 downwash, bit 2 formation scenarios)
     int device;
     int KG;                 // lanes per env
     int block;              // threads per block
@@ -209,6 +217,8 @@ static void fill_const(const qs_config &c, DevConst &d)
     d.grace_steps = (float)(1.5 * control_freq);                           // quadrotor_multi.py:156
     d.final_grace_steps = (float)(5.0 * control_freq);                     // quadrotor_multi.py:160
     d.control_dt = (float)(1.0 / control_freq);                            // quadrotor_multi.py:91
+    d.control_freq = (float)control_freq;
+    for (int a = 0; a < 3; ++a) d.cube_dim[a] = c.cube_dim[a] > 0 ? c.cube_dim[a] : 1;
     d.small_angle = (std::sqrt(3.0) * c.omega_max * c.dt * 0.5 <= 0.25) ? 1 : 0;
 }
 
@@ -273,7 +283,15 @@ static int validate(const qs_config *c, std::string &why)
         int cells = c->obst_area_len * c->obst_area_wid;
         if (cells < 1 || cells > 64 || c->num_obstacles < 0 || c->num_obstacles > QS_MAX_OBSTACLES) { why = "obstacle grid must have <= 64 cells"; return 0; }
         if (cells - c->num_obstacles < c->num_agents) { why = "not enough free cells for the drones"; return 0; }
-    } else if (c->scenario != QS_SCENARIO_STATIC_SAME_GOAL) { why = "obstacle scenario without use_obstacles"; return 0; }
+    } else {
+        const int sc = c->scenario, K = c->num_agents;
+        const bool formation = sc == QS_SCENARIO_STATIC_SAME_GOAL || (sc >= QS_SCENARIO_STATIC_DIFF_GOAL && sc <= QS_SCENARIO_SWARM_VS_SWARM);
+        if (!formation) { why = "obstacle scenario without use_obstacles"; return 0; }
+        // a sphere of n < 3 drones still has 3 goal rows (scenarios/utils.py:77-80): scenarios permuting stored rows need rows == drones
+        if (sc == QS_SCENARIO_SWAP_GOALS && K < 3) { why = "swap_goals needs num_agents >= 3"; return 0; }
+        if (sc == QS_SCENARIO_SWARM_VS_SWARM && K < 2) { why = "swarm_vs_swarm needs num_agents >= 2"; return 0; }
+        if (sc == QS_SCENARIO_MIX && K == 2) { why = "mix needs num_agents == 1 or >= 3"; return 0; }
+    }
     if (!(c->mass > 0) || !(c->inertia[0] > 0) || !(c->inertia[1] > 0) || !(c->inertia[2] > 0)) { why = "bad mass / inertia"; return 0; }
     return 1;
 }
@@ -353,7 +371,8 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     fill_const(*cfg, e->dc);
     e->fork = cfg->env_mode == QS_MODE_FORK;
     e->A = e->fork ? 2 : 4;
-    e->feat = (cfg->use_obstacles ? 1 : 0) | ((cfg->use_downwash && cfg->num_agents > 1) ? 2 : 0);
+    const bool scen_feat = !cfg->use_obstacles && cfg->env_mode == QS_MODE_UPSTREAM && cfg->scenario != QS_SCENARIO_STATIC_SAME_GOAL;
+    e->feat = (cfg->use_obstacles ? 1 : 0) | ((cfg->use_downwash && cfg->num_agents > 1) ? 2 : 0) | (scen_feat ? 4 : 0);
     fill_fork(*cfg, e->fc);
     memset(&e->fp, 0, sizeof(e->fp));
     const int N = cfg->num_envs, K = cfg->num_agents;
@@ -384,6 +403,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     size_t o_step = off; off += align((size_t)N * sizeof(uint32_t));
     size_t o_ecnt = off; off += align((size_t)N * EC_COUNT * sizeof(int));
     size_t o_obst = off; off += align((cfg->use_obstacles ? (size_t)N * QS_MAX_OBSTACLES : 1) * sizeof(float2));
+    size_t o_scen = off; off += align((scen_feat ? (size_t)N * QS_SC_COUNT : 1) * sizeof(float));
     size_t o_stats = off; off += align(sizeof(qs_stats));
     size_t fplane_off[FP_COUNT] = {0}, o_evader = 0, o_fflags = 0;
     if (e->fork) {
@@ -400,6 +420,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     for (int p = 0; p < PL_COUNT; ++p) e->dp.plane[p] = (float4 *)(b + plane_off[p]);
     e->dp.tick = (int *)(b + o_tick); e->dp.svd_ctr = (int *)(b + o_svd); e->dp.step_ctr = (uint32_t *)(b + o_step);
     e->dp.ecnt = (int *)(b + o_ecnt); e->dp.obst_xy = (float2 *)(b + o_obst); e->dp.stats = (qs_stats *)(b + o_stats);
+    e->dp.scen = scen_feat ? (float4 *)(b + o_scen) : nullptr;
     if (e->fork) {
         for (int p = 0; p < FP_COUNT; ++p) e->fp.plane[p] = (float4 *)(b + fplane_off[p]);
         e->fp.evader = (float2 *)(b + o_evader); e->fp.flags = (int *)(b + o_fflags);
@@ -454,7 +475,7 @@ int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     const LaunchShape shape = { e->grid, e->block, e->smem_bytes };
     if (e->fork) launchers(e->KG).fork_reset(shape, s, e->dc, e->fc, e->dp, e->fp, env_mask, obs);
-    else launchers(e->KG).reset(e->cfg.use_obstacles != 0, shape, s, e->dc, e->dp, env_mask, obs);
+    else launchers(e->KG).reset(e->feat, shape, s, e->dc, e->dp, env_mask, obs);
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
@@ -567,6 +588,7 @@ static int state_io(qs_env *e, const qs_state_view *view, void *stream, int set)
     v.cmds_damp = view->cmds_damp; v.ou = view->ou; v.goal = view->goal; v.flags = view->flags; v.col_mask = view->col_mask;
     v.tick = view->tick; v.svd_ctr = view->svd_ctr; v.step_ctr = view->step_ctr;
     v.obst_xy = e->cfg.use_obstacles ? view->obst_xy : nullptr;      // obstacle storage exists only with use_obstacles
+    v.scenario = e->dp.scen ? view->scenario : nullptr;
     v.pid = e->fork ? view->pid : nullptr; v.heading = e->fork ? view->heading : nullptr; v.evader = e->fork ? view->evader : nullptr;
     const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents;
     state_io_kernel<<<(int)((nd + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->dc, e->dp, e->fp, v, set);

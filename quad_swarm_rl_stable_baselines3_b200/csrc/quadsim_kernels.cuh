@@ -41,6 +41,8 @@ struct DevConst {
     float rew_pos, rew_effort, rew_crash, rew_orient, rew_spin, rew_col, rew_col_smooth, rew_col_obst;
     float thr_col, thr_fall, thr_obst, obst_rad, sdf_res;
     float spawn_box, spawn_min_z, approach_metric, grace_steps, final_grace_steps, control_dt;
+    float control_freq;                                           // sim_freq / sim_steps (quadrotor_single.py:160)
+    int cube_dim[3];                                              // qs_config.cube_dim
 };
 
 enum { PL_POS_VX = 0, PL_V_W, PL_W_R0, PL_R1, PL_R2_FLAGS, PL_ROT_DAMP, PL_CMDS_DAMP, PL_OU, PL_GOAL, PL_DIST_RING,
@@ -57,6 +59,7 @@ struct DevPtrs {
     uint32_t *step_ctr;        // [N]
     int *ecnt;                 // [N, EC_COUNT]
     float2 *obst_xy;           // [N, QS_MAX_OBSTACLES]
+    float4 *scen;              // [N, QS_SC_COUNT / 4] formation-scenario rows (formation scenarios only, else null)
     qs_stats *stats;           // device aggregate
 };
 
@@ -744,8 +747,13 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
     }
 }
 
+}  // namespace qs
+#include "scenario_kernels.cuh"
+namespace qs {
+
 // Reset of one environment (QuadrotorEnvMulti.reset, quadrotor_multi.py:440-519), executed by the env's lane group.
-template <int KG, bool OBST>
+// SCEN: one of the formation scenarios (scenario_kernels.cuh) instead of the fixed static_same_goal.
+template <int KG, bool OBST, bool SCEN>
 __device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P, const Rng &g, int env, int d, bool valid, Drone &q,
                                             int &scenario_now)
 {
@@ -754,6 +762,11 @@ __device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P,
         int scen = 0;
         obstacle_scenario_reset(c, g, d, valid && d == 0, P.obst_xy + (size_t)env * QS_MAX_OBSTACLES, spawn, goal, scen);
         scenario_now = scen;
+    } else if (SCEN) {
+        goal[0] = goal[1] = 0.f; goal[2] = 2.0f;
+        if (env < c.N) formation_reset(c, g, d, valid && d == 0, reinterpret_cast<float *>(P.scen + (size_t)env * (QS_SC_COUNT / 4)), goal);
+        spawn[0] = goal[0]; spawn[1] = goal[1]; spawn[2] = goal[2];     // e.spawn_point = scenario.goals[i], quadrotor_multi.py:469-470
+        scenario_now = c.scenario;
     } else {
         goal[0] = 0.f; goal[1] = 0.f; goal[2] = 2.0f;                     // static_same_goal: formation size 0 (scenarios/utils.py:30)
         spawn[0] = 0.f; spawn[1] = 0.f; spawn[2] = 2.0f;
@@ -841,7 +854,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
                                                    uint8_t *__restrict__ reset_success)
 {
     extern __shared__ __align__(16) float smem[];
-    constexpr bool OBST = (FEAT & 1) != 0, DOWNWASH = (FEAT & 2) != 0;
+    constexpr bool OBST = (FEAT & 1) != 0, DOWNWASH = (FEAT & 2) != 0, SCEN = (FEAT & 4) != 0;
     const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5, warps_per_block = blockDim.x >> 5;
     const int d = lane % KG;
     const uint32_t gmask = group_mask<KG>(lane);
@@ -1146,6 +1159,14 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     }
     q.colmask = rowmask;                                               // :568
 
+    // ---- 4. scenario.step() (:701): goals may move.  The self observation below still belongs to the old goal unless an
+    // impulse forces its recomputation (:711-712)
+    float og[3] = { q.goal[0], q.goal[1], q.goal[2] };
+    if (SCEN) {
+        if (env < c.N) formation_scenario_step<KG>(c, g, d, valid && d == 0, gmask, lane, tick, reinterpret_cast<float *>(P.scen + (size_t)env * (QS_SC_COUNT / 4)), stage, q.goal);
+        if (flag) { og[0] = q.goal[0]; og[1] = q.goal[1]; og[2] = q.goal[2]; }
+    }
+
     // ---- episode counters (leader lane) (:557-565, 578-581, 631-635)
     if (valid && d == 0) {
         int *ec = P.ecnt + env * EC_COUNT;
@@ -1163,7 +1184,11 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 
     // ---- 5. observations (:703-720).  Self obs carries fresh sensor noise if any impulse fired (:711-712)
     float vs[3] = { q.v[0], q.v[1], q.v[2] };                          // self.vel snapshot, :705-709
-    if (valid) self_obs(c, g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d, q, orow);
+    if (valid) {
+        if (SCEN) { float t; t = q.goal[0]; q.goal[0] = og[0]; og[0] = t; t = q.goal[1]; q.goal[1] = og[1]; og[1] = t; t = q.goal[2]; q.goal[2] = og[2]; og[2] = t; }
+        self_obs(c, g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d, q, orow);
+        if (SCEN) { q.goal[0] = og[0]; q.goal[1] = og[1]; q.goal[2] = og[2]; }
+    }
     group_obs_tail<KG, OBST, false>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
     if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }
 
@@ -1225,7 +1250,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
                 for (int m = 0; m < 4; ++m) q.ou[m] = isfinite(q.ou[m]) ? q.ou[m] : 0.f;
                 if (!isfinite(vs[0] + vs[1] + vs[2])) { vs[0] = vs[1] = vs[2] = 0.f; }
             }
-            group_reset<KG, OBST>(c, P, g, env, d, valid, q, scen);
+            group_reset<KG, OBST, SCEN>(c, P, g, env, d, valid, q, scen);
             tick = 0;
             if (valid) {
                 if (d == 0) {
@@ -1246,7 +1271,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 
     // ---- write back
     if (valid) {
-        store_drone(P, gi, q, all_done);
+        store_drone(P, gi, q, SCEN || all_done);
         if (d == 0) { P.tick[env] = tick; P.svd_ctr[env] = svd; P.step_ctr[env] = g.step + 1u; }
     }
     __syncwarp();
@@ -1258,7 +1283,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 // ----------------------------------------------------------------------------------------------------------------
 // explicit reset (QuadrotorEnvMulti.reset through VecEnv.reset)
 // ----------------------------------------------------------------------------------------------------------------
-template <int KG, bool OBST>
+template <int KG, bool OBST, bool SCEN>
 __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevConst c, const __grid_constant__ DevPtrs P,
                                                     const uint8_t *__restrict__ env_mask, float *__restrict__ obs)
 {
@@ -1295,7 +1320,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
     }
     int scen = 0;
     if (valid) {
-        group_reset<KG, OBST>(c, P, g, env, d, true, q, scen);
+        group_reset<KG, OBST, SCEN>(c, P, g, env, d, true, q, scen);
         if (d == 0) {
             int *ec = P.ecnt + env * EC_COUNT;
 #pragma unroll
@@ -1331,6 +1356,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
 struct StateView {
     float *pos, *vel, *rot, *omega, *rot_damp, *cmds_damp, *ou, *goal;
     int *flags; uint32_t *col_mask; int *tick, *svd_ctr; uint32_t *step_ctr; float *obst_xy;
+    float *scenario;                    // formation scenarios: [N, QS_SC_COUNT]
     float *pid, *heading, *evader;      // fork mode
 };
 

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .config import PARAM_KEYS, QsStateViewC, QsStatsC, QuadSimConfig
+from .config import PARAM_KEYS, QS_SC_COUNT, QsStateViewC, QsStatsC, QuadSimConfig
 
 _STATE_SHAPES = {"pos": (3, torch.float32), "vel": (3, torch.float32), "rot": (9, torch.float32),
                  "omega": (3, torch.float32), "rot_damp": (4, torch.float32), "cmds_damp": (4, torch.float32),
@@ -53,6 +53,8 @@ class QuadSwarmSim:
         self.reset_success = torch.zeros((self.N,), dtype=torch.uint8, device=dev)   # reset_info["success"] of envs that just finished
         self.want_terminal_obs = True
         self.is_fork = cfg.env_mode == "fork"
+        # formation scenarios keep a per-env scenario row on the device (static_same_goal needs none)
+        self.has_scenario_state = (not self.is_fork) and (not cfg.use_obstacles) and cfg.quads_mode != "static_same_goal"
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -146,7 +148,8 @@ class QuadSwarmSim:
     def get_state(self, fields=None) -> Dict[str, torch.Tensor]:
         n = self.N * self.K
         names = list(fields) if fields is not None else (list(_STATE_SHAPES) + list(_ENV_FIELDS) + ["obst_xy"] +
-                                                         (list(_FORK_SHAPES) + ["evader"] if self.is_fork else []))
+                                                         (list(_FORK_SHAPES) + ["evader"] if self.is_fork else []) +
+                                                         (["scenario"] if self.has_scenario_state else []))
         shapes = dict(_STATE_SHAPES, **_FORK_SHAPES)
         out = {}
         for name in names:
@@ -159,6 +162,8 @@ class QuadSwarmSim:
                 out[name] = torch.zeros((self.N, 64, 2), dtype=torch.float32, device=self.device)
             elif name == "evader":
                 out[name] = torch.zeros((self.N, 2), dtype=torch.float32, device=self.device)
+            elif name == "scenario":        # QS_SC_* rows (include/quadsim.h): the reference scenario object's state
+                out[name] = torch.zeros((self.N, QS_SC_COUNT), dtype=torch.float32, device=self.device)
             else:
                 raise KeyError(name)
         v = self._view(out)
@@ -193,6 +198,9 @@ class QuadSwarmSim:
             elif name == "evader":
                 t = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val)
                 keep[name] = t.to(device=self.device, dtype=torch.float32).reshape(self.N, 2).contiguous()
+            elif name == "scenario":
+                t = torch.as_tensor(np.asarray(val) if not torch.is_tensor(val) else val)
+                keep[name] = t.to(device=self.device, dtype=torch.float32).reshape(self.N, QS_SC_COUNT).contiguous()
             else:
                 raise KeyError(name)
         v = self._view(keep)

@@ -71,6 +71,8 @@ def push_state(sim, oracles, cfg):
                     flags=st["flags"][sl] & 0xFF, col_mask=st["col_mask"][sl].astype(np.uint32),
                     tick=int(st["tick"][e]), svd_ctr=int(st["svd_ctr"][e]), step_ctr=int(st["step_ctr"][e]),
                     obst_xy=st["obst_xy"][e, :cfg.num_obstacles].astype(np.float64) if cfg.use_obstacles else None)
+        if "scenario" in st:                      # formation scenarios: the scenario object's state (QS_SC_* row)
+            o.set_scenario(st["scenario"][e].astype(np.float64))
     return st
 
 
@@ -203,6 +205,13 @@ def run_parity(name, cfg, sim, oracles, kind, steps, hook=None):
         worst["vel"] = max(worst["vel"], relerr(st["vel"][rows], os_["vel"][rows], 1.0))
         worst["rot"] = max(worst["rot"], relerr(st["rot"][rows], os_["rot"][rows], 1.0))
         worst["omega"] = max(worst["omega"], relerr(st["omega"][rows], os_["omega"][rows], 1.0))
+        if "scenario" in st:
+            ref_rows = np.stack([o.get_scenario() for o in oracles])
+            np.testing.assert_allclose(st["goal"][rows], os_["goal"][rows], atol=3e-6, err_msg=f"step {s}: goals")
+            assert np.array_equal(st["scenario"][env_ok][:, [0, 1, 9, 10]], ref_rows[env_ok][:, [0, 1, 9, 10]]), f"step {s}: scenario ids / timers"
+            np.testing.assert_allclose(st["scenario"][env_ok], ref_rows[env_ok], atol=3e-6, err_msg=f"step {s}: scenario rows")
+            worst["goal"] = max(worst.get("goal", 0.0), float(np.abs(st["goal"][rows] - os_["goal"][rows]).max()))
+            cnt["goal_moves"] = cnt.get("goal_moves", 0) + int((np.abs(st["goal"] - pre["goal"]).max(axis=1) > 0).reshape(N, K).any(axis=1).sum())
         worst["obs"] = max(worst["obs"], relerr(obs[rows], ref_obs[rows], 1.0))
         worst["rew"] = max(worst["rew"], float(np.abs(rew[rows] - ref_rew[rows]).max()))
         drows = rows & done
