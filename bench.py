@@ -198,8 +198,12 @@ def main():
                              obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2, seed=0, env_id_offset=rank * n_envs)
 
     def make(n_envs, workload="cfg2"):
-        cfg = (cfg3_config(n_envs) if workload == "cfg3" else
-               QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, seed=0, env_id_offset=rank * n_envs))
+        if workload == "cfg3":
+            cfg = cfg3_config(n_envs)
+        elif workload == "mix":      # the upstream training recipe --quads_mode=mix (swarm_rl/runs/quad_multi_mix_baseline.py:13-16)
+            cfg = QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, quads_mode="mix", seed=0, env_id_offset=rank * n_envs)
+        else:
+            cfg = QuadSimConfig(num_envs=n_envs, num_agents=AGENTS, seed=0, env_id_offset=rank * n_envs)
         sim = QuadSwarmSim(cfg, device=dev)
         sim.want_terminal_obs = False
         gen = torch.Generator(device=dev)
@@ -295,6 +299,18 @@ def main():
         barrier()
         cfg3_ms = e0.elapsed_time(e1) / ns3
         del sim3, pool3
+        # the formation-scenario kernel variant: quads_mode=mix, 9 scenarios drawn per episode
+        simm, poolm = make(n_envs, "mix")
+        for i in range(20):
+            simm.step(poolm[i % POOL])
+        barrier()
+        e0.record(stream)
+        for i in range(ns3):
+            simm.step(poolm[i % POOL])
+        e1.record(stream)
+        barrier()
+        mix_ms = e0.elapsed_time(e1) / ns3
+        del simm, poolm
         # configs[0] family: the fork env sb_train.py trains on (4 chasers, PID pre-controller, 8 control steps per call)
         fcfg = QuadSimConfig.fork_default(num_envs=n_envs, seed=0, env_id_offset=rank * n_envs)
         simf = QuadSwarmSim(fcfg, device=dev)
@@ -315,13 +331,13 @@ def main():
         del simf, poolf
     else:
         d_small = 54
-        cfg3_ms = fork_ms = 0.0
+        cfg3_ms = fork_ms = mix_ms = 0.0
         fork_agents, fork_sub = 4, 8
 
-    t = torch.tensor([total_ms, e2e_ms, small_ms or 0.0, cfg3_ms, fork_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, small_ms or 0.0, cfg3_ms, fork_ms, mix_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, small_ms_max, cfg3_ms, fork_ms = (float(v) for v in t)
+    total_ms, e2e_ms, small_ms_max, cfg3_ms, fork_ms, mix_ms = (float(v) for v in t)
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -366,6 +382,12 @@ def main():
                                       "ms_per_step": cfg3_ms, "value": world * nd / (cfg3_ms * 1e-3), "unit": "drone-steps/s",
                                       "roofline_frac": 453.0 * nd / (cfg3_ms * 1e-3) / 1e9 / peak,
                                       "algorithmic_bytes_per_drone_step": 453.0}
+            line["mix_scenarios"] = {"workload": "upstream training recipe quads_mode=mix: 65536 envs x 8 quads per GPU, one of 9 formation "
+                                                 "scenarios per episode (goals moving every step in 3 of them), obs 54",
+                                     "ms_per_step": mix_ms, "value": world * nd / (mix_ms * 1e-3), "unit": "drone-steps/s",
+                                     "roofline_frac": (ALGO_BYTES_PER_DRONE_STEP + 16.0 + 12.0) * nd / (mix_ms * 1e-3) / 1e9 / peak,
+                                     "algorithmic_bytes_per_drone_step": ALGO_BYTES_PER_DRONE_STEP + 16.0 + 12.0,
+                                     "note": "+16 B goal written every step, +96 B scenario row per env read (12 B per drone)"}
             line["fork_k4"] = {"workload": "fork env of sb_train.py: 65536 envs x 4 chasers per GPU, dynamic_repulsive, one call = 8 control steps",
                                "ms_per_call": fork_ms, "value": world * n_envs * fork_agents * fork_sub / (fork_ms * 1e-3),
                                "unit": "drone-steps/s (control steps)",

@@ -17,7 +17,8 @@
  *   qs_get_state/qs_set_state      envs[i].dynamics.{pos,vel,rot,omega,...} attribute access
  *                                  (gym_art/quadrotor_multi/quadrotor_dynamics.py:180-191)
  *   qs_set_param             rew_coeff updates / set_capture_radius  quadrotor_multi.py:101-112, quadrotor_multi_rewards.py:210-211
- *   qs_episode_stats         infos[i]['episode_extra_stats']       gym_art/quadrotor_multi/quadrotor_multi.py:739-831
+ *   qs_episode_stats         infos[i]['episode_extra_stats'] summed over a rollout   gym_art/quadrotor_multi/quadrotor_multi.py:739-831
+ *   qs_episode_records       infos[i]['episode_extra_stats'] per finished episode    (same lines)
  *
  * Conventions
  *   - plain C types only; all device pointers are raw CUDA device addresses (e.g. torch tensor.data_ptr()).
@@ -275,6 +276,30 @@ typedef struct qs_stats {
     double  reward_sum;           /* sum of all per-agent rewards of finished episodes */
 } qs_stats;
 
+/* Per-episode record: what the reference puts in infos[i]['episode_extra_stats'] when an episode ends
+ * (quadrotor_multi.py:739-831, quadrotor_multi_rewards.py:886-978).  One row of QS_ER_COUNT int32 per env, describing the LAST
+ * episode that env finished, plus one float4 per drone.  QS_ER_SEQ counts the episodes the env has finished since creation, so
+ * a reader can tell a fresh record from an old one; the VecEnv layer reads the rows of the envs whose done flag is set. */
+enum { QS_ER_SEQ = 0,                 /* episodes finished by this env so far (0: no record yet) */
+       QS_ER_SCENARIO = 1,            /* QS_SCENARIO_* of the finished episode -> the f'{scenario_name}/...' keys */
+       QS_ER_NUM_COLLISIONS = 2,      /* num_collisions */
+       QS_ER_COLLISIONS_AFTER_SETTLE = 3,
+       QS_ER_COLLISIONS_FINAL_5S = 4,
+       QS_ER_COLLISIONS_ROOM = 5, QS_ER_COLLISIONS_FLOOR = 6, QS_ER_COLLISIONS_WALL = 7, QS_ER_COLLISIONS_CEILING = 8,
+       QS_ER_COLLISIONS_OBST = 9,     /* num_collisions_obst_quad */
+       QS_ER_COLLISIONS_OBST_AFTER_SETTLE = 10,
+       QS_ER_AGENTS_SUCCESS = 11,     /* metric/agent_success_rate * K */
+       QS_ER_AGENTS_DEADLOCK = 12,    /* metric/agent_deadlock_rate * K */
+       QS_ER_AGENTS_COLLIDED = 13,    /* metric/agent_col_rate * K */
+       QS_ER_AGENTS_NEIGHBOR_COL = 14,/* metric/agent_neighbor_col_rate * K */
+       QS_ER_AGENTS_OBST_COL = 15,    /* metric/agent_obst_col_rate * K */
+       QS_ER_EP_LEN = 16,             /* control steps of the episode */
+       QS_ER_SUCCESS = 17,            /* fork mode: reset_info["success"]; upstream: 0 */
+       QS_ER_NONFINITE = 18,          /* the episode was cut because a NaN/Inf appeared */
+       QS_ER_COUNT = 20 };
+/* per-drone part: { distance_to_goal_1s, distance_to_goal_3s, distance_to_goal_5s, 0 } of the finished episode.  The fork env
+ * never fills its distance log (quadrotor_multi_rewards.py:797 is commented out), so there the three are NaN as in the reference. */
+
 typedef struct qs_env qs_env;
 
 size_t      qs_config_size(void);     /* sizeof(qs_config), for binding self-checks */
@@ -329,6 +354,12 @@ int qs_set_param(qs_env *env, int key, double value);
 
 /* copies the aggregate episode statistics to *out (host); synchronises `stream`.  reset != 0 zeroes them. */
 int qs_episode_stats(qs_env *env, qs_stats *out, int reset, void *stream);
+
+/* Per-episode records (QS_ER_*).  env_rec: int32 [N, QS_ER_COUNT]; agent_rec: float [N*K, 4]; either may be NULL.
+ * qs_episode_records copies device-to-device on `stream` without synchronising; the _host variant copies to host memory and
+ * returns after the stream has drained. */
+int qs_episode_records(qs_env *env, int32_t *env_rec, float *agent_rec, void *stream);
+int qs_episode_records_host(qs_env *env, int32_t *env_rec_host, float *agent_rec_host, void *stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ def lib():
         L.qo_set_obstacles.argtypes = [C.c_void_p, dp, C.c_int]
         L.qo_get_obstacles.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int)]
         L.qo_get_stats.argtypes = [C.c_void_p, C.POINTER(QsStatsC)]
+        L.qo_get_record.argtypes = [C.c_void_p, C.c_void_p, dp]
         L.qo_get_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.qo_set_param.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.qo_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
@@ -204,6 +205,12 @@ class OracleEnv:
         s = QsStatsC()
         lib().qo_get_stats(self.h, C.byref(s))
         return s.as_dict()
+
+    def record(self):
+        """(env_rec int32 [QS_ER_COUNT], agent_rec float64 [K, 4]) of the last finished episode (include/quadsim.h QS_ER_*)."""
+        env_rec, agent_rec = np.zeros(20, dtype=np.int32), np.zeros((self.K, 4))
+        lib().qo_get_record(self.h, _vp(env_rec), _dp(agent_rec))
+        return env_rec, agent_rec
 
     def diag(self):
         new_pairs = np.zeros(self.K, dtype=np.uint32)

@@ -86,6 +86,9 @@ typedef struct qo_env {
     int col_room, col_floor, col_wall, col_ceiling;
     int obst_col_per_episode, obst_col_after_settle;
     qs_stats stats;
+    /* record of the last finished episode: infos[i]['episode_extra_stats'] (QS_ER_* layout of include/quadsim.h) */
+    int32_t ep_rec[QS_ER_COUNT];
+    double ep_agent[QS_MAX_AGENTS][4];
     /* last-step diagnostics for tests */
     uint32_t last_new_pairs[QS_MAX_AGENTS];
     int32_t last_neighbors[QS_MAX_AGENTS][QS_MAX_AGENTS];
@@ -752,6 +755,27 @@ static void env_reset(qo_env *e, double *obs)
     }
 }
 
+/* infos[i]['episode_extra_stats'] of the episode that just ended (quadrotor_multi.py:739-831), in the QS_ER_* layout */
+static void write_episode_record(qo_env *e, int ep_len, int success, int nonfinite)
+{
+    int32_t *r = e->ep_rec;
+    int K = e->K, n_succ = 0, n_dead = 0, n_col = 0, n_ncol = 0, n_ocol = 0;
+    for (int i = 0; i < K; ++i) {
+        const qo_drone *q = &e->d[i];
+        int ok = q->col_agent_ok && q->col_obst_ok;
+        n_succ += ok && q->reached_goal; n_dead += ok && !q->reached_goal; n_col += !ok;
+        n_ncol += !q->col_agent_ok; n_ocol += !q->col_obst_ok;
+    }
+    r[QS_ER_SEQ] += 1; r[QS_ER_SCENARIO] = e->scenario_now;
+    r[QS_ER_NUM_COLLISIONS] = e->collisions_per_episode; r[QS_ER_COLLISIONS_AFTER_SETTLE] = e->collisions_after_settle;
+    r[QS_ER_COLLISIONS_FINAL_5S] = e->collisions_final_5s; r[QS_ER_COLLISIONS_ROOM] = e->col_room; r[QS_ER_COLLISIONS_FLOOR] = e->col_floor;
+    r[QS_ER_COLLISIONS_WALL] = e->col_wall; r[QS_ER_COLLISIONS_CEILING] = e->col_ceiling; r[QS_ER_COLLISIONS_OBST] = e->obst_col_per_episode;
+    r[QS_ER_COLLISIONS_OBST_AFTER_SETTLE] = e->obst_col_after_settle;
+    r[QS_ER_AGENTS_SUCCESS] = n_succ; r[QS_ER_AGENTS_DEADLOCK] = n_dead; r[QS_ER_AGENTS_COLLIDED] = n_col;
+    r[QS_ER_AGENTS_NEIGHBOR_COL] = n_ncol; r[QS_ER_AGENTS_OBST_COL] = n_ocol;
+    r[QS_ER_EP_LEN] = ep_len; r[QS_ER_SUCCESS] = success; r[QS_ER_NONFINITE] = nonfinite;
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* QuadrotorEnvMulti.step, quadrotor_multi.py:521-842                                                 */
 /* ------------------------------------------------------------------------------------------------ */
@@ -898,13 +922,15 @@ static void env_step(qo_env *e, const double *actions, double *obs, double *rew,
         s->num_collisions_with_floor += e->col_floor; s->num_collisions_with_wall += e->col_wall;
         s->num_collisions_with_ceiling += e->col_ceiling; s->num_collisions_obst_quad += e->obst_col_per_episode;
         s->num_collisions_obst_quad_after_settle += e->obst_col_after_settle;
+        write_episode_record(e, tick, 0, 0);
         for (int i = 0; i < K; ++i) {
             qo_drone *q = &e->d[i];
             int ok = q->col_agent_ok && q->col_obst_ok;
             s->agents_success += ok && q->reached_goal; s->agents_deadlock += ok && !q->reached_goal; s->agents_collided += !ok;
-            if (q->n1) s->distance_to_goal_1s += (1.0 / c->dt) * q->sum1 / q->n1;
-            if (q->n3) s->distance_to_goal_3s += (1.0 / c->dt) * q->sum3 / q->n3;
-            if (q->n5) s->distance_to_goal_5s += (1.0 / c->dt) * q->sum5 / q->n5;
+            double d1 = q->n1 ? (1.0 / c->dt) * q->sum1 / q->n1 : 0.0, d3 = q->n3 ? (1.0 / c->dt) * q->sum3 / q->n3 : 0.0,
+                   d5 = q->n5 ? (1.0 / c->dt) * q->sum5 / q->n5 : 0.0;
+            s->distance_to_goal_1s += d1; s->distance_to_goal_3s += d3; s->distance_to_goal_5s += d5;
+            e->ep_agent[i][0] = d1; e->ep_agent[i][1] = d3; e->ep_agent[i][2] = d5; e->ep_agent[i][3] = 0.0;
             s->reward_sum += q->ep_reward;
         }
         env_reset(e, obs);                                        /* :836 */
@@ -925,6 +951,7 @@ qo_env *qo_create(const qs_config *cfg, int env_index)
     e->K = cfg->num_agents;
     e->gid = (uint32_t)(cfg->env_id_offset + env_index);
     e->approach_metric = cfg->approach_goal_metric;
+    e->scenario_now = cfg->scenario;
     for (int i = 0; i < e->K; ++i) { double I[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }; memcpy(e->d[i].rot, I, sizeof(I)); e->d[i].col_agent_ok = e->d[i].col_obst_ok = 1; }
     return e;
 }
@@ -1058,6 +1085,11 @@ int qo_generate_goals(int formation, double size, int n, const double *center, d
 void qo_set_obstacles(qo_env *e, const double *xy, int n) { e->n_obst = n; for (int m = 0; m < n; ++m) { e->obst_xy[m][0] = xy[2 * m]; e->obst_xy[m][1] = xy[2 * m + 1]; } }
 void qo_get_obstacles(const qo_env *e, double *xy, int *n) { *n = e->n_obst; for (int m = 0; m < e->n_obst; ++m) { xy[2 * m] = e->obst_xy[m][0]; xy[2 * m + 1] = e->obst_xy[m][1]; } }
 void qo_get_stats(const qo_env *e, qs_stats *out) { *out = e->stats; }
+void qo_get_record(const qo_env *e, int32_t *env_rec, double *agent_rec)
+{
+    memcpy(env_rec, e->ep_rec, sizeof(e->ep_rec));
+    for (int i = 0; i < e->K; ++i) memcpy(agent_rec + 4 * i, e->ep_agent[i], sizeof(double) * 4);
+}
 void qo_get_diag(const qo_env *e, uint32_t *new_pairs, int32_t *neighbors, int32_t *impulse_flag)
 {
     for (int i = 0; i < e->K; ++i) {

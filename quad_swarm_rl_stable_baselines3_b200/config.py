@@ -22,6 +22,51 @@ SCENARIOS = {"static_same_goal": 0, "o_mix": 1, "o_random": 2, "o_static_same_go
 FORMATION_SCENARIOS = ("static_same_goal", "static_diff_goal", "dynamic_same_goal", "dynamic_diff_goal", "swap_goals",
                        "dynamic_formations", "mix", "ep_lissajous3D", "ep_rand_bezier", "swarm_vs_swarm")
 QS_SC_COUNT = 24       # floats per env of formation-scenario state (include/quadsim.h QS_SC_*)
+SCENARIO_NAMES = {v: k for k, v in SCENARIOS.items()}
+# qs_episode_records layout (include/quadsim.h QS_ER_*)
+QS_ER_COUNT = 20
+ER = dict(seq=0, scenario=1, num_collisions=2, num_collisions_after_settle=3, num_collisions_final_5_s=4,
+          num_collisions_with_room=5, num_collisions_with_floor=6, num_collisions_with_wall=7, num_collisions_with_ceiling=8,
+          num_collisions_obst_quad=9, num_collisions_obst_quad_after_settle=10, agents_success=11, agents_deadlock=12,
+          agents_collided=13, agents_neighbor_col=14, agents_obst_col=15, ep_len=16, success=17, nonfinite=18)
+
+
+def episode_extra_stats(env_rec, agent_rec, num_agents: int, use_obstacles: bool) -> dict:
+    """infos[i]['episode_extra_stats'] of the reference (quadrotor_multi.py:739-831, quadrotor_multi_rewards.py:886-978) for one
+    agent, from the env's record row (`env_rec`, QS_ER_COUNT ints) and that agent's row of the per-drone part (`agent_rec`)."""
+    name = SCENARIO_NAMES.get(int(env_rec[ER["scenario"]]), "unknown")
+    if name == "o_mix":
+        name = "mix"
+    K = float(num_agents)
+    d1, d3, d5 = (float(agent_rec[0]), float(agent_rec[1]), float(agent_rec[2]))
+    g = lambda k: int(env_rec[ER[k]])  # noqa: E731
+    s = {
+        "num_collisions": g("num_collisions"),
+        "num_collisions_with_room": g("num_collisions_with_room"),
+        "num_collisions_with_floor": g("num_collisions_with_floor"),
+        "num_collisions_with_wall": g("num_collisions_with_wall"),
+        "num_collisions_with_ceiling": g("num_collisions_with_ceiling"),
+        "num_collisions_after_settle": g("num_collisions_after_settle"),
+        f"{name}/num_collisions": g("num_collisions_after_settle"),
+        "num_collisions_final_5_s": g("num_collisions_final_5_s"),
+        f"{name}/num_collisions_final_5_s": g("num_collisions_final_5_s"),
+        "distance_to_goal_1s": d1, "distance_to_goal_3s": d3, "distance_to_goal_5s": d5,
+        f"{name}/distance_to_goal_1s": d1, f"{name}/distance_to_goal_3s": d3, f"{name}/distance_to_goal_5s": d5,
+    }
+    if use_obstacles:
+        s["num_collisions_obst_quad"] = g("num_collisions_obst_quad")
+        s["num_collisions_obst_quad_after_settle"] = g("num_collisions_obst_quad_after_settle")
+        s[f"{name}/num_collisions_obst"] = g("num_collisions_obst_quad")
+        # distance_to_goal_3_5 / distance_to_goal_5 are zeroed at reset and never updated in the reference (:493-494)
+        s["num_collisions_obst_quad_3_5"] = s[f"{name}/num_collisions_obst_quad_3_5"] = 0
+        s["num_collisions_obst_quad_5"] = s[f"{name}/num_collisions_obst_quad_5"] = 0
+    for key, col in (("agent_success_rate", "agents_success"), ("agent_deadlock_rate", "agents_deadlock"),
+                     ("agent_col_rate", "agents_collided"), ("agent_neighbor_col_rate", "agents_neighbor_col"),
+                     ("agent_obst_col_rate", "agents_obst_col")):
+        s["metric/" + key] = s[f"{name}/{key}"] = g(col) / K
+    return s
+
+
 ENV_MODES = {"upstream": 0, "fork": 1}
 OBS_REPR = {"xyz_vxyz_R_omega": 0, "xyz_vxyz_R_omega_floor": 1, "xyz_vxyz_R_omega_wall": 2,
             "cdist_cdistdot_dist_distdot_angle_angledot": 3, "cdist_cdistdot_dist_distdot_sangle_angledot": 4,

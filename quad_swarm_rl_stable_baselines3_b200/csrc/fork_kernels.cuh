@@ -473,6 +473,8 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         __syncwarp();
     }
     // ---- episode counters: accumulate, and on done flush to the aggregate and reset (the VecEnv worker's env.reset())
+    uint32_t b_col = 0u;
+    if (any_done) b_col = __ballot_sync(gmask, valid && (q.flags & F_COL_AGENT)) & gmask;
     if (env_ok && d == 0) {
         int *pe = P.ecnt + env * EC_COUNT;
         if (any_done) {
@@ -486,7 +488,18 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
             atomicAdd((unsigned long long *)&st->num_collisions_with_floor, (unsigned long long)(pe[EC_FLOOR] + ec[EC_FLOOR]));
             atomicAdd((unsigned long long *)&st->num_collisions_with_wall, (unsigned long long)(pe[EC_WALL] + ec[EC_WALL]));
             atomicAdd((unsigned long long *)&st->num_collisions_with_ceiling, (unsigned long long)(pe[EC_CEIL] + ec[EC_CEIL]));
+            atomicAdd((unsigned long long *)&st->agents_collided, (unsigned long long)__popc(b_col));
             if (bad_any) atomicAdd((unsigned long long *)&st->nonfinite_resets, 1ull);
+            // per-episode record (infos[i]['episode_extra_stats'], quadrotor_multi_rewards.py:886-978): the fork env never marks a
+            // goal as reached (its distance log is commented out, :797), so every collision-free agent counts as deadlocked
+            int *er = P.ep_rec + (size_t)env * QS_ER_COUNT;
+            er[QS_ER_SEQ] += 1;
+            er[QS_ER_SCENARIO] = QS_SCENARIO_DYNAMIC_REPULSIVE;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) er[QS_ER_NUM_COLLISIONS + k] = pe[k] + ec[k];
+            er[QS_ER_AGENTS_SUCCESS] = 0; er[QS_ER_AGENTS_DEADLOCK] = c.K - __popc(b_col); er[QS_ER_AGENTS_COLLIDED] = __popc(b_col);
+            er[QS_ER_AGENTS_NEIGHBOR_COL] = __popc(b_col); er[QS_ER_AGENTS_OBST_COL] = 0;
+            er[QS_ER_EP_LEN] = tick; er[QS_ER_SUCCESS] = (fflags & FF_SUCCESS) ? 1 : 0; er[QS_ER_NONFINITE] = bad_any ? 1 : 0;
 #pragma unroll
             for (int k = 0; k < EC_COUNT; ++k) pe[k] = 0;
             if (reset_success != nullptr) reset_success[env] = (fflags & FF_SUCCESS) ? 1 : 0;
@@ -496,8 +509,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         }
     }
     if (any_done) {
-        const uint32_t b_col = __ballot_sync(gmask, valid && (q.flags & F_COL_AGENT)) & gmask;
-        if (env_ok && d == 0) atomicAdd((unsigned long long *)&P.stats->agents_collided, (unsigned long long)__popc(b_col));
+        if (valid) P.ep_agent[gi] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), 0.f);
         // ---- QuadrotorEnvMulti.reset (quadrotor_multi_rewards.py:541-629) + Scenario_dynamic_repulsive.reset (:66-82)
         if (bad_any) {
 #pragma unroll

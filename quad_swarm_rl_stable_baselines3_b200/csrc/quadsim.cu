@@ -404,6 +404,8 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     size_t o_ecnt = off; off += align((size_t)N * EC_COUNT * sizeof(int));
     size_t o_obst = off; off += align((cfg->use_obstacles ? (size_t)N * QS_MAX_OBSTACLES : 1) * sizeof(float2));
     size_t o_scen = off; off += align((scen_feat ? (size_t)N * QS_SC_COUNT : 1) * sizeof(float));
+    size_t o_erec = off; off += align((size_t)N * QS_ER_COUNT * sizeof(int));
+    size_t o_eagent = off; off += align(nd * sizeof(float4));
     size_t o_stats = off; off += align(sizeof(qs_stats));
     size_t fplane_off[FP_COUNT] = {0}, o_evader = 0, o_fflags = 0;
     if (e->fork) {
@@ -421,6 +423,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     e->dp.tick = (int *)(b + o_tick); e->dp.svd_ctr = (int *)(b + o_svd); e->dp.step_ctr = (uint32_t *)(b + o_step);
     e->dp.ecnt = (int *)(b + o_ecnt); e->dp.obst_xy = (float2 *)(b + o_obst); e->dp.stats = (qs_stats *)(b + o_stats);
     e->dp.scen = scen_feat ? (float4 *)(b + o_scen) : nullptr;
+    e->dp.ep_rec = (int *)(b + o_erec); e->dp.ep_agent = (float4 *)(b + o_eagent);
     if (e->fork) {
         for (int p = 0; p < FP_COUNT; ++p) e->fp.plane[p] = (float4 *)(b + fplane_off[p]);
         e->fp.evader = (float2 *)(b + o_evader); e->fp.flags = (int *)(b + o_fflags);
@@ -626,6 +629,29 @@ int qs_episode_stats(qs_env *e, qs_stats *out, int reset, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     QS_CUDA(e, cudaMemcpyAsync(out, e->dp.stats, sizeof(qs_stats), cudaMemcpyDeviceToHost, s));
     if (reset) QS_CUDA(e, cudaMemsetAsync(e->dp.stats, 0, sizeof(qs_stats), s));
+    QS_CUDA(e, cudaStreamSynchronize(s));
+    return QS_OK;
+}
+
+int qs_episode_records(qs_env *e, int32_t *env_rec, float *agent_rec, void *stream)
+{
+    if (!e) return fail(e, QS_ERR_NULL, "qs_episode_records: null handle");
+    DeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)e->cfg.num_envs, nd = N * e->cfg.num_agents;
+    if (env_rec) QS_CUDA(e, cudaMemcpyAsync(env_rec, e->dp.ep_rec, N * QS_ER_COUNT * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (agent_rec) QS_CUDA(e, cudaMemcpyAsync(agent_rec, e->dp.ep_agent, nd * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+    return QS_OK;
+}
+
+int qs_episode_records_host(qs_env *e, int32_t *env_rec_host, float *agent_rec_host, void *stream)
+{
+    if (!e) return fail(e, QS_ERR_NULL, "qs_episode_records_host: null handle");
+    DeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)e->cfg.num_envs, nd = N * e->cfg.num_agents;
+    if (env_rec_host) QS_CUDA(e, cudaMemcpyAsync(env_rec_host, e->dp.ep_rec, N * QS_ER_COUNT * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (agent_rec_host) QS_CUDA(e, cudaMemcpyAsync(agent_rec_host, e->dp.ep_agent, nd * sizeof(float4), cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaStreamSynchronize(s));
     return QS_OK;
 }

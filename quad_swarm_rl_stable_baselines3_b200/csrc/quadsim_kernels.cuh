@@ -60,6 +60,8 @@ struct DevPtrs {
     int *ecnt;                 // [N, EC_COUNT]
     float2 *obst_xy;           // [N, QS_MAX_OBSTACLES]
     float4 *scen;              // [N, QS_SC_COUNT / 4] formation-scenario rows (formation scenarios only, else null)
+    int *ep_rec;               // [N, QS_ER_COUNT] record of the last finished episode per env (QS_ER_*)
+    float4 *ep_agent;          // [N*K] per-drone part of that record
     qs_stats *stats;           // device aggregate
 };
 
@@ -1219,9 +1221,23 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
                 float4 sums = valid ? P.plane[PL_DIST_SUMS][gi] : make_float4(0.f, 0.f, 0.f, 0.f);
                 float inv_dt = 1.0f / c.dt;
                 float m1 = inv_dt * sums.x / (float)min(100, tick), m3 = inv_dt * sums.y / (float)min(300, tick), m5 = inv_dt * sums.z / (float)min(500, tick);
+                // per-episode record (infos[i]['episode_extra_stats'], :739-831): per-drone part, then the env row below
+                if (valid) P.ep_agent[gi] = make_float4(m1, m3, m5, 0.f);
+                const uint32_t b_ncol = __ballot_sync(gmask, (q.flags & F_COL_AGENT) && valid) & gmask;
+                const uint32_t b_ocol = __ballot_sync(gmask, (q.flags & F_COL_OBST) && valid) & gmask;
 #pragma unroll
                 for (int off = KG / 2; off > 0; off >>= 1) {
                     m1 += __shfl_xor_sync(gmask, m1, off); m3 += __shfl_xor_sync(gmask, m3, off); m5 += __shfl_xor_sync(gmask, m5, off);
+                }
+                if (valid && d == 0) {
+                    int *er = P.ep_rec + (size_t)env * QS_ER_COUNT;
+                    er[QS_ER_SEQ] += 1;
+                    er[QS_ER_SCENARIO] = OBST ? scen_now : (SCEN ? (int)P.scen[(size_t)env * (QS_SC_COUNT / 4)].x : QS_SCENARIO_STATIC_SAME_GOAL);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) er[QS_ER_NUM_COLLISIONS + k] = ec[k];
+                    er[QS_ER_AGENTS_SUCCESS] = __popc(b_succ); er[QS_ER_AGENTS_DEADLOCK] = __popc(b_dead); er[QS_ER_AGENTS_COLLIDED] = __popc(b_col);
+                    er[QS_ER_AGENTS_NEIGHBOR_COL] = __popc(b_ncol); er[QS_ER_AGENTS_OBST_COL] = __popc(b_ocol);
+                    er[QS_ER_EP_LEN] = tick; er[QS_ER_SUCCESS] = 0; er[QS_ER_NONFINITE] = bad_ballot ? 1 : 0;
                 }
                 if (valid && d == 0) {
                     atomicAdd((unsigned long long *)&st->episodes, 1ull);

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from .config import PARAM_KEYS, QS_SC_COUNT, QsStateViewC, QsStatsC, QuadSimConfig
+from .config import PARAM_KEYS, QS_ER_COUNT, QS_SC_COUNT, QsStateViewC, QsStatsC, QuadSimConfig
 
 _STATE_SHAPES = {"pos": (3, torch.float32), "vel": (3, torch.float32), "rot": (9, torch.float32),
                  "omega": (3, torch.float32), "rot_damp": (4, torch.float32), "cmds_damp": (4, torch.float32),
@@ -208,6 +208,25 @@ class QuadSwarmSim:
             rc = self._lib.qs_set_state(self._h, C.byref(v), self._stream())
         _capi.check(self._h, rc, "qs_set_state")
         torch.cuda.current_stream(self.device).synchronize()
+
+    def episode_records(self) -> Dict[str, torch.Tensor]:
+        """Record of the last finished episode per env (QS_ER_* rows, include/quadsim.h) as CUDA tensors:
+        {"env": int32 [N, QS_ER_COUNT], "agent": float32 [N*K, 4]}.  No host synchronisation."""
+        env = torch.empty((self.N, QS_ER_COUNT), dtype=torch.int32, device=self.device)
+        agent = torch.empty((self.N * self.K, 4), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.qs_episode_records(self._h, env.data_ptr(), agent.data_ptr(), self._stream())
+        _capi.check(self._h, rc, "qs_episode_records")
+        return {"env": env, "agent": agent}
+
+    def episode_records_host(self, env_out: Optional[np.ndarray] = None, agent_out: Optional[np.ndarray] = None):
+        """Same, into host arrays (allocated if not given); returns (env_rec [N, QS_ER_COUNT] int32, agent_rec [N*K, 4] float32)."""
+        env = np.empty((self.N, QS_ER_COUNT), dtype=np.int32) if env_out is None else env_out
+        agent = np.empty((self.N * self.K, 4), dtype=np.float32) if agent_out is None else agent_out
+        with torch.cuda.device(self.device):
+            rc = self._lib.qs_episode_records_host(self._h, env.ctypes.data, agent.ctypes.data, self._stream())
+        _capi.check(self._h, rc, "qs_episode_records_host")
+        return env, agent
 
     # parameters / stats ------------------------------------------------------------------------------
     def set_rew_coeff(self, **coeffs):

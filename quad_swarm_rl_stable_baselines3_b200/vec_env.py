@@ -23,7 +23,7 @@ from typing import Any, List, Optional, Sequence
 
 import numpy as np
 
-from .config import OBS_REPR_DIM, QuadSimConfig
+from .config import OBS_REPR_DIM, QS_ER_COUNT, QuadSimConfig, episode_extra_stats
 
 try:                                             # the real base class when SB3 is installed (it is not in the build image)
     from stable_baselines3.common.vec_env.base_vec_env import VecEnv as _SB3VecEnv
@@ -149,6 +149,10 @@ class QuadSwarmVecEnv(_Base):
         self._actions = self._host_array((n, cfg.act_dim), np.float32)
         self.reset_infos = tuple({} for _ in range(self.n_envs))
         self.capture_radius = float(cfg.fork.capture_radius)
+        # per-episode records -> infos[i]['episode_extra_stats']; fetched only on steps where some env finished
+        self.episode_infos = hasattr(sim, "episode_records_host")
+        self._erec = np.zeros((self.n_envs, QS_ER_COUNT), dtype=np.int32)
+        self._arec = np.zeros((n, 4), dtype=np.float32)
 
     @classmethod
     def from_reference_cfg(cls, rcfg, num_envs: int, device=None, **kw):
@@ -197,10 +201,17 @@ class QuadSwarmVecEnv(_Base):
         shared: dict = {}
         infos: List[dict] = [shared] * self.num_envs
         reset_infos: List[Optional[dict]] = [None] * self.n_envs
-        for e in np.flatnonzero(env_done):
+        finished = np.flatnonzero(env_done)
+        if finished.size and self.episode_infos:
+            # infos[i]['episode_extra_stats'] of the episodes that just ended (quadrotor_multi.py:739-831)
+            self.sim.episode_records_host(self._erec, self._arec)
+        for e in finished:
             reset_infos[e] = {"success": bool(self._succ[e])} if self.cfg.env_mode == "fork" else {}
             for k in range(K):
-                infos[e * K + k] = {"terminal_observation": self._term[e * K + k].copy()}
+                info = {"terminal_observation": self._term[e * K + k].copy()}
+                if self.episode_infos:
+                    info["episode_extra_stats"] = episode_extra_stats(self._erec[e], self._arec[e * K + k], K, self.cfg.use_obstacles)
+                infos[e * K + k] = info
         self.reset_infos = tuple(reset_infos)
         return obs, rews, dones, infos
 

@@ -133,7 +133,7 @@ def gen_traces(traces=None, tape_seed=1234, compact=False):
         env = rh.make_upstream_env(tape=tape, **spec["env"])
         rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
         rec = {k: [] for k in ("actions", "obs", "rew", "done", "tn", "tu", "tc", "n_tn", "n_tu", "n_tc", "tick",
-                               "obst_xy", "scenario", "ep_stats", "ep_step", "sc_row")}
+                               "obst_xy", "scenario", "ep_stats", "ep_step", "sc_row", "ep_detail", "ep_scenario")}
         snaps = {k: [] for k in STATE_KEYS}
 
         def push_tape(m):
@@ -195,6 +195,14 @@ def gen_traces(traces=None, tape_seed=1234, compact=False):
                     round(e0["metric/agent_col_rate"] * K),
                     sum(x["distance_to_goal_1s"] for x in es), sum(x["distance_to_goal_3s"] for x in es),
                     sum(x["distance_to_goal_5s"] for x in es)])
+                if compact:
+                    # the whole record per agent: distances, the two extra rates and the scenario the keys are prefixed with
+                    sname = env.scenario.name()[9:] if False else [k for k in e0 if k.endswith("/agent_success_rate") and not k.startswith("metric/")][0].split("/")[0]
+                    rec["ep_detail"].append(np.array([[x["distance_to_goal_1s"], x["distance_to_goal_3s"], x["distance_to_goal_5s"],
+                                                       x["metric/agent_neighbor_col_rate"], x["metric/agent_obst_col_rate"],
+                                                       x[f"{sname}/distance_to_goal_3s"], x[f"{sname}/num_collisions"]] for x in es]))
+                    rec["ep_scenario"].append(sname)
+                    rec["ep_keys"] = sorted(k.replace(sname, "<scenario>") for k in e0)
         out = dict(
             actions=np.array(rec["actions"]), obs=np.array(rec["obs"]), rew=np.array(rec["rew"]),
             done=np.array(rec["done"]), tick=np.array(rec["tick"]),
@@ -210,6 +218,9 @@ def gen_traces(traces=None, tape_seed=1234, compact=False):
         if compact:
             out["scenario"] = np.array(rec["scenario"])
             out["sc_row"] = np.array(rec["sc_row"])
+            out["ep_detail"] = np.array(rec["ep_detail"])
+            out["ep_scenario"] = np.array(rec["ep_scenario"])
+            out["ep_keys"] = np.array(rec["ep_keys"])
             out["obs"] = out["obs"].astype(np.float32)
             out["actions"] = out["actions"].astype(np.float32)
             for k in ("on_floor", "crashed_floor", "crashed_wall", "crashed_ceiling"):

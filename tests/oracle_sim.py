@@ -34,6 +34,13 @@ class OracleSim:
                     reset_success[e] = int(bool(o.last_reset_success))
         return obs, rew, done.view(np.bool_)
 
+    def episode_records_host(self, env_out=None, agent_out=None):
+        env = np.empty((self.N, 20), np.int32) if env_out is None else env_out
+        agent = np.empty((self.N * self.K, 4), np.float32) if agent_out is None else agent_out
+        for e, o in enumerate(self.envs):
+            env[e], agent[e * self.K:(e + 1) * self.K] = o.record()
+        return env, agent
+
     def set_capture_radius(self, v):
         for o in self.envs:
             o.set_param(PARAM_KEYS["capture_radius"], float(v))

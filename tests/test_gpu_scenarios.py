@@ -80,7 +80,8 @@ def test_scenario_parity(name):
             # jump to just before the 5 s resampling of the Bezier arc (tick % 500 == 0)
             sim.set_state(tick=torch.full((N,), 496, dtype=torch.int32))
 
-    worst, cnt = run_parity("scen_" + name, cfg, sim, oracles, "hover", steps, hook)
+    # the Bezier test jumps the tick forward, which breaks the fixed-length-episode assumption of the distance windows
+    worst, cnt = run_parity("scen_" + name, cfg, sim, oracles, "hover", steps, hook, check_records=not name.startswith("bezier"))
     assert worst["goal"] <= 3e-6
     if not name.startswith("static") and not name.startswith("bezier"):
         assert cnt["done"] >= N

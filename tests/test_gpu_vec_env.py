@@ -38,6 +38,10 @@ def test_fork_vec_env_on_gpu_matches_oracle_backed_facade():
             if "terminal_observation" in i1:
                 n_reset += 1
                 np.testing.assert_allclose(i1["terminal_observation"], i2["terminal_observation"], atol=2e-3)
+                e1, e2 = i1["episode_extra_stats"], i2["episode_extra_stats"]      # quadrotor_multi_rewards.py:886-978
+                assert set(e1) == set(e2) and "dynamic_repulsive/agent_col_rate" in e1
+                for k in e1:
+                    assert (np.isnan(e1[k]) and np.isnan(e2[k])) or abs(e1[k] - e2[k]) < 1e-6, (k, e1[k], e2[k])
     assert n_reset > 0
     gpu.env_method("set_capture_radius", 0.4)
     assert gpu.get_attr("capture_radius") == [0.4] * cfg.num_envs
@@ -65,6 +69,9 @@ def test_upstream_vec_env_tensor_and_host_faces_agree():
             term = b_env.sim.terminal_obs.cpu().numpy()
             for r in rows[:8]:
                 assert np.array_equal(infos[r]["terminal_observation"], term[r])
+                es = infos[r]["episode_extra_stats"]
+                assert es["num_collisions"] >= es["num_collisions_after_settle"] >= 0 and es["distance_to_goal_1s"] > 0
+                assert abs(es["metric/agent_success_rate"] + es["metric/agent_deadlock_rate"] + es["metric/agent_col_rate"] - 1.0) < 1e-6
     assert dones >= 1
     st = a_env.sim.episode_stats(reduce=True)
     assert st["episodes"] >= cfg.num_envs

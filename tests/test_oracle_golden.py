@@ -11,7 +11,7 @@ import pytest
 
 from oracle import OracleEnv
 from quad_swarm_rl_stable_baselines3_b200 import quad_model
-from quad_swarm_rl_stable_baselines3_b200.config import QuadSimConfig
+from quad_swarm_rl_stable_baselines3_b200.config import QuadSimConfig, episode_extra_stats
 
 PHYS = ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou")
 
@@ -199,6 +199,22 @@ def test_env_trace(golden_dir, name):
             np.testing.assert_allclose(delta[12:], ep_rows[s][12:], rtol=1e-9, atol=1e-9, err_msg=f"step {s} distance_to_goal windows")
             assert cur["episodes"] - prev_stats["episodes"] == 1
             prev_stats = cur
+            # the per-episode record -> the dict the VecEnv layer hands out as infos[i]['episode_extra_stats']
+            env_rec, agent_rec = o.record()
+            ep_i = list(ep_rows).index(s)
+            assert env_rec[0] == ep_i + 1 and env_rec[16] == cfg.ep_len + 1
+            np.testing.assert_array_equal(env_rec[2:14], ep_rows[s][:12].astype(np.int32))
+            np.testing.assert_allclose(agent_rec[:, :3].sum(axis=0), ep_rows[s][12:], rtol=1e-9, atol=1e-9)
+            if compact:
+                det, sname = g["ep_detail"][ep_i], str(g["ep_scenario"][ep_i])
+                for i in range(K):
+                    d = episode_extra_stats(env_rec, agent_rec[i], K, cfg.use_obstacles)
+                    assert sorted(k.replace(sname, "<scenario>") for k in d) == list(g["ep_keys"]), sorted(d)
+                    ref_vals = dict(zip(("distance_to_goal_1s", "distance_to_goal_3s", "distance_to_goal_5s",
+                                         "metric/agent_neighbor_col_rate", "metric/agent_obst_col_rate",
+                                         f"{sname}/distance_to_goal_3s", f"{sname}/num_collisions"), det[i]))
+                    for k, v in ref_vals.items():
+                        assert abs(d[k] - v) <= 1e-9 * max(1.0, abs(v)), (s, i, k, d[k], v)
     assert n_done >= 1
     assert not ep_rows or len(ep_rows) == n_done
     if name in ("smallroom_k8", "crowd_k16", "cfg3_obst_k8"):

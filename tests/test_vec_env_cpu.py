@@ -80,7 +80,36 @@ def test_upstream_vec_env_matches_direct_oracle():
         if done.any():
             n_done += 1
             assert all(r == {} for r in env.reset_infos)
+            # infos[i]['episode_extra_stats'] with the reference's keys (quadrotor_multi.py:739-831)
+            for i in (0, 7, 23):
+                es = infos[i]["episode_extra_stats"]
+                assert {"num_collisions", "num_collisions_after_settle", "static_same_goal/num_collisions", "distance_to_goal_1s",
+                        "static_same_goal/distance_to_goal_5s", "metric/agent_success_rate", "metric/agent_col_rate",
+                        "static_same_goal/agent_deadlock_rate", "metric/agent_neighbor_col_rate"} <= set(es)
+                assert "num_collisions_obst_quad" not in es
+                assert abs(es["metric/agent_success_rate"] + es["metric/agent_deadlock_rate"] + es["metric/agent_col_rate"] - 1.0) < 1e-12
+                assert es["distance_to_goal_1s"] > 0 and es["distance_to_goal_1s"] == es["static_same_goal/distance_to_goal_1s"]
+            assert infos[0]["episode_extra_stats"]["distance_to_goal_1s"] != infos[1]["episode_extra_stats"]["distance_to_goal_1s"]
     assert n_done >= 1
+    # the per-episode records add up to the rollout aggregate
+    tot = env.sim.episode_stats()
+    assert tot["episodes"] == n_done * cfg.num_envs
+
+
+def test_mix_vec_env_infos_name_the_scenario_of_the_episode():
+    cfg = QuadSimConfig(num_envs=6, num_agents=4, quads_mode="mix", neighbor_visible_num=2, ep_time=0.05, seed=9)
+    env = QuadSwarmVecEnv(cfg, sim=OracleSim(cfg))
+    env.reset()
+    names = set()
+    for t in range(40):
+        obs, rew, done, infos = env.step(np.zeros((24, 4), np.float32))
+        for e in np.flatnonzero(done.reshape(6, 4)[:, 0]):
+            es = infos[e * 4]["episode_extra_stats"]
+            prefixed = [k.split("/")[0] for k in es if k.endswith("/agent_success_rate") and not k.startswith("metric/")]
+            assert len(prefixed) == 1
+            names.add(prefixed[0])
+    assert len(names) >= 5 and names <= {"static_same_goal", "static_diff_goal", "ep_lissajous3D", "ep_rand_bezier", "dynamic_same_goal",
+                                         "dynamic_diff_goal", "dynamic_formations", "swap_goals", "swarm_vs_swarm"}
 
 
 def test_from_reference_cfg_with_the_real_dataclass():
