@@ -1,4 +1,6 @@
 // kernels_kg.cu -- instantiates every kernel for ONE lane-group width (compile with -DQS_KG=1|2|4|8|16|32).
+#include <cstdlib>
+
 #include "launch.h"
 
 #ifndef QS_KG
@@ -10,13 +12,29 @@ namespace {
 
 constexpr int KG = QS_KG;
 
+// Shared-memory attributes of one kernel.  `block` > 0: size the shared-memory carve-out to what the resident blocks need
+// (+1 KB per block of driver reservation) and leave the rest of the unified array to L1.  The step kernels stream their state
+// (no L1 reuse) but spill a few registers at the 128-register cap; with the maximum carve-out L1 shrinks to ~28 KB, the 16
+// resident warps' stack frames do not fit and every spill reload becomes an L2 round trip (profiles/README.md, v5: 89.3 ->
+// 86.3 us).  `block` == 0 (persistent form, whose prefetch buffers need all of it): maximum carve-out.
 template <typename... Args>
-void set_attr(size_t bytes, void (*kernel)(Args...))
+void set_attr(size_t bytes, void (*kernel)(Args...), int block = 0)
 {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    // the kernels stream their state (no L1 reuse): give the whole unified L1/shared array to shared memory so that the
-    // observation tiles never limit the number of resident blocks
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int carve = cudaSharedmemCarveoutMaxShared;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (block > 0) {
+        int nblk = 0, dev = 0, smem_sm = 233472;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, kernel, block, bytes) == cudaSuccess && nblk > 0) {
+            const long long need = (long long)nblk * ((long long)bytes + 1024);
+            carve = (int)((need * 100 + smem_sm - 1) / smem_sm) + 2;
+            if (carve > 100) carve = 100;
+        }
+    }
+    if (const char *e = getenv("QS_CARVEOUT")) { int v = atoi(e); if (v >= 0 && v <= 100) carve = v; }   // tuning knob (percent of max shared)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
 }
 
 // feature sets of the upstream step kernel: bit 0 obstacles, bit 1 downwash, bit 2 formation scenarios (never with obstacles)
@@ -42,11 +60,11 @@ void prepare(int feat, size_t smem_plain, size_t smem_persist, int block, int *p
 {
     *persist_blocks_per_sm = 0;
     if (fork) {
-        set_attr(smem_plain, fork_step_kernel<KG>);
+        set_attr(smem_plain, fork_step_kernel<KG>, block);
         set_attr(smem_plain, fork_reset_kernel<KG>);
         return;
     }
-    QS_FEAT_SWITCH(feat, set_attr(smem_plain, step_kernel<KG, false, FEAT>));
+    QS_FEAT_SWITCH(feat, set_attr(smem_plain, step_kernel<KG, false, FEAT>, block));
     set_attr(smem_plain, reset_kernel<KG, false, false>);
     set_attr(smem_plain, reset_kernel<KG, true, false>);
     set_attr(smem_plain, reset_kernel<KG, false, true>);

@@ -434,7 +434,8 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     e->persist = false; e->grid_persist = 0; e->smem_persist = 0;
     {
         const size_t pf_floats = (tiles_floats + obst_floats + 3) & ~(size_t)3;
-        if (!e->fork) e->smem_persist = pf_floats * sizeof(float) + (size_t)warps * PF_SLOTS * 32 * sizeof(float4) + (size_t)warps * sizeof(uint64_t);
+        if (!e->fork) e->smem_persist = pf_floats * sizeof(float) + (size_t)warps * PF_SLOTS * 32 * sizeof(float4) + (size_t)warps * sizeof(uint64_t) +
+                                       (size_t)warps * 3 * (32 / e->KG) * sizeof(int);     // prefetch buffers, mbarriers, per-env scalars
         int per_sm = 0;
         launchers(e->KG).prepare(e->feat, e->smem_bytes, e->smem_persist, e->block, &per_sm, e->fork);
         // Measured (profiles/README.md): hiding the start-of-tile HBM latency does not pay on this kernel -- with 16 resident

@@ -160,9 +160,10 @@ struct Drone {
 
 __device__ __forceinline__ void load_drone(const DevPtrs &P, int gi, Drone &q)
 {
-    float4 a = P.plane[PL_POS_VX][gi], b = P.plane[PL_V_W][gi], c = P.plane[PL_W_R0][gi], d = P.plane[PL_R1][gi],
-           e = P.plane[PL_R2_FLAGS][gi], f = P.plane[PL_ROT_DAMP][gi], g = P.plane[PL_CMDS_DAMP][gi],
-           h = P.plane[PL_OU][gi], k = P.plane[PL_GOAL][gi];
+    // streamed once per step: keep them out of L1, which then holds the few spilled registers of the kernel
+    float4 a = __ldcs(P.plane[PL_POS_VX] + gi), b = __ldcs(P.plane[PL_V_W] + gi), c = __ldcs(P.plane[PL_W_R0] + gi), d = __ldcs(P.plane[PL_R1] + gi),
+           e = __ldcs(P.plane[PL_R2_FLAGS] + gi), f = __ldcs(P.plane[PL_ROT_DAMP] + gi), g = __ldcs(P.plane[PL_CMDS_DAMP] + gi),
+           h = __ldcs(P.plane[PL_OU] + gi), k = __ldcs(P.plane[PL_GOAL] + gi);
     q.p[0] = a.x; q.p[1] = a.y; q.p[2] = a.z; q.v[0] = a.w; q.v[1] = b.x; q.v[2] = b.y;
     q.w[0] = b.z; q.w[1] = b.w; q.w[2] = c.x;
     q.R[0] = c.y; q.R[1] = c.z; q.R[2] = c.w; q.R[3] = d.x; q.R[4] = d.y; q.R[5] = d.z; q.R[6] = d.w; q.R[7] = e.x; q.R[8] = e.y;
@@ -690,44 +691,54 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                         r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
                     }
                 }
+#ifndef QS_AB_GENERIC_RANK
+            } else if (KG <= 8) {
+#else
+            } else if (KG <= 0) {
+#endif
+                // stable rank count with the ranks packed 4 bits per candidate: one compare + one select + one add per pair.
+                // Lanes that are not candidates (self, j >= K) carry +inf and therefore rank behind every real candidate, so a
+                // rank below V (< K - 1) always belongs to a real one.  The packed form also lets the row writes be a rolled
+                // loop (unrolled they are 8 x 30 instructions executed once each; the hot path must stay inside the 32 KB
+                // L1.5 instruction cache).
+                uint32_t acc[4] = { 0u, 0u, 0u, 0u };                   // four independent chains instead of one of 28 dependent adds
+#pragma unroll
+                for (int a = 0, n = 0; a < KG; ++a)
+#pragma unroll
+                    for (int b = a + 1; b < KG; ++b, ++n) acc[n & 3] += (met[b] < met[a]) ? (1u << (4 * a)) : (1u << (4 * b));
+                const uint32_t pk = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                if (valid) {
+#pragma unroll 1
+                    for (int j = 0; j < KG; ++j) {
+                        const int rk = (int)((pk >> (4 * j)) & 15u);
+                        if (rk < c.V) {
+                            float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                            float *r = o + c.S + 6 * rk;
+                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                            r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
+                        }
+                    }
+                }
             } else {
                 int rank[KG];
-    #pragma unroll
+#pragma unroll
                 for (int j = 0; j < KG; ++j) rank[j] = 0;
-    #pragma unroll
+#pragma unroll
                 for (int a = 0; a < KG; ++a)
-    #pragma unroll
+#pragma unroll
                     for (int b = a + 1; b < KG; ++b) {
                         bool b_first = met[b] < met[a];
                         rank[a] += b_first ? 1 : 0;
                         rank[b] += b_first ? 0 : 1;
                     }
                 if (valid) {
-                    if (KG <= 8) {
-                        // ranks packed 4 bits per candidate so that the row writes can be a rolled loop: the unrolled form is
-                        // 8 x 30 instructions of code executed once each, and the hot path must stay inside the 32 KB L1.5 I-cache
-                        uint32_t pk = 0u;
-    #pragma unroll
-                        for (int j = 0; j < KG; ++j) pk |= (uint32_t)((met[j] < INF) ? rank[j] : 15) << (4 * j);
-    #pragma unroll 1
-                        for (int j = 0; j < KG; ++j) {
-                            const int rk = (int)((pk >> (4 * j)) & 15u);
-                            if (rk < c.V) {
-                                float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
-                                float *r = o + c.S + 6 * rk;
-                                r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
-                                r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
-                            }
-                        }
-                    } else {
-    #pragma unroll
-                        for (int j = 0; j < KG; ++j) {
-                            if (rank[j] < c.V && met[j] < INF) {
-                                float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
-                                float *r = o + c.S + 6 * rank[j];
-                                r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
-                                r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
-                            }
+#pragma unroll
+                    for (int j = 0; j < KG; ++j) {
+                        if (rank[j] < c.V && met[j] < INF) {
+                            float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
+                            float *r = o + c.S + 6 * rank[j];
+                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                            r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
                         }
                     }
                 }
@@ -784,6 +795,35 @@ __device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P,
     q.flags = 0; q.colmask = 0u;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// TMA bulk store shared -> global of one contiguous run (16-byte aligned, size a multiple of 16), tracked by the issuing
+// thread's bulk async-group
+__device__ __forceinline__ void bulk_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread waits until its bulk stores have finished READING shared memory (the source may then be overwritten)
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make this thread's shared-memory writes visible to the async proxy (TMA) before a bulk store reads them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// The warp's observation tile (rows contiguous in global memory) leaves shared memory as ONE TMA bulk store issued by lane 0
+// when the run is 16-byte aligned (it is for every BASELINE shape: K * D * 4 bytes per env is a multiple of 16); the caller
+// must call bulk_store_wait_read() on lane 0 + __syncwarp() before the tile is written again or the block exits.
+__device__ __forceinline__ bool warp_store_tile_bulk(const float *tile, float *dst, int count, int lane)
+{
+    if (((((size_t)dst) & 15) == 0) && ((count & 3) == 0)) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store_1d(dst, tile, (uint32_t)count * 4u);
+        return true;
+    }
+    for (int i = lane; i < count; i += 32) __stcs(dst + i, tile[i]);
+    return false;
+}
+
 // coalesced copy of the warp's observation tile (rows contiguous in global memory) out of shared memory
 __device__ __forceinline__ void warp_store_tile(const float *tile, float *dst, int count, int lane)
 {
@@ -807,7 +847,6 @@ __device__ __forceinline__ void warp_store_tile(const float *tile, float *dst, i
 //                  non-persistent form, profiles/README.md) is paid once per warp instead of once per tile.
 enum { PF_SLOTS = 12, PF_RING = 9, PF_SUMS = 10, PF_ACT = 11 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -835,6 +874,14 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): the per-env scalars of the next warp-tile travel without a register
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // lane 0 of a warp: fetch the inputs of warp-tile `wt` (rows gi0 .. gi0+cnt-1 of every plane) into the warp's buffer
 __device__ __forceinline__ void prefetch_tile(const DevPtrs &P, const float4 *actions, float4 *pf, uint64_t *bar, int gi0, int cnt)
@@ -879,17 +926,19 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     const size_t pf_off = (ob_off + (size_t)warps_per_block * ob_per_warp * 2 + 3) & ~(size_t)3;
     float4 *pf = reinterpret_cast<float4 *>(smem + pf_off) + (size_t)warp_in_block * PF_SLOTS * 32;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pf_off + (size_t)warps_per_block * PF_SLOTS * 32 * 4) + warp_in_block;
+    // per-env scalars (tick, svd counter, RNG step counter) of the next tile: 3 x GPW ints per warp behind the mbarriers.  Kept in
+    // registers they were spilled right after the load, which stalled the warp for the whole HBM latency (profiles/README.md v5)
+    int *sc = reinterpret_cast<int *>(smem + pf_off + (size_t)warps_per_block * PF_SLOTS * 32 * 4 + (size_t)warps_per_block * 2) + warp_in_block * (3 * GPW);
     uint32_t phase = 0u;
     int wt = (int)blockIdx.x * warps_per_block + warp_in_block;
-    int nx_tick = 0, nx_svd = 0;
-    uint32_t nx_step = 0u;
     if (PERSIST) {
         if (lane == 0) mbar_init(bar, 1);
         __syncwarp();
         if (wt < n_wt) {
             if (lane == 0) prefetch_tile(P, actions, pf, bar, wt * GPW * c.K, max(0, min(GPW, c.N - wt * GPW)) * c.K);
             const int e0 = wt * GPW + lane / KG;
-            if (e0 < c.N) { nx_tick = P.tick[e0]; nx_svd = P.svd_ctr[e0]; nx_step = P.step_ctr[e0]; }
+            if (e0 < c.N && d == 0) { cp_async4(sc + lane / KG, P.tick + e0); cp_async4(sc + GPW + lane / KG, P.svd_ctr + e0); cp_async4(sc + 2 * GPW + lane / KG, P.step_ctr + e0); }
+            cp_async_commit();
         }
     }
     for (; wt < n_wt; wt += wt_stride) {
@@ -906,8 +955,10 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     int scen_now = 0;
     float4 ring = make_float4(0.f, 0.f, 0.f, 0.f), sums = make_float4(0.f, 0.f, 0.f, 0.f);
     if (PERSIST) {
-        tick = nx_tick; svd = nx_svd; g.step = nx_step;
+        cp_async_wait_all();
+        __syncwarp();
         if (env < c.N) {
+            tick = sc[lane / KG]; svd = sc[GPW + lane / KG]; g.step = (uint32_t)sc[2 * GPW + lane / KG];
             if (OBST) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
             g.gid = (uint32_t)(c.env_id_offset + env);
         }
@@ -924,7 +975,8 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         if (wn < n_wt) {
             if (lane == 0) prefetch_tile(P, actions, pf, bar, wn * GPW * c.K, max(0, min(GPW, c.N - wn * GPW)) * c.K);
             const int e1 = wn * GPW + lane / KG;
-            if (e1 < c.N) { nx_tick = P.tick[e1]; nx_svd = P.svd_ctr[e1]; nx_step = P.step_ctr[e1]; }
+            if (e1 < c.N && d == 0) { cp_async4(sc + lane / KG, P.tick + e1); cp_async4(sc + GPW + lane / KG, P.svd_ctr + e1); cp_async4(sc + 2 * GPW + lane / KG, P.step_ctr + e1); }
+            cp_async_commit();
         }
     } else {
         if (env < c.N) {                                                // env-level scalars: every lane of the group
@@ -935,8 +987,8 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         if (valid) {
             load_drone(P, gi, q);
             act = __ldcs(actions + gi);
-            ring = P.plane[PL_DIST_RING][gi];                           // issued with the state loads: one exposed HBM latency per thread
-            if (c.ep_len - tick < 500) sums = P.plane[PL_DIST_SUMS][gi];    // last-5-s window (:762-767): needed late, fetched early
+            ring = __ldcs(P.plane[PL_DIST_RING] + gi);                  // issued with the state loads: one exposed HBM latency per thread
+            if (c.ep_len - tick < 500) sums = __ldcs(P.plane[PL_DIST_SUMS] + gi);    // last-5-s window (:762-767): needed late, fetched early
         }
     }
     if (!valid) {
@@ -991,6 +1043,12 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     const uint32_t bad_ballot = __ballot_sync(QS_FULL, bad) & gmask;
     const bool all_done = (tick > c.ep_len) || (bad_ballot != 0u);     // quadrotor_single.py:366-367
 
+#ifdef QS_BULK_STORE
+    if (PERSIST) {                                                      // the previous tile's bulk store has read the observation tile
+        if (lane == 0) bulk_store_wait_read();
+        __syncwarp();
+    }
+#endif
     // ---- 1.1 drone-drone collisions (collisions/quadrotors.py:63-103, quadrotor_multi.py:537-568)
     uint32_t rowmask = 0u;
     float prox = 0.f;
@@ -1053,6 +1111,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     reward += c.rew_col * ((unique_any_nonzero && is_unique) ? -1.0f : 0.0f);
     reward += -1.0f * (c.control_dt * prox);
     if (OBST) reward += c.rew_col_obst * (obst_new ? -1.0f : 0.0f);
+    if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }      // final here: not carried (spilled) across the impulse / observation code
 
     // distance_to_goal log: reached-goal flag from the mean of the last 5 entries, and the 1/3/5 s windows (:651-655, 762-767)
     if (valid) {
@@ -1192,8 +1251,6 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         if (SCEN) { q.goal[0] = og[0]; q.goal[1] = og[1]; q.goal[2] = og[2]; }
     }
     group_obs_tail<KG, OBST, false>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
-    if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }
-
     // ---- 7. dones (:739-838): episode stats, then the env resets itself and returns the new episode's first observation
     const uint32_t done_ballot = __ballot_sync(QS_FULL, all_done && valid);
     if (__builtin_expect(done_ballot != 0u, 0)) {
@@ -1291,9 +1348,17 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         if (d == 0) { P.tick[env] = tick; P.svd_ctr[env] = svd; P.step_ctr[env] = g.step + 1u; }
     }
     __syncwarp();
+#ifdef QS_BULK_STORE
+    if (warp_rows > 0) warp_store_tile_bulk(tile, obs + (size_t)warp_env0 * c.K * c.D, warp_rows * c.D, lane);
+    if (!PERSIST && lane == 0) bulk_store_wait_read();                  // shared memory must outlive the copy
+#else
     if (warp_rows > 0) warp_store_tile(tile, obs + (size_t)warp_env0 * c.K * c.D, warp_rows * c.D, lane);
+#endif
     __syncwarp();                                                       // the tile and the exchange buffer are reused by the next warp-tile
     }   // warp-tile loop
+#ifdef QS_BULK_STORE
+    if (PERSIST && lane == 0) bulk_store_wait_read();
+#endif
 }
 
 // ----------------------------------------------------------------------------------------------------------------
