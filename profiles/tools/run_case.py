@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run a few steps of one named workload (profiling aid for ncu): run_case.py <cfg2|cfg3|cfg4|fork> [envs] [steps]"""
+"""Run a few steps of one named workload (profiling aid for ncu): run_case.py <cfg2|cfg3|cfg4|fork|mix> [envs] [steps]"""
 import os
 import sys
 
@@ -17,6 +17,7 @@ cfg = {"cfg2": lambda: QuadSimConfig(num_envs=n, num_agents=8),
        "cfg3": lambda: QuadSimConfig(num_envs=n, num_agents=8, quads_mode="mix", use_obstacles=True, use_downwash=True,
                                      obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2),
        "cfg4": lambda: QuadSimConfig(num_envs=n, num_agents=32),
+       "mix": lambda: QuadSimConfig(num_envs=n, num_agents=8, quads_mode="mix"),
        "fork": lambda: QuadSimConfig.fork_default(num_envs=n)}[case]()
 sim = QuadSwarmSim(cfg, device="cuda:0")
 sim.want_terminal_obs = False

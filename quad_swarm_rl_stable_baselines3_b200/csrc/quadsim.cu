@@ -389,7 +389,9 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     const int rows_per_warp = (32 / e->KG) * K;
     // exchange buffers + observation tiles (+ the staged obstacle centres of the upstream step kernel)
     const size_t tiles_floats = (((size_t)warps * 256 + (size_t)warps * rows_per_warp * e->dc.D) + 3) & ~(size_t)3;
-    const size_t obst_floats = (cfg->use_obstacles ? (size_t)warps * (32 / e->KG) * cfg->num_obstacles * 2 : 0);
+    // staged per warp-tile behind the tiles: the obstacle centres, or (formation scenarios, never with obstacles) the scenario rows
+    const size_t obst_floats = cfg->use_obstacles ? (size_t)warps * (32 / e->KG) * cfg->num_obstacles * 2
+                                                  : (scen_feat ? (size_t)warps * (32 / e->KG) * QS_SC_COUNT : 0);
     e->smem_bytes = (tiles_floats + obst_floats) * sizeof(float);
     if (e->smem_bytes > 200 * 1024) { delete e; return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: observation tile does not fit in shared memory"); }
 

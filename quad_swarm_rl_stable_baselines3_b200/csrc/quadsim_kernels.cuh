@@ -944,6 +944,9 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     const int ob_per_warp = OBST ? GPW * c.M : 0;
     float2 *ob_sm = reinterpret_cast<float2 *>(smem + ob_off) + (size_t)warp_in_block * ob_per_warp;
     const float2 *ob_env = ob_sm + (lane / KG) * c.M;
+    // formation scenarios (never with obstacles): the scenario rows of this warp-tile's envs live where the obstacle centres would
+    float4 *sc_sm = reinterpret_cast<float4 *>(smem + ob_off) + (size_t)warp_in_block * (GPW * (QS_SC_COUNT / 4));
+    const float4 *sc_env = sc_sm + (lane / KG) * (QS_SC_COUNT / 4);
     // prefetch buffer + mbarrier of this warp (PERSIST only), 16-byte aligned
     const size_t pf_off = (ob_off + (size_t)warps_per_block * ob_per_warp * 2 + 3) & ~(size_t)3;
     float4 *pf = reinterpret_cast<float4 *>(smem + pf_off) + (size_t)warp_in_block * PF_SLOTS * 32;
@@ -976,6 +979,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
     int scen_now = 0;
     float4 ring = make_float4(0.f, 0.f, 0.f, 0.f), sums = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 sc_row[(QS_SC_COUNT / 4 + KG - 1) / KG];
     if (PERSIST) {
         cp_async_wait_all();
         __syncwarp();
@@ -1006,12 +1010,25 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             if (OBST) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
             g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
         }
+        if (SCEN && env < c.N) {                                        // scenario row: loaded with the state, parked in shared memory
+#pragma unroll
+            for (int k = 0; k < (QS_SC_COUNT / 4 + KG - 1) / KG; ++k)
+                if (d + k * KG < QS_SC_COUNT / 4) sc_row[k] = P.scen[(size_t)env * (QS_SC_COUNT / 4) + d + k * KG];
+        }
         if (valid) {
             load_drone(P, gi, q);
             act = __ldcs(actions + gi);
             ring = __ldcs(P.plane[PL_DIST_RING] + gi);                  // issued with the state loads: one exposed HBM latency per thread
             if (c.ep_len - tick < 500) sums = __ldcs(P.plane[PL_DIST_SUMS] + gi);    // last-5-s window (:762-767): needed late, fetched early
         }
+    }
+    if (SCEN && !PERSIST) {
+        if (env < c.N) {
+#pragma unroll
+            for (int k = 0; k < (QS_SC_COUNT / 4 + KG - 1) / KG; ++k)
+                if (d + k * KG < QS_SC_COUNT / 4) sc_sm[(lane / KG) * (QS_SC_COUNT / 4) + d + k * KG] = sc_row[k];
+        }
+        __syncwarp();
     }
     if (!valid) {
 #pragma unroll
@@ -1248,7 +1265,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     // impulse forces its recomputation (:711-712)
     float og[3] = { q.goal[0], q.goal[1], q.goal[2] };
     if (SCEN) {
-        if (env < c.N) formation_scenario_step<KG>(c, g, d, valid && d == 0, gmask, lane, tick, reinterpret_cast<float *>(P.scen + (size_t)env * (QS_SC_COUNT / 4)), stage, q.goal);
+        if (env < c.N) formation_scenario_step<KG>(c, g, d, valid && d == 0, gmask, lane, tick, sc_env, reinterpret_cast<float *>(P.scen + (size_t)env * (QS_SC_COUNT / 4)), stage, q.goal);
         if (flag) { og[0] = q.goal[0]; og[1] = q.goal[1]; og[2] = q.goal[2]; }
     }
 
@@ -1313,7 +1330,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
                 if (valid && d == 0) {
                     int *er = P.ep_rec + (size_t)env * QS_ER_COUNT;
                     er[QS_ER_SEQ] += 1;
-                    er[QS_ER_SCENARIO] = OBST ? scen_now : (SCEN ? (int)P.scen[(size_t)env * (QS_SC_COUNT / 4)].x : QS_SCENARIO_STATIC_SAME_GOAL);
+                    er[QS_ER_SCENARIO] = OBST ? scen_now : (SCEN ? (int)sc_env[0].x : QS_SCENARIO_STATIC_SAME_GOAL);
 #pragma unroll
                     for (int k = 0; k < 9; ++k) er[QS_ER_NUM_COLLISIONS + k] = ec[k];
                     er[QS_ER_AGENTS_SUCCESS] = __popc(b_succ); er[QS_ER_AGENTS_DEADLOCK] = __popc(b_dead); er[QS_ER_AGENTS_COLLIDED] = __popc(b_col);

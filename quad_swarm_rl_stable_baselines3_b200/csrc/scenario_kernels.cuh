@@ -209,9 +209,10 @@ static __device__ __noinline__ void formation_reset(const DevConst &c, const Rng
 
 // Goal changes that happen every 4-6 s (or every 5 s for the Bezier resampling): rare, out of line.
 // Every lane of the group calls it; returns this lane's new goal.  `stage` is the warp's exchange buffer (swap_goals).
-static __device__ __noinline__ void scenario_event(const DevConst &c, const Rng g, int scen, int d, bool leader, uint32_t gmask, int lane, int base,
-                                                   float *row, float4 *stage, float *goal)
+static __device__ __noinline__ float3 scenario_event(const DevConst &c, const Rng g, int scen, int d, bool leader, uint32_t gmask, int lane, int base,
+                                                     float *row, float4 *stage, float3 goal_in)
 {
+    float goal[3] = { goal_in.x, goal_in.y, goal_in.z };                // by value: the caller's goal stays in registers
     const int K = c.K;
     const float box = c.spawn_box;
     float4 *r4 = reinterpret_cast<float4 *>(row);
@@ -287,20 +288,23 @@ static __device__ __noinline__ void scenario_event(const DevConst &c, const Rng 
         for (int r = 0; r < 3; ++r) { aux9[r] = goal[r]; if (!found) { aux9[3 + r] = goal[r]; aux9[6 + r] = goal[r]; } }
     }
     if (leader) scen_store_row(row, scen, f, center, ctl, increase, speed, aux9);
+    return make_float3(goal[0], goal[1], goal[2]);
 }
 
 // scenario.step() (quadrotor_multi.py:701) with the already incremented tick.  Group-uniform control flow.
+// `rs`: the env's scenario row as staged in shared memory at the top of the kernel (its global load travels with the state
+// loads instead of being waited for here); `row`: the row in global memory, written by the leader lane when it changes.
 template <int KG>
 __device__ __forceinline__ void formation_scenario_step(const DevConst &c, const Rng &g, int d, bool leader, uint32_t gmask, int lane, int tick,
-                                                        float *row, float4 *stage, float *goal)
+                                                        const float4 *rs, float *row, float4 *stage, float *goal)
 {
     float4 *r4 = reinterpret_cast<float4 *>(row);
-    const float4 a0 = r4[0];
+    const float4 a0 = rs[0];
     const int scen = (int)a0.x;
     if (scen == QS_SCENARIO_STATIC_SAME_GOAL || scen == QS_SCENARIO_STATIC_DIFF_GOAL) return;
     const int base = lane & ~(KG - 1);
     if (scen == QS_SCENARIO_DYNAMIC_FORMATIONS) {                       // dynamic_formations.py:22-40, every step
-        const float4 a1 = r4[1], a2 = r4[2];
+        const float4 a1 = rs[1], a2 = rs[2];
         float size = a0.z, speed = a2.w;
         int increase = (int)a2.z;
         if (size <= -a1.x) { increase = 1; speed = 1.0f + 2.0f * rng_u(g, SITE_SCENARIO, 0xFF, 10, 6); }
@@ -308,22 +312,27 @@ __device__ __forceinline__ void formation_scenario_step(const DevConst &c, const
         size += increase ? 0.001f * speed : -0.001f * speed;
         const float center[3] = { a1.z, a1.w, a2.x };
         formation_goal((int)a0.y, size, c.K, center, a0.w, c.cube_dim[0], d, goal);
-        __syncwarp(gmask);
         if (leader) { r4[0] = make_float4(a0.x, a0.y, size, a0.w); r4[2] = make_float4(a2.x, a2.y, (float)increase, speed); }
     } else if (scen == QS_SCENARIO_EP_LISSAJOUS3D) {                    // ep_lissajous3D.py:9-25: a=0.03 b=c=0.01 n=m=2 phi=psi=90 rad
         const float t = (float)tick / c.control_freq;
         goal[0] += 0.03f * sinf(t); goal[1] += 0.01f * sinf(2.0f * t + 90.0f); goal[2] += 0.01f * cosf(2.0f * t + 90.0f);
     } else if (scen == QS_SCENARIO_EP_RAND_BEZIER) {                    // ep_rand_bezier.py:8-45
         const int control_steps = (int)(5.0f * c.control_freq), t = tick % control_steps;
-        if (t == 0 || tick == 1) scenario_event(c, g, scen, d, leader, gmask, lane, base, row, stage, goal);
+        if (t == 0 || tick == 1) {
+            const float3 ng = scenario_event(c, g, scen, d, leader, gmask, lane, base, row, stage, make_float3(goal[0], goal[1], goal[2]));
+            goal[0] = ng.x; goal[1] = ng.y; goal[2] = ng.z;
+        }
         if (t != 0 && tick > 1) {
-            const float4 b3 = r4[3], b4 = r4[4], b5 = r4[5];
+            const float4 b3 = rs[3], b4 = rs[4], b5 = rs[5];
             const float u = (float)t / (float)(control_steps - 1), w0 = (1.0f - u) * (1.0f - u), w1 = 2.0f * (1.0f - u) * u, w2 = u * u;
             goal[0] = w0 * b3.x + w1 * b3.w + w2 * b4.z; goal[1] = w0 * b3.y + w1 * b4.x + w2 * b4.w; goal[2] = w0 * b3.z + w1 * b4.y + w2 * b5.x;
         }
     } else {                                                            // timer scenarios: goals change when tick % control_step_for_sec == 0
-        const int ctl = (int)r4[2].y;
-        if (ctl > 0 && tick % ctl == 0 && tick > 0) scenario_event(c, g, scen, d, leader, gmask, lane, base, row, stage, goal);
+        const int ctl = (int)rs[2].y;
+        if (ctl > 0 && tick % ctl == 0 && tick > 0) {
+            const float3 ng = scenario_event(c, g, scen, d, leader, gmask, lane, base, row, stage, make_float3(goal[0], goal[1], goal[2]));
+            goal[0] = ng.x; goal[1] = ng.y; goal[2] = ng.z;
+        }
     }
 }
 
