@@ -17,6 +17,9 @@
 #define QS_FULL 0xffffffffu
 #define QS_PRAGMA_(x) _Pragma(#x)
 #define QS_UNROLL(n) QS_PRAGMA_(unroll n)
+#ifndef QS_DW_UNROLL
+#define QS_DW_UNROLL 1          // downwash source-loop iterations in flight
+#endif
 #ifndef QS_PAIR_UNROLL
 #define QS_PAIR_UNROLL 4        // pair-pass iterations in flight
 #endif
@@ -1183,7 +1186,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         stage[2 * lane + 1] = make_float4(q.R[2], q.R[5], q.R[8], 0.f);
         __syncwarp(gmask);
         bool hit = false;
-#pragma unroll 1
+        QS_UNROLL(QS_DW_UNROLL)
         for (int i = 0; i < c.K; ++i) {
             const float4 sp = stage[2 * (base + i)];
             float rx = px0 - sp.x, ry = py0 - sp.y, rz = pz0 - sp.z;
