@@ -382,7 +382,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     // small batches: 64-thread blocks so that every SM gets work; large batches: 128
     e->block = (lanes < (long long)sms * 2 * 128) ? 64 : 128;
-    if (const char *tb = getenv("QS_BLOCK")) { int v = atoi(tb); if (v == 32 || v == 64 || v == 128) e->block = v; }   // tuning knob
+    if (const char *tb = getenv("QS_BLOCK")) { int v = atoi(tb); if (v == 32 || v == 64 || v == 128 || v == 256) e->block = v; }   // tuning knob
     if (e->block < e->KG) e->block = e->KG;
     e->grid = (int)((lanes + e->block - 1) / e->block);
     const int warps = e->block / 32 > 0 ? e->block / 32 : 1;
