@@ -660,7 +660,8 @@ __device__ __forceinline__ void obstacle_sdf_and_hit(const DevConst &c, const fl
 }
 
 // SDF = false: the caller already wrote the SDF patch of these positions (step path: together with the hit test)
-template <int KG, bool OBST, bool SDF>
+// COMPACT: the rolled, branchy form of the row writes for kernel variants whose hot code is already at the instruction-cache limit
+template <int KG, bool OBST, bool SDF, bool COMPACT = false>
 __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *ob, int d, int lane, uint32_t gmask, bool valid,
                                                const Drone &q, const float *vs, float *o, float4 *stage)
 {
@@ -719,10 +720,10 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                     for (int b = a + 1; b < KG; ++b, ++n) acc[n & 3] += (met[b] < met[a]) ? (1u << (4 * a)) : (1u << (4 * b));
                 const uint32_t pk = (acc[0] + acc[1]) + (acc[2] + acc[3]);
                 if (valid) {
-#if QS_NB_PRED > 0
+                    if (QS_NB_PRED > 0 && !COMPACT) {
                     // loads and arithmetic for every candidate, only the six stores under the predicate: no divergent branch
                     // (and its reconvergence) per iteration, and two iterations in flight hide the shared-memory latency
-                    QS_UNROLL(QS_NB_PRED)
+                    QS_UNROLL((QS_NB_PRED > 0 ? QS_NB_PRED : 1))
                     for (int j = 0; j < KG; ++j) {
                         const int rk = (int)((pk >> (4 * j)) & 15u);
                         const float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
@@ -731,7 +732,7 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                         float *r = o + c.S + 6 * rk;
                         if (rk < c.V) { r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5; }
                     }
-#else
+                    } else {
 #pragma unroll 1
                     for (int j = 0; j < KG; ++j) {
                         const int rk = (int)((pk >> (4 * j)) & 15u);
@@ -742,7 +743,7 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                             r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
                         }
                     }
-#endif
+                    }
                 }
             } else {
                 int rank[KG];
@@ -1101,8 +1102,9 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         // pre-filter on the squared distance (slightly widened), exact `<=` tests on the rounded distance only for near pairs
         const float thr_far = fmaxf(c.thr_col, c.thr_fall), fall2 = thr_far * thr_far * 1.0001f;
         // four iterations in flight: rolled (one at a time) every iteration waited out its own shared-memory load (80.6 vs 84.6 us);
-        // fully unrolled the hot code outgrows the instruction cache again (QS_PAIR_UNROLL is a tuning knob)
-        QS_UNROLL(QS_PAIR_UNROLL)
+        // fully unrolled the hot code outgrows the instruction cache again (QS_PAIR_UNROLL is a tuning knob).  The formation-scenario
+        // variant, whose hot code is larger, stays rolled (100.8 vs 103.8 us)
+        QS_UNROLL((SCEN ? 1 : QS_PAIR_UNROLL))
         for (int j = 0; j < KG; ++j) {
             float4 o4 = stage[2 * (base + j)];
             float dx = q.p[0] - o4.x, dy = q.p[1] - o4.y, dz = q.p[2] - o4.z;
@@ -1294,7 +1296,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         self_obs(c, g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d, q, orow);
         if (SCEN) { q.goal[0] = og[0]; q.goal[1] = og[1]; q.goal[2] = og[2]; }
     }
-    group_obs_tail<KG, OBST, false>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
+    group_obs_tail<KG, OBST, false, SCEN>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
     // ---- 7. dones (:739-838): episode stats, then the env resets itself and returns the new episode's first observation
     const uint32_t done_ballot = __ballot_sync(QS_FULL, all_done && valid);
     if (__builtin_expect(done_ballot != 0u, 0)) {
