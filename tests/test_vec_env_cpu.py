@@ -141,3 +141,21 @@ def test_from_reference_cfg_with_the_real_dataclass():
     assert cfg.obs_dim == 7 + 3 * 3 and cfg.to_c().fork.cam_pixel_noise == 0.0 and cfg.to_c().neighbor_obs_type == 6
     obs_space, act_space = make_spaces(cfg)
     assert obs_space.shape == (16,) and act_space.shape == (2,)
+
+
+def test_episode_extra_stats_keys_with_obstacles():
+    """The obstacle env adds the obstacle counters and names the scenario the episode actually ran (mix -> o_random | o_static_same_goal)."""
+    cfg = QuadSimConfig(num_envs=2, num_agents=4, quads_mode="mix", use_obstacles=True, use_downwash=True, neighbor_visible_num=2,
+                        obs_repr="xyz_vxyz_R_omega_floor", ep_time=0.05, seed=3)
+    env = QuadSwarmVecEnv(cfg, sim=OracleSim(cfg))
+    env.reset()
+    seen = set()
+    for t in range(30):
+        obs, rew, done, infos = env.step(np.zeros((8, 4), np.float32))
+        for e in np.flatnonzero(done.reshape(2, 4)[:, 0]):
+            es = infos[e * 4 + 1]["episode_extra_stats"]
+            name = [k.split("/")[0] for k in es if k.endswith("/num_collisions_obst")][0]
+            seen.add(name)
+            assert {"num_collisions_obst_quad", "num_collisions_obst_quad_after_settle", f"{name}/num_collisions_obst_quad_3_5",
+                    "num_collisions_obst_quad_5", "metric/agent_obst_col_rate", f"{name}/agent_obst_col_rate"} <= set(es)
+    assert seen and seen <= {"o_random", "o_static_same_goal"}
