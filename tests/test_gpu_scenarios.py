@@ -118,3 +118,40 @@ def test_mix_long_run_statistics():
     assert np.abs(frac[used] - 1 / 9).max() < 0.02, frac
     assert frac[[1, 2, 3, 4, 10]].sum() == 0
     assert sim.episode_stats()["episodes"] >= 2 * cfg.num_envs
+
+
+def test_mix_goal_invariants_full_size():
+    """Size-independent properties at the BASELINE batch size (65536 envs x 8 quads, quads_mode=mix): scenarios with one common
+    goal give every drone the same goal; circle / grid / cube formations are centred on formation_center by construction
+    (scenarios/base.py:60-112), for swarm_vs_swarm each half on its own goal centre; a shuffle permutes rows, it never duplicates one."""
+    cfg = QuadSimConfig(seed=31, num_envs=65536, num_agents=8, quads_mode="mix", ep_time=1.0)
+    sim = _sim(cfg)
+    sim.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    checked = dict(common=0, centred=0, swarm=0)
+    for s in range(230):
+        sim.step(torch.rand((cfg.num_envs * 8, 4), device="cuda", generator=g) * 0.3 - 0.1)
+        if s % 45 != 44:
+            continue
+        st = sim.get_state(("scenario", "goal"))
+        row, goal = st["scenario"].double(), st["goal"].double().reshape(cfg.num_envs, 8, 3)
+        scen, form = row[:, 0].long(), row[:, 1].long()
+        common = (scen == 0) | (scen == 6) | (scen == 11) | (scen == 12)
+        spread = (goal - goal[:, :1]).abs().amax(dim=(1, 2))
+        assert spread[common].max().item() == 0.0
+        checked["common"] += int(common.sum())
+        symmetric = (form != 3)                                         # every formation but the sphere is mean-centred / symmetric
+        cen = ((scen == 5) | (scen == 7) | (scen == 8) | (scen == 9)) & symmetric
+        err = (goal.mean(dim=1) - row[:, 6:9]).abs().amax(dim=1)
+        assert err[cen].max().item() < 2e-6, err[cen].max().item()
+        checked["centred"] += int(cen.sum())
+        sw = (scen == 13) & symmetric
+        e1 = (goal[:, :4].mean(dim=1) - row[:, 12:15]).abs().amax(dim=1)
+        e2 = (goal[:, 4:].mean(dim=1) - row[:, 15:18]).abs().amax(dim=1)
+        assert e1[sw].max().item() < 2e-6 and e2[sw].max().item() < 2e-6
+        checked["swarm"] += int(sw.sum())
+        # distinct rows: formations with a positive size never give two drones the same goal
+        sized = ((scen == 5) | (scen == 7) | (scen == 8)) & (row[:, 2] > 0.2)
+        d = (goal[:, :, None, :] - goal[:, None, :, :]).norm(dim=-1) + torch.eye(8, device=goal.device, dtype=goal.dtype) * 10
+        assert d[sized].amin().item() > 0.05
+    assert min(checked.values()) > 10000, checked
