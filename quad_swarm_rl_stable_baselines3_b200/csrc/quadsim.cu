@@ -137,6 +137,9 @@ struct qs_env {
     // pinned host staging + device io buffers for the *_host entry points
     float *h_act, *h_obs, *h_rew, *h_term; uint8_t *h_done, *h_succ;
     float *d_act, *d_obs, *d_rew, *d_term; uint8_t *d_done, *d_succ;
+    // qs_step_host pipeline: env chunks alternate between two internal streams so that the D2H of one chunk overlaps the H2D and
+    // the kernel of the next
+    cudaStream_t cs[2]; cudaEvent_t ev_in, ev_out[2]; bool pipe_ready;
     long long launches;
     bool host_ready;        // staging buffers of the *_host entry points are allocated
     std::string err;
@@ -368,6 +371,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     e->cfg = *cfg; e->device = device; e->launches = 0; e->host_ready = false;
     e->h_act = e->h_obs = e->h_rew = e->h_term = nullptr; e->h_done = e->h_succ = nullptr;
     e->d_act = e->d_obs = e->d_rew = e->d_term = nullptr; e->d_done = e->d_succ = nullptr;
+    e->pipe_ready = false;
     fill_const(*cfg, e->dc);
     e->fork = cfg->env_mode == QS_MODE_FORK;
     e->A = e->fork ? 2 : 4;
@@ -464,6 +468,10 @@ int qs_destroy(qs_env *e)
     if (e->h_succ) cudaFreeHost(e->h_succ);
     if (e->d_term) cudaFree(e->d_term);
     if (e->d_succ) cudaFree(e->d_succ);
+    if (e->pipe_ready) {
+        for (int i = 0; i < 2; ++i) { cudaStreamDestroy(e->cs[i]); cudaEventDestroy(e->ev_out[i]); }
+        cudaEventDestroy(e->ev_in);
+    }
     delete e;
     return QS_OK;
 }
@@ -487,24 +495,48 @@ int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
     return QS_OK;
 }
 
+// One step of envs [e0, e0 + n) of the handle: the same kernels on offset views of the state (environments are independent, and the
+// RNG is keyed by the global env id, so a step done in chunks is bitwise the step done at once).  e0 must be a multiple of 32.
+static void launch_step_range(qs_env *e, int e0, int n, cudaStream_t s, const float *actions, float *obs, float *rew, uint8_t *done,
+                              float *terminal_obs, uint8_t *reset_success)
+{
+    const int K = e->cfg.num_agents;
+    const size_t r0 = (size_t)e0 * K;
+    DevConst c = e->dc;
+    DevPtrs P = e->dp;
+    c.N = n; c.env_id_offset += e0;
+    for (int p = 0; p < PL_COUNT; ++p) P.plane[p] += r0;
+    P.tick += e0; P.svd_ctr += e0; P.step_ctr += e0; P.ecnt += (size_t)e0 * EC_COUNT; P.ep_rec += (size_t)e0 * QS_ER_COUNT; P.ep_agent += r0;
+    if (e->cfg.use_obstacles) P.obst_xy += (size_t)e0 * QS_MAX_OBSTACLES;
+    if (P.scen) P.scen += (size_t)e0 * (QS_SC_COUNT / 4);
+    const int grid = (int)(((long long)n * e->KG + e->block - 1) / e->block);
+    const size_t D = (size_t)e->dc.D;
+    actions += r0 * e->A; obs += r0 * D; rew += r0; done += r0;
+    if (terminal_obs) terminal_obs += r0 * D;
+    if (reset_success) reset_success += e0;
+    if (e->fork) {
+        ForkPtrs F = e->fp;
+        for (int p = 0; p < FP_COUNT; ++p) F.plane[p] += r0;
+        F.evader += e0; F.flags += e0;
+        launchers(e->KG).fork_step({ grid, e->block, e->smem_bytes }, s, c, e->fc, P, F, (const float2 *)actions, obs, rew, done, terminal_obs,
+                                   reset_success);
+    } else if (e->persist) {
+        launchers(e->KG).step(true, e->feat, { grid < e->grid_persist ? grid : e->grid_persist, e->block, e->smem_persist }, s, c, P,
+                              (const float4 *)actions, obs, rew, done, terminal_obs, reset_success);
+    } else {
+        launchers(e->KG).step(false, e->feat, { grid, e->block, e->smem_bytes }, s, c, P, (const float4 *)actions, obs, rew, done, terminal_obs,
+                              reset_success);
+    }
+    e->launches += 1;
+}
+
 int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *done, float *terminal_obs, uint8_t *reset_success,
             void *stream)
 {
     if (!e || !actions || !obs || !rew || !done) return fail(e, QS_ERR_NULL, "qs_step: null argument");
     if (((size_t)actions & 15) != 0) return fail(e, QS_ERR_SHAPE, "qs_step: actions must be 16-byte aligned");
     DeviceGuard guard(e->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (e->fork) {
-        launchers(e->KG).fork_step({ e->grid, e->block, e->smem_bytes }, s, e->dc, e->fc, e->dp, e->fp, (const float2 *)actions, obs, rew,
-                                   done, terminal_obs, reset_success);
-    } else if (e->persist) {
-        launchers(e->KG).step(true, e->feat, { e->grid_persist, e->block, e->smem_persist }, s, e->dc, e->dp, (const float4 *)actions, obs,
-                              rew, done, terminal_obs, reset_success);
-    } else {
-        launchers(e->KG).step(false, e->feat, { e->grid, e->block, e->smem_bytes }, s, e->dc, e->dp, (const float4 *)actions, obs, rew, done,
-                              terminal_obs, reset_success);
-    }
-    e->launches += 1;
+    launch_step_range(e, 0, e->cfg.num_envs, (cudaStream_t)stream, actions, obs, rew, done, terminal_obs, reset_success);
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
 }
@@ -558,13 +590,50 @@ int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *r
     const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rew_host), pd = is_pinned(done_host);
     const bool pt = terminal_obs_host && is_pinned(terminal_obs_host), ps = reset_success_host && is_pinned(reset_success_host);
     if (!pa) memcpy(e->h_act, actions_host, nd * A * sizeof(float));
-    QS_CUDA(e, cudaMemcpyAsync(e->d_act, pa ? actions_host : e->h_act, nd * A * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = qs_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, terminal_obs_host ? e->d_term : nullptr,
-                 reset_success_host ? e->d_succ : nullptr, stream);
-    if (rc) return rc;
-    QS_CUDA(e, cudaMemcpyAsync(pr ? rew_host : e->h_rew, e->d_rew, nd * sizeof(float), cudaMemcpyDeviceToHost, s));
-    QS_CUDA(e, cudaMemcpyAsync(pd ? done_host : e->h_done, e->d_done, nd, cudaMemcpyDeviceToHost, s));
-    QS_CUDA(e, cudaMemcpyAsync(po ? obs_host : e->h_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    const float *src_act = pa ? actions_host : e->h_act;
+    float *dst_obs = po ? obs_host : e->h_obs, *dst_rew = pr ? rew_host : e->h_rew;
+    uint8_t *dst_done = pd ? done_host : e->h_done;
+    // Large batches: the step is PCIe-bound (D2H of the observations), so the env range is cut into chunks that alternate between two
+    // internal streams -- while chunk i's observations travel to the host, chunk i+1's actions arrive and its kernel runs.  Chunks are
+    // >= 8192 envs (a kernel launch below that is latency-bound) and start at multiples of 32 envs (16-byte alignment of every view).
+    int chunks = (int)(N / 8192);
+    if (chunks > 8) chunks = 8;
+    if (const char *pc = getenv("QS_HOST_CHUNKS")) chunks = atoi(pc);      // tuning knob / tests
+    if (chunks < 1) chunks = 1;
+    if (chunks > 1 && !e->pipe_ready) {
+        cudaError_t r = cudaSuccess;
+        for (int i = 0; i < 2 && r == cudaSuccess; ++i) { r = cudaStreamCreateWithFlags(&e->cs[i], cudaStreamNonBlocking); if (r == cudaSuccess) r = cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming); }
+        if (r == cudaSuccess) r = cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming);
+        if (r != cudaSuccess) return fail(e, QS_ERR_CUDA, std::string("qs_step_host: pipeline streams: ") + cudaGetErrorString(r));
+        e->pipe_ready = true;
+    }
+    float *d_term = terminal_obs_host ? e->d_term : nullptr;
+    uint8_t *d_succ = reset_success_host ? e->d_succ : nullptr;
+    if (chunks == 1) {
+        QS_CUDA(e, cudaMemcpyAsync(e->d_act, src_act, nd * A * sizeof(float), cudaMemcpyHostToDevice, s));
+        launch_step_range(e, 0, (int)N, s, e->d_act, e->d_obs, e->d_rew, e->d_done, d_term, d_succ);
+        QS_CUDA(e, cudaMemcpyAsync(dst_rew, e->d_rew, nd * sizeof(float), cudaMemcpyDeviceToHost, s));
+        QS_CUDA(e, cudaMemcpyAsync(dst_done, e->d_done, nd, cudaMemcpyDeviceToHost, s));
+        QS_CUDA(e, cudaMemcpyAsync(dst_obs, e->d_obs, nd * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+        const size_t K = (size_t)e->cfg.num_agents;
+        QS_CUDA(e, cudaEventRecord(e->ev_in, s));                       // work queued on the caller's stream comes first
+        QS_CUDA(e, cudaStreamWaitEvent(e->cs[0], e->ev_in, 0));
+        QS_CUDA(e, cudaStreamWaitEvent(e->cs[1], e->ev_in, 0));
+        const size_t per = (((N + chunks - 1) / chunks) + 31) & ~(size_t)31;
+        int i = 0;
+        for (size_t e0 = 0; e0 < N; e0 += per, ++i) {
+            const size_t n = (e0 + per <= N) ? per : N - e0, r0 = e0 * K, rows = n * K;
+            cudaStream_t t = e->cs[i & 1];
+            QS_CUDA(e, cudaMemcpyAsync(e->d_act + r0 * A, src_act + r0 * A, rows * A * sizeof(float), cudaMemcpyHostToDevice, t));
+            launch_step_range(e, (int)e0, (int)n, t, e->d_act, e->d_obs, e->d_rew, e->d_done, d_term, d_succ);
+            QS_CUDA(e, cudaMemcpyAsync(dst_obs + r0 * D, e->d_obs + r0 * D, rows * D * sizeof(float), cudaMemcpyDeviceToHost, t));
+            QS_CUDA(e, cudaMemcpyAsync(dst_rew + r0, e->d_rew + r0, rows * sizeof(float), cudaMemcpyDeviceToHost, t));
+            QS_CUDA(e, cudaMemcpyAsync(dst_done + r0, e->d_done + r0, rows, cudaMemcpyDeviceToHost, t));
+        }
+        for (int k = 0; k < 2; ++k) { QS_CUDA(e, cudaEventRecord(e->ev_out[k], e->cs[k])); QS_CUDA(e, cudaStreamWaitEvent(s, e->ev_out[k], 0)); }
+    }
+    QS_CUDA(e, cudaGetLastError());
     if (reset_success_host) QS_CUDA(e, cudaMemcpyAsync(ps ? reset_success_host : e->h_succ, e->d_succ, N, cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaStreamSynchronize(s));
     if (!po) memcpy(obs_host, e->h_obs, nd * D * sizeof(float));

@@ -75,3 +75,45 @@ def test_upstream_vec_env_tensor_and_host_faces_agree():
     assert dones >= 1
     st = a_env.sim.episode_stats(reduce=True)
     assert st["episodes"] >= cfg.num_envs
+
+
+@pytest.mark.parametrize("mode", ["upstream", "mix", "obstacles", "fork"])
+def test_host_path_chunked_pipeline_is_bitwise_the_single_launch(mode, monkeypatch):
+    """qs_step_host cuts large batches into env chunks on two internal streams (D2H of one chunk overlaps the H2D + kernel of the
+    next).  Environments are independent and the RNG is keyed by the global env id, so the chunked step must equal the single
+    launch bit for bit -- observations, rewards, dones, terminal observations, reset_infos and the episode records."""
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200.sim import QuadSwarmSim
+    kw = dict(num_envs=200, num_agents=8, ep_time=0.06, seed=5)
+    if mode == "mix":
+        cfg = QuadSimConfig(quads_mode="mix", **kw)
+    elif mode == "obstacles":
+        cfg = QuadSimConfig(quads_mode="mix", use_obstacles=True, use_downwash=True, obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2, **kw)
+    elif mode == "fork":
+        cfg = QuadSimConfig.fork_default(num_envs=200, num_agents=4, ep_time=0.3, capture_radius=2.5, seed=5)
+    else:
+        cfg = QuadSimConfig(**kw)
+    monkeypatch.setenv("QS_HOST_CHUNKS", "1")
+    a_sim = QuadSwarmSim(cfg, device="cuda:0")
+    monkeypatch.setenv("QS_HOST_CHUNKS", "3")                       # 200 envs -> chunks of 96, 96, 8
+    b_sim = QuadSwarmSim(cfg, device="cuda:0")
+    n, D, A = cfg.num_envs * cfg.num_agents, cfg.obs_dim, cfg.act_dim
+    assert np.array_equal(a_sim.reset_host(), b_sim.reset_host())
+    rs = np.random.RandomState(1)
+    dones = 0
+    for t in range(12):
+        act = rs.uniform(-1, 1, (n, A)).astype(np.float32)
+        outs = []
+        for k, sim in enumerate((a_sim, b_sim)):
+            monkeypatch.setenv("QS_HOST_CHUNKS", "1" if k == 0 else "3")
+            term, succ = np.zeros((n, D), np.float32), np.zeros(cfg.num_envs, np.uint8)
+            obs, rew, done = sim.step_host(act, terminal_obs=term, reset_success=succ)
+            outs.append((obs.copy(), rew.copy(), np.asarray(done).copy(), term, succ, *sim.episode_records_host()))
+        for x, y in zip(*outs):
+            assert np.array_equal(x, y, equal_nan=True)
+        dones += int(outs[0][2].any())
+    assert dones >= 1
+    sa, sb = a_sim.get_state(), b_sim.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert a_sim.episode_stats()["episodes"] == b_sim.episode_stats()["episodes"] > 0
