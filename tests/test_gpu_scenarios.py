@@ -155,3 +155,29 @@ def test_mix_goal_invariants_full_size():
         d = (goal[:, :, None, :] - goal[:, None, :, :]).norm(dim=-1) + torch.eye(8, device=goal.device, dtype=goal.dtype) * 10
         assert d[sized].amin().item() > 0.05
     assert min(checked.values()) > 10000, checked
+
+
+def test_mix_shards_reproduce_the_single_gpu_run():
+    """Multi-GPU sharding of the formation scenarios: two handles owning envs [0, 32) and [32, 64) (env_id_offset) reproduce the
+    64-env handle bit for bit -- scenario draws, goals, observations, episode records -- because every draw is keyed by the
+    global env id."""
+    kw = dict(num_agents=8, quads_mode="mix", ep_time=0.25, seed=77)
+    whole = _sim(QuadSimConfig(num_envs=64, **kw))
+    parts = [_sim(QuadSimConfig(num_envs=32, env_id_offset=o, **kw)) for o in (0, 32)]
+    o_w = whole.reset().clone()
+    o_p = torch.cat([p.reset() for p in parts])
+    assert torch.equal(o_w, o_p)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for s in range(60):
+        a = torch.rand((64 * 8, 4), device="cuda", generator=g) * 0.4 - 0.1
+        ow, rw, dw = whole.step(a)
+        outs = [p.step(a[i * 256:(i + 1) * 256].contiguous()) for i, p in enumerate(parts)]
+        assert torch.equal(ow, torch.cat([o[0] for o in outs])) and torch.equal(rw, torch.cat([o[1] for o in outs]))
+        assert torch.equal(dw, torch.cat([o[2] for o in outs]))
+    sw = whole.get_state(("scenario", "goal"))
+    sp = [p.get_state(("scenario", "goal")) for p in parts]
+    assert torch.equal(sw["scenario"], torch.cat([x["scenario"] for x in sp])) and torch.equal(sw["goal"], torch.cat([x["goal"] for x in sp]))
+    rw_ = whole.episode_records()
+    rp = [p.episode_records() for p in parts]
+    assert torch.equal(rw_["env"], torch.cat([x["env"] for x in rp])) and torch.equal(rw_["agent"], torch.cat([x["agent"] for x in rp]))
+    assert int(rw_["env"][:, 0].min()) >= 2                       # every env finished at least two episodes
