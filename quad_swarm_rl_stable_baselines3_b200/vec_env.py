@@ -124,6 +124,18 @@ class _PlainVecEnv:
 _Base = _SB3VecEnv if _SB3VecEnv is not None else _PlainVecEnv
 
 
+class AnnealSchedule:
+    """`swarm_rl/env_wrappers/quad_utils.py:13-17`: a reward coefficient that grows linearly from 0 to `final_value` over
+    `anneal_env_steps` training steps (the upstream recipe anneals quadcol_bin, quadcol_bin_smooth_max and quadcol_bin_obst,
+    quad_utils.py:78-89)."""
+
+    def __init__(self, coeff_name: str, final_value: float, anneal_env_steps: float):
+        self.coeff_name, self.final_value, self.anneal_env_steps = coeff_name, float(final_value), float(anneal_env_steps)
+
+    def value(self, approx_total_training_steps: float) -> float:
+        return min(self.final_value * approx_total_training_steps / self.anneal_env_steps, self.final_value)   # reward_shaping.py:116
+
+
 class QuadSwarmVecEnv(_Base):
     def __init__(self, cfg: QuadSimConfig, device=None, sim=None):
         """`sim`: an object with QuadSwarmSim's host interface (tests inject an oracle-backed one on CPU boxes)."""
@@ -214,6 +226,14 @@ class QuadSwarmVecEnv(_Base):
                 infos[e * K + k] = info
         self.reset_infos = tuple(reset_infos)
         return obs, rews, dones, infos
+
+    def anneal_reward_coefficients(self, approx_total_training_steps: float, schedules: Sequence[AnnealSchedule]) -> dict:
+        """The annealing step of `QuadsRewardShapingWrapper.step` (swarm_rl/env_wrappers/reward_shaping.py:109-118): set every
+        scheduled coefficient to its value at this point of training (one `qs_set_param` each, effective from the next step).
+        Returns the `z_anneal_<name>` entries the wrapper adds to `episode_extra_stats`."""
+        values = {sch.coeff_name: sch.value(approx_total_training_steps) for sch in schedules}
+        self.sim.set_rew_coeff(**values)
+        return {f"z_anneal_{k}": v for k, v in values.items()}
 
     def close(self) -> None:
         if self.closed:

@@ -159,3 +159,22 @@ def test_episode_extra_stats_keys_with_obstacles():
             assert {"num_collisions_obst_quad", "num_collisions_obst_quad_after_settle", f"{name}/num_collisions_obst_quad_3_5",
                     "num_collisions_obst_quad_5", "metric/agent_obst_col_rate", f"{name}/agent_obst_col_rate"} <= set(es)
     assert seen and seen <= {"o_random", "o_static_same_goal"}
+
+
+def test_reward_coefficient_annealing_hook():
+    """AnnealSchedule / anneal_reward_coefficients = the annealing branch of QuadsRewardShapingWrapper (reward_shaping.py:109-118)."""
+    from quad_swarm_rl_stable_baselines3_b200.vec_env import AnnealSchedule
+    cfg = QuadSimConfig(num_envs=1, num_agents=8, seed=4, rew_coeff=dict(quadcol_bin=0.0, quadcol_bin_smooth_max=0.0))
+    env = QuadSwarmVecEnv(cfg, sim=OracleSim(cfg))
+    env.reset()
+    sched = [AnnealSchedule("quadcol_bin", 5.0, 1000.0), AnnealSchedule("quadcol_bin_smooth_max", 10.0, 1000.0)]
+    assert env.anneal_reward_coefficients(250.0, sched) == {"z_anneal_quadcol_bin": 1.25, "z_anneal_quadcol_bin_smooth_max": 2.5}
+    assert env.anneal_reward_coefficients(4000.0, sched) == {"z_anneal_quadcol_bin": 5.0, "z_anneal_quadcol_bin_smooth_max": 10.0}
+    # the coefficients reach the simulator: drones spawn within the proximity fall-off of each other often enough that the
+    # smooth penalty changes the reward of the very next step
+    ref = OracleSim(cfg)
+    ref.reset_host()
+    a = np.zeros((8, 4), np.float32)
+    r_env = env.step(a)[1]
+    r_ref = ref.step_host(a)[1]
+    assert (r_env <= r_ref + 1e-9).all()
