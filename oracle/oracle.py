@@ -56,6 +56,8 @@ def lib():
         L.qo_set_obstacles.argtypes = [C.c_void_p, dp, C.c_int]
         L.qo_get_obstacles.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int)]
         L.qo_get_stats.argtypes = [C.c_void_p, C.POINTER(QsStatsC)]
+        L.qo_col_norm_and_new_vel_obst.argtypes = [dp, dp, dp, dp]
+        L.qo_col_norm_and_new_vel_obst.restype = C.c_double
         L.qo_get_record.argtypes = [C.c_void_p, C.c_void_p, dp]
         L.qo_get_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.qo_set_param.argtypes = [C.c_void_p, C.c_int, C.c_double]
@@ -222,6 +224,14 @@ class OracleEnv:
 
     def set_param(self, key: int, value: float):
         lib().qo_set_param(self.h, key, value)
+
+
+def col_norm_and_new_vel_obst(pos, vel, obst_pos):
+    """compute_col_norm_and_new_vel_obst of the oracle (collisions/obstacles.py:8-21) -> (vnew, collision_norm)."""
+    p, v, o = (np.ascontiguousarray(x, dtype=np.float64) for x in (pos, vel, obst_pos))
+    n = np.zeros(3)
+    vnew = lib().qo_col_norm_and_new_vel_obst(_dp(p), _dp(v), _dp(o), _dp(n))
+    return float(vnew), n
 
 
 def generate_goals(formation: int, size: float, n: int, center, layer_dist: float) -> np.ndarray:

@@ -523,14 +523,24 @@ static void pair_impulse(qo_env *e, int i, int j)
 }
 
 /* perform_collision_with_obstacle, collisions/obstacles.py:9-50 */
+/* compute_col_norm_and_new_vel_obst, collisions/obstacles.py:8-21: unit horizontal normal from the obstacle axis to the drone and
+ * the velocity component along it (the reference's own unit test holds one known answer for it,
+ * collisions/test/unit_test/obstacles.py:6-18) */
+static double col_norm_and_new_vel_obst(const double *pos, const double *vel, const double *op, double *n)
+{
+    n[0] = pos[0] - op[0]; n[1] = pos[1] - op[1]; n[2] = 0.0;
+    double nm = norm3(n), den = (nm == 0.0) ? nm + QO_EPS_COL : nm;
+    for (int a = 0; a < 3; ++a) n[a] /= den;
+    return dot3(vel, n);
+}
+
 static void obstacle_impulse(qo_env *e, int i, int m)
 {
     const qs_config *c = &e->c;
     qo_drone *q = &e->d[i];
     double op[3] = { e->obst_xy[m][0], e->obst_xy[m][1], c->room_dims[2] / 2.0 };
-    double n[3] = { q->pos[0] - op[0], q->pos[1] - op[1], 0.0 };
-    double nm = norm3(n), den = (nm == 0.0) ? nm + QO_EPS_COL : nm;
-    for (int a = 0; a < 3; ++a) n[a] /= den;
+    double n[3];
+    col_norm_and_new_vel_obst(q->pos, q->vel, op, n);
     double vm = norm3(q->vel);
     double nv[3] = { vm * n[0], vm * n[1], vm * n[2] }, noise[3] = { 0, 0, 0 };
     for (int att = 0; att < 3; ++att) {
@@ -1080,6 +1090,11 @@ int qo_generate_goals(int formation, double size, int n, const double *center, d
     s.formation = formation; s.size = size;
     s.per_layer = (formation >= QF_GRID_H && formation <= QF_GRID_YZ) ? 50 : 8;
     return scen_generate_goals(&s, n, center, layer_dist, (double (*)[3])out, cube_dim);
+}
+
+double qo_col_norm_and_new_vel_obst(const double *pos, const double *vel, const double *obst_pos, double *norm_out)
+{
+    return col_norm_and_new_vel_obst(pos, vel, obst_pos, norm_out);
 }
 
 void qo_set_obstacles(qo_env *e, const double *xy, int n) { e->n_obst = n; for (int m = 0; m < n; ++m) { e->obst_xy[m][0] = xy[2 * m]; e->obst_xy[m][1] = xy[2 * m + 1]; } }

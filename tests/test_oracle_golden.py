@@ -57,6 +57,15 @@ def test_survey_known_answer_dynamics():
                                                     0.4903482300512643], rtol=1e-13)
 
 
+def test_reference_unit_test_known_answer_obstacle_normal():
+    """The one meaningful known answer in the reference's own tests (collisions/test/unit_test/obstacles.py:6-18):
+    pos (0,0,0), vel (1,0,0), obstacle at (0.5,0.5,5) -> vnew = -sqrt(2)/2, collision normal (-sqrt(2)/2, -sqrt(2)/2, 0)."""
+    from oracle import col_norm_and_new_vel_obst
+    vnew, n = col_norm_and_new_vel_obst([0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.5, 0.5, 5.0])
+    assert round(vnew, 6) == round(-np.sqrt(2) / 2.0, 6)
+    np.testing.assert_allclose(n, [-np.sqrt(2) / 2.0, -np.sqrt(2) / 2.0, 0.0], atol=1e-15)
+
+
 def test_dynamics_jit_on(golden_dir):
     """JIT-ON reference QuadrotorDynamics.step: free flight, SVD at sub-step 100, floor touch and sliding.
     One-step teacher-forced comparison (floor friction chatter is chaotic, so free-running traces are only
