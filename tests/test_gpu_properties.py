@@ -149,3 +149,55 @@ def test_device_noise_statistics():
     assert abs(rho - 0.85) < 0.01                                           # x' = 0.85 x + sigma n
     c = np.corrcoef(npos[:, 0].cpu().numpy(), npos[:, 1].cpu().numpy())[0, 1]
     assert abs(c) < 0.02                                                    # independent components
+
+
+@pytest.mark.parametrize("name,cfg_fn", [
+    ("ragged_k3", lambda: QuadSimConfig(num_envs=37, num_agents=3, neighbor_visible_num=1, ep_time=0.05, seed=1)),
+    ("ragged_k8", lambda: QuadSimConfig(num_envs=131, num_agents=8, ep_time=0.05, seed=2)),
+    ("ragged_mix_k5", lambda: QuadSimConfig(num_envs=29, num_agents=5, quads_mode="mix", neighbor_visible_num=2, ep_time=0.05, seed=3)),
+    ("ragged_obst_k6", lambda: QuadSimConfig(num_envs=21, num_agents=6, quads_mode="mix", use_obstacles=True, use_downwash=True,
+                                             obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2, ep_time=0.05, seed=4)),
+    ("ragged_k32", lambda: QuadSimConfig(num_envs=7, num_agents=32, ep_time=0.05, seed=5)),
+    ("ragged_fork_k4", lambda: QuadSimConfig.fork_default(num_envs=45, num_agents=4, ep_time=0.3, capture_radius=2.6, seed=6)),
+])
+def test_output_buffers_are_never_overrun(name, cfg_fn):
+    """compute-sanitizer is not available on the GPU pool, so the bounds of every caller-provided output are checked with guard
+    bands: obs / rew / done / terminal_obs / reset_success / episode records sit in the middle of larger canary-filled buffers
+    (batch sizes that are not multiples of the warp tile, lane groups that are not full), and after resets, steps and episode
+    ends the canaries are intact.  Goes through the C-ABI directly."""
+    import ctypes as C
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200 import _capi
+    cfg = cfg_fn()
+    sim = _sim(cfg)
+    L, h = _capi.lib(), sim._h
+    N, K, D, A = cfg.num_envs, cfg.num_agents, cfg.obs_dim, cfg.act_dim
+    n, PAD = N * K, 4096                                   # PAD elements of guard band on each side (16-byte multiples)
+
+    def guarded(count, dtype, fill):
+        buf = torch.full((count + 2 * PAD,), fill, dtype=dtype, device="cuda")
+        return buf, buf[PAD:PAD + count]
+
+    bufs = {k: guarded(c, dt, f) for k, (c, dt, f) in dict(
+        obs=(n * D, torch.float32, -777.0), rew=(n, torch.float32, -777.0), done=(n, torch.uint8, 0xAB), term=(n * D, torch.float32, -777.0),
+        succ=(N, torch.uint8, 0xAB), erec=(N * 20, torch.int32, -777), arec=(n * 4, torch.float32, -777.0)).items()}
+    ptr = {k: C.c_void_p(v[1].data_ptr()) for k, v in bufs.items()}
+    stream = sim._stream()
+    assert L.qs_reset(h, None, ptr["obs"], stream) == 0
+    g = torch.Generator(device="cuda").manual_seed(1)
+    finished = 0
+    for s in range(40):
+        act = (torch.rand((n, A), device="cuda", generator=g) * 2 - 1).contiguous()
+        assert L.qs_step(h, C.c_void_p(act.data_ptr()), ptr["obs"], ptr["rew"], ptr["done"], ptr["term"], ptr["succ"], stream) == 0
+        assert L.qs_episode_records(h, ptr["erec"], ptr["arec"], stream) == 0
+        finished += int(bufs["done"][1].any())
+        if s == 20:                                        # a masked reset in the middle
+            mask = (torch.arange(N, device="cuda") % 3 == 0).to(torch.uint8)
+            assert L.qs_reset(h, C.c_void_p(mask.data_ptr()), ptr["obs"], stream) == 0
+    torch.cuda.synchronize()
+    assert finished >= 2
+    for k, (buf, view) in bufs.items():
+        fill = buf[0].item()
+        assert bool((buf[:PAD] == fill).all()) and bool((buf[PAD + view.numel():] == fill).all()), f"{name}: guard band of {k} overwritten"
+    assert bool(torch.isfinite(bufs["obs"][1]).all()) and bool((bufs["obs"][1] != -777.0).all())      # and the inside was written everywhere
+    assert bool((bufs["rew"][1] != -777.0).all()) and bool((bufs["done"][1] <= 1).all())
