@@ -17,6 +17,9 @@
 #define QS_FULL 0xffffffffu
 #define QS_PRAGMA_(x) _Pragma(#x)
 #define QS_UNROLL(n) QS_PRAGMA_(unroll n)
+#ifndef QS_SDF_UNROLL
+#define QS_SDF_UNROLL 2         // obstacle-loop iterations in flight (SDF patch + hit test)
+#endif
 #ifndef QS_DW_UNROLL
 #define QS_DW_UNROLL 1          // downwash source-loop iterations in flight
 #endif
@@ -643,6 +646,7 @@ __device__ __forceinline__ void obstacle_sdf_and_hit(const DevConst &c, const fl
 #pragma unroll
     for (int a = 0; a < 9; ++a) md[a] = 10000.0f;                       // (100)^2
     hit = -1;
+    QS_UNROLL(QS_SDF_UNROLL)
     for (int m = 0; m < c.M; ++m) {
         const float2 xy = ob[m];
         float dx2[3], dy2[3];
@@ -685,10 +689,11 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                 float ss = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3 + r4 * r4 + r5 * r5;
                 met[j] = (j < c.K && j != d) ? fmaxf(ss, 1.0e-4f) : INF;
             }
-            if (KG >= 16 && c.V * 3 < 2 * (KG - 1)) {
-                // few rows out of many candidates (6 of 31): V rounds of first-minimum selection cost ~3 KG instructions
-                // each, the all-pairs rank count below ~2 KG (KG - 1).  Wide groups only: the 8-lane kernels keep a single
-                // selection path (their hot code has to stay inside the instruction cache).
+            if ((KG >= 16 || (OBST && KG >= 4)) && c.V * 3 < 2 * (KG - 1)) {
+                // few rows out of many candidates (6 of 31; 2 of 7 in the obstacle recipe): V rounds of first-minimum selection cost
+                // ~3 KG instructions each, the all-pairs rank count below ~2 KG (KG - 1) plus a row pass over every candidate.
+                // Compiled into the wide-group kernels and the obstacle variants only: the plain 8-lane kernel keeps a single
+                // selection path (its hot code has to stay inside the instruction cache).
 #pragma unroll 1
                 for (int sidx = 0; sidx < c.V; ++sidx) {
                     float best = INF; int jb = 0;
@@ -1044,9 +1049,17 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         q.flags = 0; q.colmask = 0;
     }
     if (OBST) {
-        for (int k = lane; k < ob_per_warp; k += 32) {
-            const int e = k / c.M, m = k - e * c.M;
-            ob_sm[k] = (warp_env0 + e < c.N) ? P.obst_xy[(size_t)(warp_env0 + e) * QS_MAX_OBSTACLES + m] : make_float2(0.f, 0.f);
+        // all loads first, then the shared-memory stores: load -> store per trip serialised one HBM round trip per trip at the top of
+        // every warp (the 12-obstacle scenario needs two trips: 48 centres per warp-tile)
+        for (int k0 = lane; k0 < ob_per_warp; k0 += 128) {
+            float2 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int k = k0 + 32 * t, e = k / c.M, m = k - e * c.M;
+                v[t] = (k < ob_per_warp && warp_env0 + e < c.N) ? __ldcs(P.obst_xy + (size_t)(warp_env0 + e) * QS_MAX_OBSTACLES + m) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (k0 + 32 * t < ob_per_warp) ob_sm[k0 + 32 * t] = v[t];
         }
         __syncwarp();
     }
