@@ -656,7 +656,8 @@ static void obstacle_scenario_reset(qo_env *e)
     int scen = c->scenario;
     if (scen == QS_SCENARIO_O_MIX) {
         int mode_index = (int)floor(rnd_u(e, SITE_SCENARIO, 0xFF, 1, 0) * 100.0);
-        scen = (mode_index % 2 == 0) ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
+        /* a single drone draws from QUADS_MODE_LIST_OBSTACLES_SINGLE = ['o_random'] (mix.py:49-51, utils.py:23) */
+        scen = (K == 1 || mode_index % 2 == 0) ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
     }
     e->scenario_now = scen;
     /* free cells in row-major order (np.where, o_static_same_goal.py:37-38) */

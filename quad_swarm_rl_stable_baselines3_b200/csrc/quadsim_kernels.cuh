@@ -559,7 +559,8 @@ static __device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, c
     int scen = c.scenario;
     if (scen == QS_SCENARIO_O_MIX) {
         int mode_index = (int)floorf(rng_u(g, SITE_SCENARIO, 0xFF, 1, 0) * 100.0f);
-        scen = (mode_index % 2 == 0) ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
+        // a single drone draws from QUADS_MODE_LIST_OBSTACLES_SINGLE = ['o_random'] (mix.py:49-51, utils.py:23)
+        scen = (K == 1 || mode_index % 2 == 0) ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
     }
     scenario_now = scen;
     unsigned char freec[64];

@@ -45,6 +45,9 @@ TRACES = {
                          steps=330, act="hover"),
     # cfg4 shape: 32 quads
     "cfg4_k32": dict(env=dict(num_agents=32, ep_time=0.5), steps=70, act="uniform"),
+    # single drone with obstacles: mix draws from the one-entry list ['o_random'] whatever the mode index
+    "obst_k1": dict(env=dict(num_agents=1, quads_mode="mix", use_obstacles=True, obs_repr="xyz_vxyz_R_omega_floor",
+                             neighbor_visible_num=0, neighbor_obs_type="none", ep_time=0.3), steps=200, act="hover"),
     # no sensor noise / all neighbours visible / wall obs
     "nonoise_k4": dict(env=dict(num_agents=4, sense_noise=None, neighbor_visible_num=-1,
                                 obs_repr="xyz_vxyz_R_omega_wall", ep_time=0.6), steps=130, act="uniform"),
@@ -399,7 +402,8 @@ def gen_dyn_jit():
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which == "traces":
-        gen_traces()
+        only = sys.argv[2:]
+        gen_traces({k: v for k, v in TRACES.items() if not only or k in only})
     elif which == "scenarios":
         gen_formations()
         only = sys.argv[2:]

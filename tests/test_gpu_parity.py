@@ -41,6 +41,8 @@ CONFIGS = {
                             obs_repr="xyz_vxyz_R_omega_wall", ep_time=0.3),
     "single_k1": dict(num_envs=70, num_agents=1, neighbor_obs_type="none", neighbor_visible_num=0, ep_time=0.3),
     "odd_k3": dict(num_envs=21, num_agents=3, neighbor_visible_num=1, ep_time=0.3),
+    "single_k1_obst": dict(num_envs=40, num_agents=1, quads_mode="mix", use_obstacles=True, neighbor_obs_type="none", neighbor_visible_num=0,
+                           obs_repr="xyz_vxyz_R_omega_floor", ep_time=0.3),
     "odd_k6_obst": dict(num_envs=9, num_agents=6, quads_mode="o_random", use_obstacles=True, neighbor_visible_num=3,
                         obs_repr="xyz_vxyz_R_omega_floor", ep_time=0.3),
 }
@@ -245,7 +247,7 @@ def run_parity(name, cfg, sim, oracles, kind, steps, hook=None, check_records=Tr
 @pytest.mark.parametrize("name,kind,steps", [
     ("cfg2_k8", "uniform", 60), ("cfg3_obst_k8", "hover", 60), ("cfg4_k32", "uniform", 40),
     ("smallroom_k8", "high", 70), ("crowd_k16", "hover", 60), ("nonoise_wall_k4", "uniform", 45),
-    ("single_k1", "uniform", 45), ("odd_k3", "uniform", 45), ("odd_k6_obst", "hover", 45)])
+    ("single_k1", "uniform", 45), ("odd_k3", "uniform", 45), ("odd_k6_obst", "hover", 45), ("single_k1_obst", "hover", 45)])
 def test_single_step_parity(name, kind, steps):
     cfg, sim, oracles = make_pair(name)
     sim.reset()

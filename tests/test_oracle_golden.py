@@ -101,7 +101,7 @@ def test_dynamics_jit_on(golden_dir):
         assert g[f"r{r}_on_floor"].sum() > 50           # the run does include floor contact
 
 
-TRACE_NAMES = ["cfg2_k8", "smallroom_k8", "crowd_k16", "cfg3_obst_k8", "cfg4_k32", "nonoise_k4"]
+TRACE_NAMES = ["cfg2_k8", "smallroom_k8", "crowd_k16", "cfg3_obst_k8", "cfg4_k32", "nonoise_k4", "obst_k1"]
 # formation scenarios: compact fixtures -- float32 observations / actions, bit-packed flags, and the
 # reference scenario object's own state per step (QS_SC_* row)
 SCENARIO_TRACE_NAMES = ["scen_static_diff_k8", "scen_static_diff_k12", "scen_dyn_same_k3", "scen_dyn_diff_k4", "scen_swap_k3",
