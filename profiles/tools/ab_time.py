@@ -16,7 +16,8 @@ sys.path.insert(0, %r)
 from quad_swarm_rl_stable_baselines3_b200.config import QuadSimConfig
 from quad_swarm_rl_stable_baselines3_b200.sim import QuadSwarmSim
 case = sys.argv[1]
-n = 16384 if case == "cfg4" else 65536
+import os
+n = int(os.environ.get("AB_ENVS", "16384" if case == "cfg4" else "65536"))
 cfg = {"cfg2": lambda: QuadSimConfig(num_envs=n, num_agents=8),
        "mix": lambda: QuadSimConfig(num_envs=n, num_agents=8, quads_mode="mix"),
        "cfg3": lambda: QuadSimConfig(num_envs=n, num_agents=8, quads_mode="mix", use_obstacles=True, use_downwash=True,
