@@ -444,9 +444,9 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
                                        (size_t)warps * 3 * (32 / e->KG) * sizeof(int);     // prefetch buffers, mbarriers, per-env scalars
         int per_sm = 0;
         launchers(e->KG).prepare(e->feat, e->smem_bytes, e->smem_persist, e->block, &per_sm, e->fork);
-        // Measured (profiles/README.md): hiding the start-of-tile HBM latency does not pay on this kernel -- with 16 resident
-        // warps per SM the other warps already cover it (88.3 us plain vs 90.1 us persistent at 65536 envs) -- so the
-        // persistent form is opt-in (QS_PERSIST=1); it is kept bitwise-tested against the plain form.
+        // Measured (profiles/README.md): the persistent form does not pay on this kernel (79.0 us plain vs 86.9 us persistent at
+        // 65536 envs): its prefetch buffers need the maximum carve-out, which leaves L1 too small for the spilled registers.  It is
+        // opt-in (QS_PERSIST=1) and kept bitwise-tested against the plain form.
         const char *pe = getenv("QS_PERSIST");
         const bool want = pe ? atoi(pe) != 0 : false;
         if (!e->fork && per_sm > 0 && want) { e->persist = true; e->grid_persist = (e->grid < per_sm * sms) ? e->grid : per_sm * sms; }
