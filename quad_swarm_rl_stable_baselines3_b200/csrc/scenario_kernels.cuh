@@ -28,7 +28,9 @@ __device__ __forceinline__ void scen_params(int scen, int &nform, float &low, fl
 __device__ __forceinline__ void grid_dims(int num, int &d1, int &d2)
 {
     int a = 1;
+#pragma unroll 1
     while ((a + 1) * (a + 1) <= num) ++a;
+#pragma unroll 1
     while (a > 1 && (num % a) != 0) --a;
     d1 = a; d2 = num / a;
 }
@@ -59,6 +61,18 @@ __device__ __forceinline__ void goal_by_formation(int orient, float p0, float p1
     else { g[0] = layer; g[1] = p0; g[2] = p1; }
 }
 
+// generate_points, scenarios/utils.py:77-93: point j of the m-point spiral on the unit sphere.  Out of line: the two general-range
+// sincosf carry ~1400 instructions of slow-path code that would otherwise sit inside every caller (instruction-cache budget).
+static __device__ __noinline__ float3 sphere_point(float m, int r)
+{
+    const float x = 0.1f + 1.2f * m, start = -1.0f + 1.0f / (m - 1.0f), inc = (2.0f - 2.0f / (m - 1.0f)) / (m - 1.0f);
+    const float t = start + (float)r * inc, sg = (t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f);
+    const float b = 1.5707963267948966f * sg * (1.0f - sqrtf(fmaxf(1.0f - fabsf(t), 0.f)));
+    float sa, ca, sb, cb;
+    sincosf(t * x, &sa, &ca); sincosf(b, &sb, &cb);
+    return make_float3(ca * cb, sa * cb, sb);
+}
+
 // Row r of QuadrotorScenario.generate_goals(n, centre, layer_dist), scenarios/base.py:42-116.  n <= 32 < 50, so a grid is
 // always a single layer; circles stack layers of 8.
 __device__ __forceinline__ void formation_goal(int f, float size, int n, const float *center, float layer_dist, int cube_fd, int r, float *out)
@@ -71,19 +85,14 @@ __device__ __forceinline__ void formation_goal(int f, float size, int n, const f
         goal_by_formation(f, size * cs, size * sn, (float)(r / per) * layer_dist, out);
 #pragma unroll
         for (int a = 0; a < 3; ++a) out[a] += center[a];
-    } else if (f == QF_SPHERE) {                                        // generate_points, utils.py:77-93
-        const float m = (float)max(n, 3);
-        const float x = 0.1f + 1.2f * m, start = -1.0f + 1.0f / (m - 1.0f), inc = (2.0f - 2.0f / (m - 1.0f)) / (m - 1.0f);
-        const float t = start + (float)r * inc, sg = (t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f);
-        const float b = 1.5707963267948966f * sg * (1.0f - sqrtf(fmaxf(1.0f - fabsf(t), 0.f)));
-        float sa, ca, sb, cb;
-        sincosf(t * x, &sa, &ca); sincosf(b, &sb, &cb);
-        out[0] = size * (ca * cb) + center[0]; out[1] = size * (sa * cb) + center[1]; out[2] = size * sb + center[2];
+    } else if (f == QF_SPHERE) {
+        const float3 pt = sphere_point((float)max(n, 3), r);
+        out[0] = size * pt.x + center[0]; out[1] = size * pt.y + center[1]; out[2] = size * pt.z + center[2];
     } else if (f <= QF_GRID_YZ) {
-        int d1, d2, s0 = 0, s1 = 0;
+        int d1, d2;
         grid_dims(n, d1, d2);
-        for (int i = 0; i < n; ++i) { s0 += i % d2; s1 += (i / d2) % d1; }
-        const float m0 = size * (float)s0 / (float)n, m1 = size * (float)s1 / (float)n;
+        // d1 * d2 == n (d1 divides n), so the column / row indices i % d2 and (i / d2) % d1 average to (d2 - 1) / 2 and (d1 - 1) / 2
+        const float m0 = size * 0.5f * (float)(d2 - 1), m1 = size * 0.5f * (float)(d1 - 1);
         float g[3], mg[3];
         goal_by_formation(f - QF_GRID_H, size * (float)(r % d2), size * (float)((r / d2) % d1), 0.f, g);
         goal_by_formation(f - QF_GRID_H, m0, m1, 0.f, mg);
@@ -92,6 +101,7 @@ __device__ __forceinline__ void formation_goal(int f, float size, int n, const f
     } else {                                                            // cube, base.py:100-112 (x is offset by formation_center[2])
         const int fd = max(cube_fd, 1);
         int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll 1
         for (int i = 0; i < n; ++i) { s0 += i / (fd * fd); s1 += (i / fd) % fd; s2 += i % fd; }
         const float inv = 1.0f / (float)n;
         const float g0 = center[2] + size * (float)(r / (fd * fd)), m0 = center[2] + size * (float)s0 * inv;
