@@ -31,7 +31,7 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, 
             if (v.cmds_damp) for (int a = 0; a < 4; ++a) q.cd[a] = v.cmds_damp[4 * gi + a];
             if (v.ou) for (int a = 0; a < 4; ++a) q.ou[a] = v.ou[4 * gi + a];
             if (v.goal) for (int a = 0; a < 3; ++a) q.goal[a] = v.goal[3 * gi + a];
-            if (v.flags) q.flags = v.flags[gi];
+            if (v.flags) q.flags = (v.flags[gi] & ~F_SCEN_OSTATIC) | (q.flags & F_SCEN_OSTATIC);   // the episode's scenario bit is not caller state
             if (v.col_mask) q.colmask = v.col_mask[gi];
             store_drone(P, gi, q, true);
         } else {

@@ -83,7 +83,11 @@ struct DevPtrs {
 enum { F_ON_FLOOR = 1, F_CR_FLOOR = 2, F_CR_WALL = 4, F_CR_CEIL = 8, F_PREV_WALL = 16, F_PREV_CEIL = 32,
        F_PREV_ROOM = 64, F_PREV_OBST = 128, F_REACHED = 256, F_COL_AGENT = 512, F_COL_OBST = 1024,
        // transient (last sub-step): the drone sits exactly on a wall plane (collisions/room.py:14-15 `pos == room_box`)
-       F_AT_XLO = 2048, F_AT_XHI = 4096, F_AT_YLO = 8192, F_AT_YHI = 16384 };
+       F_AT_XLO = 2048, F_AT_XHI = 4096, F_AT_YLO = 8192, F_AT_YHI = 16384,
+       // obstacle `mix`: this episode runs o_static_same_goal (else o_random).  Kept per drone in the flag word, which the step kernel
+       // loads anyway: as a separate per-env load it was spilled right after the load, which stalled the warp for a whole HBM round
+       // trip before the state loads were even issued (ncu, profiles/README.md)
+       F_SCEN_OSTATIC = 32768 };
 
 // RNG sites: DESIGN.md "RNG contract" (identical table in oracle/quadsim_oracle.c)
 enum { SITE_OU = 0, SITE_SENSOR = 1, SITE_SENSOR_IMPULSE = 2, SITE_SENSOR_RESET = 3, SITE_FLOOR_YAW = 4,
@@ -824,7 +828,7 @@ __device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P,
     q.v[0] = q.v[1] = q.v[2] = 0.f; q.w[0] = q.w[1] = q.w[2] = 0.f;
 #pragma unroll
     for (int m = 0; m < 4; ++m) { q.rd[m] = 0.f; q.cd[m] = 0.f; }
-    q.flags = 0; q.colmask = 0u;
+    q.flags = (OBST && scenario_now == QS_SCENARIO_O_STATIC_SAME_GOAL) ? F_SCEN_OSTATIC : 0; q.colmask = 0u;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -995,7 +999,6 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         __syncwarp();
         if (env < c.N) {
             tick = sc[lane / KG]; svd = sc[GPW + lane / KG]; g.step = (uint32_t)sc[2 * GPW + lane / KG];
-            if (OBST) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
             g.gid = (uint32_t)(c.env_id_offset + env);
         }
         mbar_wait(bar, phase);
@@ -1017,7 +1020,6 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     } else {
         if (env < c.N) {                                                // env-level scalars: every lane of the group
             tick = P.tick[env]; svd = P.svd_ctr[env];
-            if (OBST) scen_now = P.ecnt[env * EC_COUNT + EC_SCENARIO];
             g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
         }
         if (SCEN && env < c.N) {                                        // scenario row: loaded with the state, parked in shared memory
@@ -1176,6 +1178,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     if (OBST) reward += c.rew_col_obst * (obst_new ? -1.0f : 0.0f);
     if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }      // final here: not carried (spilled) across the impulse / observation code
 
+    if (OBST) scen_now = (q.flags & F_SCEN_OSTATIC) ? QS_SCENARIO_O_STATIC_SAME_GOAL : QS_SCENARIO_O_RANDOM;
     // distance_to_goal log: reached-goal flag from the mean of the last 5 entries, and the 1/3/5 s windows (:651-655, 762-767)
     if (valid) {
         float dlog = c.dt * dist;                                      // -rewraw_pos
