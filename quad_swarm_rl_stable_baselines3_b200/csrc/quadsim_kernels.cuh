@@ -994,6 +994,14 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     int scen_now = 0;
     float4 ring = make_float4(0.f, 0.f, 0.f, 0.f), sums = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 sc_row[(QS_SC_COUNT / 4 + KG - 1) / KG];
+    float2 ob_v[4];                                                     // obstacle centres: issued first, they depend on nothing
+    if (OBST) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int k = lane + 32 * t, e = k / c.M, m = k - e * c.M;
+            ob_v[t] = (k < ob_per_warp && warp_env0 + e < c.N) ? __ldcs(P.obst_xy + (size_t)(warp_env0 + e) * QS_MAX_OBSTACLES + m) : make_float2(0.f, 0.f);
+        }
+    }
     if (PERSIST) {
         cp_async_wait_all();
         __syncwarp();
@@ -1055,9 +1063,11 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         q.flags = 0; q.colmask = 0;
     }
     if (OBST) {
-        // all loads first, then the shared-memory stores: load -> store per trip serialised one HBM round trip per trip at the top of
-        // every warp (the 12-obstacle scenario needs two trips: 48 centres per warp-tile)
-        for (int k0 = lane; k0 < ob_per_warp; k0 += 128) {
+        // obstacle centres of this warp-tile's envs -> shared memory.  The first 128 were loaded before the state (above); every
+        // load is issued before the first shared-memory store (a load -> store loop serialises one HBM round trip per trip)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (lane + 32 * t < ob_per_warp) ob_sm[lane + 32 * t] = ob_v[t];
+        for (int k0 = lane + 128; k0 < ob_per_warp; k0 += 128) {        // more than 32 obstacles per env: further trips
             float2 v[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
