@@ -88,3 +88,23 @@ def test_fork_config_validation():
         QuadSimConfig(quads_mode="dynamic_repulsive").to_c()   # fork scenario in upstream mode
     with pytest.raises(ValueError):
         QuadSimConfig.fork_default(use_obstacles=True).to_c()
+
+
+def test_step_kernel_prologues_issue_every_load_before_the_first_consumer():
+    """Static SASS check of the built objects (profiles/tools/prologue_check.py): in every shipped step-kernel variant all
+    prologue loads are issued before the first instruction that consumes an in-flight load.  A consumer in between serialises two
+    HBM round trips at the top of every warp (cost 3-5 % twice in round 1)."""
+    import importlib.util
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    objdir = os.path.join(root, "build", "obj")
+    if shutil.which("cuobjdump") is None or not os.path.exists(os.path.join(objdir, "kernels_kg8.o")):
+        pytest.skip("needs cuobjdump and the objects of an in-tree build")
+    spec = importlib.util.spec_from_file_location("prologue_check", os.path.join(root, "profiles", "tools", "prologue_check.py"))
+    pc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pc)
+    for obj, sub in pc.KERNELS:
+        r = pc.analyse(os.path.join(objdir, obj), sub)
+        assert r is not None, sub
+        assert r["loads"] >= 12 and r["first_use"] is not None, r
+        assert r["late_loads"] == [], r
