@@ -238,7 +238,8 @@ typedef struct qs_state_view {
     float *ou;           /* [N*K,4] OU thrust-noise state */
     float *goal;         /* [N*K,3] */
     int32_t *flags;      /* [N*K]   bit0 on_floor, bit1 crashed_floor, bit2 crashed_wall, bit3 crashed_ceiling,
-                                    bit4 prev_new_wall, bit5 prev_new_ceiling, bit6 prev_new_room, bit7 prev_obst_hit */
+                                    bit4 prev_new_wall, bit5 prev_new_ceiling, bit6 prev_new_room, bit7 prev_obst_hit;
+                                    higher bits are internal (bit 15: the obstacle scenario of the episode, kept by qs_set_state) */
     uint32_t *col_mask;  /* [N*K]   previous-step collision row (bit j set: pair (i,j) collided last step) */
     int32_t *tick;       /* [N]     per-env episode tick */
     int32_t *svd_ctr;    /* [N]     sub-steps since the last re-orthonormalisation */
