@@ -19,6 +19,8 @@
  *   qs_set_param             rew_coeff updates / set_capture_radius  quadrotor_multi.py:101-112, quadrotor_multi_rewards.py:210-211
  *   qs_episode_stats         infos[i]['episode_extra_stats'] summed over a rollout   gym_art/quadrotor_multi/quadrotor_multi.py:739-831
  *   qs_episode_records       infos[i]['episode_extra_stats'] per finished episode    (same lines)
+ *   qs_set_reward_info       infos[i]['rewards'] of every step        gym_art/quadrotor_multi/quadrotor_single.py:69-84, quadrotor_multi.py:642-649
+ *                            infos[i]['goal_dist'] (fork env)         gym_art/quadrotor_multi/quadrotor_single_rewards.py:457
  *
  * Conventions
  *   - plain C types only; all device pointers are raw CUDA device addresses (e.g. torch tensor.data_ptr()).
@@ -361,6 +363,19 @@ int qs_episode_stats(qs_env *env, qs_stats *out, int reset, void *stream);
  * returns after the stream has drained. */
 int qs_episode_records(qs_env *env, int32_t *env_rec, float *agent_rec, void *stream);
 int qs_episode_records_host(qs_env *env, int32_t *env_rec_host, float *agent_rec_host, void *stream);
+
+/* Per-step reward breakdown (optional, off by default).  rew_info: device float [N*K, QS_RI_COUNT], 16-byte aligned, owned by
+ * the caller; from the next qs_step on every step writes, per drone, the RAW reward terms of the reference's
+ * infos[i]["rewards"] (each already multiplied by dt where the reference does: quadrotor_single.py:69-84): the weighted entries are
+ * raw * rew_coeff (Python side).  Fork mode writes infos[i]['goal_dist'] (quadrotor_single_rewards.py:457) into slot 0 and zeros
+ * elsewhere -- its 'rewards' dict is empty in the reference.  NULL switches the output off again. */
+enum { QS_RI_RAW_POS = 0,           /* rewraw_pos = rewraw_main; fork mode: goal_dist */
+       QS_RI_RAW_ACTION = 1, QS_RI_RAW_CRASH = 2, QS_RI_RAW_ORIENT = 3, QS_RI_RAW_SPIN = 4,
+       QS_RI_RAW_QUADCOL = 5,       /* rewraw_quadcol: -1 / 0 */
+       QS_RI_PROXIMITY = 6,         /* rew_proximity */
+       QS_RI_RAW_QUADCOL_OBST = 7,  /* rewraw_quadcol_obstacle: -1 / 0 */
+       QS_RI_COUNT = 8 };
+int qs_set_reward_info(qs_env *env, float *rew_info);
 
 #ifdef __cplusplus
 }

@@ -61,9 +61,15 @@ def lib():
         L.qo_get_record.argtypes = [C.c_void_p, C.c_void_p, dp]
         L.qo_get_diag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.qo_set_param.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.qo_get_margins.argtypes = [C.c_void_p, dp]
+        L.qo_get_reward_info.argtypes = [C.c_void_p, dp]
         L.qo_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
         L.qo_batch_step.argtypes = [C.POINTER(C.c_void_p), C.c_int, dp, dp, dp, C.POINTER(C.c_uint8)]
         L.qo_batch_reset.argtypes = [C.POINTER(C.c_void_p), C.c_int, dp]
+        L.qo_batch_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, dp, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint8), C.c_int]
+        L.qo_batch_run.restype = C.c_longlong
+        L.qo_omp_threads.restype = C.c_int
+        L.qo_set_tick.argtypes = [C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -222,6 +228,22 @@ class OracleEnv:
         lib().qo_get_diag(self.h, _vp(new_pairs), _vp(nb), C.byref(flag))
         return dict(new_pairs=new_pairs, neighbors=nb[:, :self.cfg.visible], impulse_flag=int(flag.value))
 
+    def reward_info(self):
+        """Raw reward terms of the last step, [K, 8] in QS_RI_* order (infos[i]["rewards"]; fork mode: goal_dist in column 0)."""
+        out = np.zeros((self.K, 8))
+        lib().qo_get_reward_info(self.h, _dp(out))
+        return out
+
+    MARGIN_CLASSES = ("pair", "falloff", "obst", "floor", "wall", "ceil", "yaw", "rank", "reach", "liftoff")
+
+    def margins(self):
+        """Distance of the last step's threshold decisions from their thresholds, per class, in fp32 ulps of the operands'
+        magnitude (min over the env; 1e300 = the class made no decision).  A discrete disagreement with the fp32 kernel is a
+        tie only if the class that produces that flag is within a few ulps here."""
+        m = np.zeros(lib().qo_margin_count())
+        lib().qo_get_margins(self.h, _dp(m))
+        return dict(zip(self.MARGIN_CLASSES, m))
+
     def set_param(self, key: int, value: float):
         lib().qo_set_param(self.h, key, value)
 
@@ -280,3 +302,15 @@ class OracleBatch:
         else:
             list(self.pool.map(run, self.slices))
         return self.obs, self.rew, self.done
+
+    def set_ticks(self, ticks):
+        """Episode clock of every env (bench.py staggers them so that resets are spread over the timed window)."""
+        for e, t in zip(self.envs, ticks):
+            lib().qo_set_tick(e.h, int(t))
+
+    def run(self, action_pool, steps: int) -> int:
+        """`steps` lock-step batch steps inside one native call on `self.threads` OpenMP threads (action set s % pool at
+        step s).  Returns the number of episodes that finished.  This is what bench.py times as the CPU arm."""
+        a = np.ascontiguousarray(action_pool, dtype=np.float64).reshape(-1, self.N * self.K * self.envs[0].A)
+        return int(lib().qo_batch_run(self.handles, self.N, _dp(a), a.shape[0], int(steps), _dp(self.obs), _dp(self.rew),
+                                      self.done.ctypes.data_as(C.POINTER(C.c_uint8)), self.threads))

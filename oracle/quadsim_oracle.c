@@ -17,6 +17,9 @@
  * counter-based generator specified in DESIGN.md ("RNG contract"), identical to the CUDA kernels'.
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -61,6 +64,12 @@ typedef struct {
     int n_goals, n1_rows;
 } qo_scen;
 
+enum { QO_MG_PAIR = 0, QO_MG_FALLOFF, QO_MG_OBST, QO_MG_FLOOR, QO_MG_WALL, QO_MG_CEIL, QO_MG_YAW, QO_MG_RANK, QO_MG_REACH, QO_MG_LIFTOFF, QO_MG_COUNT };
+/* fp32 unit in the last place at magnitude |x| (>= 2^-126) */
+static double ulp32(double x) { x = fabs(x); if (x < 1.17549435e-38) x = 1.17549435e-38; int ex; frexp(x, &ex); return ldexp(1.0, ex - 24); }
+struct qo_env;
+static void mg_note(struct qo_env *e, int cls, double value, double threshold, double scale);
+
 typedef struct qo_env {
     qs_config c;
     qo_scen sc;
@@ -93,11 +102,23 @@ typedef struct qo_env {
     uint32_t last_new_pairs[QS_MAX_AGENTS];
     int32_t last_neighbors[QS_MAX_AGENTS][QS_MAX_AGENTS];
     int last_impulse_flag;
+    /* distance of every threshold decision of the last step from its threshold, in fp32 ulps of the operands' magnitude (min per class):
+     * the parity tests accept a discrete disagreement with the fp32 kernel only where this proves a tie */
+    double margin[QO_MG_COUNT];
+    /* infos[i]["rewards"] raw terms of the last step (QS_RI_* order; fork mode: goal_dist in slot 0) */
+    double rew_info[QS_MAX_AGENTS][QS_RI_COUNT];
     /* tape */
     const double *tn, *tu, *tc;
     int nn, nu, nc, in_, iu, ic;
     int use_tape;
 } qo_env;
+
+static void mg_note(struct qo_env *e, int cls, double value, double threshold, double scale)
+{
+    double m = fabs(value - threshold) / ulp32(fmax(fabs(scale), fabs(threshold)));
+    if (m < e->margin[cls]) e->margin[cls] = m;
+}
+static void mg_clear(struct qo_env *e) { for (int k = 0; k < QO_MG_COUNT; ++k) e->margin[k] = 1e300; }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* Philox4x32-10 + unit transforms (DESIGN.md "RNG contract")                                         */
@@ -287,6 +308,8 @@ static void dynamics_substep(qo_env *e, int i, const double *cmd_in, int substep
     q->pos[0] = clampd(bx, -hx, hx); q->pos[1] = clampd(by, -hy, hy); q->pos[2] = clampd(bz, 0.0, hz);
     q->crashed_wall = !(bx == q->pos[0] && by == q->pos[1]);
     q->crashed_ceiling = bz > q->pos[2];
+    mg_note(e, QO_MG_WALL, fabs(bx), hx, hx); mg_note(e, QO_MG_WALL, fabs(by), hy, hy); mg_note(e, QO_MG_CEIL, bz, hz, hz);
+    mg_note(e, QO_MG_FLOOR, q->pos[2], c->arm, fmax(fabs(q->pos[2]), fabs(dt * q->vel[2])));
 
     /* --- floor_interaction_numba, quadrotor_dynamics.py:576-646 (floor_threshold = arm, :385) --- */
     double thr[3] = { 0, 0, thrust_sum }, force[3];
@@ -295,6 +318,7 @@ static void dynamics_substep(qo_env *e, int i, const double *cmd_in, int substep
         q->pos[2] = c->arm;
         matvec3(q->rot, thr, force);
         if (q->on_floor) {
+            mg_note(e, QO_MG_LIFTOFF, force[2] / c->mass, QO_GRAV, QO_GRAV);    /* acc_z = max(0, .): whether a resting drone lifts off */
             double theta = atan2(q->rot[3], q->rot[0] + QO_EPS_DYN);
             yaw_rot(theta, q->rot);
             double fr = c->floor_mu * (c->mass * QO_GRAV - force[2]);
@@ -338,7 +362,7 @@ static void drone_control_step(qo_env *e, int i, const double *action, const int
 }
 
 /* compute_reward_weighted, quadrotor_single.py:34-92 (dt = physics dt, :362-364) */
-static double base_reward(const qo_env *e, int i, const double *action, double *rewraw_pos)
+static double base_reward(qo_env *e, int i, const double *action, double *rewraw_pos)
 {
     const qs_config *c = &e->c;
     const qo_drone *q = &e->d[i];
@@ -349,6 +373,9 @@ static double base_reward(const qo_env *e, int i, const double *action, double *
     double spin = sqrt(q->omega[0] * q->omega[0] + q->omega[1] * q->omega[1] + q->omega[2] * q->omega[2]);
     double crash = q->on_floor ? 1.0 : 0.0;
     *rewraw_pos = c->dt * (-dist);
+    double *ri = e->rew_info[i];                                  /* rew_info entries are dt * (-raw cost), quadrotor_single.py:69-84 */
+    ri[QS_RI_RAW_POS] = c->dt * -dist; ri[QS_RI_RAW_ACTION] = c->dt * -effort; ri[QS_RI_RAW_CRASH] = c->dt * -crash;
+    ri[QS_RI_RAW_ORIENT] = c->dt * -orient; ri[QS_RI_RAW_SPIN] = c->dt * -spin;
     return -c->dt * (c->rew_pos * dist + c->rew_effort * effort + c->rew_crash * crash + c->rew_orient * orient +
                      c->rew_spin * spin);
 }
@@ -426,6 +453,9 @@ static void neighbor_obs(qo_env *e, int i, double *o)
     for (int a = 0; a < n; ++a) order[a] = a;
     if (V < K - 1) {                                             /* :352-371 argsort (ties: lowest index first) */
         for (int a = 1; a < n; ++a) { int x = order[a], b = a - 1; while (b >= 0 && metric[order[b]] > metric[x]) { order[b + 1] = order[b]; --b; } order[b + 1] = x; }
+    }
+    if (V < K - 1) {                                             /* a tie = two candidates whose metrics are within fp32 round-off, one of them chosen */
+        for (int a = 0; a < V && a + 1 < n; ++a) mg_note(e, QO_MG_RANK, metric[order[a]], metric[order[a + 1]], metric[order[a + 1]]);
     }
     double lim_p[3] = { c->room_dims[0], c->room_dims[1], c->room_dims[2] };   /* room_range, quadrotor_single.py:279,295 */
     double lim_v = 2.0 * 3.0;                                                  /* 2 * vxyz_max, quadrotor_single.py:296 */
@@ -726,6 +756,7 @@ static void drone_reset(qo_env *e, int i)
     double theta = atan2(hy, hx);
     for (int att = 0; att < 64; ++att) {
         double t = -QO_PI + 2.0 * QO_PI * rnd_u(e, SITE_SPAWN, i, 1, att);
+        mg_note(e, QO_MG_YAW, cos(t) * hx + sin(t) * hy, 0.5, 1.0);
         if (!(cos(t) * hx + sin(t) * hy < 0.5)) { theta = t; break; }
     }
     yaw_rot(theta, q->rot);
@@ -820,6 +851,10 @@ static void env_step(qo_env *e, const double *actions, double *obs, double *rew,
         for (int j = i + 1; j < K; ++j) {
             double dx = e->d[i].pos[0] - e->d[j].pos[0], dy = e->d[i].pos[1] - e->d[j].pos[1], dz = e->d[i].pos[2] - e->d[j].pos[2];
             double dist = sqrt(dx * dx + dy * dy + dz * dz);
+            {
+                double sc = 0; for (int a = 0; a < 3; ++a) sc = fmax(sc, fmax(fabs(e->d[i].pos[a]), fabs(e->d[j].pos[a])));
+                mg_note(e, QO_MG_PAIR, dist, thr_col, sc); mg_note(e, QO_MG_FALLOFF, dist, thr_fall, sc);
+            }
             if (dist <= thr_col) { row[i] |= 1u << j; row[j] |= 1u << i; }
             if (dist <= thr_fall) { double pen = pen_ratio * dist + c->rew_quadcol_bin_smooth_max; prox[i] += pen; prox[j] += pen; }  /* quadrotors.py:95-103 */
         }
@@ -850,6 +885,7 @@ static void env_step(qo_env *e, const double *actions, double *obs, double *rew,
         for (int i = 0; i < K; ++i)
             for (int m = 0; m < e->n_obst; ++m) {
                 double dx = e->d[i].pos[0] - e->obst_xy[m][0], dy = e->d[i].pos[1] - e->obst_xy[m][1];
+                mg_note(e, QO_MG_OBST, sqrt(dx * dx + dy * dy), thr_o, fmax(fabs(e->d[i].pos[0]), fabs(e->d[i].pos[1])));
                 if (sqrt(dx * dx + dy * dy) <= thr_o) { obst_hit[i] = m; break; }
             }
         for (int i = 0; i < K; ++i) {
@@ -883,11 +919,14 @@ static void env_step(qo_env *e, const double *actions, double *obs, double *rew,
         rew[i] += c->rew_quadcol_bin * rc;
         rew[i] += -1.0 * ((c->dt * c->sim_steps) * prox[i]);
         if (c->use_obstacles) rew[i] += c->rew_quadcol_bin_obst * (obst_new[i] ? -1.0 : 0.0);   /* :594-597 */
+        e->rew_info[i][QS_RI_RAW_QUADCOL] = rc; e->rew_info[i][QS_RI_PROXIMITY] = -1.0 * ((c->dt * c->sim_steps) * prox[i]);   /* :642-649 */
+        e->rew_info[i][QS_RI_RAW_QUADCOL_OBST] = (c->use_obstacles && obst_new[i]) ? -1.0 : 0.0;
         qo_drone *q = &e->d[i];
         double dlog = -rewraw_pos[i];                             /* :651 */
         q->dist_hist[q->dist_n % 5] = dlog; q->dist_n++;
         if (q->dist_n >= 5 && !q->reached_goal) {
             double m5 = 0; for (int a = 0; a < 5; ++a) m5 += q->dist_hist[a];
+            mg_note(e, QO_MG_REACH, (m5 / 5.0) / c->dt, e->approach_metric, (m5 / 5.0) / c->dt);
             if ((m5 / 5.0) / c->dt < e->approach_metric) q->reached_goal = 1;
         }
         /* running sums for distance_to_goal_{1,3,5}s (:762-767): windows are the last 100/300/500 control steps of a
@@ -982,9 +1021,10 @@ void qo_set_tape(qo_env *e, const double *normals, int nn, const double *uniform
 /* how far the tape was consumed (tests assert it was consumed exactly) */
 void qo_tape_pos(const qo_env *e, int *in_, int *iu, int *ic) { *in_ = e->in_; *iu = e->iu; *ic = e->ic; }
 
-void qo_reset(qo_env *e, double *obs) { if (is_fork(e)) fork_env_reset(e, obs); else env_reset(e, obs); e->step_ctr += 1; }
+void qo_reset(qo_env *e, double *obs) { mg_clear(e); if (is_fork(e)) fork_env_reset(e, obs); else env_reset(e, obs); e->step_ctr += 1; }
 void qo_step(qo_env *e, const double *actions, double *obs, double *rew, uint8_t *done, double *terminal_obs, uint8_t *reset_success)
 {
+    mg_clear(e);
     if (is_fork(e)) fork_env_step(e, actions, obs, rew, done, terminal_obs, reset_success);
     else { env_step(e, actions, obs, rew, done, terminal_obs); if (reset_success && done[0]) *reset_success = 0; }
 }
@@ -1101,6 +1141,10 @@ double qo_col_norm_and_new_vel_obst(const double *pos, const double *vel, const 
 void qo_set_obstacles(qo_env *e, const double *xy, int n) { e->n_obst = n; for (int m = 0; m < n; ++m) { e->obst_xy[m][0] = xy[2 * m]; e->obst_xy[m][1] = xy[2 * m + 1]; } }
 void qo_get_obstacles(const qo_env *e, double *xy, int *n) { *n = e->n_obst; for (int m = 0; m < e->n_obst; ++m) { xy[2 * m] = e->obst_xy[m][0]; xy[2 * m + 1] = e->obst_xy[m][1]; } }
 void qo_get_stats(const qo_env *e, qs_stats *out) { *out = e->stats; }
+void qo_get_reward_info(const qo_env *e, double *out) { for (int i = 0; i < e->K; ++i) memcpy(out + (size_t)i * QS_RI_COUNT, e->rew_info[i], sizeof(double) * QS_RI_COUNT); }
+/* min distance-to-threshold of the last qo_step / qo_reset per decision class, in fp32 ulps (QO_MG_* order; 1e300 = class not exercised) */
+void qo_get_margins(const qo_env *e, double *out) { for (int k = 0; k < QO_MG_COUNT; ++k) out[k] = e->margin[k]; }
+int qo_margin_count(void) { return QO_MG_COUNT; }
 void qo_get_record(const qo_env *e, int32_t *env_rec, double *agent_rec)
 {
     memcpy(env_rec, e->ep_rec, sizeof(e->ep_rec));
@@ -1141,3 +1185,40 @@ void qo_batch_reset(qo_env **envs, int n, double *obs)
     int K = envs[0]->K, D = any_obs_dim(&envs[0]->c);
     for (int k = 0; k < n; ++k) qo_reset(envs[k], obs + (size_t)k * K * D);
 }
+
+/* `steps` lock-step batch steps on `threads` OpenMP threads inside ONE native call (no Python dispatch per step): envs are cut
+ * into static slices, every thread steps its slice, one barrier per step -- the data parallelism of the reference's
+ * SubprocVecEnvCustom (one worker per env group, step_wait = barrier) at its cheapest.  actions: pool of `pool` action sets
+ * [pool][n*K*A], step s uses set s % pool.  Returns the number of env resets (finished episodes) seen. */
+long long qo_batch_run(qo_env **envs, int n, const double *actions, int pool, int steps, double *obs, double *rew, uint8_t *done, int threads)
+{
+    if (n <= 0 || steps <= 0 || pool <= 0) return 0;
+    const int K = envs[0]->K, D = any_obs_dim(&envs[0]->c), A = any_act_dim(&envs[0]->c);
+    long long resets = 0;
+#ifdef _OPENMP
+    if (threads < 1) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads) reduction(+ : resets)
+#endif
+    {
+        for (int s = 0; s < steps; ++s) {
+            const double *a = actions + (size_t)(s % pool) * n * K * A;
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+            for (int k = 0; k < n; ++k) {
+                qo_step(envs[k], a + (size_t)k * K * A, obs + (size_t)k * K * D, rew + (size_t)k * K, done + (size_t)k * K, NULL, NULL);
+                resets += done[(size_t)k * K] ? 1 : 0;
+            }
+        }
+    }
+    return resets;
+}
+int qo_omp_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void qo_set_tick(qo_env *e, int tick) { e->tick = tick; }

@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXPORTS = ("qs_config_size", "qs_stats_size", "qs_api_version", "qs_last_error", "qs_create", "qs_destroy",
            "qs_num_envs", "qs_num_agents", "qs_obs_dim", "qs_act_dim", "qs_launch_count", "qs_reset", "qs_step",
            "qs_reset_host", "qs_step_host", "qs_get_state", "qs_set_state", "qs_set_param", "qs_episode_stats",
-           "qs_episode_records", "qs_episode_records_host")
+           "qs_episode_records", "qs_episode_records_host", "qs_set_reward_info")
 
 
 KG_VALUES = (1, 2, 4, 8, 16, 32)
@@ -99,6 +99,7 @@ def lib():
     L.qs_episode_stats.argtypes = [vp, C.POINTER(QsStatsC), i32, vp]
     L.qs_episode_records.argtypes = [vp, vp, vp, vp]
     L.qs_episode_records_host.argtypes = [vp, vp, vp, vp]
+    L.qs_set_reward_info.argtypes = [vp, vp]
     L.qs_philox_probe.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32), fp]
     if L.qs_config_size() != C.sizeof(QsConfigC) or L.qs_stats_size() != C.sizeof(QsStatsC):
         raise RuntimeError("qs_config / qs_stats layout mismatch between config.py and include/quadsim.h")

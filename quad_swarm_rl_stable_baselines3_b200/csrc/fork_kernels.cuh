@@ -444,7 +444,12 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
             bad_any = bad_now;
             any_done = any_cap || timeout || bad_now;
             // ---- self observation of the last executed sub-step (goal = evader before scenario.step)
-            if (valid && (any_done || sub == f.substeps - 1)) fork_self_obs(c, g, SITE_SENSOR, d, q, angle, ang_vel, orow);
+            if (valid && (any_done || sub == f.substeps - 1)) {
+                fork_self_obs(c, g, SITE_SENSOR, d, q, angle, ang_vel, orow);
+                // infos[i]['goal_dist'] of the last executed sub-step (quadrotor_single_rewards.py:457): 3-D distance to self.goal
+                if (__builtin_expect(P.rew_info != nullptr, 0))
+                    P.rew_info[2 * gi] = make_float4(norm3f(q.p[0] - q.goal[0], q.p[1] - q.goal[1], q.p[2] - q.goal[2]), 0.f, 0.f, 0.f);
+            }
             // ---- scenario.step (:848)
             evader_advance(f, efx, efy, ex, ey);
             q.goal[0] = ex; q.goal[1] = ey; q.goal[2] = 2.0f;

@@ -1,5 +1,8 @@
 // kernels_kg.cu -- instantiates every kernel for ONE lane-group width (compile with -DQS_KG=1|2|4|8|16|32).
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "launch.h"
 
@@ -17,12 +20,29 @@ constexpr int KG = QS_KG;
 // (no L1 reuse) but spill a few registers at the 128-register cap; with the maximum carve-out L1 shrinks to ~28 KB, the 16
 // resident warps' stack frames do not fit and every spill reload becomes an L2 round trip (profiles/README.md, v5: 89.3 ->
 // 86.3 us).  `block` == 0 (persistent form, whose prefetch buffers need all of it): maximum carve-out.
+// The attributes belong to the kernel instantiation on a device, not to a handle: several handles (train env + eval env, as
+// sb_train.py runs them) share them, so both the dynamic shared-memory limit and the carve-out are only ever RAISED -- a later,
+// smaller handle must not pull the limit below what an earlier one launches with (cudaErrorInvalidValue on its next step).
+struct AttrState { int max_bytes = 0; int carve = -1; };
+inline AttrState &attr_state(const void *kernel)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, AttrState> table;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    return table[std::make_pair(dev, kernel)];
+}
+
 template <typename... Args>
 void set_attr(size_t bytes, void (*kernel)(Args...), int block = 0)
 {
-    if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    AttrState &st = attr_state(reinterpret_cast<const void *>(kernel));
+    if (bytes > 48 * 1024 && (int)bytes > st.max_bytes) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        st.max_bytes = (int)bytes;
+    }
     int carve = cudaSharedmemCarveoutMaxShared;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (block > 0) {
         int nblk = 0, dev = 0, smem_sm = 233472;
         cudaGetDevice(&dev);
@@ -34,7 +54,11 @@ void set_attr(size_t bytes, void (*kernel)(Args...), int block = 0)
         }
     }
     if (const char *e = getenv("QS_CARVEOUT")) { int v = atoi(e); if (v >= 0 && v <= 100) carve = v; }   // tuning knob (percent of max shared)
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (carve == cudaSharedmemCarveoutMaxShared) carve = 100;
+    if (carve > st.carve) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        st.carve = carve;
+    }
 }
 
 // feature sets of the upstream step kernel: bit 0 obstacles, bit 1 downwash, bit 2 formation scenarios (never with obstacles)

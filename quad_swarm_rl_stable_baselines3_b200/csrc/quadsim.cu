@@ -17,11 +17,11 @@ namespace qs {
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, int set)
 {
-    int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    int nd = c.N * c.K;
+    const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // 24 * gi exceeds 2^31 at the largest admitted batches
+    const size_t nd = (size_t)c.N * c.K;
     if (gi < nd) {
         Drone q;
-        load_drone(P, gi, q);
+        load_drone(P, (int)gi, q);                                       // gi < nd <= 2^30 (validate())
         if (set) {
             if (v.pos) for (int a = 0; a < 3; ++a) q.p[a] = v.pos[3 * gi + a];
             if (v.vel) for (int a = 0; a < 3; ++a) q.v[a] = v.vel[3 * gi + a];
@@ -33,7 +33,7 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, 
             if (v.goal) for (int a = 0; a < 3; ++a) q.goal[a] = v.goal[3 * gi + a];
             if (v.flags) q.flags = (v.flags[gi] & ~F_SCEN_OSTATIC) | (q.flags & F_SCEN_OSTATIC);   // the episode's scenario bit is not caller state
             if (v.col_mask) q.colmask = v.col_mask[gi];
-            store_drone(P, gi, q, true);
+            store_drone(P, (int)gi, q, true);
         } else {
             if (v.pos) for (int a = 0; a < 3; ++a) v.pos[3 * gi + a] = q.p[a];
             if (v.vel) for (int a = 0; a < 3; ++a) v.vel[3 * gi + a] = q.v[a];
@@ -59,11 +59,11 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, 
             else { float4 x = F.plane[FP_HEADING][gi]; v.heading[3 * gi] = x.x; v.heading[3 * gi + 1] = x.y; v.heading[3 * gi + 2] = x.z; }
         }
     }
-    if (gi < c.N && F.evader != nullptr && v.evader) {
+    if (gi < (size_t)c.N && F.evader != nullptr && v.evader) {
         if (set) F.evader[gi] = make_float2(v.evader[2 * gi], v.evader[2 * gi + 1]);
         else { float2 x = F.evader[gi]; v.evader[2 * gi] = x.x; v.evader[2 * gi + 1] = x.y; }
     }
-    if (gi < c.N) {
+    if (gi < (size_t)c.N) {
         if (set) {
             if (v.tick) P.tick[gi] = v.tick[gi];
             if (v.svd_ctr) P.svd_ctr[gi] = v.svd_ctr[gi];
@@ -75,16 +75,16 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, 
         }
     }
     if (v.scenario && P.scen) {
-        int tot = c.N * QS_SC_COUNT;
+        const size_t tot = (size_t)c.N * QS_SC_COUNT;
         float *rows = reinterpret_cast<float *>(P.scen);
-        for (int k = gi; k < tot; k += gridDim.x * blockDim.x) {
+        for (size_t k = gi; k < tot; k += (size_t)gridDim.x * blockDim.x) {
             if (set) rows[k] = v.scenario[k];
             else v.scenario[k] = rows[k];
         }
     }
     if (v.obst_xy) {
-        int tot = c.N * QS_MAX_OBSTACLES;
-        for (int k = gi; k < tot; k += gridDim.x * blockDim.x) {
+        const size_t tot = (size_t)c.N * QS_MAX_OBSTACLES;
+        for (size_t k = gi; k < tot; k += (size_t)gridDim.x * blockDim.x) {
             if (set) P.obst_xy[k] = make_float2(v.obst_xy[2 * k], v.obst_xy[2 * k + 1]);
             else { float2 xy = P.obst_xy[k]; v.obst_xy[2 * k] = xy.x; v.obst_xy[2 * k + 1] = xy.y; }
         }
@@ -386,7 +386,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     // small batches: 64-thread blocks so that every SM gets work; large batches: 128
     e->block = (lanes < (long long)sms * 2 * 128) ? 64 : 128;
-    if (const char *tb = getenv("QS_BLOCK")) { int v = atoi(tb); if (v == 32 || v == 64 || v == 128 || v == 256) e->block = v; }   // tuning knob
+    if (const char *tb = getenv("QS_BLOCK")) { int v = atoi(tb); if ((v == 32 || v == 64 || v == 128 || v == 256) && v <= QS_STEP_MAXTHREADS) e->block = v; }   // tuning knob (the step kernels are compiled for <= QS_STEP_MAXTHREADS threads)
     if (e->block < e->KG) e->block = e->KG;
     e->grid = (int)((lanes + e->block - 1) / e->block);
     const int warps = e->block / 32 > 0 ? e->block / 32 : 1;
@@ -506,6 +506,7 @@ static void launch_step_range(qs_env *e, int e0, int n, cudaStream_t s, const fl
     DevPtrs P = e->dp;
     c.N = n; c.env_id_offset += e0;
     for (int p = 0; p < PL_COUNT; ++p) P.plane[p] += r0;
+    if (P.rew_info) P.rew_info += 2 * r0;
     P.tick += e0; P.svd_ctr += e0; P.step_ctr += e0; P.ecnt += (size_t)e0 * EC_COUNT; P.ep_rec += (size_t)e0 * QS_ER_COUNT; P.ep_agent += r0;
     if (e->cfg.use_obstacles) P.obst_xy += (size_t)e0 * QS_MAX_OBSTACLES;
     if (P.scen) P.scen += (size_t)e0 * (QS_SC_COUNT / 4);
@@ -576,15 +577,25 @@ int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *r
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t N = (size_t)e->cfg.num_envs, nd = N * e->cfg.num_agents, D = (size_t)e->dc.D, A = (size_t)e->A;
-    if (terminal_obs_host && !e->d_term) {
-        QS_CUDA(e, cudaMalloc(&e->d_term, nd * D * sizeof(float)));
-        QS_CUDA(e, cudaMemsetAsync(e->d_term, 0, nd * D * sizeof(float), s));
-        QS_CUDA(e, cudaMallocHost(&e->h_term, nd * D * sizeof(float)));
+    if (terminal_obs_host && !(e->d_term && e->h_term)) {                // device + pinned pair: all or nothing
+        cudaError_t r = e->d_term ? cudaSuccess : cudaMalloc(&e->d_term, nd * D * sizeof(float));
+        if (r == cudaSuccess) r = cudaMemsetAsync(e->d_term, 0, nd * D * sizeof(float), s);
+        if (r == cudaSuccess) r = cudaMallocHost(&e->h_term, nd * D * sizeof(float));
+        if (r != cudaSuccess) {
+            if (e->d_term) cudaFree(e->d_term);
+            e->d_term = nullptr; e->h_term = nullptr;
+            return fail(e, QS_ERR_CUDA, std::string("qs_step_host: terminal-observation buffers: ") + cudaGetErrorString(r));
+        }
     }
-    if (reset_success_host && !e->d_succ) {
-        QS_CUDA(e, cudaMalloc(&e->d_succ, N));
-        QS_CUDA(e, cudaMemsetAsync(e->d_succ, 0, N, s));
-        QS_CUDA(e, cudaMallocHost(&e->h_succ, N));
+    if (reset_success_host && !(e->d_succ && e->h_succ)) {
+        cudaError_t r = e->d_succ ? cudaSuccess : cudaMalloc(&e->d_succ, N);
+        if (r == cudaSuccess) r = cudaMemsetAsync(e->d_succ, 0, N, s);
+        if (r == cudaSuccess) r = cudaMallocHost(&e->h_succ, N);
+        if (r != cudaSuccess) {
+            if (e->d_succ) cudaFree(e->d_succ);
+            e->d_succ = nullptr; e->h_succ = nullptr;
+            return fail(e, QS_ERR_CUDA, std::string("qs_step_host: reset-success buffers: ") + cudaGetErrorString(r));
+        }
     }
     // page-locked caller buffers are DMA'd directly; pageable ones are staged through the handle's pinned buffers
     const bool pa = is_pinned(actions_host), po = is_pinned(obs_host), pr = is_pinned(rew_host), pd = is_pinned(done_host);
@@ -691,6 +702,14 @@ int qs_set_param(qs_env *e, int key, double value)
     }
     fill_const(e->cfg, e->dc);
     fill_fork(e->cfg, e->fc);
+    return QS_OK;
+}
+
+int qs_set_reward_info(qs_env *e, float *rew_info)
+{
+    if (!e) return QS_ERR_NULL;
+    if (((size_t)rew_info & 15) != 0) return fail(e, QS_ERR_SHAPE, "qs_set_reward_info: buffer must be 16-byte aligned");
+    e->dp.rew_info = reinterpret_cast<float4 *>(rew_info);
     return QS_OK;
 }
 

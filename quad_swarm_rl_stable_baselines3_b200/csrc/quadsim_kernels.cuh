@@ -76,6 +76,7 @@ struct DevPtrs {
     float4 *scen;              // [N, QS_SC_COUNT / 4] formation-scenario rows (formation scenarios only, else null)
     int *ep_rec;               // [N, QS_ER_COUNT] record of the last finished episode per env (QS_ER_*)
     float4 *ep_agent;          // [N*K] per-drone part of that record
+    float4 *rew_info;          // [N*K, 2] optional (null = off): the raw reward terms of the step, infos[i]["rewards"] (QS_RI_*)
     qs_stats *stats;           // device aggregate
 };
 
@@ -1107,6 +1108,8 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         float spin = norm3f(q.w[0], q.w[1], q.w[2]);
         float crash = on_floor ? 1.0f : 0.0f;
         reward = -c.dt * (c.rew_pos * dist + c.rew_effort * effort + c.rew_crash * crash + c.rew_orient * orient + c.rew_spin * spin);
+        // infos[i]["rewards"] raw terms, each scaled by dt like the reference's rew_info (quadrotor_single.py:69-84)
+        if (__builtin_expect(P.rew_info != nullptr, 0) && valid) P.rew_info[2 * gi] = make_float4(-c.dt * dist, -c.dt * effort, -c.dt * crash, -c.dt * orient);
     }
     tick += 1;
     // a non-finite state cannot be stepped further: force-reset the env and count it (reference raises, quadrotor_single.py:87-90)
@@ -1186,6 +1189,9 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     reward += c.rew_col * ((unique_any_nonzero && is_unique) ? -1.0f : 0.0f);
     reward += -1.0f * (c.control_dt * prox);
     if (OBST) reward += c.rew_col_obst * (obst_new ? -1.0f : 0.0f);
+    if (__builtin_expect(P.rew_info != nullptr, 0) && valid)          // (:642-649) rewraw_spin, rewraw_quadcol, rew_proximity, rewraw_quadcol_obstacle
+        P.rew_info[2 * gi + 1] = make_float4(-c.dt * norm3f(q.w[0], q.w[1], q.w[2]), (unique_any_nonzero && is_unique) ? -1.0f : 0.0f,
+                                             -1.0f * (c.control_dt * prox), (OBST && obst_new) ? -1.0f : 0.0f);
     if (valid) { rew[gi] = reward; done[gi] = all_done ? 1 : 0; }      // final here: not carried (spilled) across the impulse / observation code
 
     if (OBST) scen_now = (q.flags & F_SCEN_OSTATIC) ? QS_SCENARIO_O_STATIC_SAME_GOAL : QS_SCENARIO_O_RANDOM;
@@ -1354,6 +1360,9 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
                 float4 sums = valid ? P.plane[PL_DIST_SUMS][gi] : make_float4(0.f, 0.f, 0.f, 0.f);
                 float inv_dt = 1.0f / c.dt;
                 float m1 = inv_dt * sums.x / (float)min(100, tick), m3 = inv_dt * sums.y / (float)min(300, tick), m5 = inv_dt * sums.z / (float)min(500, tick);
+                if (bad_ballot) {                                       // a diverged env must not poison the aggregates: its record and sums carry zeros
+                    m1 = isfinite(m1) ? m1 : 0.f; m3 = isfinite(m3) ? m3 : 0.f; m5 = isfinite(m5) ? m5 : 0.f;
+                }
                 // per-episode record (infos[i]['episode_extra_stats'], :739-831): per-drone part, then the env row below
                 if (valid) P.ep_agent[gi] = make_float4(m1, m3, m5, 0.f);
                 const uint32_t b_ncol = __ballot_sync(gmask, (q.flags & F_COL_AGENT) && valid) & gmask;

@@ -151,6 +151,9 @@ class DevicePPO:
         torch.manual_seed(seed)                                   # same initial weights on every rank
         self.policy = QuadActorCritic(cfg, self.p.hidden, self.p.neighbor_hidden, self.p.neighbor_encoder).to(self.device)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.p.learning_rate, eps=1e-5)
+        # identical weights everywhere, but every rank draws its own exploration noise and minibatch permutations
+        rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+        torch.manual_seed(seed + 1 + rank)
         n, T, D, A = cfg.num_envs * cfg.num_agents, self.p.n_steps, cfg.obs_dim, cfg.act_dim
         dev = self.device
         self.obs_buf = torch.empty((T, n, D), device=dev)

@@ -52,6 +52,8 @@ class QuadSwarmSim:
         self.terminal_obs = torch.zeros((n, self.D), dtype=torch.float32, device=dev)
         self.reset_success = torch.zeros((self.N,), dtype=torch.uint8, device=dev)   # reset_info["success"] of envs that just finished
         self.want_terminal_obs = True
+        self.rew_info = None                      # per-step reward terms (enable_reward_info)
+        self.rew_coeff_overrides: Dict[str, float] = {}
         self.is_fork = cfg.env_mode == "fork"
         # formation scenarios keep a per-env scenario row on the device (static_same_goal needs none)
         self.has_scenario_state = (not self.is_fork) and (not cfg.use_obstacles) and cfg.quads_mode != "static_same_goal"
@@ -173,6 +175,28 @@ class QuadSwarmSim:
         torch.cuda.current_stream(self.device).synchronize()
         return out
 
+    def get_state_host(self, fields=None) -> Dict[str, np.ndarray]:
+        """`get_state` as numpy arrays (the `envs[i].dynamics.*` views of the QuadrotorEnvMulti facade read through this)."""
+        return {k: v.cpu().numpy() for k, v in self.get_state(fields).items()}
+
+    # per-step reward breakdown: infos[i]["rewards"] / infos[i]["goal_dist"] -------------------------------------------------
+    def enable_reward_info(self, on: bool = True) -> Optional[torch.Tensor]:
+        """Switch the per-step reward-term output on (QS_RI_* columns, include/quadsim.h).  Returns the CUDA tensor
+        [N*K, 8] the next steps fill (owned by this object), or None when switched off."""
+        if on:
+            if getattr(self, "rew_info", None) is None:
+                self.rew_info = torch.zeros((self.N * self.K, 8), dtype=torch.float32, device=self.device)
+            ptr = C.c_void_p(self.rew_info.data_ptr())
+        else:
+            self.rew_info, ptr = None, None
+        _capi.check(self._h, self._lib.qs_set_reward_info(self._h, ptr), "qs_set_reward_info")
+        return self.rew_info
+
+    def reward_info_host(self) -> np.ndarray:
+        if getattr(self, "rew_info", None) is None:
+            raise RuntimeError("reward info is off: call enable_reward_info() first")
+        return self.rew_info.cpu().numpy()
+
     def set_state(self, **fields):
         n = self.N * self.K
         keep = {}
@@ -235,6 +259,7 @@ class QuadSwarmSim:
             if k not in PARAM_KEYS:
                 raise KeyError(k)
             _capi.check(self._h, self._lib.qs_set_param(self._h, PARAM_KEYS[k], float(v)), "qs_set_param")
+            self.rew_coeff_overrides[k] = float(v)
 
     def set_capture_radius(self, value: float):
         """QuadrotorEnvMulti.set_capture_radius (quadrotor_multi_rewards.py:210-211), all envs of this handle."""

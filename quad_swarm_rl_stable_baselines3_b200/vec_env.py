@@ -210,8 +210,7 @@ class QuadSwarmVecEnv(_Base):
         dones = self._done.view(np.bool_).copy()
         rews = self._rew.copy()
         env_done = dones.reshape(self.n_envs, K)[:, 0]
-        shared: dict = {}
-        infos: List[dict] = [shared] * self.num_envs
+        infos: List[dict] = [{} for _ in range(self.num_envs)]      # one dict per agent row, as the reference's workers return
         reset_infos: List[Optional[dict]] = [None] * self.n_envs
         finished = np.flatnonzero(env_done)
         if finished.size and self.episode_infos:

@@ -124,7 +124,22 @@ def gen_formations():
     print("formations:", len(index), "cases ->", os.path.getsize(path) // 1024, "KiB")
 
 
-def gen_traces(traces=None, tape_seed=1234, compact=False):
+def trace_seed(name, base):
+    """Every trace draws from its own stream (seeded from its name), so adding, removing or reordering traces never changes the
+    others: `python make_golden.py traces <name>` reproduces the committed file of that name alone."""
+    import zlib
+    return (zlib.crc32(name.encode()) ^ base) & 0x7FFFFFFF
+
+
+def reseed(tape, name, base, salt=0):
+    """salt: a per-trace constant in the trace table, chosen so that the trace covers the events its test asserts (a capture)."""
+    import numpy as np
+    tape.rs = np.random.RandomState(trace_seed(name if not salt else f"{name}#{salt}", base))
+    tape.kinds.clear()
+    tape.vals.clear()
+
+
+def gen_traces(traces=None, tape_seed=1234, compact=False, out_dir=None):
     os.environ["NUMBA_DISABLE_JIT"] = "1"
     import numpy as np
     import ref_harness as rh
@@ -133,6 +148,7 @@ def gen_traces(traces=None, tape_seed=1234, compact=False):
     rh.install_tape(tape)
     for name, spec in (TRACES if traces is None else traces).items():
         K = spec["env"]["num_agents"]
+        reseed(tape, name, tape_seed)
         env = rh.make_upstream_env(tape=tape, **spec["env"])
         rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
         rec = {k: [] for k in ("actions", "obs", "rew", "done", "tn", "tu", "tc", "n_tn", "n_tu", "n_tc", "tick",
@@ -233,7 +249,7 @@ def gen_traces(traces=None, tape_seed=1234, compact=False):
             print(f"    scenarios={sorted(set(rec['scenario']))} formations={sorted(set(int(r[1]) for r in rec['sc_row']))} "
                   f"steps with goal changes={goal_moves}")
         out["env_kwargs"] = np.array(repr(spec["env"]))
-        path = os.path.join(HERE, f"trace_{name}.npz")
+        path = os.path.join(out_dir or HERE, f"trace_{name}.npz")
         np.savez_compressed(path, **out)
         print(f"{name}: steps={spec['steps']} dones={events['done']} floor={int(np.array(snaps['on_floor']).any(axis=1).sum())} "
               f"wall={int(np.array(snaps['crashed_wall']).sum())} ceil={int(np.array(snaps['crashed_ceiling']).sum())} "
@@ -245,13 +261,13 @@ FORK_TRACES = {
     # sb_train.py defaults: 4 chasers, dist_angle neighbours, capture radius 3.0 -> frequent immediate captures + timeouts
     "fork_k4": dict(env=dict(num_agents=4, episode_duration=1.6), steps=110, radius={40: 1.0, 80: 2.6}),
     # BASELINE configs[0]: single quadrotor
-    "fork_k1": dict(env=dict(num_agents=1, episode_duration=1.0, initial_capture_radius=2.4), steps=60, radius={}),
+    "fork_k1": dict(salt=3, env=dict(num_agents=1, episode_duration=1.0, initial_capture_radius=2.4), steps=60, radius={}),
     # sangle reprs, 3 nearest of 7 neighbours
     "fork_k8_sangle": dict(env=dict(num_agents=8, episode_duration=0.8, initial_capture_radius=2.2,
                                     obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot",
                                     neighbor_obs_type="dist_sangle", neighbor_visible_num=3), steps=50, radius={}),
     # the author's current sweep (sb_train.py:122-137): camera-model neighbour observations, here with pixel noise on
-    "fork_k4_cam": dict(env=dict(num_agents=4, episode_duration=0.8, initial_capture_radius=2.4,
+    "fork_k4_cam": dict(salt=3, env=dict(num_agents=4, episode_duration=0.8, initial_capture_radius=2.4,
                                  obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot", neighbor_obs_type="ndist_nsangle"),
                         steps=40, radius={}),
     # camera model + ranking (2 nearest of 5): the ranking pass draws its own pixel noise
@@ -267,7 +283,7 @@ FORK_TRACES = {
 FORK_STATE_KEYS = STATE_KEYS + ("pid", "angle", "ang_vel", "evader", "heading")
 
 
-def gen_fork_traces():
+def gen_fork_traces(only=(), out_dir=None):
     """The env sb_train.py trains on, driven the way SubprocVecEnvCustom's worker drives it
     (swarm_rl/env_wrappers/subproc_vec_env_custom.py:35-52): step, and on any(done) keep the terminal observation and reset."""
     os.environ["NUMBA_DISABLE_JIT"] = "1"
@@ -279,7 +295,10 @@ def gen_fork_traces():
     tape = rh.Tape(seed=4321)
     rh.install_tape(tape)
     for name, spec in FORK_TRACES.items():
+        if only and name not in only:
+            continue
         K = spec["env"]["num_agents"]
+        reseed(tape, name, 4321, spec.get("salt", 0))
         with contextlib.redirect_stdout(io.StringIO()):
             env = rh.make_fork_env(tape=tape, **spec["env"])
         rs = np.random.RandomState(sum(map(ord, name)))
@@ -338,7 +357,7 @@ def gen_fork_traces():
         for k in FORK_STATE_KEYS:
             out["s_" + k] = np.array(snaps[k])
         out["env_kwargs"] = np.array(repr(spec["env"]))
-        path = os.path.join(HERE, f"trace_{name}.npz")
+        path = os.path.join(out_dir or HERE, f"trace_{name}.npz")
         np.savez_compressed(path, **out)
         print(f"{name}: steps={spec['steps']} dones={n_done} captures={n_succ} draws N={len(out['tn'])} U={len(out['tu'])} "
               f"-> {os.path.getsize(path) // 1024} KiB")
@@ -401,15 +420,17 @@ def gen_dyn_jit():
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    out_dir = os.environ.get("QS_GOLDEN_OUT") or None       # tests regenerate into a scratch directory and compare
     if which == "traces":
         only = sys.argv[2:]
-        gen_traces({k: v for k, v in TRACES.items() if not only or k in only})
+        gen_traces({k: v for k, v in TRACES.items() if not only or k in only}, out_dir=out_dir)
     elif which == "scenarios":
-        gen_formations()
         only = sys.argv[2:]
-        gen_traces({k: v for k, v in SCENARIO_TRACES.items() if not only or k in only}, tape_seed=2468, compact=True)
+        if not only:
+            gen_formations()
+        gen_traces({k: v for k, v in SCENARIO_TRACES.items() if not only or k in only}, tape_seed=2468, compact=True, out_dir=out_dir)
     elif which == "fork":
-        gen_fork_traces()
+        gen_fork_traces(sys.argv[2:], out_dir=out_dir)
     elif which == "dyn":
         gen_dyn_jit()
     else:   # separate interpreters: NUMBA_DISABLE_JIT must be decided before numba is imported

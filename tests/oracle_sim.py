@@ -59,3 +59,27 @@ class OracleSim:
 
     def close(self):
         self.closed = True
+
+    # ---- what the QuadrotorEnvMulti facade needs beyond the VecEnv surface ---------------------------------------
+    def get_state_host(self, fields=None):
+        sts = [o.get_state() for o in self.envs]
+        per_drone = ("pos", "vel", "rot", "omega", "rot_damp", "cmds_damp", "ou", "goal", "flags", "col_mask")
+        out = {k: np.concatenate([np.asarray(s[k]).reshape(self.K, -1) for s in sts]).astype(
+            np.int32 if k in ("flags", "col_mask") else np.float32) for k in per_drone}
+        for k in ("flags", "col_mask"):
+            out[k] = out[k].reshape(-1)
+        for k in ("tick", "svd_ctr", "step_ctr"):
+            out[k] = np.array([s[k] for s in sts], dtype=np.int32)
+        return out if fields is None else {k: out[k] for k in fields}
+
+    def set_state(self, **fields):
+        K = self.K
+        for e, o in enumerate(self.envs):
+            o.set_state(**{k: np.asarray(v, dtype=np.float64).reshape(self.N * K, -1)[e * K:(e + 1) * K] for k, v in fields.items()})
+
+    def enable_reward_info(self, on=True):
+        self._ri = bool(on)
+        return self._ri or None
+
+    def reward_info_host(self):
+        return np.concatenate([o.reward_info() for o in self.envs]).astype(np.float32)

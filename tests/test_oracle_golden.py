@@ -325,3 +325,23 @@ def test_fork_env_trace(golden_dir, name):
     if name in ("fork_k4", "fork_k1", "fork_k8_sangle", "fork_k4_cam"):
         assert n_succ >= 1
     assert o.stats()["episodes"] == n_done and o.stats()["episodes_success"] == n_succ
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference only exists in the build container")
+@pytest.mark.parametrize("kind,name", [("traces", "nonoise_k4"), ("traces", "obst_k1"), ("fork", "fork_k1"), ("scenarios", "scen_swap_k3")])
+def test_committed_goldens_regenerate_from_the_reference(kind, name, tmp_path):
+    """`make_golden.py <kind> <name>` on the unmodified reference reproduces the committed fixture array for array: every trace
+    draws from its own tape stream (seeded from its name), so a fixture does not depend on which other traces are generated."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, QS_GOLDEN_OUT=str(tmp_path))
+    subprocess.run([sys.executable, os.path.join(here, "golden", "make_golden.py"), kind, name], check=True, env=env,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    new = np.load(tmp_path / f"trace_{name}.npz", allow_pickle=True)
+    old = np.load(os.path.join(here, "golden", f"trace_{name}.npz"), allow_pickle=True)
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        a, b = old[k], new[k]
+        assert a.shape == b.shape and a.dtype == b.dtype, k
+        assert np.array_equal(a, b, equal_nan=True) if a.dtype.kind == "f" else np.array_equal(a, b), k
