@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A/B timing of library variants on ONE box: ab_time.py <case> <lib.so[:ENV=VAL...]> [<lib.so> ...]
 Each variant runs in its own process (QS_LIB_PATH), `rounds` times in alternation; prints min / median ms per step.
-case: cfg2 | cfg3 | cfg4 | fork | mix  (65536 envs; cfg4: 16384)."""
+case: cfg2 | cfg3 | cfg4 | fork | mix  (65536 envs; cfg4: 16384).  AB_STEADY=0 skips the steady-state pre-roll (round-1 behaviour)."""
 import json
 import os
 import statistics
@@ -29,6 +29,11 @@ sim.want_terminal_obs = False
 g = torch.Generator(device="cuda").manual_seed(1)
 pool = torch.rand((8, cfg.num_envs * cfg.num_agents, cfg.act_dim), device="cuda", generator=g) * 2 - 1
 sim.reset()
+if os.environ.get("AB_STEADY", "1") == "1":      # the bench's steady state: staggered episode clocks + more than one episode of pre-roll
+    sim.set_state(tick=torch.randint(0, cfg.ep_len, (cfg.num_envs,), generator=g, device="cuda", dtype=torch.int32))
+    pre = cfg.ep_len // (cfg.fork.substeps if cfg.env_mode == "fork" else 1) + 64
+    for i in range(pre):
+        sim.step(pool[i %% 8])
 for i in range(50):
     sim.step(pool[i %% 8])
 out = []

@@ -223,6 +223,8 @@ static void fill_const(const qs_config &c, DevConst &d)
     d.control_freq = (float)control_freq;
     for (int a = 0; a < 3; ++a) d.cube_dim[a] = c.cube_dim[a] > 0 ? c.cube_dim[a] : 1;
     d.small_angle = (std::sqrt(3.0) * c.omega_max * c.dt * 0.5 <= 0.25) ? 1 : 0;
+    d.lin_one = (c.motor_linearity == 1.0) ? 1 : 0;
+    d.no_omega_damp = (c.damp_omega_quadratic == 0.0) ? 1 : 0;
 }
 
 static void fill_fork(const qs_config &c, ForkConst &f)
@@ -396,7 +398,9 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     // staged per warp-tile behind the tiles: the obstacle centres, or (formation scenarios, never with obstacles) the scenario rows
     const size_t obst_floats = cfg->use_obstacles ? (size_t)warps * (32 / e->KG) * cfg->num_obstacles * 2
                                                   : (scen_feat ? (size_t)warps * (32 / e->KG) * QS_SC_COUNT : 0);
-    e->smem_bytes = (tiles_floats + obst_floats) * sizeof(float);
+    // QS_PARK: 3 float4 per thread (goal, distance ring, window sums) parked in shared memory while the dynamics run
+    const size_t park_floats = (QS_PARK && !e->fork) ? (size_t)12 * e->block : 0;
+    e->smem_bytes = (((tiles_floats + obst_floats + 3) & ~(size_t)3) + park_floats) * sizeof(float);
     if (e->smem_bytes > 200 * 1024) { delete e; return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: observation tile does not fit in shared memory"); }
 
     // one slab: planes, per-env scalars, obstacle centres, stats

@@ -35,6 +35,18 @@
 #ifndef QS_STEP_MAXTHREADS
 #define QS_STEP_MAXTHREADS 128
 #endif
+#ifndef QS_PARK
+#define QS_PARK 0               // 1: goal / distance ring / window sums travel global -> shared by LDGSTS (no registers while the dynamics run).
+#endif                          //    Measured slower (cfg2 79.3 -> 85.1 us, profiles/README.md round 2): off.
+#ifndef QS_EARLY_STORE
+#define QS_EARLY_STORE 1        // motor-lag and OU planes are written back right after the dynamics (12 registers dead for the rest of the step)
+#endif
+#ifndef QS_QUAT_ROUNDTRIP
+#define QS_QUAT_ROUNDTRIP 0     // 1: evaluate the zero-noise R -> quaternion -> R round trip of the sensor model literally
+#endif
+#ifndef QS_BODY_RODRIGUES
+#define QS_BODY_RODRIGUES 1     // rotate by exp([w_body]x) on the right instead of exp([R w_body]x) on the left (same matrix)
+#endif
 #define QS_PI_F 3.14159265358979323846f
 
 namespace qs {
@@ -46,6 +58,7 @@ struct DevConst {
     int N, K, scenario, obs_repr, nbr_type, V, use_obstacles, use_downwash, apply_force, sense_noise;
     int ep_len, sim_steps, svd_period, obst_L, obst_W, M, D, S;   // D obs dim, S self-obs dim
     int small_angle;                                              // sqrt(3) * omega_max * dt / 2 <= 0.25 rad
+    int lin_one, no_omega_damp;                                   // motor_linearity == 1 / damp_omega_quadratic == 0: the terms drop out (warp-uniform)
     uint32_t key0, key1;
     long long env_id_offset;
     float dt, hx, hy, hz, room_l, room_w, room_h, gravity, mass, inv_mass;
@@ -177,12 +190,13 @@ struct Drone {
     uint32_t colmask;
 };
 
+template <bool WITH_GOAL = true>
 __device__ __forceinline__ void load_drone(const DevPtrs &P, int gi, Drone &q)
 {
     // streamed once per step: keep them out of L1, which then holds the few spilled registers of the kernel
     float4 a = __ldcs(P.plane[PL_POS_VX] + gi), b = __ldcs(P.plane[PL_V_W] + gi), c = __ldcs(P.plane[PL_W_R0] + gi), d = __ldcs(P.plane[PL_R1] + gi),
            e = __ldcs(P.plane[PL_R2_FLAGS] + gi), f = __ldcs(P.plane[PL_ROT_DAMP] + gi), g = __ldcs(P.plane[PL_CMDS_DAMP] + gi),
-           h = __ldcs(P.plane[PL_OU] + gi), k = __ldcs(P.plane[PL_GOAL] + gi);
+           h = __ldcs(P.plane[PL_OU] + gi), k = WITH_GOAL ? __ldcs(P.plane[PL_GOAL] + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
     q.p[0] = a.x; q.p[1] = a.y; q.p[2] = a.z; q.v[0] = a.w; q.v[1] = b.x; q.v[2] = b.y;
     q.w[0] = b.z; q.w[1] = b.w; q.w[2] = c.x;
     q.R[0] = c.y; q.R[1] = c.z; q.R[2] = c.w; q.R[3] = d.x; q.R[4] = d.y; q.R[5] = d.z; q.R[6] = d.w; q.R[7] = e.x; q.R[8] = e.y;
@@ -209,6 +223,15 @@ __device__ __forceinline__ void load_drone_smem(const float4 *pf, int row, Drone
     q.goal[0] = k.x; q.goal[1] = k.y; q.goal[2] = k.z;
 }
 
+// the motor-lag (rot_damp, cmds_damp) and thrust-noise planes: final as soon as the dynamics have run
+__device__ __forceinline__ void store_motor_planes(const DevPtrs &P, int gi, const Drone &q)
+{
+    P.plane[PL_ROT_DAMP][gi] = make_float4(q.rd[0], q.rd[1], q.rd[2], q.rd[3]);
+    P.plane[PL_CMDS_DAMP][gi] = make_float4(q.cd[0], q.cd[1], q.cd[2], q.cd[3]);
+    P.plane[PL_OU][gi] = make_float4(q.ou[0], q.ou[1], q.ou[2], q.ou[3]);
+}
+
+template <bool WITH_MOTOR = true>
 __device__ __forceinline__ void store_drone(const DevPtrs &P, int gi, const Drone &q, bool store_goal)
 {
     P.plane[PL_POS_VX][gi] = make_float4(q.p[0], q.p[1], q.p[2], q.v[0]);
@@ -216,9 +239,7 @@ __device__ __forceinline__ void store_drone(const DevPtrs &P, int gi, const Dron
     P.plane[PL_W_R0][gi] = make_float4(q.w[2], q.R[0], q.R[1], q.R[2]);
     P.plane[PL_R1][gi] = make_float4(q.R[3], q.R[4], q.R[5], q.R[6]);
     P.plane[PL_R2_FLAGS][gi] = make_float4(q.R[7], q.R[8], __int_as_float(q.flags), __uint_as_float(q.colmask));
-    P.plane[PL_ROT_DAMP][gi] = make_float4(q.rd[0], q.rd[1], q.rd[2], q.rd[3]);
-    P.plane[PL_CMDS_DAMP][gi] = make_float4(q.cd[0], q.cd[1], q.cd[2], q.cd[3]);
-    P.plane[PL_OU][gi] = make_float4(q.ou[0], q.ou[1], q.ou[2], q.ou[3]);
+    if (WITH_MOTOR) store_motor_planes(P, gi, q);
     if (store_goal) P.plane[PL_GOAL][gi] = make_float4(q.goal[0], q.goal[1], q.goal[2], 0.0f);
 }
 
@@ -268,14 +289,19 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
         q.rd[m] = tau * (sqrtf(cm) - q.rd[m]) + q.rd[m];
         float cdm = clampf(q.rd[m] * q.rd[m] + cm * q.ou[m], 0.0f, 1.0f);
         q.cd[m] = cdm;
-        float th = c.thrust_max[m] * ((1.0f - c.lin) * cdm * cdm + c.lin * cdm);
+        float th = c.lin_one ? c.thrust_max[m] * cdm : c.thrust_max[m] * ((1.0f - c.lin) * cdm * cdm + c.lin * cdm);
         tq0 += c.pcx[m] * th; tq1 += c.pcy[m] * th; tq2 += c.pcz[m] * th + c.torque_max[m] * c.ccw[m] * cdm;
         thrust += th;
     }
-    // Rodrigues rotation about the world-frame angular velocity (:544-551)
+    // Rodrigues rotation about the world-frame angular velocity (:544-551): R <- exp([R w]x dt) R.  Since exp([R w]x) = R exp([w]x) R^T
+    // this is R exp([w]x dt) -- the same matrix, built from the body-frame rate directly (no R w product, |R w| = |w|)
+#if QS_BODY_RODRIGUES
+    float wx = q.w[0], wy = q.w[1], wz = q.w[2];
+#else
     float wx = q.R[0] * q.w[0] + q.R[1] * q.w[1] + q.R[2] * q.w[2];
     float wy = q.R[3] * q.w[0] + q.R[4] * q.w[1] + q.R[5] * q.w[2];
     float wz = q.R[6] * q.w[0] + q.R[7] * q.w[1] + q.R[8] * q.w[2];
+#endif
     float wn = norm3f(wx, wy, wz);
     if (wn != 0.0f) {
         float inv = 1.0f / wn, kx = wx * inv, ky = wy * inv, kz = wz * inv;
@@ -292,12 +318,21 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
         float d10 = sn * kz + oc * kx * ky, d11 = 1.f + oc * (ky * ky - 1.f), d12 = -sn * kx + oc * ky * kz;
         float d20 = -sn * ky + oc * kx * kz, d21 = sn * kx + oc * ky * kz, d22 = 1.f + oc * (kz * kz - 1.f);
         float n[9];
+#if QS_BODY_RODRIGUES
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {                                  // R dR
+            n[3 * i] = q.R[3 * i] * d00 + q.R[3 * i + 1] * d10 + q.R[3 * i + 2] * d20;
+            n[3 * i + 1] = q.R[3 * i] * d01 + q.R[3 * i + 1] * d11 + q.R[3 * i + 2] * d21;
+            n[3 * i + 2] = q.R[3 * i] * d02 + q.R[3 * i + 1] * d12 + q.R[3 * i + 2] * d22;
+        }
+#else
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             n[j] = d00 * q.R[j] + d01 * q.R[3 + j] + d02 * q.R[6 + j];
             n[3 + j] = d10 * q.R[j] + d11 * q.R[3 + j] + d12 * q.R[6 + j];
             n[6 + j] = d20 * q.R[j] + d21 * q.R[3 + j] + d22 * q.R[6 + j];
         }
+#endif
 #pragma unroll
         for (int j = 0; j < 9; ++j) q.R[j] = n[j];
     }
@@ -307,8 +342,11 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
         float i0 = c.inertia[0] * q.w[0], i1 = c.inertia[1] * q.w[1], i2 = c.inertia[2] * q.w[2];
         float cr0 = -q.w[1] * i2 + q.w[2] * i1, cr1 = -q.w[2] * i0 + q.w[0] * i2, cr2 = -q.w[0] * i1 + q.w[1] * i0;
         float wd0 = c.inv_inertia[0] * (cr0 + tq0), wd1 = c.inv_inertia[1] * (cr1 + tq1), wd2 = c.inv_inertia[2] * (cr2 + tq2);
-        float q0 = clampf(c.damp_wq * q.w[0] * q.w[0], 0.f, 1.f), q1 = clampf(c.damp_wq * q.w[1] * q.w[1], 0.f, 1.f),
-              q2 = clampf(c.damp_wq * q.w[2] * q.w[2], 0.f, 1.f);
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        if (!c.no_omega_damp) {
+            q0 = clampf(c.damp_wq * q.w[0] * q.w[0], 0.f, 1.f); q1 = clampf(c.damp_wq * q.w[1] * q.w[1], 0.f, 1.f);
+            q2 = clampf(c.damp_wq * q.w[2] * q.w[2], 0.f, 1.f);
+        }
         q.w[0] = clampf(q.w[0] + (1.f - q0) * dt * wd0, -c.omega_max, c.omega_max);
         q.w[1] = clampf(q.w[1] + (1.f - q1) * dt * wd1, -c.omega_max, c.omega_max);
         q.w[2] = clampf(q.w[2] + (1.f - q2) * dt * wd2, -c.omega_max, c.omega_max);
@@ -381,6 +419,14 @@ __device__ __forceinline__ void self_obs(const DevConst &c, const Rng &g, int si
         p0 += c.s_pos * n.x; p1 += c.s_pos * n.y; p2 += c.s_pos * n.z;
         v0 += c.s_vel * n.w; v1 += c.s_vel * m.x; v2 += c.s_vel * m.y;
         w0 += c.s_gyro * m.z; w1 += c.s_gyro * m.w; w2 += c.s_gyro * l.x;
+#if !QS_QUAT_ROUNDTRIP
+        // R -> quaternion -> R round trip with zero rotation noise (sensor_noise.py:34-63, 205-210; quad_utils.py:162-168): the identity
+        // on rotation matrices.  In the float64 reference it returns R to 1e-16; evaluated literally in fp32 it only adds round-off
+        // (~3e-7) on top of R, so the observation carries R itself (closer to the reference than the literal form, and ~50
+        // instructions + 2 SFU operations less per drone-step)
+#pragma unroll
+        for (int a = 0; a < 9; ++a) o[6 + a] = q.R[a];
+#else
         // R -> quaternion -> R round trip (sensor_noise.py:34-63, 205-210; quad_utils.py:162-168), zero rotation noise
         const float *R = q.R;
         float tr = R[0] + R[4] + R[8], qw, qx, qy, qz, S;
@@ -398,6 +444,7 @@ __device__ __forceinline__ void self_obs(const DevConst &c, const Rng &g, int si
         o[6] = 1.0f - 2.f * qy * qy - 2.f * qz * qz; o[7] = 2.f * qx * qy - 2.f * qz * qw; o[8] = 2.f * qx * qz + 2.f * qy * qw;
         o[9] = 2.f * qx * qy + 2.f * qz * qw; o[10] = 1.0f - 2.f * qx * qx - 2.f * qz * qz; o[11] = 2.f * qy * qz - 2.f * qx * qw;
         o[12] = 2.f * qx * qz - 2.f * qy * qw; o[13] = 2.f * qy * qz + 2.f * qx * qw; o[14] = 1.0f - 2.f * qx * qx - 2.f * qy * qy;
+#endif
     } else {
 #pragma unroll
         for (int a = 0; a < 9; ++a) o[6 + a] = q.R[a];
@@ -548,32 +595,148 @@ __device__ __forceinline__ void choice_fy(const Rng &g, int aux, int n, int k, u
 
 // obst_generation_given_density (quadrotor_multi.py:405-426) + Scenario_o_random / o_static_same_goal .reset
 // (scenarios/obstacles/o_random.py:26-52, o_static_same_goal.py:27-48, o_base.py:69-81,124-153).
-// Every lane of the group evaluates it redundantly (same keys -> same values); lane `drone` keeps its own spawn/goal.
-static __device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rng g, int drone, bool leader, float2 *obst_xy,
-                                                     float *spawn, float *goal, int &scenario_now)
+//
+// Called by ALL lanes of the env's lane group (`gmask`), converged.  An auto-reset inside the step kernel keeps its whole warp --
+// and, in the last wave of the grid, the whole kernel -- waiting, so the latency of this function is what a steady-state step pays
+// for resets (profiles/README.md, round 2).  Hence:
+//   * every uniform the scenario needs (7 streams, <= 2 + (M + 4 K) / 4 Philox blocks) is drawn ONCE, one block per lane of the
+//     group in parallel, into `scratch` (the group's rows of the observation tile, which the reset observation overwrites anyway);
+//     the sequential form evaluated a whole Philox block per uniform, every lane redundantly;
+//   * the sequential part (two or three partial Fisher-Yates shuffles, the free-cell list, the largest-empty-square scan) runs on
+//     the group's first lane only, on byte arrays in shared memory (they were thread-local memory), and publishes one spawn cell
+//     and one goal cell per drone;
+//   * the new obstacle centres also go to `obst_sm` (the warp's staged copy) so that the SDF of the reset observation does not
+//     chain M dependent global loads.
+// Same counters, same arithmetic, same results as the sequential form (which remains as the fallback when `scratch` is too small).
+__device__ __forceinline__ int obst_rng_blocks(int M, int K) { return ((M + 3) >> 2) + 4 * ((K + 3) >> 2) + 2; }
+__device__ __forceinline__ int obst_scratch_floats(int M, int K) { return 4 * obst_rng_blocks(M, K) + 16 + 16 + 16; }   // table + cells[64] + free[64] + result[64]
+
+static __device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, const Rng g, int d, int KG, uint32_t gmask, bool store, float2 *obst_xy,
+                                                     float2 *obst_sm, float *scratch, int cap, float *spawn, float *goal, int &scenario_now)
 {
-    const int L = c.obst_L, W = c.obst_W, M = c.M, K = c.K;
+    const int L = c.obst_L, W = c.obst_W, M = c.M, K = c.K, cells = L * W;
+    const int nb0 = (M + 3) >> 2, nbK = (K + 3) >> 2, nblk = nb0 + 4 * nbK + 2;
+    const bool fast = scratch != nullptr && cap >= obst_scratch_floats(M, K);
+    float *utab = scratch;
+    unsigned char *arr = reinterpret_cast<unsigned char *>(scratch + 4 * nblk), *freec = arr + 64, *res = arr + 128;
+    // block e of the table: streams in the order aux 0 (obstacle cells), 2 (spawn cells), 5 (goal cells), 3 (spawn z), 6 (goal z), 1 (mix), 4 (goal z, shared)
+    const int off2 = nb0, off5 = nb0 + nbK, off3 = nb0 + 2 * nbK, off6 = nb0 + 3 * nbK, off1 = nb0 + 4 * nbK, off4 = off1 + 1;
+    if (fast) {
+        __syncwarp(gmask);                                              // the tile rows are free: terminal observations were copied out
+        for (int e = d; e < nblk; e += KG) {
+            int aux, blk;
+            if (e < off2) { aux = 0; blk = e; }
+            else if (e < off5) { aux = 2; blk = e - off2; }
+            else if (e < off3) { aux = 5; blk = e - off5; }
+            else if (e < off6) { aux = 3; blk = e - off3; }
+            else if (e < off1) { aux = 6; blk = e - off6; }
+            else if (e < off4) { aux = 1; blk = 0; }
+            else { aux = 4; blk = 0; }
+            float u[4];
+            rng_u4(g, SITE_SCENARIO, 0xFF, aux, blk, u);
+            *reinterpret_cast<float4 *>(utab + 4 * e) = make_float4(u[0], u[1], u[2], u[3]);
+        }
+        __syncwarp(gmask);
+    }
+#define QS_OBST_U(aux, off, idx) (fast ? utab[4 * (off) + (idx)] : rng_u(g, SITE_SCENARIO, 0xFF, (aux), (idx)))
+    int scen = c.scenario;
+    if (scen == QS_SCENARIO_O_MIX) {
+        int mode_index = (int)floorf(QS_OBST_U(1, off1, 0) * 100.0f);
+        // a single drone draws from QUADS_MODE_LIST_OBSTACLES_SINGLE = ['o_random'] (mix.py:49-51, utils.py:23)
+        scen = (K == 1 || mode_index % 2 == 0) ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
+    }
+    scenario_now = scen;
+    if (fast) {
+        if (d == 0) {
+            // k distinct ids of n: partial Fisher-Yates (oracle rnd_choice), in place on arr[0..n)
+            for (int i = 0; i < cells; i += 4) *reinterpret_cast<uint32_t *>(arr + i) = 0x03020100u + 0x01010101u * (uint32_t)i;
+            for (int t = 0; t < M; ++t) {
+                int r = min(t + (int)floorf(utab[t] * (float)(cells - t)), cells - 1);
+                unsigned char tmp = arr[t]; arr[t] = arr[r]; arr[r] = tmp;
+            }
+            unsigned long long map = 0ull;                              // bit rid*W + cid
+            for (int m = 0; m < M; ++m) {
+                int rid = arr[m] / W, cid = arr[m] - rid * W;
+                map |= 1ull << (rid * W + cid);
+                float x, y;
+                cell_center(c, rid + L * cid, x, y);
+                if (store) obst_xy[m] = make_float2(x, y);
+                if (obst_sm != nullptr) obst_sm[m] = make_float2(x, y);
+            }
+            int nf = 0;
+            for (int cell = 0; cell < cells; ++cell) if (!((map >> cell) & 1ull)) freec[nf++] = (unsigned char)cell;   // row-major (rid, cid)
+            for (int i = 0; i < nf; i += 4) *reinterpret_cast<uint32_t *>(arr + i) = 0x03020100u + 0x01010101u * (uint32_t)i;
+            for (int t = 0; t < K; ++t) {
+                int r = min(t + (int)floorf(utab[4 * off2 + t] * (float)(nf - t)), nf - 1);
+                unsigned char tmp = arr[t]; arr[t] = arr[r]; arr[r] = tmp;
+            }
+            for (int t = 0; t < K; ++t) res[t] = freec[arr[t]];
+            if (scen == QS_SCENARIO_O_STATIC_SAME_GOAL) {
+                // largest empty square; dp row/col 0 copy the obstacle map itself (o_base.py:134-136).  Two rolling rows of the table.
+                unsigned char *prev = arr, *cur = freec;               // the free-cell list is no longer needed
+                int max_size = 0, cx = 0, cy = 0;
+                for (int j = 0; j < W; ++j) prev[j] = (unsigned char)((map >> j) & 1ull);
+                for (int r = 1; r < L; ++r) {
+                    cur[0] = (unsigned char)((map >> (r * W)) & 1ull);
+                    for (int j = 1; j < W; ++j) {
+                        int v = 0;
+                        if (!((map >> (r * W + j)) & 1ull)) {
+                            v = min(min((int)prev[j], (int)cur[j - 1]), (int)prev[j - 1]) + 1;
+                            if (v > max_size) { max_size = v; cx = r - (max_size - 1) / 2; cy = j - (max_size - 1) / 2; }
+                        }
+                        cur[j] = (unsigned char)v;
+                    }
+                    unsigned char *t = prev; prev = cur; cur = t;
+                }
+                res[K] = (unsigned char)cx; res[K + 1] = (unsigned char)cy;
+            } else {
+                for (int i = 0; i < nf; i += 4) *reinterpret_cast<uint32_t *>(arr + i) = 0x03020100u + 0x01010101u * (uint32_t)i;
+                for (int t = 0; t < K; ++t) {
+                    int r = min(t + (int)floorf(utab[4 * off5 + t] * (float)(nf - t)), nf - 1);
+                    unsigned char tmp = arr[t]; arr[t] = arr[r]; arr[r] = tmp;
+                }
+                for (int t = 0; t < K; ++t) res[K + t] = freec[arr[t]];
+            }
+        }
+        __syncwarp(gmask);
+        const int dk = d < K ? d : 0;
+        {
+            const int cell = res[dk], rid = cell / W, cid = cell - rid * W;
+            cell_center(c, rid + L * cid, spawn[0], spawn[1]);
+            spawn[2] = 1.0f + 2.0f * utab[4 * off3 + dk];
+        }
+        if (scen == QS_SCENARIO_O_STATIC_SAME_GOAL) {
+            cell_center(c, (int)res[K] + W * (int)res[K + 1], goal[0], goal[1]);
+            goal[2] = 1.5f + 1.5f * utab[4 * off4];
+        } else {
+            const int cell = res[K + dk], rid = cell / W, cid = cell - rid * W;
+            cell_center(c, rid + L * cid, goal[0], goal[1]);
+            goal[2] = 1.0f + 2.0f * utab[4 * off6 + dk];
+        }
+        __syncwarp(gmask);                                              // the scratch rows are rewritten by the reset observation next
+        return;
+    }
+#undef QS_OBST_U
+    // ---- sequential form: every lane evaluates everything (same keys -> same values)
+    const int drone = d;
+    const bool leader = store && d == 0;
     unsigned char a[64];
     choice_fy(g, 0, L * W, M, a);
     unsigned long long map = 0ull;                                      // bit rid*W + cid
     for (int m = 0; m < M; ++m) {
         int rid = a[m] / W, cid = a[m] - rid * W;
         map |= 1ull << (rid * W + cid);
-        if (leader) { float x, y; cell_center(c, rid + L * cid, x, y); obst_xy[m] = make_float2(x, y); }
+        float x, y;
+        cell_center(c, rid + L * cid, x, y);
+        if (leader) obst_xy[m] = make_float2(x, y);
+        if (d == 0 && obst_sm != nullptr) obst_sm[m] = make_float2(x, y);
     }
-    int scen = c.scenario;
-    if (scen == QS_SCENARIO_O_MIX) {
-        int mode_index = (int)floorf(rng_u(g, SITE_SCENARIO, 0xFF, 1, 0) * 100.0f);
-        // a single drone draws from QUADS_MODE_LIST_OBSTACLES_SINGLE = ['o_random'] (mix.py:49-51, utils.py:23)
-        scen = (K == 1 || mode_index % 2 == 0) ? QS_SCENARIO_O_RANDOM : QS_SCENARIO_O_STATIC_SAME_GOAL;
-    }
-    scenario_now = scen;
-    unsigned char freec[64];
+    unsigned char freel[64];
     int nf = 0;
-    for (int cell = 0; cell < L * W; ++cell) if (!((map >> cell) & 1ull)) freec[nf++] = (unsigned char)cell;   // row-major (rid, cid)
+    for (int cell = 0; cell < L * W; ++cell) if (!((map >> cell) & 1ull)) freel[nf++] = (unsigned char)cell;   // row-major (rid, cid)
     {
         choice_fy(g, 2, nf, K, a);
-        int cell = freec[a[drone < K ? drone : 0]], rid = cell / W, cid = cell - rid * W;
+        int cell = freel[a[drone < K ? drone : 0]], rid = cell / W, cid = cell - rid * W;
         cell_center(c, rid + L * cid, spawn[0], spawn[1]);
         spawn[2] = 1.0f + 2.0f * rng_u(g, SITE_SCENARIO, 0xFF, 3, drone);
     }
@@ -596,7 +759,7 @@ static __device__ __noinline__ void obstacle_scenario_reset(const DevConst &c, c
         goal[2] = 1.5f + 1.5f * rng_u(g, SITE_SCENARIO, 0xFF, 4, 0);
     } else {
         choice_fy(g, 5, nf, K, a);
-        int cell = freec[a[drone < K ? drone : 0]], rid = cell / W, cid = cell - rid * W;
+        int cell = freel[a[drone < K ? drone : 0]], rid = cell / W, cid = cell - rid * W;
         cell_center(c, rid + L * cid, goal[0], goal[1]);
         goal[2] = 1.0f + 2.0f * rng_u(g, SITE_SCENARIO, 0xFF, 6, drone);
     }
@@ -644,7 +807,8 @@ __device__ __forceinline__ uint32_t group_mask(int lane) { return (KG == 32) ? Q
 // a14 in one pass over the env's obstacles: the 3x3 SDF patch (get_surround_sdfs, obstacles/utils.py:5-27; the min over
 // obstacles commutes with the sqrt) and the first obstacle the drone touches (collision_detection, obstacles/utils.py:31-43:
 // 2-D distance <= arm + size/2, lowest index wins) -- the centre cell of the patch IS that distance.
-__device__ __forceinline__ void obstacle_sdf_and_hit(const DevConst &c, const float2 *ob, float px, float py, float *r, int &hit)
+// brute-force form: every obstacle against every patch point
+__device__ __forceinline__ void obstacle_sdf_and_hit_all(const DevConst &c, const float2 *ob, float px, float py, float *r, int &hit)
 {
     const float gx[3] = { px - c.sdf_res, px, px + c.sdf_res }, gy[3] = { py - c.sdf_res, py, py + c.sdf_res };
     const float obst2 = c.thr_obst * c.thr_obst * 1.0001f;
@@ -669,8 +833,64 @@ __device__ __forceinline__ void obstacle_sdf_and_hit(const DevConst &c, const fl
     for (int a = 0; a < 9; ++a) r[a] = sqrtf(md[a]) - c.obst_rad;
 }
 
+// Step-path form.  The nine patch points lie within delta = sqrt(2) * sdf_res of the drone, so an obstacle can be the nearest one of
+// SOME patch point only if its distance from the drone is <= d_min + 2 delta (d_j(s) >= d_j - delta and min_k d_k(s) <= d_min + delta).
+// Pass 1 measures every centre from the drone only (5 instead of ~35 instructions each; it is also the hit test -- the centre point of
+// the patch IS that distance), pass 2 evaluates the 3x3 patch against the few centres inside that bound (typically 1-3 of 12).  The
+// minimum over a subset that contains every possible minimiser is the same number, bit for bit, as the minimum over all centres.
+// More than QS_SDF_LIST candidates, or more than 16 obstacles: the brute-force form.
+#ifndef QS_SDF_LIST
+#define QS_SDF_LIST 0           // measured SLOWER than the brute-force form (cfg3 102.4 -> 110.5 us): fewer instructions but less ILP. Off.
+#endif
+__device__ __forceinline__ void obstacle_sdf_and_hit(const DevConst &c, const float2 *ob, float px, float py, float *r, int &hit)
+{
+    if (QS_SDF_LIST == 0 || c.M > 16) { obstacle_sdf_and_hit_all(c, ob, px, py, r, hit); return; }
+    const float obst2 = c.thr_obst * c.thr_obst * 1.0001f;
+    float d2[16], dmin2 = 10000.0f;
+    hit = -1;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        if (m < c.M) {                                                  // warp-uniform
+            const float2 xy = ob[m];
+            const float dx = px - xy.x, dy = py - xy.y;
+            d2[m] = dx * dx + dy * dy;
+            dmin2 = fminf(dmin2, d2[m]);
+            if (d2[m] <= obst2 && hit < 0 && __fsqrt_rn(d2[m]) <= c.thr_obst) hit = m;
+        } else d2[m] = 3.0e38f;
+    }
+    const float lim = sqrtf(dmin2) + 2.8285f * c.sdf_res, lim2 = lim * lim * 1.0001f;    // 2 sqrt(2) sdf_res, widened against round-off
+    uint32_t list = 0u;
+    int n = 0;
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+        if (d2[m] <= lim2) { list |= (n < QS_SDF_LIST) ? ((uint32_t)m << (8 * n)) : 0u; ++n; }
+    if (__builtin_expect(n > QS_SDF_LIST, 0)) { int h2; obstacle_sdf_and_hit_all(c, ob, px, py, r, h2); return; }
+    const float gx[3] = { px - c.sdf_res, px, px + c.sdf_res }, gy[3] = { py - c.sdf_res, py, py + c.sdf_res };
+    float md[9];
+#pragma unroll
+    for (int a = 0; a < 9; ++a) md[a] = 10000.0f;                       // (100)^2: the value the patch carries when there is no obstacle at all
+    for (int t = 0; t < n; ++t) {
+        const float2 xy = ob[(list >> (8 * t)) & 255u];
+        float dx2[3], dy2[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { float dx = gx[a] - xy.x, dy = gy[a] - xy.y; dx2[a] = dx * dx; dy2[a] = dy * dy; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) md[a * 3 + b] = fminf(md[a * 3 + b], dx2[a] + dy2[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 9; ++a) r[a] = sqrtf(md[a]) - c.obst_rad;
+}
+
 // SDF = false: the caller already wrote the SDF patch of these positions (step path: together with the hit test)
 // COMPACT: the rolled, branchy form of the row writes for kernel variants whose hot code is already at the instruction-cache limit
+// Relative position of a neighbour, clipped to the observation Box (quadrotor_multi.py:337-339).  In the step path both positions
+// come out of the dynamics' room clip (|x|,|y| <= room/2, 0 <= z <= room_h), so the difference cannot leave the Box and the clip is
+// the identity; only the reset path (drones may spawn outside a small room) evaluates it.
+template <bool CLIP>
+__device__ __forceinline__ float rel_pos(float x, float lim) { return CLIP ? clampf(x, -lim, lim) : x; }
+
 template <int KG, bool OBST, bool SDF, bool COMPACT = false>
 __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *ob, int d, int lane, uint32_t gmask, bool valid,
                                                const Drone &q, const float *vs, float *o, float4 *stage)
@@ -710,7 +930,7 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                     if (valid) {
                         float4 a = stage[2 * (base + jb)], b = stage[2 * (base + jb) + 1];
                         float *r = o + c.S + 6 * sidx;
-                        r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                        r[0] = rel_pos<SDF>(a.x - q.p[0], c.room_l); r[1] = rel_pos<SDF>(a.y - q.p[1], c.room_w); r[2] = rel_pos<SDF>(a.z - q.p[2], c.room_h);
                         r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
                     }
                 }
@@ -738,7 +958,7 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                     for (int j = 0; j < KG; ++j) {
                         const int rk = (int)((pk >> (4 * j)) & 15u);
                         const float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
-                        const float r0 = clampf(a.x - q.p[0], -c.room_l, c.room_l), r1 = clampf(a.y - q.p[1], -c.room_w, c.room_w), r2 = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                        const float r0 = rel_pos<SDF>(a.x - q.p[0], c.room_l), r1 = rel_pos<SDF>(a.y - q.p[1], c.room_w), r2 = rel_pos<SDF>(a.z - q.p[2], c.room_h);
                         const float r3 = clampf(b.x - vs[0], -6.f, 6.f), r4 = clampf(b.y - vs[1], -6.f, 6.f), r5 = clampf(b.z - vs[2], -6.f, 6.f);
                         float *r = o + c.S + 6 * rk;
                         if (rk < c.V) { r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5; }
@@ -750,7 +970,7 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                         if (rk < c.V) {
                             float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
                             float *r = o + c.S + 6 * rk;
-                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                            r[0] = rel_pos<SDF>(a.x - q.p[0], c.room_l); r[1] = rel_pos<SDF>(a.y - q.p[1], c.room_w); r[2] = rel_pos<SDF>(a.z - q.p[2], c.room_h);
                             r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
                         }
                     }
@@ -774,7 +994,7 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                         if (rank[j] < c.V && met[j] < INF) {
                             float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
                             float *r = o + c.S + 6 * rank[j];
-                            r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                            r[0] = rel_pos<SDF>(a.x - q.p[0], c.room_l); r[1] = rel_pos<SDF>(a.y - q.p[1], c.room_w); r[2] = rel_pos<SDF>(a.z - q.p[2], c.room_h);
                             r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
                         }
                     }
@@ -786,14 +1006,14 @@ __device__ __forceinline__ void group_obs_tail(const DevConst &c, const float2 *
                 int sidx = j - (j > d ? 1 : 0);
                 float4 a = stage[2 * (base + j)], b = stage[2 * (base + j) + 1];
                 float *r = o + c.S + 6 * sidx;
-                r[0] = clampf(a.x - q.p[0], -c.room_l, c.room_l); r[1] = clampf(a.y - q.p[1], -c.room_w, c.room_w); r[2] = clampf(a.z - q.p[2], -c.room_h, c.room_h);
+                r[0] = rel_pos<SDF>(a.x - q.p[0], c.room_l); r[1] = rel_pos<SDF>(a.y - q.p[1], c.room_w); r[2] = rel_pos<SDF>(a.z - q.p[2], c.room_h);
                 r[3] = clampf(b.x - vs[0], -6.f, 6.f); r[4] = clampf(b.y - vs[1], -6.f, 6.f); r[5] = clampf(b.z - vs[2], -6.f, 6.f);
             }
         }
     }
     if (OBST && SDF && valid) {
         int hit;
-        obstacle_sdf_and_hit(c, ob, q.p[0], q.p[1], o + c.S + ((c.nbr_type == QS_NEIGHBOR_POS_VEL) ? 6 * c.V : 0), hit);
+        obstacle_sdf_and_hit_all(c, ob, q.p[0], q.p[1], o + c.S + ((c.nbr_type == QS_NEIGHBOR_POS_VEL) ? 6 * c.V : 0), hit);
     }
 }
 
@@ -803,14 +1023,19 @@ namespace qs {
 
 // Reset of one environment (QuadrotorEnvMulti.reset, quadrotor_multi.py:440-519), executed by the env's lane group.
 // SCEN: one of the formation scenarios (scenario_kernels.cuh) instead of the fixed static_same_goal.
+// Must be called by every lane of the env's lane group (`gmask`), converged.  `scratch`: `cap` floats of shared memory owned by the
+// group whose contents are dead (its rows of the observation tile); `obst_sm`: the env's slot of the warp's staged obstacle centres
+// (null where there is none).
 template <int KG, bool OBST, bool SCEN>
-__device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P, const Rng &g, int env, int d, bool valid, Drone &q,
-                                            int &scenario_now)
+__device__ __forceinline__ void group_reset(const DevConst &c, const DevPtrs &P, const Rng &g, int env, int d, bool valid, uint32_t gmask, float *scratch,
+                                            int cap, float2 *obst_sm, Drone &q, int &scenario_now)
 {
     float spawn[3], goal[3], out[5];
     if (OBST) {
         int scen = 0;
-        obstacle_scenario_reset(c, g, d, valid && d == 0, P.obst_xy + (size_t)env * QS_MAX_OBSTACLES, spawn, goal, scen);
+        float *sc16 = reinterpret_cast<float *>((reinterpret_cast<size_t>(scratch) + 15) & ~(size_t)15);     // 16-byte aligned table
+        obstacle_scenario_reset(c, g, d, KG, gmask, env < c.N, P.obst_xy + (size_t)env * QS_MAX_OBSTACLES, obst_sm, sc16,
+                                cap - (int)(sc16 - scratch), spawn, goal, scen);
         scenario_now = scen;
     } else if (SCEN) {
         goal[0] = goal[1] = 0.f; goal[2] = 2.0f;
@@ -917,6 +1142,13 @@ __device__ __forceinline__ void cp_async4(void *dst_smem, const void *src_gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS.128): data that is consumed late in the step travels without holding registers
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
+{
+    // no "memory" clobber: the copy must not fence the surrounding prologue loads (the reads of the destination sit behind
+    // cp_async_wait_all(), which does clobber memory)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -964,6 +1196,12 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     const float4 *sc_env = sc_sm + (lane / KG) * (QS_SC_COUNT / 4);
     // prefetch buffer + mbarrier of this warp (PERSIST only), 16-byte aligned
     const size_t pf_off = (ob_off + (size_t)warps_per_block * ob_per_warp * 2 + 3) & ~(size_t)3;
+    // parking area of the plain form (QS_PARK): goal / distance ring / window sums of every thread, 3 x blockDim float4, behind the
+    // staged obstacle centres or scenario rows
+    constexpr bool PARK = QS_PARK && !PERSIST;
+    const size_t park_off = (ob_off + (OBST ? (size_t)warps_per_block * ob_per_warp * 2 : (SCEN ? (size_t)warps_per_block * GPW * QS_SC_COUNT : 0)) + 3) & ~(size_t)3;
+    float4 *park = reinterpret_cast<float4 *>(smem + park_off) + threadIdx.x;
+    const int park_stride = blockDim.x;
     float4 *pf = reinterpret_cast<float4 *>(smem + pf_off) + (size_t)warp_in_block * PF_SLOTS * 32;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + pf_off + (size_t)warps_per_block * PF_SLOTS * 32 * 4) + warp_in_block;
     // per-env scalars (tick, svd counter, RNG step counter) of the next tile: 3 x GPW ints per warp behind the mbarriers.  Kept in
@@ -1027,24 +1265,34 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             cp_async_commit();
         }
     } else {
-        if (env < c.N) {                                                // env-level scalars: every lane of the group
-            tick = P.tick[env]; svd = P.svd_ctr[env];
-            g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
-        }
-        if (SCEN && env < c.N) {                                        // scenario row: loaded with the state, parked in shared memory
+        // Every prologue load is UNCONDITIONAL on a clamped, always-valid row (lanes past the batch / past K re-read a valid row and are
+        // overwritten below): one straight-line block, so that all loads are issued before the first consumer.  Under `if (valid)` the
+        // compiler closed the divergent region with register moves of the loaded values in front of the per-env scalar loads -- a
+        // second serialised HBM round trip at the top of every warp (profiles/tools/prologue_check.py guards this in the SASS).
+        const int env_c = min(env, c.N - 1), gi_c = env_c * c.K + min(d, c.K - 1);
+        tick = P.tick[env_c]; svd = P.svd_ctr[env_c];
+        g.gid = (uint32_t)(c.env_id_offset + env_c); g.step = P.step_ctr[env_c];
+        if (SCEN) {                                                     // scenario row: loaded with the state, parked in shared memory
 #pragma unroll
             for (int k = 0; k < (QS_SC_COUNT / 4 + KG - 1) / KG; ++k)
-                if (d + k * KG < QS_SC_COUNT / 4) sc_row[k] = P.scen[(size_t)env * (QS_SC_COUNT / 4) + d + k * KG];
+                sc_row[k] = P.scen[(size_t)env_c * (QS_SC_COUNT / 4) + min(d + k * KG, QS_SC_COUNT / 4 - 1)];
         }
-        if (valid) {
-            load_drone(P, gi, q);
-            act = __ldcs(actions + gi);
-            ring = __ldcs(P.plane[PL_DIST_RING] + gi);                  // issued with the state loads: one exposed HBM latency per thread
-            // The last-5-s window sums (:762-767) are only needed in the last 500 steps of an episode, but the load is unconditional:
-            // a predicate on `tick` made the compiler wait for the tick load BEFORE issuing the state loads above -- two serialised
-            // HBM round trips at the top of every warp (79.0 -> 76.6 us for 16 extra bytes read per drone-step)
-            sums = __ldcs(P.plane[PL_DIST_SUMS] + gi);
+        load_drone<!PARK>(P, gi_c, q);
+        act = __ldcs(actions + gi_c);
+        // The last-5-s window sums (:762-767) are only needed in the last 500 steps of an episode, but the load is unconditional: a
+        // predicate on `tick` made the compiler wait for the tick load BEFORE issuing the state loads (79.0 -> 76.6 us for 16 extra
+        // bytes read per drone-step).  QS_PARK: goal, distance ring and window sums are not needed before the dynamics have run
+        // (~1100 instructions), so they go global -> shared directly (LDGSTS) and hold no registers meanwhile.
+        if (PARK) {
+            cp_async16(park, P.plane[PL_GOAL] + gi_c);
+            cp_async16(park + park_stride, P.plane[PL_DIST_RING] + gi_c);
+            cp_async16(park + 2 * park_stride, P.plane[PL_DIST_SUMS] + gi_c);
+            cp_async_commit();
+        } else {
+            ring = __ldcs(P.plane[PL_DIST_RING] + gi_c);
+            sums = __ldcs(P.plane[PL_DIST_SUMS] + gi_c);
         }
+        if (env >= c.N) { tick = 0; svd = 0; g.gid = 0; g.step = 0; }
     }
     if (SCEN && !PERSIST) {
         if (env < c.N) {
@@ -1097,6 +1345,13 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             if (fire) svd = 0;
             dynamics_substep(c, g, d, q, cmd, s, fire);
         }
+#if QS_EARLY_STORE
+        store_motor_planes(P, gi, q);                                  // final (a reset below rewrites them): 12 registers less from here on
+#endif
+    }
+    if (PARK) {
+        cp_async_wait_all();                                           // this thread's parked rows have landed
+        if (valid) { const float4 k = park[0]; q.goal[0] = k.x; q.goal[1] = k.y; q.goal[2] = k.z; }
     }
     // ---- compute_reward_weighted (quadrotor_single.py:34-92), dt = physics dt
     const bool on_floor = (q.flags & F_ON_FLOOR) != 0;
@@ -1197,6 +1452,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     if (OBST) scen_now = (q.flags & F_SCEN_OSTATIC) ? QS_SCENARIO_O_STATIC_SAME_GOAL : QS_SCENARIO_O_RANDOM;
     // distance_to_goal log: reached-goal flag from the mean of the last 5 entries, and the 1/3/5 s windows (:651-655, 762-767)
     if (valid) {
+        if (PARK) { ring = park[park_stride]; sums = park[2 * park_stride]; }
         float dlog = c.dt * dist;                                      // -rewraw_pos
         if (tick >= 5 && !(q.flags & F_REACHED)) {
             float m5 = (ring.x + ring.y + ring.z + ring.w + dlog) / 5.0f;
@@ -1404,11 +1660,24 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             }
             int scen = 0;
             if (bad_ballot) {                                           // do not let NaNs leak through the persistent noise state
+#if QS_EARLY_STORE
+                if (valid) { const float4 h = P.plane[PL_OU][gi]; q.ou[0] = h.x; q.ou[1] = h.y; q.ou[2] = h.z; q.ou[3] = h.w; }   // written above by this thread
+#endif
 #pragma unroll
                 for (int m = 0; m < 4; ++m) q.ou[m] = isfinite(q.ou[m]) ? q.ou[m] : 0.f;
+#if QS_EARLY_STORE
+                if (valid) P.plane[PL_OU][gi] = make_float4(q.ou[0], q.ou[1], q.ou[2], q.ou[3]);
+#endif
                 if (!isfinite(vs[0] + vs[1] + vs[2])) { vs[0] = vs[1] = vs[2] = 0.f; }
             }
-            group_reset<KG, OBST, SCEN>(c, P, g, env, d, valid, q, scen);
+            group_reset<KG, OBST, SCEN>(c, P, g, env, d, valid, gmask, tile + (size_t)(lane / KG) * c.K * c.D, c.K * c.D,
+                                        OBST ? ob_sm + (lane / KG) * c.M : nullptr, q, scen);
+#if QS_EARLY_STORE
+            if (valid) {                                                // the motor lag restarts at rest (quadrotor_dynamics.py:176-178)
+                P.plane[PL_ROT_DAMP][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                P.plane[PL_CMDS_DAMP][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#endif
             tick = 0;
             if (valid) {
                 if (d == 0) {
@@ -1422,14 +1691,15 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             __threadfence_block();                                      // obstacle centres written by the leader lane
             __syncwarp(gmask);
             if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
-            group_obs_tail<KG, OBST, true>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
+            // the new obstacle centres are in the warp's staged copy as well (written by the group's first lane inside the reset)
+            group_obs_tail<KG, OBST, true>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
         }
         __syncwarp();
     }
 
     // ---- write back
     if (valid) {
-        store_drone(P, gi, q, SCEN || all_done);
+        store_drone<!QS_EARLY_STORE>(P, gi, q, SCEN || all_done);
         if (d == 0) { P.tick[env] = tick; P.svd_ctr[env] = svd; P.step_ctr[env] = g.step + 1u; }
     }
     __syncwarp();
@@ -1471,10 +1741,10 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
     Drone q;
     Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
     float vs[3] = { 0.f, 0.f, 0.f };
+    if (env < c.N) { g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env]; }     // every lane of the group: the reset draws cooperatively
     if (in_range) {
         load_drone(P, gi, q);
         vs[0] = q.v[0]; vs[1] = q.v[1]; vs[2] = q.v[2];                 // self.vel is not refreshed by reset (quadrotor_multi.py:477)
-        g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
     } else {
 #pragma unroll
         for (int a = 0; a < 3; ++a) { q.p[a] = 0.f; q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
@@ -1485,8 +1755,9 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
         q.flags = 0; q.colmask = 0;
     }
     int scen = 0;
+    const bool grp = env < c.N && (env_mask == nullptr || env_mask[env] != 0);      // uniform over the env's lane group
+    if (grp) group_reset<KG, OBST, SCEN>(c, P, g, env, d, valid, gmask, tile + (size_t)(lane / KG) * c.K * c.D, c.K * c.D, nullptr, q, scen);
     if (valid) {
-        group_reset<KG, OBST, SCEN>(c, P, g, env, d, true, q, scen);
         if (d == 0) {
             int *ec = P.ecnt + env * EC_COUNT;
 #pragma unroll
