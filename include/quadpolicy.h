@@ -1,0 +1,74 @@
+/*
+ * quadpolicy.h -- C-ABI of the fused policy forward used by the device-resident rollouts.
+ *
+ * Replaces, for rollout collection, the per-step forward of the reference's policy
+ * (priban42/quad-swarm-rl-stable-baselines3, paths relative to the reference root):
+ *
+ *   qp_create / qp_destroy   ActorCriticPolicyCustomSeparateWeights.__init__ / _build   swarm_rl/models/ActorCriticPolicyCustom.py:284-411
+ *                            QuadMultiEncoder.__init__ (one per tower)                  swarm_rl/models/quad_multi_model.py:250-331
+ *   qp_set_weights           the state_dict of one tower (nn.Linear weights [out, in], biases)
+ *   qp_forward               ActorCriticPolicyCustom.forward / predict_values: action mean of the actor tower and value of the
+ *                            critic tower for a batch of observations           ActorCriticPolicyCustom.py:430-480,
+ *                            QuadMultiEncoder.forward                           quad_multi_model.py:333-354,
+ *                            QuadNeighborhoodEncoderDeepsets.forward            quad_multi_model.py:16-41
+ *
+ * Architecture built: self encoder S -> 256 -> 256, deep-sets neighbour encoder (S + W) -> 256 -> 256 averaged over V neighbours,
+ * feed-forward 512 -> 512, all tanh; heads 512 -> A (actor) and 512 -> 1 (critic).  bf16 operands, fp32 accumulation
+ * (tcgen05 tensor cores); biases, heads and outputs fp32.  Sampling and log-probabilities stay with the caller (state-independent
+ * log-std diagonal Gaussian, ActorCriticPolicyCustom.py:312).
+ *
+ * All pointers are CUDA device addresses unless stated; `stream` is a cudaStream_t passed as void*.  Calls return 0 or a negative
+ * qp_status; qp_last_error() gives a message.  A handle is bound to one device and is not thread-safe.
+ */
+#ifndef QUADPOLICY_H_
+#define QUADPOLICY_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QP_API_VERSION 1
+
+typedef enum { QP_OK = 0, QP_ERR_NULL = -1, QP_ERR_BAD_CONFIG = -2, QP_ERR_CUDA = -3 } qp_status;
+
+typedef struct {
+    int32_t api_version; /* QP_API_VERSION */
+    int32_t self_dim;    /* S: 18 / 19 / 24 (quad_utils.py:30-38) */
+    int32_t nbr_dim;     /* W: 6 for pos_vel (quad_utils.py:40-58); S + W <= 32 */
+    int32_t num_nbr;     /* V: neighbour rows in the observation, 0 = no neighbour encoder */
+    int32_t hidden;      /* rnn_size: 256 (the only width built) */
+    int32_t act_dim;     /* A <= 8 */
+} qp_config;
+
+/* one tower's parameters: device pointers to fp32 arrays in nn.Linear layout (weight [out, in] row-major, bias [out]) */
+typedef struct {
+    const float *self_w1, *self_b1; /* [256, S], [256] */
+    const float *self_w2, *self_b2; /* [256, 256], [256] */
+    const float *nbr_w1, *nbr_b1;   /* [256, S + W], [256]   (ignored when num_nbr == 0) */
+    const float *nbr_w2, *nbr_b2;   /* [256, 256], [256] */
+    const float *ff_w, *ff_b;       /* [512, 512], [512]; input = [self encoder | neighbour encoder] */
+    const float *head_w, *head_b;   /* actor: [A, 512], [A]; critic: [1, 512], [1] */
+} qp_tower_weights;
+
+typedef struct qp_policy qp_policy;
+
+size_t qp_config_size(void);
+const char *qp_last_error(const qp_policy *p);
+int qp_create(const qp_config *cfg, int device, qp_policy **out);
+int qp_destroy(qp_policy *p);
+int64_t qp_launch_count(const qp_policy *p);
+
+/* (re)pack one tower's weights into the kernel's bf16 tile images; tower 0 = actor, 1 = critic.  Asynchronous on `stream`. */
+int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *stream);
+
+/* obs: [n, obs_stride] fp32 (self block first, then V neighbour rows of W values, as Appendix B of SURVEY.md);
+ * mean: [n, A]; value: [n].  One kernel launch, nothing touches the host. */
+int qp_forward(qp_policy *p, const float *obs, int n, int obs_stride, float *mean, float *value, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADPOLICY_H_ */

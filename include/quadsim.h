@@ -245,7 +245,8 @@ typedef struct qs_state_view {
     uint32_t *col_mask;  /* [N*K]   previous-step collision row (bit j set: pair (i,j) collided last step) */
     int32_t *tick;       /* [N]     per-env episode tick */
     int32_t *svd_ctr;    /* [N]     sub-steps since the last re-orthonormalisation */
-    uint32_t *step_ctr;  /* [N]     control steps since creation (RNG counter) */
+    uint32_t *step_ctr;  /* [N]     RNG launch counter of the HANDLE (steps + resets so far; a fork step counts fork.substeps), reported
+                                    per env.  qs_set_state reads entry 0 and sets the handle's counter (DESIGN.md "RNG contract") */
     float *obst_xy;      /* [N, QS_MAX_OBSTACLES, 2] obstacle centres (first num_obstacles valid) */
     float *scenario;     /* [N, QS_SC_COUNT] formation-scenario state (QS_SC_*); only for the formation scenarios */
     /* fork mode (NULL / ignored otherwise) */

@@ -24,7 +24,7 @@ if r.returncode:
     sys.stderr.write(r.stderr)
     sys.exit(1)
 objdir = os.path.join(ROOT, "build", "obj")
-objs = [os.path.join(objdir, "quadsim.o")] + [os.path.join(objdir, f"kernels_kg{k}.o") for k in (1, 2, 4, 8, 16, 32) if k != KG] + [obj]
+objs = [os.path.join(objdir, "quadsim.o"), os.path.join(objdir, "policy.o")] + [os.path.join(objdir, f"kernels_kg{k}.o") for k in (1, 2, 4, 8, 16, 32) if k != KG] + [obj]
 outdir = os.path.join(ROOT, "variants")      # travels to the GPU box (build/ is gpurun-ignored); *.so is git-ignored
 os.makedirs(outdir, exist_ok=True)
 subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", os.path.join(outdir, f"{name}.so")] + objs)

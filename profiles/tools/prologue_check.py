@@ -16,7 +16,7 @@ KERNELS = [("kernels_kg8.o", "step_kernelILi8ELb0ELi0E"), ("kernels_kg8.o", "ste
            ("kernels_kg8.o", "step_kernelILi8ELb0ELi2E"), ("kernels_kg8.o", "step_kernelILi8ELb0ELi3E"),
            ("kernels_kg8.o", "step_kernelILi8ELb0ELi4E"), ("kernels_kg8.o", "step_kernelILi8ELb0ELi6E"),
            ("kernels_kg32.o", "step_kernelILi32ELb0ELi0E"), ("kernels_kg4.o", "fork_step_kernelILi4E")]
-WINDOW = 300          # instructions from the kernel entry that count as prologue
+WINDOW = 200          # instructions from the first state load that count as prologue
 
 
 def analyse(obj, sub):
@@ -28,7 +28,10 @@ def analyse(obj, sub):
         ins = [re.sub(r"/\*[0-9a-f]+\*/", "", l).strip().split(";")[0].strip() for l in block.splitlines()
                if re.match(r"\s+/\*[0-9a-f]{4}\*/", l)]
         pending, first_use, loads = {}, None, []
-        for k, i in enumerate(ins[:WINDOW]):
+        # the prologue = everything up to WINDOW instructions past the first 16-byte state load (round 2: the generator loop of the
+        # step's regular draws runs BEFORE the loads, behind L2 prefetches of the same rows, so the loads no longer sit at the entry)
+        first_ld = next((k for k, i in enumerate(ins) if "LDG.E" in i and ".128" in i), 0)
+        for k, i in enumerate(ins[:first_ld + WINDOW]):
             body = re.sub(r"^@!?U?P\d+\s+", "", i)
             toks = body.split(None, 1)
             if len(toks) < 2:
@@ -39,7 +42,9 @@ def analyse(obj, sub):
             used = [r for r in pending if re.search(r"\b" + r + r"\b(?!\d)", srcs) or (op.startswith("ST") and re.search(r"\b" + r + r"\b", args))]
             if used and first_use is None:
                 first_use = (k, i)
-            if "LDG" in op and "CONSTANT" not in op:      # LDG.CONSTANT: table loads of the libm slow paths, not prologue traffic
+            # LDG.CONSTANT: table loads of the libm slow paths; LDG.STRONG: the hot blocks' own look-up of their tile (reset-first
+            # scheduling, executed by the first few blocks of the grid only) -- neither is prologue traffic of the state
+            if "LDG" in op and "CONSTANT" not in op and "STRONG" not in op:
                 loads.append(k)
                 m = re.match(r"R(\d+)", dst)
                 if m:

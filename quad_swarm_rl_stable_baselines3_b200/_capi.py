@@ -24,6 +24,8 @@ EXPORTS = ("qs_config_size", "qs_stats_size", "qs_api_version", "qs_last_error",
            "qs_num_envs", "qs_num_agents", "qs_obs_dim", "qs_act_dim", "qs_launch_count", "qs_reset", "qs_step",
            "qs_reset_host", "qs_step_host", "qs_get_state", "qs_set_state", "qs_set_param", "qs_episode_stats",
            "qs_episode_records", "qs_episode_records_host", "qs_set_reward_info")
+# every symbol include/quadpolicy.h declares (fused policy forward, csrc/policy_kernels.cu)
+POLICY_EXPORTS = ("qp_config_size", "qp_last_error", "qp_create", "qp_destroy", "qp_launch_count", "qp_set_weights", "qp_forward")
 
 
 KG_VALUES = (1, 2, 4, 8, 16, 32)
@@ -34,8 +36,10 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, de
     lane-group width (kernels_kg.cu, -DQS_KG=n) plus the host API (quadsim.cu), compiled in parallel, then linked."""
     from concurrent.futures import ThreadPoolExecutor
     root = os.path.dirname(_PKG)
-    deps = [os.path.join(CSRC, f) for f in ("quadsim.cu", "kernels_kg.cu", "quadsim_kernels.cuh", "fork_kernels.cuh", "scenario_kernels.cuh", "launch.h")]
+    deps = [os.path.join(CSRC, f) for f in ("quadsim.cu", "kernels_kg.cu", "quadsim_kernels.cuh", "fork_kernels.cuh", "scenario_kernels.cuh", "launch.h",
+                                            "policy_kernels.cu")]
     deps.append(os.path.join(root, "include", "quadsim.h"))
+    deps.append(os.path.join(root, "include", "quadpolicy.h"))
     if not force and out is None and os.path.exists(LIB_PATH) and all(
             (not os.path.exists(d)) or os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
@@ -46,7 +50,8 @@ def build(force: bool = False, verbose: bool = False, out: str | None = None, de
     objdir = os.path.join(root, "build", "obj" if out is None else "obj_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
-    jobs = [([nvcc] + flags + ["-c", os.path.join(CSRC, "quadsim.cu"), "-o", os.path.join(objdir, "quadsim.o")])]
+    jobs = [([nvcc] + flags + ["-c", os.path.join(CSRC, "quadsim.cu"), "-o", os.path.join(objdir, "quadsim.o")]),
+            ([nvcc] + flags + ["-c", os.path.join(CSRC, "policy_kernels.cu"), "-o", os.path.join(objdir, "policy.o")])]
     for kg in KG_VALUES:
         jobs.append([nvcc] + flags + [f"-DQS_KG={kg}", "-c", os.path.join(CSRC, "kernels_kg.cu"), "-o", os.path.join(objdir, f"kernels_kg{kg}.o")])
 
@@ -101,6 +106,16 @@ def lib():
     L.qs_episode_records_host.argtypes = [vp, vp, vp, vp]
     L.qs_set_reward_info.argtypes = [vp, vp]
     L.qs_philox_probe.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32), fp]
+    # fused policy forward (include/quadpolicy.h)
+    L.qp_config_size.restype = C.c_size_t
+    L.qp_last_error.restype = C.c_char_p
+    L.qp_last_error.argtypes = [vp]
+    L.qp_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.qp_destroy.argtypes = [vp]
+    L.qp_launch_count.argtypes = [vp]
+    L.qp_launch_count.restype = C.c_int64
+    L.qp_set_weights.argtypes = [vp, i32, vp, vp]
+    L.qp_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     if L.qs_config_size() != C.sizeof(QsConfigC) or L.qs_stats_size() != C.sizeof(QsStatsC):
         raise RuntimeError("qs_config / qs_stats layout mismatch between config.py and include/quadsim.h")
     _lib = L

@@ -338,10 +338,10 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
     float pid[24], angle = 0.f, ang_vel = 0.f, hsnap = 0.f, ex = 1.f, ey = 0.f;
     float2 act = make_float2(0.f, 0.f);
     int tick = 0, svd = 0, fflags = 0;
-    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
+    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = c.rng_step;      // sub-step s of this call draws from counter rng_step + s
     if (env_ok) {
         tick = P.tick[env]; svd = P.svd_ctr[env];
-        g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env];
+        g.gid = (uint32_t)(c.env_id_offset + env);
         float2 e2 = F.evader[env]; ex = e2.x; ey = e2.y;
         fflags = F.flags[env];
     }
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         F.plane[FP_HEADING][gi] = make_float4(angle, ang_vel, hsnap, 0.f);
     }
     if (env_ok && d == 0) {
-        P.tick[env] = tick; P.svd_ctr[env] = svd; P.step_ctr[env] = g.step + 1u;
+        P.tick[env] = tick; P.svd_ctr[env] = svd;
         F.evader[env] = make_float2(ex, ey); F.flags[env] = fflags;
     }
     __syncwarp();
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
     Drone q;
     float angle = 0.f, ang_vel = 0.f, hsnap = 0.f, ex = 1.f, ey = 0.f;
     int fflags = 0;
-    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
+    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = c.rng_step;      // sub-step s of this call draws from counter rng_step + s
 #pragma unroll
     for (int a = 0; a < 3; ++a) { q.p[a] = 1.0e6f * (float)(lane + 1); q.v[a] = 0.f; q.w[a] = 0.f; q.goal[a] = 0.f; }
 #pragma unroll
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
 #pragma unroll
     for (int a = 0; a < 4; ++a) { q.rd[a] = q.cd[a] = q.ou[a] = 0.f; }
     q.flags = 0; q.colmask = 0;
-    if (env_ok) { g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env]; fflags = F.flags[env]; }
+    if (env_ok) { g.gid = (uint32_t)(c.env_id_offset + env); fflags = F.flags[env]; }
     if (env_ok && d < c.K) { load_drone(P, gi, q); float4 h = F.plane[FP_HEADING][gi]; ang_vel = h.y; hsnap = h.z; }
     float u[4], t[4];
     rng_u4(g, SITE_SCENARIO, 0xFF, 7, d >> 1, u);
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
         int *pe = P.ecnt + env * EC_COUNT;
 #pragma unroll
         for (int k = 0; k < EC_COUNT; ++k) pe[k] = 0;
-        P.tick[env] = 0; P.step_ctr[env] = g.step + 1u;
+        P.tick[env] = 0;
         F.evader[env] = make_float2(ex, ey); F.flags[env] = FF_PLACED;
     }
     fork_neighbor_obs<KG>(c, f, g, d, lane, gmask, valid, q, angle, hsnap, orow + c.S, stage);

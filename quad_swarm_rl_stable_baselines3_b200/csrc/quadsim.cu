@@ -67,11 +67,11 @@ __global__ void state_io_kernel(DevConst c, DevPtrs P, ForkPtrs F, StateView v, 
         if (set) {
             if (v.tick) P.tick[gi] = v.tick[gi];
             if (v.svd_ctr) P.svd_ctr[gi] = v.svd_ctr[gi];
-            if (v.step_ctr) P.step_ctr[gi] = v.step_ctr[gi];
+            // step_ctr: the RNG launch counter belongs to the handle (host side, state_io below)
         } else {
             if (v.tick) v.tick[gi] = P.tick[gi];
             if (v.svd_ctr) v.svd_ctr[gi] = P.svd_ctr[gi];
-            if (v.step_ctr) v.step_ctr[gi] = P.step_ctr[gi];
+            if (v.step_ctr) v.step_ctr[gi] = c.rng_step;                // one counter per handle, reported per env
         }
     }
     if (v.scenario && P.scen) {
@@ -141,6 +141,10 @@ struct qs_env {
     // the kernel of the next
     cudaStream_t cs[2]; cudaEvent_t ev_in, ev_out[2]; bool pipe_ready;
     long long launches;
+    // reset-first scheduling of the plain upstream step kernel (DevPtrs::hot_*): three rotating buffers in the slab
+    int *hot_list[3], *hot_cnt[3], *hot_flag[3];
+    int hot_cap, hot_blocks; unsigned hot_phase; bool hot;
+    uint32_t rng_step;      // Philox counter word 1: +1 per step / reset call (+ fork.substeps per fork step); the same for every env of the handle
     bool host_ready;        // staging buffers of the *_host entry points are allocated
     std::string err;
 };
@@ -370,7 +374,7 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     DeviceGuard guard(device);
 
     qs_env *e = new qs_env();
-    e->cfg = *cfg; e->device = device; e->launches = 0; e->host_ready = false;
+    e->cfg = *cfg; e->device = device; e->launches = 0; e->host_ready = false; e->rng_step = 0;
     e->h_act = e->h_obs = e->h_rew = e->h_term = nullptr; e->h_done = e->h_succ = nullptr;
     e->d_act = e->d_obs = e->d_rew = e->d_term = nullptr; e->d_done = e->d_succ = nullptr;
     e->pipe_ready = false;
@@ -399,7 +403,8 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     const size_t obst_floats = cfg->use_obstacles ? (size_t)warps * (32 / e->KG) * cfg->num_obstacles * 2
                                                   : (scen_feat ? (size_t)warps * (32 / e->KG) * QS_SC_COUNT : 0);
     // QS_PARK: 3 float4 per thread (goal, distance ring, window sums) parked in shared memory while the dynamics run
-    const size_t park_floats = (QS_PARK && !e->fork) ? (size_t)12 * e->block : 0;
+    // (QS_EARLY_RNG: 4 float4 per thread -- the step's 16 pre-generated normals -- in the same per-thread scratch slots)
+    const size_t park_floats = e->fork ? 0 : (QS_EARLY_RNG ? (size_t)19 * e->block : (QS_PARK ? (size_t)12 * e->block : 0));
     e->smem_bytes = (((tiles_floats + obst_floats + 3) & ~(size_t)3) + park_floats) * sizeof(float);
     if (e->smem_bytes > 200 * 1024) { delete e; return fail(nullptr, QS_ERR_BAD_CONFIG, "qs_create: observation tile does not fit in shared memory"); }
 
@@ -417,6 +422,10 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     size_t o_erec = off; off += align((size_t)N * QS_ER_COUNT * sizeof(int));
     size_t o_eagent = off; off += align(nd * sizeof(float4));
     size_t o_stats = off; off += align(sizeof(qs_stats));
+    const int n_wt = (N + (32 / e->KG) - 1) / (32 / e->KG);              // warp-tiles
+    e->hot_cap = 128; e->hot_blocks = e->hot_cap / warps;
+    size_t o_hot[3];
+    for (int b3 = 0; b3 < 3; ++b3) { o_hot[b3] = off; off += align((size_t)(e->hot_cap + 64 + n_wt) * sizeof(int)); }
     size_t fplane_off[FP_COUNT] = {0}, o_evader = 0, o_fflags = 0;
     if (e->fork) {
         for (int p = 0; p < FP_COUNT; ++p) { fplane_off[p] = off; off += align(nd * sizeof(float4)); }
@@ -430,10 +439,17 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
     if (r != cudaSuccess) { cudaFree(e->slab); delete e; return fail(nullptr, QS_ERR_CUDA, std::string("qs_create: cudaMemset: ") + cudaGetErrorString(r)); }
     char *b = (char *)e->slab;
     for (int p = 0; p < PL_COUNT; ++p) e->dp.plane[p] = (float4 *)(b + plane_off[p]);
-    e->dp.tick = (int *)(b + o_tick); e->dp.svd_ctr = (int *)(b + o_svd); e->dp.step_ctr = (uint32_t *)(b + o_step);
+    e->dp.tick = (int *)(b + o_tick); e->dp.svd_ctr = (int *)(b + o_svd);
+    (void)o_step;
     e->dp.ecnt = (int *)(b + o_ecnt); e->dp.obst_xy = (float2 *)(b + o_obst); e->dp.stats = (qs_stats *)(b + o_stats);
     e->dp.scen = scen_feat ? (float4 *)(b + o_scen) : nullptr;
     e->dp.ep_rec = (int *)(b + o_erec); e->dp.ep_agent = (float4 *)(b + o_eagent);
+    for (int b3 = 0; b3 < 3; ++b3) {                                    // [count (64 ints: own cache line) | list | flags]
+        e->hot_cnt[b3] = (int *)(b + o_hot[b3]); e->hot_list[b3] = e->hot_cnt[b3] + 64; e->hot_flag[b3] = e->hot_list[b3] + e->hot_cap;
+    }
+    e->hot_phase = 0;
+    e->hot = !e->fork;
+    if (const char *hv = getenv("QS_HOT")) e->hot = e->hot && atoi(hv) != 0;   // tuning knob: 0 = plain block order
     if (e->fork) {
         for (int p = 0; p < FP_COUNT; ++p) e->fp.plane[p] = (float4 *)(b + fplane_off[p]);
         e->fp.evader = (float2 *)(b + o_evader); e->fp.flags = (int *)(b + o_fflags);
@@ -492,9 +508,11 @@ int qs_reset(qs_env *e, const uint8_t *env_mask, float *obs, void *stream)
     DeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     const LaunchShape shape = { e->grid, e->block, e->smem_bytes };
+    e->dc.rng_step = e->rng_step;
     if (e->fork) launchers(e->KG).fork_reset(shape, s, e->dc, e->fc, e->dp, e->fp, env_mask, obs);
     else launchers(e->KG).reset(e->feat, shape, s, e->dc, e->dp, env_mask, obs);
     e->launches += 1;
+    e->rng_step += 1u;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
 }
@@ -508,10 +526,10 @@ static void launch_step_range(qs_env *e, int e0, int n, cudaStream_t s, const fl
     const size_t r0 = (size_t)e0 * K;
     DevConst c = e->dc;
     DevPtrs P = e->dp;
-    c.N = n; c.env_id_offset += e0;
+    c.N = n; c.env_id_offset += e0; c.rng_step = e->rng_step;
     for (int p = 0; p < PL_COUNT; ++p) P.plane[p] += r0;
     if (P.rew_info) P.rew_info += 2 * r0;
-    P.tick += e0; P.svd_ctr += e0; P.step_ctr += e0; P.ecnt += (size_t)e0 * EC_COUNT; P.ep_rec += (size_t)e0 * QS_ER_COUNT; P.ep_agent += r0;
+    P.tick += e0; P.svd_ctr += e0; P.ecnt += (size_t)e0 * EC_COUNT; P.ep_rec += (size_t)e0 * QS_ER_COUNT; P.ep_agent += r0;
     if (e->cfg.use_obstacles) P.obst_xy += (size_t)e0 * QS_MAX_OBSTACLES;
     if (P.scen) P.scen += (size_t)e0 * (QS_SC_COUNT / 4);
     const int grid = (int)(((long long)n * e->KG + e->block - 1) / e->block);
@@ -529,7 +547,17 @@ static void launch_step_range(qs_env *e, int e0, int n, cudaStream_t s, const fl
         launchers(e->KG).step(true, e->feat, { grid < e->grid_persist ? grid : e->grid_persist, e->block, e->smem_persist }, s, c, P,
                               (const float4 *)actions, obs, rew, done, terminal_obs, reset_success);
     } else {
-        launchers(e->KG).step(false, e->feat, { grid, e->block, e->smem_bytes }, s, c, P, (const float4 *)actions, obs, rew, done, terminal_obs,
+        int g2 = grid;
+        if (e->hot && e0 == 0 && n == e->cfg.num_envs) {                // full-range launches only: tile ids are relative to the launch
+            const unsigned ph = e->hot_phase++;
+            const int cur = ph % 3, nxt = (ph + 1) % 3, clr = (ph + 2) % 3;
+            P.hot_list_cur = e->hot_list[cur]; P.hot_cnt_cur = e->hot_cnt[cur]; P.hot_flag_cur = e->hot_flag[cur];
+            P.hot_list_next = e->hot_list[nxt]; P.hot_cnt_next = e->hot_cnt[nxt]; P.hot_flag_next = e->hot_flag[nxt];
+            P.hot_cnt_clear = e->hot_cnt[clr];
+            P.hot_cap = e->hot_cap; P.hot_blocks = e->hot_blocks;
+            g2 += e->hot_blocks;
+        }
+        launchers(e->KG).step(false, e->feat, { g2, e->block, e->smem_bytes }, s, c, P, (const float4 *)actions, obs, rew, done, terminal_obs,
                               reset_success);
     }
     e->launches += 1;
@@ -542,6 +570,7 @@ int qs_step(qs_env *e, const float *actions, float *obs, float *rew, uint8_t *do
     if (((size_t)actions & 15) != 0) return fail(e, QS_ERR_SHAPE, "qs_step: actions must be 16-byte aligned");
     DeviceGuard guard(e->device);
     launch_step_range(e, 0, e->cfg.num_envs, (cudaStream_t)stream, actions, obs, rew, done, terminal_obs, reset_success);
+    e->rng_step += e->fork ? (uint32_t)e->cfg.fork.substeps : 1u;
     QS_CUDA(e, cudaGetLastError());
     return QS_OK;
 }
@@ -648,6 +677,7 @@ int qs_step_host(qs_env *e, const float *actions_host, float *obs_host, float *r
         }
         for (int k = 0; k < 2; ++k) { QS_CUDA(e, cudaEventRecord(e->ev_out[k], e->cs[k])); QS_CUDA(e, cudaStreamWaitEvent(s, e->ev_out[k], 0)); }
     }
+    e->rng_step += e->fork ? (uint32_t)e->cfg.fork.substeps : 1u;        // every chunk of this step drew from the same counter
     QS_CUDA(e, cudaGetLastError());
     if (reset_success_host) QS_CUDA(e, cudaMemcpyAsync(ps ? reset_success_host : e->h_succ, e->d_succ, N, cudaMemcpyDeviceToHost, s));
     QS_CUDA(e, cudaStreamSynchronize(s));
@@ -681,6 +711,13 @@ static int state_io(qs_env *e, const qs_state_view *view, void *stream, int set)
     v.scenario = e->dp.scen ? view->scenario : nullptr;
     v.pid = e->fork ? view->pid : nullptr; v.heading = e->fork ? view->heading : nullptr; v.evader = e->fork ? view->evader : nullptr;
     const size_t nd = (size_t)e->cfg.num_envs * e->cfg.num_agents;
+    if (set && view->step_ctr) {                                        // the handle's RNG launch counter = entry 0 of the (device) array
+        uint32_t h = 0;
+        QS_CUDA(e, cudaMemcpyAsync(&h, view->step_ctr, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        QS_CUDA(e, cudaStreamSynchronize((cudaStream_t)stream));
+        e->rng_step = h;
+    }
+    e->dc.rng_step = e->rng_step;
     state_io_kernel<<<(int)((nd + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->dc, e->dp, e->fp, v, set);
     e->launches += 1;
     QS_CUDA(e, cudaGetLastError());

@@ -38,6 +38,12 @@
 #ifndef QS_PARK
 #define QS_PARK 0               // 1: goal / distance ring / window sums travel global -> shared by LDGSTS (no registers while the dynamics run).
 #endif                          //    Measured slower (cfg2 79.3 -> 85.1 us, profiles/README.md round 2): off.
+#ifndef QS_EARLY_RNG
+#define QS_EARLY_RNG 1          // the step's regular draws (OU + sensor noise) are generated in the shadow of the prologue loads
+#endif
+#ifndef QS_PREFETCH
+#define QS_PREFETCH -1          // with QS_EARLY_RNG: 1 = prefetch the warp's state rows into L2, draw, then load (L2 hits); 2 = prefetch into
+#endif                          // L1; 0 = load first, then draw; -1 = per variant as measured (profiles/README.md round 2: formation scenarios 1, others 0)
 #ifndef QS_EARLY_STORE
 #define QS_EARLY_STORE 1        // motor-lag and OU planes are written back right after the dynamics (12 registers dead for the rest of the step)
 #endif
@@ -60,6 +66,7 @@ struct DevConst {
     int small_angle;                                              // sqrt(3) * omega_max * dt / 2 <= 0.25 rad
     int lin_one, no_omega_damp;                                   // motor_linearity == 1 / damp_omega_quadratic == 0: the terms drop out (warp-uniform)
     uint32_t key0, key1;
+    uint32_t rng_step;                                            // Philox counter word 1: launches (steps + resets) of the handle so far
     long long env_id_offset;
     float dt, hx, hy, hz, room_l, room_w, room_h, gravity, mass, inv_mass;
     float inertia[3], inv_inertia[3], thrust_max[4], torque_max[4], pcx[4], pcy[4], pcz[4], ccw[4];
@@ -83,12 +90,18 @@ struct DevPtrs {
     float4 *plane[PL_COUNT];   // each [N*K]
     int *tick;                 // [N]
     int *svd_ctr;              // [N]
-    uint32_t *step_ctr;        // [N]
     int *ecnt;                 // [N, EC_COUNT]
     float2 *obst_xy;           // [N, QS_MAX_OBSTACLES]
     float4 *scen;              // [N, QS_SC_COUNT / 4] formation-scenario rows (formation scenarios only, else null)
     int *ep_rec;               // [N, QS_ER_COUNT] record of the last finished episode per env (QS_ER_*)
     float4 *ep_agent;          // [N*K] per-drone part of that record
+    // reset-first scheduling (step kernel, plain form): warp-tiles whose envs finish their episode in THIS step were listed by the
+    // previous step and are processed by the first `hot_blocks` blocks of the grid, so that the long auto-reset path overlaps the
+    // rest of the grid instead of extending its tail.  Three buffers rotate: consumed now / produced now / count cleared now.
+    int *hot_list_cur, *hot_cnt_cur, *hot_flag_cur;   // flags: one int per warp-tile (set = a hot block owns this tile in this step)
+    int *hot_list_next, *hot_cnt_next, *hot_flag_next;
+    int *hot_cnt_clear;
+    int hot_cap, hot_blocks;
     float4 *rew_info;          // [N*K, 2] optional (null = off): the raw reward terms of the step, infos[i]["rewards"] (QS_RI_*)
     qs_stats *stats;           // device aggregate
 };
@@ -411,11 +424,20 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
 // ----------------------------------------------------------------------------------------------------------------
 // a9  self observation: SensorNoise.add_noise_numba + state_xyz_vxyz_R_omega* (sensor_noise.py:172-261, get_state.py:226-292)
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void self_obs(const DevConst &c, const Rng &g, int site, int drone, const Drone &q, float *o)
+// the three noise blocks of one self observation (9 of the 12 normals are used)
+struct SensorNoise { float4 n, m, l; };
+__device__ __forceinline__ SensorNoise sensor_noise(const Rng &g, int site, int drone)
+{
+    SensorNoise s;
+    s.n = rng_n4v(g, site, drone, 0, 0); s.m = rng_n4v(g, site, drone, 0, 1); s.l = rng_n4v(g, site, drone, 0, 2);
+    return s;
+}
+
+__device__ __forceinline__ void self_obs(const DevConst &c, const SensorNoise &sn, const Drone &q, float *o)
 {
     float p0 = q.p[0], p1 = q.p[1], p2 = q.p[2], v0 = q.v[0], v1 = q.v[1], v2 = q.v[2], w0 = q.w[0], w1 = q.w[1], w2 = q.w[2];
     if (c.sense_noise) {
-        const float4 n = rng_n4v(g, site, drone, 0, 0), m = rng_n4v(g, site, drone, 0, 1), l = rng_n4v(g, site, drone, 0, 2);
+        const float4 n = sn.n, m = sn.m, l = sn.l;
         p0 += c.s_pos * n.x; p1 += c.s_pos * n.y; p2 += c.s_pos * n.z;
         v0 += c.s_vel * n.w; v1 += c.s_vel * m.x; v2 += c.s_vel * m.y;
         w0 += c.s_gyro * m.z; w1 += c.s_gyro * m.w; w2 += c.s_gyro * l.x;
@@ -1149,6 +1171,14 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem)
     // cp_async_wait_all(), which does clobber memory)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem));
 }
+__device__ __forceinline__ void prefetch_row(const void *p)
+{
+#if QS_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -1198,7 +1228,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     const size_t pf_off = (ob_off + (size_t)warps_per_block * ob_per_warp * 2 + 3) & ~(size_t)3;
     // parking area of the plain form (QS_PARK): goal / distance ring / window sums of every thread, 3 x blockDim float4, behind the
     // staged obstacle centres or scenario rows
-    constexpr bool PARK = QS_PARK && !PERSIST;
+    constexpr bool PARK = QS_PARK && !PERSIST && !QS_EARLY_RNG;        // the two users of the per-thread scratch slots exclude each other
     const size_t park_off = (ob_off + (OBST ? (size_t)warps_per_block * ob_per_warp * 2 : (SCEN ? (size_t)warps_per_block * GPW * QS_SC_COUNT : 0)) + 3) & ~(size_t)3;
     float4 *park = reinterpret_cast<float4 *>(smem + park_off) + threadIdx.x;
     const int park_stride = blockDim.x;
@@ -1209,13 +1239,27 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     int *sc = reinterpret_cast<int *>(smem + pf_off + (size_t)warps_per_block * PF_SLOTS * 32 * 4 + (size_t)warps_per_block * 2) + warp_in_block * (3 * GPW);
     uint32_t phase = 0u;
     int wt = (int)blockIdx.x * warps_per_block + warp_in_block;
+#ifndef QS_HOT_MODE
+#define QS_HOT_MODE 1           // 0: reset-first scheduling compiled out
+#endif
+    const bool HOT = QS_HOT_MODE && !PERSIST && QS_EARLY_RNG && P.hot_flag_cur != nullptr;   // warp-uniform (the flag travels with the early-draw scalars)
+    bool hot_role = false;
+    if (HOT) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *P.hot_cnt_clear = 0;  // the buffer the previous step consumed: the next step produces into it
+        if ((int)blockIdx.x < P.hot_blocks) {
+            // (volatile loads: the hot blocks' own dependent look-up, marked so that prologue_check.py can tell it from the state loads)
+            if (wt >= min(*(volatile int *)P.hot_cnt_cur, P.hot_cap)) return;   // no listed tile for this warp
+            wt = ((volatile int *)P.hot_list_cur)[wt];
+            hot_role = true;
+        } else wt -= P.hot_blocks * warps_per_block;
+    }
     if (PERSIST) {
         if (lane == 0) mbar_init(bar, 1);
         __syncwarp();
         if (wt < n_wt) {
             if (lane == 0) prefetch_tile(P, actions, pf, bar, wt * GPW * c.K, max(0, min(GPW, c.N - wt * GPW)) * c.K);
             const int e0 = wt * GPW + lane / KG;
-            if (e0 < c.N && d == 0) { cp_async4(sc + lane / KG, P.tick + e0); cp_async4(sc + GPW + lane / KG, P.svd_ctr + e0); cp_async4(sc + 2 * GPW + lane / KG, P.step_ctr + e0); }
+            if (e0 < c.N && d == 0) { cp_async4(sc + lane / KG, P.tick + e0); cp_async4(sc + GPW + lane / KG, P.svd_ctr + e0); }
             cp_async_commit();
         }
     }
@@ -1229,7 +1273,9 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     Drone q;
     float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
     int tick = 0, svd = 0;
-    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
+    // The RNG counter is (global env id, launch counter, site | drone | aux, block): nothing in it is loaded from memory, so the
+    // step's regular draws can be generated while the state loads are in flight (below)
+    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = c.rng_step;
     int scen_now = 0;
     float4 ring = make_float4(0.f, 0.f, 0.f, 0.f), sums = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 sc_row[(QS_SC_COUNT / 4 + KG - 1) / KG];
@@ -1241,11 +1287,33 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             ob_v[t] = (k < ob_per_warp && warp_env0 + e < c.N) ? __ldcs(P.obst_xy + (size_t)(warp_env0 + e) * QS_MAX_OBSTACLES + m) : make_float2(0.f, 0.f);
         }
     }
+    // ---- the step's regular draws -- OU thrust noise (numba_utils.py:103) and the sensor noise of the self observation
+    // (sensor_noise.py:240-259) -- depend on (global env id, launch counter, drone) only, none of which is loaded: four Philox blocks +
+    // Box-Muller (~15 % of the step's instructions) run in the shadow of the state's trip from HBM instead of after it.  The
+    // generator is inlined in a rolled 4-trip loop (a call would make the compiler move in-flight load destinations out of the
+    // callee's registers first, i.e. wait for the loads) and parks its 16 normals in the thread's shared-memory slots, so they
+    // hold no registers while the dynamics run.
+    constexpr bool EARLY = QS_EARLY_RNG && !PERSIST;
+    constexpr int PFM = (QS_PREFETCH >= 0) ? QS_PREFETCH : ((SCEN || KG >= 32) ? 1 : 0);
+    float4 *nz = reinterpret_cast<float4 *>(smem + park_off) + threadIdx.x;      // [4][blockDim.x]
+    const int nz_stride = blockDim.x;
+    auto early_draws = [&]() {
+        const int nblk = c.sense_noise ? 4 : 1;
+#pragma unroll 1
+        for (int i = 0; i < nblk; ++i) {
+            const uint32_t c2 = (i == 0 ? (uint32_t)SITE_OU : (uint32_t)SITE_SENSOR) | ((uint32_t)d << 8);
+            const uint4 r = philox4x32_10(g.gid, g.step, c2, i == 0 ? 0u : (uint32_t)(i - 1), g.k0, g.k1);
+            float4 n;
+            box_muller(r.x, r.y, n.x, n.y);
+            box_muller(r.z, r.w, n.z, n.w);
+            nz[i * nz_stride] = n;
+        }
+    };
     if (PERSIST) {
         cp_async_wait_all();
         __syncwarp();
         if (env < c.N) {
-            tick = sc[lane / KG]; svd = sc[GPW + lane / KG]; g.step = (uint32_t)sc[2 * GPW + lane / KG];
+            tick = sc[lane / KG]; svd = sc[GPW + lane / KG];
             g.gid = (uint32_t)(c.env_id_offset + env);
         }
         mbar_wait(bar, phase);
@@ -1261,7 +1329,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         if (wn < n_wt) {
             if (lane == 0) prefetch_tile(P, actions, pf, bar, wn * GPW * c.K, max(0, min(GPW, c.N - wn * GPW)) * c.K);
             const int e1 = wn * GPW + lane / KG;
-            if (e1 < c.N && d == 0) { cp_async4(sc + lane / KG, P.tick + e1); cp_async4(sc + GPW + lane / KG, P.svd_ctr + e1); cp_async4(sc + 2 * GPW + lane / KG, P.step_ctr + e1); }
+            if (e1 < c.N && d == 0) { cp_async4(sc + lane / KG, P.tick + e1); cp_async4(sc + GPW + lane / KG, P.svd_ctr + e1); }
             cp_async_commit();
         }
     } else {
@@ -1270,8 +1338,34 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
         // compiler closed the divergent region with register moves of the loaded values in front of the per-env scalar loads -- a
         // second serialised HBM round trip at the top of every warp (profiles/tools/prologue_check.py guards this in the SASS).
         const int env_c = min(env, c.N - 1), gi_c = env_c * c.K + min(d, c.K - 1);
-        tick = P.tick[env_c]; svd = P.svd_ctr[env_c];
-        g.gid = (uint32_t)(c.env_id_offset + env_c); g.step = P.step_ctr[env_c];
+        g.gid = (uint32_t)(c.env_id_offset + env_c);
+        if (EARLY && PFM) {
+            // Pending register loads in front of the generator loop make the compiler copy some of their destinations out of the loop's
+            // registers first -- i.e. wait for the first load.  So the rows are PREFETCHED (no destination registers), the draws run
+            // while they travel from HBM, and the loads proper follow as cache hits.
+#pragma unroll
+            for (int pl = 0; pl < PL_COUNT; ++pl) prefetch_row(P.plane[pl] + gi_c);
+            prefetch_row(actions + gi_c);
+            if (d == 0) { prefetch_row(P.tick + env_c); prefetch_row(P.svd_ctr + env_c); }
+            int *sl = reinterpret_cast<int *>(smem + park_off + 16 * blockDim.x) + 3 * threadIdx.x;
+            if (HOT) { cp_async4(sl + 2, P.hot_flag_cur + min(wt, n_wt - 1)); cp_async_commit(); }
+            early_draws();
+            if (HOT) {
+                cp_async_wait_all();
+                if (!hot_role && sl[2] != 0) {
+                    if (lane == 0 && wt < n_wt) P.hot_flag_cur[wt] = 0;
+                    return;
+                }
+            }
+        }
+        if (EARLY && !PFM) {
+            // The two per-env scalars travel global -> shared (LDGSTS) and are read after the draws below: as pending register loads
+            // the compiler copied them out of the generator loop's registers first, i.e. waited for them before the loop.
+            int *sl = reinterpret_cast<int *>(smem + park_off + 16 * blockDim.x) + 3 * threadIdx.x;
+            cp_async4(sl, P.tick + env_c); cp_async4(sl + 1, P.svd_ctr + env_c);
+            if (HOT) cp_async4(sl + 2, P.hot_flag_cur + min(wt, n_wt - 1));
+            cp_async_commit();
+        } else { tick = P.tick[env_c]; svd = P.svd_ctr[env_c]; }
         if (SCEN) {                                                     // scenario row: loaded with the state, parked in shared memory
 #pragma unroll
             for (int k = 0; k < (QS_SC_COUNT / 4 + KG - 1) / KG; ++k)
@@ -1292,8 +1386,18 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             ring = __ldcs(P.plane[PL_DIST_RING] + gi_c);
             sums = __ldcs(P.plane[PL_DIST_SUMS] + gi_c);
         }
-        if (env >= c.N) { tick = 0; svd = 0; g.gid = 0; g.step = 0; }
     }
+    if (EARLY && !PFM) {
+        early_draws();
+        cp_async_wait_all();
+        const int *sl = reinterpret_cast<const int *>(smem + park_off + 16 * blockDim.x) + 3 * threadIdx.x;
+        tick = sl[0]; svd = sl[1];
+        if (HOT && !hot_role && sl[2] != 0) {                           // a hot block processes this tile in this step
+            if (lane == 0 && wt < n_wt) P.hot_flag_cur[wt] = 0;         // leave the buffer clean for its next use
+            return;
+        }
+    }
+    if (!PERSIST && env >= c.N) { tick = 0; svd = 0; }                 // first consumer of a loaded value: after the draws
     if (SCEN && !PERSIST) {
         if (env < c.N) {
 #pragma unroll
@@ -1335,7 +1439,7 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 #pragma unroll
     for (int m = 0; m < 4; ++m) cmd[m] = 0.5f * (clampf(a4[m], -1.0f, 1.0f) + 1.0f);
     if (valid) {
-        const float4 nv = rng_n4v(g, SITE_OU, d, 0, 0);                // OUNoiseNumba.noise, numba_utils.py:101-105
+        const float4 nv = EARLY ? nz[0] : rng_n4v(g, SITE_OU, d, 0, 0);   // OUNoiseNumba.noise, numba_utils.py:101-105
         const float n[4] = { nv.x, nv.y, nv.z, nv.w };
 #pragma unroll
         for (int m = 0; m < 4; ++m) q.ou[m] = q.ou[m] + (c.ou_theta * (0.0f - q.ou[m]) + c.ou_sigma * n[m]);
@@ -1585,7 +1689,14 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     float vs[3] = { q.v[0], q.v[1], q.v[2] };                          // self.vel snapshot, :705-709
     if (valid) {
         if (SCEN) { float t; t = q.goal[0]; q.goal[0] = og[0]; og[0] = t; t = q.goal[1]; q.goal[1] = og[1]; og[1] = t; t = q.goal[2]; q.goal[2] = og[2]; og[2] = t; }
-        self_obs(c, g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d, q, orow);
+        // fresh sensor noise only if an impulse forced the observation to be recomputed (:711-712); otherwise the draws made above
+        SensorNoise sn;
+        sn.n = sn.m = sn.l = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.sense_noise) {
+            if (__builtin_expect(flag, 0) || !EARLY) sn = sensor_noise(g, flag ? SITE_SENSOR_IMPULSE : SITE_SENSOR, d);
+            else { sn.n = nz[nz_stride]; sn.m = nz[2 * nz_stride]; sn.l = nz[3 * nz_stride]; }
+        }
+        self_obs(c, sn, q, orow);
         if (SCEN) { q.goal[0] = og[0]; q.goal[1] = og[1]; q.goal[2] = og[2]; }
     }
     group_obs_tail<KG, OBST, false, SCEN>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);
@@ -1690,7 +1801,12 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
             }
             __threadfence_block();                                      // obstacle centres written by the leader lane
             __syncwarp(gmask);
-            if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
+            if (valid) {
+                SensorNoise sn;
+                sn.n = sn.m = sn.l = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c.sense_noise) sn = sensor_noise(g, SITE_SENSOR_RESET, d);
+                self_obs(c, sn, q, orow);
+            }
             // the new obstacle centres are in the warp's staged copy as well (written by the group's first lane inside the reset)
             group_obs_tail<KG, OBST, true>(c, ob_env, d, lane, gmask, valid, q, vs, orow, stage);   // stale self.vel, quadrotor_multi.py:477-481
         }
@@ -1700,7 +1816,15 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
     // ---- write back
     if (valid) {
         store_drone<!QS_EARLY_STORE>(P, gi, q, SCEN || all_done);
-        if (d == 0) { P.tick[env] = tick; P.svd_ctr[env] = svd; P.step_ctr[env] = g.step + 1u; }
+        if (d == 0) { P.tick[env] = tick; P.svd_ctr[env] = svd; }
+    }
+    if (HOT) {
+        // tiles with an env that finishes its episode in the NEXT step (the tick is already advanced / reset): listed for the hot blocks
+        const uint32_t nb = __ballot_sync(QS_FULL, valid && d == 0 && tick >= c.ep_len);
+        if (nb != 0u && lane == 0) {
+            const int idx = atomicAdd(P.hot_cnt_next, 1);
+            if (idx < P.hot_cap) { P.hot_list_next[idx] = wt; P.hot_flag_next[wt] = 1; }
+        }
     }
     __syncwarp();
 #ifdef QS_BULK_STORE
@@ -1739,9 +1863,9 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
     float *orow = tile + (size_t)row * c.D;
 
     Drone q;
-    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = 0;
+    Rng g; g.k0 = c.key0; g.k1 = c.key1; g.gid = 0; g.step = c.rng_step;
     float vs[3] = { 0.f, 0.f, 0.f };
-    if (env < c.N) { g.gid = (uint32_t)(c.env_id_offset + env); g.step = P.step_ctr[env]; }     // every lane of the group: the reset draws cooperatively
+    if (env < c.N) g.gid = (uint32_t)(c.env_id_offset + env);          // every lane of the group: the reset draws cooperatively
     if (in_range) {
         load_drone(P, gi, q);
         vs[0] = q.v[0]; vs[1] = q.v[1]; vs[2] = q.v[2];                 // self.vel is not refreshed by reset (quadrotor_multi.py:477)
@@ -1763,7 +1887,7 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
 #pragma unroll
             for (int k = 0; k < EC_COUNT; ++k) ec[k] = 0;
             ec[EC_SCENARIO] = scen;
-            P.tick[env] = 0; P.step_ctr[env] = g.step + 1u;
+            P.tick[env] = 0;
         }
         P.plane[PL_DIST_RING][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
         P.plane[PL_DIST_SUMS][gi] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1771,7 +1895,12 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ DevC
     }
     __threadfence_block();
     __syncwarp();
-    if (valid) self_obs(c, g, SITE_SENSOR_RESET, d, q, orow);
+    if (valid) {
+        SensorNoise sn;
+        if (c.sense_noise) sn = sensor_noise(g, SITE_SENSOR_RESET, d);
+        else sn.n = sn.m = sn.l = make_float4(0.f, 0.f, 0.f, 0.f);
+        self_obs(c, sn, q, orow);
+    }
     group_obs_tail<KG, OBST, true>(c, P.obst_xy + (size_t)(env < c.N ? env : 0) * QS_MAX_OBSTACLES, d, lane, gmask, valid, q, vs, orow, stage);
     __syncwarp();
     // rows of envs that were not reset stay untouched: per-row masked copy

