@@ -7,17 +7,24 @@
 // 512 -> 512 (tanh), then the action-mean head (512 -> A) of the actor tower and the value head (512 -> 1) of the critic tower.
 // This is the one dense contraction of the system: ~3.06 MFLOP per drone row, 1.6 TFLOP per 65536 x 8 step.
 //
-// Design (one CTA per SM, persistent over 128-row tiles, 128 threads = one thread per row = one TMEM lane):
-//   * every GEMM is `tcgen05.mma.cta_group::1.kind::f16` (bf16 in, fp32 accumulate), M = 128 rows, N = 256, issued by one thread;
-//   * ACTIVATIONS NEVER LEAVE TENSOR MEMORY: the accumulator (256 fp32 columns) is read back with `tcgen05.ld`, bias + tanh are
-//     applied in registers, and the result is written with `tcgen05.st` as packed bf16 into a second TMEM region that the next
-//     layer's MMA reads as its A operand (A from TMEM, "TS" form).  TMEM map (512 columns): [0,256) accumulator, [256,384) region
-//     R1 (layer input / hidden / neighbour mean, K <= 256 bf16), [384,512) region R2 (self-encoder output, kept for the feed-forward);
-//   * weights (B operand) are pre-packed on the device into the canonical no-swizzle K-major core-matrix layout (8 rows x 16 bytes),
-//     one 32 KB image per (N = 256) x (K = 64) chunk, in the order the kernel consumes them, and streamed from L2 by 1-D bulk
-//     copies (`cp.async.bulk` + mbarrier complete_tx) through a two-stage ring;
-//   * the running sum over neighbours lives in shared memory as fp32 [256][128] (column-major: conflict-free per-row access);
-//   * the 512 -> A / 512 -> 1 heads are folded into the feed-forward epilogue on the CUDA cores (4 FMA per element).
+// Design (persistent, one CTA per SM, 128-row tiles, 10 warps with fixed roles):
+//   * warps 0-7  EPILOGUE: thread = (row, column half).  tcgen05.ld the fp32 accumulator, + bias, tanh (MUFU), then either pack to bf16
+//                and tcgen05.st it into the TMEM region the next layer's MMA reads as its A operand, or add it to the running sum
+//                over neighbours (128 fp32 registers per thread), or fold it into the heads (CUDA-core FMAs);
+//   * warp 8     MMA ISSUER (one lane): `tcgen05.mma.cta_group::1.kind::f16` (bf16 x bf16 -> fp32), M = 128, N = 128 per instruction
+//                group; first layers read A from shared memory (the 128 x 32 observation tile), every other layer reads A from
+//                TENSOR MEMORY -- activations never touch shared or global memory;
+//   * warp 9     WEIGHT PRODUCER (one lane): `cp.async.bulk` + mbarrier complete_tx.  The neighbour encoder's weights (144 KB, used
+//                V times per tile) are loaded once per tower and stay resident in shared memory; the self-encoder and feed-forward
+//                weights (656 KB per tile) stream from L2 through a 3-stage ring of 16 KB chunk images.
+//   TMEM map (512 columns): two "streams", each an accumulator of 128 fp32 columns + an activation region of 128 columns (256 bf16).
+//   The V neighbour passes alternate between the streams, so that the tensor core works on one neighbour's next half-layer while the
+//   epilogue warps run tanh over the other's -- the pass is bound by the epilogue (MUFU: 16 tanh/clk/SM, TMEM read: 64 B/clk/SM;
+//   both 2048 clk per 128 x 256 layer, the MMA 2048 clk as well), not by their sum.  Feed-forward: four N = 128 quarters ping-pong
+//   between the two accumulators; A = [self-encoder output | neighbour mean] in the two activation regions.
+//   Weight images are pre-packed on the device (qp_set_weights) into the canonical no-swizzle K-major core-matrix layout (8 rows x 16
+//   bytes), in the order the kernel consumes them.  The first layers' K is laid out [self (24) | neighbour (8)], so the self part of
+//   the observation tile is written once per tile and each neighbour pass rewrites one 16-byte chunk per row.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -32,20 +39,28 @@ namespace qp {
 constexpr int H = 256;                      // hidden width of every encoder layer
 constexpr int FF = 512;                     // feed-forward width
 constexpr int TILE_M = 128;
-constexpr int CHUNK_BYTES = 32 * 1024;      // one (N = 256) x (K = 64) bf16 weight image
-constexpr int STAGES = 2;
+constexpr int NH = 128;                     // N of one MMA group (half an encoder layer, a quarter of the feed-forward)
+constexpr int CHUNK = 16 * 1024;            // one (N = 128) x (K = 64) bf16 weight image
+constexpr int CHUNK1 = 8 * 1024;            // one (N = 128) x (K = 32) image (first layers)
+constexpr int STAGES = 3;
 constexpr int MAX_ACT = 8;
+constexpr int SELF_PAD = 24, NBR_PAD = 8;   // K layout of the first layers: [self | neighbour]
+constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS, THREADS = EPI_THREADS + 64;
+constexpr int RES_BYTES = 2 * CHUNK1 + 8 * CHUNK;                    // resident neighbour-encoder weights: 147456
+constexpr int STREAM_BYTES = 2 * CHUNK1 + 8 * CHUNK + 32 * CHUNK;    // streamed per tile: self L1, self L2, feed-forward
+constexpr int TOWER_IMG_BYTES = RES_BYTES + STREAM_BYTES;            // 819200
 
-// fp32 side parameters of one tower, in this order
+// fp32 side parameters of one tower
 struct TowerParams {
-    float b_self1[H], b_self2[H], b_nbr1[H], b_nbr2[H], b_ff[FF];
-    float head_w[MAX_ACT * FF];             // [out][512], row-major like nn.Linear.weight
+    float bias[4 * H + FF];                 // b_self1, b_self2, b_nbr1, b_nbr2, b_ff
+    float head_wt[FF * MAX_ACT];            // [512][8]: transposed nn.Linear.weight, zero-padded
     float head_b[MAX_ACT];
 };
+constexpr int B_SELF1 = 0, B_SELF2 = H, B_NBR1 = 2 * H, B_NBR2 = 3 * H, B_FF = 4 * H, N_BIAS = 4 * H + FF;
 
 struct Args {
     const float *obs; int n, stride, S, W, V, A;
-    const __nv_bfloat16 *wchunks[2];        // per tower: chunk images in consumption order (5 + 5 per neighbour pass + 16)
+    const uint8_t *wimg[2];                 // per tower: [resident block | streamed block]
     const TowerParams *params[2];
     float *mean, *value;                    // [n, A], [n]
 };
@@ -58,23 +73,34 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+// Bounded wait: a protocol error (a commit or a copy that never arrives) traps after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "QP_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra QP_DONE;\n"
-        "bra QP_WAIT;\n"
-        "QP_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if ((spin & 1023u) == 1023u) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
+    }
 }
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- tcgen05 ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -83,7 +109,7 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, N = 256, K = 16, bf16 x bf16 -> fp32
+// D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, N = 128, K = 16, bf16 x bf16 -> fp32
 __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -92,6 +118,16 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 B contiguous); LBO = distance between the two K-halves of one MMA,
 // SBO = distance between 8-row groups (cute/atom/mma_traits_sm100.hpp, "LayoutType::INTERLEAVE ((8,n),2):((1,SBO),LBO)")
@@ -139,227 +175,370 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     return r;
 }
 
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);   // F32 acc, bf16 x bf16, K-major, N 256, M 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NH >> 3) << 17) | ((128u >> 4) << 24);   // F32 acc, bf16 x bf16, K-major, N 128, M 128
 
-// shared-memory map
+// shared-memory map (223.4 KB)
 struct Smem {
-    uint8_t w[STAGES][CHUNK_BYTES];        // weight ring (1024-byte aligned by construction)
-    float nbr_sum[H][TILE_M];              // running sum over neighbours, column-major
-    uint64_t full[STAGES], empty[STAGES], acc_full;
+    uint8_t wres[RES_BYTES];               // neighbour encoder: L1 halves (2 x 8 KB), L2 (half, K chunk) (8 x 16 KB)
+    uint8_t ring[STAGES][CHUNK];           // streamed weight chunks
+    uint8_t xbuf[2][TILE_M * 32 * 2];      // per stream: the 128 x 32 bf16 first-layer input, K-chunk-major core matrices
+    float bias[N_BIAS];
+    float xchg[TILE_M][MAX_ACT];           // head partial sums of the upper column half
+    uint64_t full[STAGES], empty[STAGES], acc_full[2], epi_done[2], x_ready, res_full;
     uint32_t tmem_base;
 };
 
-// the weight stream: thread 0 keeps one chunk in flight ahead of the one being consumed
-struct Stream {
-    const uint8_t *src;                    // next chunk image in global memory
-    int issued, consumed;                  // chunk counters over the whole kernel (ring position and parity)
-};
+// element (row, k) of an x tile: K-chunk (8 elements, 16 B) major, then 8-row groups of 128 B: LBO = 2048, SBO = 128
+__device__ __forceinline__ uint32_t xoff(int row, int kchunk) { return (uint32_t)(kchunk * 2048 + (row >> 3) * 128 + (row & 7) * 16); }
 
-__device__ __forceinline__ void stream_issue(Smem &sm, Stream &st, const uint8_t *chunk, uint32_t bytes)
-{
-    const int s = st.issued % STAGES;
-    mbar_wait(&sm.empty[s], ((st.issued / STAGES) & 1) ^ 1);            // the MMAs that read this slot have completed
-    mbar_expect_tx(&sm.full[s], bytes);
-    bulk_load(sm.w[s], chunk, bytes, &sm.full[s]);
-    st.issued += 1;
-}
-
-// One GEMM: ACC[128 x 256] = A[128 x K] (TMEM columns a_col .. ) * W^T, W streamed as K / kc chunk images starting at `chunks`.
-// Called by thread 0 only.  `next`: the first chunk of the following GEMM (prefetched while this GEMM's last chunk computes), or null.
-__device__ __forceinline__ void gemm_issue(Smem &sm, Stream &st, uint32_t tmem, uint32_t acc_col, const uint32_t *a_cols, int nchunks, int kc,
-                                           const uint8_t *chunks, const uint8_t *next, uint32_t next_bytes)
-{
-    const uint32_t bytes = (uint32_t)(H * kc * 2);
-    const uint32_t sbo = (uint32_t)(kc / 8) * 128u;
-    for (int c = 0; c < nchunks; ++c) {
-        if (st.issued == st.consumed) stream_issue(sm, st, chunks + (size_t)c * CHUNK_BYTES, bytes);        // nothing in flight yet
-        if (c + 1 < nchunks) stream_issue(sm, st, chunks + (size_t)(c + 1) * CHUNK_BYTES, bytes);            // one ahead
-        else if (next != nullptr) stream_issue(sm, st, next, next_bytes);
-        const int s = st.consumed % STAGES;
-        mbar_wait(&sm.full[s], (st.consumed / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t base = smem_u32(sm.w[s]);
-        for (int k = 0; k < kc / 16; ++k)
-            mma_ts(tmem + acc_col, tmem + a_cols[c] + (uint32_t)(k * 8), smem_desc(base + (uint32_t)k * 256u, 128u, sbo), IDESC, (c | k) != 0);
-        tc_commit(&sm.empty[s]);                                        // frees the slot when these MMAs have read it
-        st.consumed += 1;
-    }
-    tc_commit(&sm.acc_full);
-}
-
-__global__ void __launch_bounds__(TILE_M, 1) policy_forward_kernel(const Args a)
+__global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    const int t = threadIdx.x, warp = t >> 5;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        mbar_init(&sm.acc_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.epi_done[s], EPI_WARPS); }
+        mbar_init(&sm.x_ready, EPI_WARPS);
+        mbar_init(&sm.res_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    for (int i = t; i < (int)sizeof(sm.xbuf) / 16; i += THREADS) reinterpret_cast<uint4 *>(sm.xbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 TMEM lanes
-    constexpr uint32_t ACC = 0, R1 = 256, R2 = 384;
-    Stream st; st.src = nullptr; st.issued = 0; st.consumed = 0;
-    uint32_t acc_parity = 0;
+    constexpr uint32_t ACC0 = 0, ACC1 = 128, R10 = 256, R11 = 384;      // TMEM columns: stream accumulators, stream activation regions
     const int S = a.S, W = a.W, V = a.V, A = a.A;
     const int n_tiles = (a.n + TILE_M - 1) / TILE_M;
+    // phase bookkeeping, advanced identically by every role: items issued per stream, tiles, ring chunks
+    uint32_t n_item[2] = { 0u, 0u }, n_tile = 0u, n_chunk = 0u;
 
-    // all threads: wait for the accumulator of the GEMM just issued
-    auto wait_acc = [&]() { mbar_wait(&sm.acc_full, acc_parity); acc_parity ^= 1u; tc_fence_after(); };
-    // all threads: activations written with tcgen05.st are ordered before the MMAs thread 0 issues next
-    auto publish = [&]() { tmem_st_wait(); tc_fence_before(); __syncthreads(); tc_fence_after(); };
-
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row = tile * TILE_M + t;
-        const bool live = row < a.n;
-        const float *orow = a.obs + (size_t)(live ? row : 0) * a.stride;
-        // the self observation, kept in registers as packed bf16 (reused by every neighbour pass)
-        uint32_t xs[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float lo = (live && 2 * k < S) ? orow[2 * k] : 0.f, hi = (live && 2 * k + 1 < S) ? orow[2 * k + 1] : 0.f;
-            xs[k] = pack_bf16(lo, hi);
+    for (int tower = 0; tower < 2; ++tower) {
+        const uint8_t *img = a.wimg[tower];
+        const TowerParams *P = a.params[tower];
+        if (warp < EPI_WARPS)
+            for (int i = t; i < N_BIAS; i += EPI_THREADS) sm.bias[i] = P->bias[i];
+        if (warp == 9 && lane == 0 && V > 0) {                          // resident neighbour-encoder weights of this tower
+            mbar_expect_tx(&sm.res_full, RES_BYTES);
+            for (int i = 0; i < RES_BYTES / CHUNK; ++i) bulk_load(sm.wres + i * CHUNK, img + (size_t)i * CHUNK, CHUNK, &sm.res_full);
         }
-        for (int tower = 0; tower < 2; ++tower) {
-            const uint8_t *wc = reinterpret_cast<const uint8_t *>(a.wchunks[tower]);
-            const TowerParams *P = a.params[tower];
-            // chunk images: [0] self L1 (K 32), [1..4] self L2, [5] nbr L1 (K 32), [6..9] nbr L2, [10..25] feed-forward (2 halves x 8)
-            const uint8_t *c_self1 = wc, *c_self2 = wc + 1 * (size_t)CHUNK_BYTES, *c_nbr1 = wc + 5 * (size_t)CHUNK_BYTES,
-                          *c_nbr2 = wc + 6 * (size_t)CHUNK_BYTES, *c_ff = wc + 10 * (size_t)CHUNK_BYTES;
-            const uint32_t cols_l1[1] = { R1 }, cols_l2[4] = { R1, R1 + 32, R1 + 64, R1 + 96 };
-            const uint32_t cols_ff[8] = { R2, R2 + 32, R2 + 64, R2 + 96, R1, R1 + 32, R1 + 64, R1 + 96 };
+        __syncthreads();
 
-            // hidden-layer epilogue: ACC -> +bias -> tanh -> packed bf16 into TMEM region `dst` (the next layer's A operand)
-            auto epilogue_to_tmem = [&](const float *bias, uint32_t dst) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < H; c0 += 32) {
-                    uint32_t v[32], u[16];
-                    tmem_ld32(lane_addr + ACC + (uint32_t)c0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        u[i] = pack_bf16(tanh_fast(__uint_as_float(v[2 * i]) + __ldg(bias + c0 + 2 * i)),
-                                         tanh_fast(__uint_as_float(v[2 * i + 1]) + __ldg(bias + c0 + 2 * i + 1)));
-                    tmem_st16(lane_addr + dst + (uint32_t)(c0 / 2), u);
+        if (warp == 9) {
+            // =========================== WEIGHT PRODUCER ===========================
+            if (lane == 0) {
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    const uint8_t *src = img + RES_BYTES;
+                    for (int i = 0; i < 42; ++i) {
+                        const uint32_t bytes = i < 2 ? CHUNK1 : CHUNK;
+                        const uint32_t slot = n_chunk % STAGES;
+                        mbar_wait(&sm.empty[slot], ((n_chunk / STAGES) & 1u) ^ 1u);      // the MMAs that read this slot have completed
+                        mbar_expect_tx(&sm.full[slot], bytes);
+                        bulk_load(sm.ring[slot], src, bytes, &sm.full[slot]);
+                        src += bytes;
+                        n_chunk += 1;
+                    }
                 }
+            }
+            __syncwarp();
+        } else if (warp == 8) {
+            // =========================== MMA ISSUER ===========================
+            if (lane == 0) {
+                const uint32_t wres = smem_u32(sm.wres), xb0 = smem_u32(sm.xbuf[0]), xb1 = smem_u32(sm.xbuf[1]);
+                auto wait_prev = [&](int s) {                            // the epilogue of the stream's previous item has drained its accumulator
+                    if (n_item[s] > 0) { mbar_wait(&sm.epi_done[s], (n_item[s] - 1u) & 1u); tc_fence_after(); }
+                };
+                auto ring_take = [&]() -> uint32_t {                     // next streamed chunk has landed
+                    const uint32_t slot = n_chunk % STAGES;
+                    mbar_wait(&sm.full[slot], (n_chunk / STAGES) & 1u);
+                    tc_fence_after();
+                    return slot;
+                };
+                auto ring_release = [&](uint32_t slot) { tc_commit(&sm.empty[slot]); n_chunk += 1; };
+                if (V > 0) mbar_wait(&sm.res_full, (uint32_t)tower & 1u);
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    mbar_wait(&sm.x_ready, n_tile & 1u);
+                    n_tile += 1;
+                    tc_fence_after();
+                    // ---- neighbour passes, two at a time on the two streams
+                    for (int j0 = 0; j0 < V; j0 += 2) {
+                        const int nact = (V - j0) < 2 ? (V - j0) : 2;
+                        for (int it = 0; it < 4; ++it)
+                            for (int s = 0; s < nact; ++s) {
+                                const uint32_t acc = tmem + (s ? ACC1 : ACC0);
+                                const int h = it & 1;
+                                wait_prev(s);
+                                if (it < 2) {                            // layer 1: A = the stream's x tile (shared memory), K = 32
+                                    const uint32_t xa = s ? xb1 : xb0, wb = wres + (uint32_t)h * CHUNK1;
+                                    for (int k = 0; k < 2; ++k)
+                                        mma_ss(acc, smem_desc(xa + (uint32_t)k * 4096u, 2048u, 128u), smem_desc(wb + (uint32_t)k * 256u, 128u, 512u), IDESC, k != 0);
+                                } else {                                 // layer 2: A = the stream's hidden activations (tensor memory), K = 256
+                                    const uint32_t r1 = tmem + (s ? R11 : R10);
+                                    for (int c = 0; c < 4; ++c) {
+                                        const uint32_t wb = wres + 2u * CHUNK1 + (uint32_t)(h * 4 + c) * CHUNK;
+                                        for (int k = 0; k < 4; ++k)
+                                            mma_ts(acc, r1 + (uint32_t)(c * 32 + k * 8), smem_desc(wb + (uint32_t)k * 256u, 128u, 1024u), IDESC, (c | k) != 0);
+                                    }
+                                }
+                                tc_commit(&sm.acc_full[s]);
+                                n_item[s] += 1;
+                            }
+                    }
+                    // ---- self encoder layer 1: halves on the two accumulators, A = x tile of stream 0 (its neighbour chunk meets zero weights)
+                    for (int s = 0; s < 2; ++s) {
+                        wait_prev(s);
+                        const uint32_t slot = ring_take();
+                        const uint32_t wb = smem_u32(sm.ring[slot]);
+                        for (int k = 0; k < 2; ++k)
+                            mma_ss(tmem + (s ? ACC1 : ACC0), smem_desc(xb0 + (uint32_t)k * 4096u, 2048u, 128u), smem_desc(wb + (uint32_t)k * 256u, 128u, 512u), IDESC, k != 0);
+                        ring_release(slot);
+                        tc_commit(&sm.acc_full[s]);
+                        n_item[s] += 1;
+                    }
+                    // ---- self encoder layer 2: A = R10 (both layer-1 epilogues must have written it)
+                    wait_prev(0);
+                    wait_prev(1);
+                    for (int s = 0; s < 2; ++s) {
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t slot = ring_take();
+                            const uint32_t wb = smem_u32(sm.ring[slot]);
+                            for (int k = 0; k < 4; ++k)
+                                mma_ts(tmem + (s ? ACC1 : ACC0), tmem + R10 + (uint32_t)(c * 32 + k * 8), smem_desc(wb + (uint32_t)k * 256u, 128u, 1024u), IDESC, (c | k) != 0);
+                            ring_release(slot);
+                        }
+                        tc_commit(&sm.acc_full[s]);
+                        n_item[s] += 1;
+                    }
+                    // ---- feed-forward: four quarters of 128 outputs, A = [R10 (self encoder) | R11 (neighbour mean)], K = 512
+                    wait_prev(0);
+                    wait_prev(1);
+                    for (int qtr = 0; qtr < 4; ++qtr) {
+                        const int s = qtr & 1;
+                        wait_prev(s);
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t slot = ring_take();
+                            const uint32_t wb = smem_u32(sm.ring[slot]);
+                            const uint32_t acol = tmem + (c < 4 ? R10 + (uint32_t)c * 32u : R11 + (uint32_t)(c - 4) * 32u);
+                            for (int k = 0; k < 4; ++k)
+                                mma_ts(tmem + (s ? ACC1 : ACC0), acol + (uint32_t)k * 8u, smem_desc(wb + (uint32_t)k * 256u, 128u, 1024u), IDESC, (c | k) != 0);
+                            ring_release(slot);
+                        }
+                        tc_commit(&sm.acc_full[s]);
+                        n_item[s] += 1;
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // =========================== EPILOGUE WARPS ===========================
+            const int row_l = 32 * (warp & 3) + lane, q = warp >> 2;     // this thread: one row, one half (64) of an accumulator's 128 columns
+            const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+            const int n_out = tower == 0 ? A : 1;
+            float nsum[128];                                             // running sum over neighbours: [layer half][64 columns of this thread]
+#pragma unroll
+            for (int i = 0; i < 128; ++i) nsum[i] = 0.f;
+
+            auto wait_acc = [&](int s) { mbar_wait(&sm.acc_full[s], n_item[s] & 1u); tc_fence_after(); };
+            auto item_done = [&](int s) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.epi_done[s]);
+                n_item[s] += 1;
+            };
+            // accumulator -> + bias -> tanh -> packed bf16 -> activation region `dst` (columns of layer half h, this thread's 64)
+            auto epi_to_tmem = [&](uint32_t acc, int bias0, int h, uint32_t dst) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    uint32_t v[32], u[16];
+                    tmem_ld32(lane_addr + acc + (uint32_t)(q * 64 + b * 32), v);
+                    const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + bias0 + h * 128 + q * 64 + b * 32);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 bb = bp[i];
+                        u[2 * i] = pack_bf16(tanh_fast(__uint_as_float(v[4 * i]) + bb.x), tanh_fast(__uint_as_float(v[4 * i + 1]) + bb.y));
+                        u[2 * i + 1] = pack_bf16(tanh_fast(__uint_as_float(v[4 * i + 2]) + bb.z), tanh_fast(__uint_as_float(v[4 * i + 3]) + bb.w));
+                    }
+                    tmem_st16(lane_addr + dst + (uint32_t)(h * 64 + q * 32 + b * 16), u);
+                }
+                tmem_st_wait();
             };
 
-            // ---- self encoder: S -> 256 -> 256
-            tmem_st16(lane_addr + R1, xs);
-            publish();
-            if (t == 0) gemm_issue(sm, st, tmem, ACC, cols_l1, 1, 32, c_self1, c_self2, H * 64 * 2);
-            wait_acc();
-            epilogue_to_tmem(P->b_self1, R1);
-            publish();
-            if (t == 0) gemm_issue(sm, st, tmem, ACC, cols_l2, 4, 64, c_self2, c_nbr1, H * 32 * 2);
-            wait_acc();
-            epilogue_to_tmem(P->b_self2, R2);                          // stays in R2 until the feed-forward
-            // ---- neighbour encoder (deep sets): mean_j tanh(W2 tanh(W1 [self, nbr_j] + b1) + b2)
-            for (int j = 0; j < V; ++j) {
-                uint32_t xn[16];
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int row = tile * TILE_M + row_l;
+                const bool live = row < a.n;
+                const float *orow = a.obs + (size_t)(live ? row : 0) * a.stride;
+                // the 16-byte neighbour chunk (K 24..31) of neighbour j
+                auto nbr_chunk = [&](int j) -> uint4 {
+                    float f[NBR_PAD];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) xn[k] = xs[k];
-                // append the neighbour's W values behind the S self values (S + W <= 32)
-                for (int i = 0; i < W; ++i) {
-                    const float v = live ? orow[S + j * W + i] : 0.f;
-                    const int k = S + i;
-                    const uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+                    for (int i = 0; i < NBR_PAD; ++i) f[i] = (live && i < W) ? __ldg(orow + S + j * W + i) : 0.f;
+                    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                };
+                // ---- x tiles of the new tile: the previous tile's MMAs have all completed (its last accumulator was waited for)
+                if (q == 0) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                        if (q == (k >> 1)) xn[q] = (k & 1) ? ((xn[q] & 0x0000FFFFu) | (b << 16)) : ((xn[q] & 0xFFFF0000u) | b);
-                }
-                tmem_st16(lane_addr + R1, xn);
-                publish();
-                if (t == 0) gemm_issue(sm, st, tmem, ACC, cols_l1, 1, 32, c_nbr1, c_nbr2, H * 64 * 2);
-                wait_acc();
-                epilogue_to_tmem(P->b_nbr1, R1);
-                publish();
-                if (t == 0) gemm_issue(sm, st, tmem, ACC, cols_l2, 4, 64, c_nbr2, (j + 1 < V) ? c_nbr1 : c_ff, (j + 1 < V) ? H * 32 * 2 : H * 64 * 2);
-                wait_acc();
-#pragma unroll 1
-                for (int c0 = 0; c0 < H; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + ACC + (uint32_t)c0, v);
+                    for (int kc = 0; kc < 3; ++kc) {
+                        float f[8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float y = tanh_fast(__uint_as_float(v[i]) + __ldg(P->b_nbr2 + c0 + i));
-                        sm.nbr_sum[c0 + i][t] = (j == 0) ? y : sm.nbr_sum[c0 + i][t] + y;
+                        for (int i = 0; i < 8; ++i) f[i] = (live && kc * 8 + i < S) ? __ldg(orow + kc * 8 + i) : 0.f;
+                        const uint4 u = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        *reinterpret_cast<uint4 *>(sm.xbuf[0] + xoff(row_l, kc)) = u;
+                        *reinterpret_cast<uint4 *>(sm.xbuf[1] + xoff(row_l, kc)) = u;
                     }
+                } else {
+                    if (V > 0) *reinterpret_cast<uint4 *>(sm.xbuf[0] + xoff(row_l, 3)) = nbr_chunk(0);
+                    if (V > 1) *reinterpret_cast<uint4 *>(sm.xbuf[1] + xoff(row_l, 3)) = nbr_chunk(1);
                 }
-                tc_fence_before();                                      // the tcgen05.ld above are ordered before the next GEMM overwrites ACC
-            }
-            // neighbour mean -> R1 (a tower without neighbours feeds zeros, like an absent encoder half)
-            {
-                const float inv = V > 0 ? 1.0f / (float)V : 0.f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < H; c0 += 32) {
-                    uint32_t u[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        u[i] = V > 0 ? pack_bf16(sm.nbr_sum[c0 + 2 * i][t] * inv, sm.nbr_sum[c0 + 2 * i + 1][t] * inv) : 0u;
-                    tmem_st16(lane_addr + R1 + (uint32_t)(c0 / 2), u);
-                }
-            }
-            publish();
-            // ---- feed-forward 512 -> 512 (two halves of 256 columns) with the head folded into its epilogue
-            const int n_out = tower == 0 ? A : 1;
-            float head[MAX_ACT];
-#pragma unroll
-            for (int o = 0; o < MAX_ACT; ++o) head[o] = 0.f;
-            for (int half = 0; half < 2; ++half) {
-                const uint8_t *next = (half == 0) ? c_ff + 8 * (size_t)CHUNK_BYTES
-                                                  : (tower == 0 ? reinterpret_cast<const uint8_t *>(a.wchunks[1])
-                                                                : (tile + (int)gridDim.x < n_tiles ? reinterpret_cast<const uint8_t *>(a.wchunks[0]) : nullptr));
-                if (t == 0) gemm_issue(sm, st, tmem, ACC, cols_ff, 8, 64, c_ff + (size_t)half * 8 * CHUNK_BYTES, next, half == 0 ? H * 64 * 2 : H * 32 * 2);
-                wait_acc();
-#pragma unroll 1
-                for (int c0 = 0; c0 < H; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + ACC + (uint32_t)c0, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int c = half * H + c0 + i;
-                        const float y = tanh_fast(__uint_as_float(v[i]) + __ldg(P->b_ff + c));
-#pragma unroll
-                        for (int o = 0; o < MAX_ACT; ++o)
-                            if (o < n_out) head[o] = fmaf(y, __ldg(P->head_w + o * FF + c), head[o]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.x_ready);
+
+                // ---- neighbour passes
+                for (int j0 = 0; j0 < V; j0 += 2) {
+                    const int nact = (V - j0) < 2 ? (V - j0) : 2;
+                    const float keep = j0 == 0 ? 0.f : 1.f;              // the first pair of passes starts the running sum
+                    for (int s = 0; s < nact; ++s) { wait_acc(s); epi_to_tmem(s ? ACC1 : ACC0, B_NBR1, 0, s ? R11 : R10); item_done(s); }
+                    for (int s = 0; s < nact; ++s) {
+                        wait_acc(s);                                     // both layer-1 MMAs of this pass have read the x tile
+                        if (q == s && j0 + s + 2 < V) {
+                            *reinterpret_cast<uint4 *>(sm.xbuf[s] + xoff(row_l, 3)) = nbr_chunk(j0 + s + 2);
+                            fence_proxy_async();
+                        }
+                        epi_to_tmem(s ? ACC1 : ACC0, B_NBR1, 1, s ? R11 : R10);
+                        item_done(s);
                     }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        for (int s = 0; s < nact; ++s) {
+                            wait_acc(s);
+                            const float kp = (s == 0) ? keep : 1.f;
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) {
+                                uint32_t v[32];
+                                tmem_ld32(lane_addr + (s ? ACC1 : ACC0) + (uint32_t)(q * 64 + b * 32), v);
+                                const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + B_NBR2 + h * 128 + q * 64 + b * 32);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 bb = bp[i];
+                                    float *ns = nsum + h * 64 + b * 32 + 4 * i;
+                                    ns[0] = fmaf(ns[0], kp, tanh_fast(__uint_as_float(v[4 * i]) + bb.x));
+                                    ns[1] = fmaf(ns[1], kp, tanh_fast(__uint_as_float(v[4 * i + 1]) + bb.y));
+                                    ns[2] = fmaf(ns[2], kp, tanh_fast(__uint_as_float(v[4 * i + 2]) + bb.z));
+                                    ns[3] = fmaf(ns[3], kp, tanh_fast(__uint_as_float(v[4 * i + 3]) + bb.w));
+                                }
+                            }
+                            item_done(s);
+                        }
                 }
-                tc_fence_before();
-                __syncthreads();                                        // every row has read ACC before the next GEMM overwrites it
-                tc_fence_after();
-            }
-            if (live) {
-                if (tower == 0) { for (int o = 0; o < A; ++o) a.mean[(size_t)row * A + o] = head[o] + __ldg(P->head_b + o); }
-                else a.value[row] = head[0] + __ldg(P->head_b);
+                // ---- neighbour mean -> R11 (no neighbours: zeros, like an absent encoder half); R11's last reader has completed
+                {
+                    const float inv = V > 0 ? 1.0f / (float)V : 0.f;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            uint32_t u[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) u[i] = pack_bf16(nsum[h * 64 + b * 32 + 2 * i] * inv, nsum[h * 64 + b * 32 + 2 * i + 1] * inv);
+                            tmem_st16(lane_addr + R11 + (uint32_t)(h * 64 + q * 32 + b * 16), u);
+                        }
+                    tmem_st_wait();
+                }
+                // ---- self encoder layer 1 (halves on the two accumulators) -> hidden in R10
+                for (int s = 0; s < 2; ++s) { wait_acc(s); epi_to_tmem(s ? ACC1 : ACC0, B_SELF1, s, R10); item_done(s); }
+                // ---- self encoder layer 2 -> R10 in place: both halves' MMAs must have read R10 before it is overwritten
+                wait_acc(0);
+                wait_acc(1);
+                for (int s = 0; s < 2; ++s) { epi_to_tmem(s ? ACC1 : ACC0, B_SELF2, s, R10); item_done(s); }
+                // ---- feed-forward quarters with the head folded in
+                float head[MAX_ACT];
+#pragma unroll
+                for (int o = 0; o < MAX_ACT; ++o) head[o] = 0.f;
+                for (int qtr = 0; qtr < 4; ++qtr) {
+                    const int s = qtr & 1;
+                    wait_acc(s);
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        uint32_t v[32];
+                        tmem_ld32(lane_addr + (s ? ACC1 : ACC0) + (uint32_t)(q * 64 + b * 32), v);
+                        const int c0 = qtr * 128 + q * 64 + b * 32;
+                        const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + B_FF + c0);
+                        const float4 *hp = reinterpret_cast<const float4 *>(P->head_wt + (size_t)c0 * MAX_ACT);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 bb = bp[i];
+                            const float y[4] = { tanh_fast(__uint_as_float(v[4 * i]) + bb.x), tanh_fast(__uint_as_float(v[4 * i + 1]) + bb.y),
+                                                 tanh_fast(__uint_as_float(v[4 * i + 2]) + bb.z), tanh_fast(__uint_as_float(v[4 * i + 3]) + bb.w) };
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float4 w0 = __ldg(hp + (4 * i + e) * 2);
+                                head[0] = fmaf(y[e], w0.x, head[0]); head[1] = fmaf(y[e], w0.y, head[1]);
+                                head[2] = fmaf(y[e], w0.z, head[2]); head[3] = fmaf(y[e], w0.w, head[3]);
+                                if (n_out > 4) {
+                                    const float4 w1 = __ldg(hp + (4 * i + e) * 2 + 1);
+                                    head[4] = fmaf(y[e], w1.x, head[4]); head[5] = fmaf(y[e], w1.y, head[5]);
+                                    head[6] = fmaf(y[e], w1.z, head[6]); head[7] = fmaf(y[e], w1.w, head[7]);
+                                }
+                            }
+                        }
+                    }
+                    item_done(s);
+                }
+                // ---- the two column halves of a row meet in shared memory; the lower half writes the outputs
+                if (q == 1) {
+#pragma unroll
+                    for (int o = 0; o < MAX_ACT; ++o) sm.xchg[row_l][o] = head[o];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                if (q == 0 && live) {
+#pragma unroll
+                    for (int o = 0; o < MAX_ACT; ++o)
+                        if (o < n_out) {
+                            const float r = head[o] + sm.xchg[row_l][o] + __ldg(P->head_b + o);
+                            if (tower == 0) a.mean[(size_t)row * A + o] = r;
+                            else a.value[row] = r;
+                        }
+                }
             }
         }
+        // tower done: every chunk consumed, every accumulator read; the resident weights and biases may be replaced
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
     }
-    // every issued chunk has been consumed (the prefetch pointers above never run past the last GEMM), TMEM can go
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ---- weight packing: nn.Linear weight [out, in] fp32 -> chunk images (bf16, canonical K-major core-matrix layout) ----------------
-// chunk image of rows n0 .. n0+255 and inputs k0 .. k0+kc-1 of W (zero beyond `in`): byte offset of element (n, k) inside the image =
-// (n / 8) * SBO + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2, SBO = (kc / 8) * 128.
-__global__ void pack_chunk_kernel(const float *w, int out_dim, int in_dim, int n0, int k0, int kc, __nv_bfloat16 *img)
+// image of rows n0 .. n0+127 and kc input slots of W: byte offset of element (n, k) = (n / 8) * SBO + (k / 8) * 128 + (n % 8) * 16 +
+// (k % 8) * 2, SBO = (kc / 8) * 128.  Slot k reads input column k0 + k, or -- first layers, `split` > 0 -- column k for k < split and
+// column len1 + (k - split) behind it (the [self | neighbour] K layout); columns beyond the matrix are zero.
+__global__ void pack_chunk_kernel(const float *w, int out_dim, int in_dim, int n0, int k0, int kc, int split, int len1, uint8_t *img)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= H * kc) return;
+    if (idx >= NH * kc) return;
     const int n = idx / kc, k = idx % kc;
-    const int gn = n0 + n, gk = k0 + k;
-    const float v = (gn < out_dim && gk < in_dim) ? w[(size_t)gn * in_dim + gk] : 0.f;
+    const int gn = n0 + n;
+    int gk = k0 + k;
+    if (split > 0) gk = k < split ? (k < len1 ? k : -1) : len1 + (k - split);
+    const float v = (gn < out_dim && gk >= 0 && gk < in_dim) ? w[(size_t)gn * in_dim + gk] : 0.f;
     const size_t off = (size_t)(n / 8) * ((size_t)(kc / 8) * 128) + (size_t)(k / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
-    img[off / 2] = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16 *>(img + off) = __float2bfloat16_rn(v);
+}
+
+// head weights [n_out, 512] -> transposed, zero-padded [512][8]
+__global__ void pack_head_kernel(const float *w, int n_out, float *wt)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= FF * MAX_ACT) return;
+    const int c = idx / MAX_ACT, o = idx % MAX_ACT;
+    wt[idx] = o < n_out ? w[(size_t)o * FF + c] : 0.f;
 }
 
 }  // namespace qp
@@ -369,7 +548,7 @@ using namespace qp;
 struct qp_policy {
     qp_config cfg;
     int device, sms;
-    __nv_bfloat16 *wchunks[2];
+    uint8_t *wimg[2];
     TowerParams *params[2];
     long long launches;
     std::string err;
@@ -383,8 +562,6 @@ static int qp_fail(qp_policy *p, int code, const std::string &m) { if (p) p->err
         if (_r != cudaSuccess) return qp_fail(p, QP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); \
     } while (0)
 
-constexpr int CHUNKS_PER_TOWER = 26;
-
 extern "C" {
 
 const char *qp_last_error(const qp_policy *p) { return p ? p->err.c_str() : g_qp_err.c_str(); }
@@ -396,8 +573,8 @@ int qp_create(const qp_config *cfg, int device, qp_policy **out)
     *out = nullptr;
     if (cfg->api_version != QP_API_VERSION) return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_create: api_version mismatch");
     if (cfg->hidden != H) return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_create: only hidden = 256 is built");
-    if (cfg->self_dim < 1 || cfg->nbr_dim < 0 || cfg->num_nbr < 0 || cfg->self_dim + cfg->nbr_dim > 32)
-        return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_create: self_dim + nbr_dim must be <= 32");
+    if (cfg->self_dim < 1 || cfg->self_dim > SELF_PAD || cfg->nbr_dim < 0 || cfg->nbr_dim > NBR_PAD || cfg->num_nbr < 0)
+        return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_create: self_dim must be in [1, 24], nbr_dim in [0, 8]");
     if (cfg->act_dim < 1 || cfg->act_dim > MAX_ACT) return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_create: act_dim out of [1, 8]");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return qp_fail(nullptr, QP_ERR_CUDA, "qp_create: no such CUDA device");
@@ -406,17 +583,22 @@ int qp_create(const qp_config *cfg, int device, qp_policy **out)
     cudaSetDevice(device);
     qp_policy *p = new qp_policy();
     p->cfg = *cfg; p->device = device; p->launches = 0;
+    p->wimg[0] = p->wimg[1] = nullptr; p->params[0] = p->params[1] = nullptr;
     cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t r = cudaSuccess;
     for (int t = 0; t < 2 && r == cudaSuccess; ++t) {
-        r = cudaMalloc(&p->wchunks[t], (size_t)CHUNKS_PER_TOWER * CHUNK_BYTES);
-        if (r == cudaSuccess) r = cudaMemset(p->wchunks[t], 0, (size_t)CHUNKS_PER_TOWER * CHUNK_BYTES);
+        r = cudaMalloc(&p->wimg[t], (size_t)TOWER_IMG_BYTES);
+        if (r == cudaSuccess) r = cudaMemset(p->wimg[t], 0, (size_t)TOWER_IMG_BYTES);
         if (r == cudaSuccess) r = cudaMalloc(&p->params[t], sizeof(TowerParams));
         if (r == cudaSuccess) r = cudaMemset(p->params[t], 0, sizeof(TowerParams));
     }
     if (r == cudaSuccess) r = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
     cudaSetDevice(prev);
-    if (r != cudaSuccess) { delete p; return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_create: ") + cudaGetErrorString(r)); }
+    if (r != cudaSuccess) {
+        for (int t = 0; t < 2; ++t) { cudaFree(p->wimg[t]); cudaFree(p->params[t]); }
+        delete p;
+        return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_create: ") + cudaGetErrorString(r));
+    }
     *out = p;
     return QP_OK;
 }
@@ -424,7 +606,7 @@ int qp_create(const qp_config *cfg, int device, qp_policy **out)
 int qp_destroy(qp_policy *p)
 {
     if (!p) return QP_ERR_NULL;
-    for (int t = 0; t < 2; ++t) { cudaFree(p->wchunks[t]); cudaFree(p->params[t]); }
+    for (int t = 0; t < 2; ++t) { cudaFree(p->wimg[t]); cudaFree(p->params[t]); }
     delete p;
     return QP_OK;
 }
@@ -438,29 +620,37 @@ int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *str
     cudaStream_t s = (cudaStream_t)stream;
     const int S = p->cfg.self_dim, SW = p->cfg.self_dim + p->cfg.nbr_dim;
     const int n_out = tower == 0 ? p->cfg.act_dim : 1;
-    __nv_bfloat16 *base = p->wchunks[tower];
-    auto img = [&](int c) { return base + (size_t)c * (CHUNK_BYTES / 2); };
-    auto pack = [&](const float *src, int out_dim, int in_dim, int n0, int k0, int kc, int chunk) {
-        pack_chunk_kernel<<<(H * kc + 255) / 256, 256, 0, s>>>(src, out_dim, in_dim, n0, k0, kc, img(chunk));
+    uint8_t *img = p->wimg[tower];
+    // one (N = 128) x kc image
+    auto pack = [&](const float *src, int out_dim, int in_dim, int n0, int k0, int kc, int split, int len1, uint8_t *dst) {
+        pack_chunk_kernel<<<(NH * kc + 255) / 256, 256, 0, s>>>(src, out_dim, in_dim, n0, k0, kc, split, len1, dst);
     };
-    pack(w->self_w1, H, S, 0, 0, 32, 0);
-    for (int c = 0; c < 4; ++c) pack(w->self_w2, H, H, 0, 64 * c, 64, 1 + c);
+    // resident block: neighbour L1 halves, neighbour L2 (half, K chunk)
     if (p->cfg.num_nbr > 0) {
-        pack(w->nbr_w1, H, SW, 0, 0, 32, 5);
-        for (int c = 0; c < 4; ++c) pack(w->nbr_w2, H, H, 0, 64 * c, 64, 6 + c);
+        for (int h = 0; h < 2; ++h) pack(w->nbr_w1, H, SW, NH * h, 0, 32, SELF_PAD, S, img + (size_t)h * CHUNK1);
+        for (int h = 0; h < 2; ++h)
+            for (int c = 0; c < 4; ++c) pack(w->nbr_w2, H, H, NH * h, 64 * c, 64, 0, 0, img + 2 * CHUNK1 + (size_t)(h * 4 + c) * CHUNK);
     }
-    for (int half = 0; half < 2; ++half)
-        for (int c = 0; c < 8; ++c) pack(w->ff_w, FF, FF, 256 * half, 64 * c, 64, 10 + half * 8 + c);
+    // streamed block, in consumption order: self L1 halves, self L2 (half, chunk), feed-forward (quarter, chunk)
+    uint8_t *st = img + RES_BYTES;
+    for (int h = 0; h < 2; ++h) pack(w->self_w1, H, S, NH * h, 0, 32, SELF_PAD, S, st + (size_t)h * CHUNK1);
+    st += 2 * CHUNK1;
+    for (int h = 0; h < 2; ++h)
+        for (int c = 0; c < 4; ++c) pack(w->self_w2, H, H, NH * h, 64 * c, 64, 0, 0, st + (size_t)(h * 4 + c) * CHUNK);
+    st += 8 * CHUNK;
+    for (int qtr = 0; qtr < 4; ++qtr)
+        for (int c = 0; c < 8; ++c) pack(w->ff_w, FF, FF, NH * qtr, 64 * c, 64, 0, 0, st + (size_t)(qtr * 8 + c) * CHUNK);
     TowerParams *P = p->params[tower];
     const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
-    QP_CUDA(p, cudaMemcpyAsync(P->b_self1, w->self_b1, H * sizeof(float), dd, s));
-    QP_CUDA(p, cudaMemcpyAsync(P->b_self2, w->self_b2, H * sizeof(float), dd, s));
+    QP_CUDA(p, cudaMemcpyAsync(P->bias + B_SELF1, w->self_b1, H * sizeof(float), dd, s));
+    QP_CUDA(p, cudaMemcpyAsync(P->bias + B_SELF2, w->self_b2, H * sizeof(float), dd, s));
     if (p->cfg.num_nbr > 0) {
-        QP_CUDA(p, cudaMemcpyAsync(P->b_nbr1, w->nbr_b1, H * sizeof(float), dd, s));
-        QP_CUDA(p, cudaMemcpyAsync(P->b_nbr2, w->nbr_b2, H * sizeof(float), dd, s));
+        QP_CUDA(p, cudaMemcpyAsync(P->bias + B_NBR1, w->nbr_b1, H * sizeof(float), dd, s));
+        QP_CUDA(p, cudaMemcpyAsync(P->bias + B_NBR2, w->nbr_b2, H * sizeof(float), dd, s));
     }
-    QP_CUDA(p, cudaMemcpyAsync(P->b_ff, w->ff_b, FF * sizeof(float), dd, s));
-    QP_CUDA(p, cudaMemcpyAsync(P->head_w, w->head_w, (size_t)n_out * FF * sizeof(float), dd, s));
+    QP_CUDA(p, cudaMemcpyAsync(P->bias + B_FF, w->ff_b, FF * sizeof(float), dd, s));
+    pack_head_kernel<<<(FF * MAX_ACT + 255) / 256, 256, 0, s>>>(w->head_w, n_out, P->head_wt);
+    QP_CUDA(p, cudaMemsetAsync(P->head_b, 0, sizeof(P->head_b), s));
     QP_CUDA(p, cudaMemcpyAsync(P->head_b, w->head_b, (size_t)n_out * sizeof(float), dd, s));
     QP_CUDA(p, cudaGetLastError());
     return QP_OK;
@@ -472,11 +662,11 @@ int qp_forward(qp_policy *p, const float *obs, int n, int obs_stride, float *mea
     if (n < 1 || obs_stride < p->cfg.self_dim + p->cfg.nbr_dim * p->cfg.num_nbr) return qp_fail(p, QP_ERR_BAD_CONFIG, "qp_forward: bad n / obs_stride");
     Args a;
     a.obs = obs; a.n = n; a.stride = obs_stride; a.S = p->cfg.self_dim; a.W = p->cfg.nbr_dim; a.V = p->cfg.num_nbr; a.A = p->cfg.act_dim;
-    for (int t = 0; t < 2; ++t) { a.wchunks[t] = p->wchunks[t]; a.params[t] = p->params[t]; }
+    for (int t = 0; t < 2; ++t) { a.wimg[t] = p->wimg[t]; a.params[t] = p->params[t]; }
     a.mean = mean; a.value = value;
     const int tiles = (n + TILE_M - 1) / TILE_M;
     const int grid = tiles < p->sms ? tiles : p->sms;
-    policy_forward_kernel<<<grid, TILE_M, sizeof(Smem) + 1024, (cudaStream_t)stream>>>(a);
+    policy_forward_kernel<<<grid, THREADS, sizeof(Smem) + 1024, (cudaStream_t)stream>>>(a);
     p->launches += 1;
     QP_CUDA(p, cudaGetLastError());
     return QP_OK;

@@ -27,6 +27,27 @@ def test_header_symbols_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_policy_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "quadpolicy.h")).read()
+    declared = set(re.findall(r"\b(qp_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_capi.POLICY_EXPORTS), declared ^ set(_capi.POLICY_EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from quad_swarm_rl_stable_baselines3_b200.fused_policy import QpConfigC
+    assert lib.qp_config_size() == C.sizeof(QpConfigC)
+
+
+def test_policy_create_without_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from quad_swarm_rl_stable_baselines3_b200.fused_policy import QpConfigC
+    h = C.c_void_p()
+    cfg = QpConfigC(1, 18, 6, 6, 256, 4)
+    assert lib.qp_create(C.byref(cfg), 0, C.byref(h)) < 0 and not h.value
+    assert b"CUDA" in lib.qp_last_error(None)
+
+
 def test_struct_layouts(lib):
     assert lib.qs_config_size() == C.sizeof(QsConfigC)
     assert lib.qs_stats_size() == C.sizeof(QsStatsC)

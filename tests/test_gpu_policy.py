@@ -1,0 +1,136 @@
+"""Fused tcgen05 policy forward (csrc/policy_kernels.cu, include/quadpolicy.h) against the torch fp32 module it replaces
+(`ppo.QuadActorCritic` = the reference's ActorCriticPolicyCustomSeparateWeights + QuadMultiEncoder,
+swarm_rl/models/ActorCriticPolicyCustom.py:284-556, swarm_rl/models/quad_multi_model.py:16-41,250-354).
+
+Two references, both plain PyTorch:
+  * fp32: the module as it is.  The kernel multiplies in bf16 (fp32 accumulation), so the tolerance is the bf16 one, stated below.
+  * bf16-emulated: the same module with weights and layer inputs rounded to bf16 at the points the kernel rounds them (everything
+    else fp32).  This pins the kernel's arithmetic (layout of every weight image, bias, tanh, neighbour mean, heads) to 2e-3.
+"""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from quad_swarm_rl_stable_baselines3_b200.config import QuadSimConfig  # noqa: E402
+
+TOL_FP32_MAX = 3e-2        # |kernel - fp32 module|, absolute, outputs are O(1): bf16 operands through 4 layers
+TOL_FP32_RMS = 6e-3
+TOL_EMU_MAX = 3e-3         # |kernel - bf16-emulated module|: accumulation order + tanh.approx (2^-11) only
+
+
+def bf16(x):
+    import torch
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def emulated_forward(pol, obs):
+    """The module's forward with the kernel's rounding points."""
+    import torch
+
+    def lin(layer, x):
+        return bf16(x) @ bf16(layer.weight).t() + layer.bias
+
+    def tower(enc, head):
+        s = obs[:, :enc.S]
+        h = torch.tanh(lin(enc.self_encoder[2], torch.tanh(lin(enc.self_encoder[0], s))))
+        if enc.kind == "mean_embed":
+            nb = obs[:, enc.S:enc.S + enc.W * enc.V].reshape(-1, enc.V, enc.W)
+            acc = 0
+            for j in range(enc.V):
+                x = torch.cat([s, nb[:, j]], dim=1)
+                acc = acc + torch.tanh(lin(enc.neighbor[2], torch.tanh(lin(enc.neighbor[0], x))))
+            m = acc * (1.0 / enc.V)
+        else:
+            m = torch.zeros_like(h)
+        w = enc.feed_forward[0].weight
+        if w.shape[1] == 256:
+            y = torch.tanh(bf16(h) @ bf16(w).t() + enc.feed_forward[0].bias)
+        else:
+            y = torch.tanh(bf16(torch.cat([h, m], dim=1)) @ bf16(w).t() + enc.feed_forward[0].bias)
+        return y @ head.weight.t() + head.bias                 # heads stay fp32 in the kernel
+
+    return tower(pol.actor, pol.action_net), tower(pol.critic, pol.value_net).squeeze(-1)
+
+
+CASES = {
+    # name: (config, rows, extra obs columns behind the neighbour block)
+    "cfg2_k8": (lambda: QuadSimConfig(num_envs=64, num_agents=8), 8192, 0),
+    "ragged_rows": (lambda: QuadSimConfig(num_envs=64, num_agents=8), 1000 + 37, 0),
+    "tiny": (lambda: QuadSimConfig(num_envs=1, num_agents=8), 5, 0),
+    "one_tile_exact": (lambda: QuadSimConfig(num_envs=16, num_agents=8), 128, 0),
+    "many_tiles": (lambda: QuadSimConfig(num_envs=64, num_agents=8), 148 * 128 * 2 + 77, 0),
+    "repr24_v2": (lambda: QuadSimConfig(num_envs=8, num_agents=8, obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2), 777, 0),
+    "no_neighbours": (lambda: QuadSimConfig(num_envs=8, num_agents=1, neighbor_visible_num=0), 600, 0),
+    "k32_v6_padded_stride": (lambda: QuadSimConfig(num_envs=4, num_agents=32, neighbor_visible_num=6), 2048 + 3, 5),
+    "fork_act2": (lambda: QuadSimConfig.fork_default(num_envs=8), 900, 0),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fused_forward_matches_torch(name):
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200.fused_policy import FusedPolicy, supported
+    from quad_swarm_rl_stable_baselines3_b200.ppo import QuadActorCritic
+    make, n, pad = CASES[name]
+    cfg = make()
+    torch.manual_seed(1234)
+    dev = torch.device("cuda:0")
+    pol = QuadActorCritic(cfg).to(dev)
+    with torch.no_grad():                                         # non-zero biases and a non-trivial head
+        for m in pol.modules():
+            if isinstance(m, torch.nn.Linear):
+                m.bias.uniform_(-0.3, 0.3)
+    if not supported(pol):
+        pytest.skip("architecture outside the fused kernel (documented in include/quadpolicy.h)")
+    fp = FusedPolicy(pol, dev)
+    D = pol.actor.S + pol.actor.W * pol.actor.V
+    obs = torch.randn(n, D + pad, device=dev) * 0.8
+    l0 = fp.launch_count
+    mean, value = fp.forward(obs)
+    torch.cuda.synchronize()
+    assert fp.launch_count == l0 + 1
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        r_mean = pol.action_net(pol.actor(obs[:, :D] if pad == 0 else obs[:, :D].contiguous()))
+        r_value = pol.value(obs[:, :D].contiguous())
+        e_mean, e_value = emulated_forward(pol, obs[:, :D].contiguous())
+    assert torch.isfinite(mean).all() and torch.isfinite(value).all()
+    d32 = torch.cat([(mean - r_mean).reshape(-1), (value - r_value).reshape(-1)])
+    demu = torch.cat([(mean - e_mean).reshape(-1), (value - e_value).reshape(-1)])
+    print(f"\n[{name}] n={n} S={fp.S} W={fp.W} V={fp.V} A={fp.A}: vs fp32 max {float(d32.abs().max()):.2e} rms {float(d32.pow(2).mean().sqrt()):.2e};"
+          f" vs bf16-emulated max {float(demu.abs().max()):.2e}; |mean| rms {float(r_mean.pow(2).mean().sqrt()):.2f}")
+    assert float(demu.abs().max()) <= TOL_EMU_MAX
+    assert float(d32.abs().max()) <= TOL_FP32_MAX
+    assert float(d32.pow(2).mean().sqrt()) <= TOL_FP32_RMS
+
+
+def test_weight_resync_and_act():
+    """`sync()` after an optimiser step re-packs the weights; `act` returns the Gaussian sample's log-probability."""
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200.fused_policy import FusedPolicy
+    from quad_swarm_rl_stable_baselines3_b200.ppo import QuadActorCritic
+    cfg = QuadSimConfig(num_envs=32, num_agents=8)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    pol = QuadActorCritic(cfg).to(dev)
+    fp = FusedPolicy(pol, dev)
+    obs = torch.randn(512, 54, device=dev)
+    m0, _ = fp.forward(obs)
+    with torch.no_grad():
+        for p in pol.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    m_stale, _ = fp.forward(obs)
+    assert torch.equal(m0, m_stale)                              # the kernel runs on its packed copy until sync()
+    fp.sync()
+    m1, v1 = fp.forward(obs)
+    with torch.no_grad():
+        r = pol.action_net(pol.actor(obs))
+    assert float((m1 - r).abs().max()) <= TOL_FP32_MAX and float((m1 - m0).abs().max()) > 0.05
+    a, logp, v = fp.act(obs)
+    d = torch.distributions.Normal(m1, pol.log_std.detach().exp().expand_as(m1))
+    assert torch.allclose(logp, d.log_prob(a).sum(-1), atol=1e-4) and torch.equal(v, v1)
