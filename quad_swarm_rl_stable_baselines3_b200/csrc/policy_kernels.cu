@@ -30,6 +30,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/quadpolicy.h"
@@ -42,11 +43,12 @@ constexpr int TILE_M = 128;
 constexpr int NH = 128;                     // N of one MMA group (half an encoder layer, a quarter of the feed-forward)
 constexpr int CHUNK = 16 * 1024;            // one (N = 128) x (K = 64) bf16 weight image
 constexpr int CHUNK1 = 8 * 1024;            // one (N = 128) x (K = 32) image (first layers)
-constexpr int STAGES = 3;
+constexpr int STAGES = 12;                  // ring slots of one 16 KB chunk: 9 hold the neighbour encoder during its passes, all 12 stream otherwise
 constexpr int MAX_ACT = 8;
 constexpr int SELF_PAD = 24, NBR_PAD = 8;   // K layout of the first layers: [self | neighbour]
-constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS, THREADS = EPI_THREADS + 64;
-constexpr int RES_BYTES = 2 * CHUNK1 + 8 * CHUNK;                    // resident neighbour-encoder weights: 147456
+constexpr int EPI_WARPS = 8, EPI_THREADS = 32 * EPI_WARPS, THREADS = EPI_THREADS + 128;   // + one warpgroup: MMA issuer, producer, 2 idle warps (setmaxnreg acts on warpgroups)
+constexpr int RES_BYTES = 2 * CHUNK1 + 8 * CHUNK;                    // neighbour-encoder weights: 147456 = 9 chunks
+constexpr int RES_CHUNKS = RES_BYTES / CHUNK;
 constexpr int STREAM_BYTES = 2 * CHUNK1 + 8 * CHUNK + 32 * CHUNK;    // streamed per tile: self L1, self L2, feed-forward
 constexpr int TOWER_IMG_BYTES = RES_BYTES + STREAM_BYTES;            // 819200
 
@@ -63,6 +65,7 @@ struct Args {
     const uint8_t *wimg[2];                 // per tower: [resident block | streamed block]
     const TowerParams *params[2];
     float *mean, *value;                    // [n, A], [n]
+    long long *trace;                       // debug (qp_debug_trace): clock64 stamps of block 0's second tile, tower 0; null = off
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +97,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             else if (now - t0 > 4000000000ll) __trap();
         }
     }
+}
+// hot-path form: one probe first (the common case on the issuer's ring: the chunk landed long ago), then the bounded loop
+__device__ __forceinline__ void mbar_wait_fast(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done) mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -140,6 +155,36 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     d |= (uint64_t)1 << 46;                                              // descriptor version (Blackwell)
     return d;                                                            // base offset 0, layout type 0 (no swizzle)
 }
+// descriptor without the start address (added as (addr >> 4): shared-memory addresses are below 2^18, the field holds 14 bits)
+__host__ __device__ constexpr uint64_t desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+constexpr uint64_t DESC_W64 = desc_hi(128u, 1024u);      // weight chunk, K = 64 per row group
+constexpr uint64_t DESC_W32 = desc_hi(128u, 512u);       // weight chunk, K = 32
+constexpr uint64_t DESC_X = desc_hi(2048u, 128u);        // x tile
+
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NH >> 3) << 17) | ((128u >> 4) << 24);   // F32 acc, bf16 x bf16, K-major, N 128, M 128
+
+// The issuing thread is one lane: every instruction it spends per MMA is serial latency in front of the tensor pipe.  These groups are
+// fully unrolled, descriptors advance by an immediate (K = 16 -> 256 B -> +16 in the address field).
+// one (N = 128) x (K = 64) weight chunk against 32 TMEM columns of A
+template <bool FIRST>
+__device__ __noinline__ void issue_chunk_ts(uint32_t acc, uint32_t a_col, uint32_t w_addr)
+{
+    const uint64_t bd = DESC_W64 | (uint64_t)(w_addr >> 4);
+    mma_ts(acc, a_col, bd, IDESC, FIRST ? 0u : 1u);
+    mma_ts(acc, a_col + 8u, bd + 16u, IDESC, 1u);
+    mma_ts(acc, a_col + 16u, bd + 32u, IDESC, 1u);
+    mma_ts(acc, a_col + 24u, bd + 48u, IDESC, 1u);
+}
+// first layers: the 128 x 32 x tile (shared memory) against an (N = 128) x (K = 32) image
+__device__ __noinline__ void issue_l1_ss(uint32_t acc, uint32_t x_addr, uint32_t w_addr)
+{
+    const uint64_t ad = DESC_X | (uint64_t)(x_addr >> 4), bd = DESC_W32 | (uint64_t)(w_addr >> 4);
+    mma_ss(acc, ad, bd, IDESC, 0u);
+    mma_ss(acc, ad + 256u, bd + 16u, IDESC, 1u);           // next K-half of the x tile: 2 chunks of 2048 B
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -152,6 +197,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -159,6 +213,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v)
                  "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
                  "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -175,32 +234,33 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     return r;
 }
 
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NH >> 3) << 17) | ((128u >> 4) << 24);   // F32 acc, bf16 x bf16, K-major, N 128, M 128
 
-// shared-memory map (223.4 KB)
+// shared-memory map (226.1 KB)
 struct Smem {
-    uint8_t wres[RES_BYTES];               // neighbour encoder: L1 halves (2 x 8 KB), L2 (half, K chunk) (8 x 16 KB)
-    uint8_t ring[STAGES][CHUNK];           // streamed weight chunks
+    uint8_t ring[STAGES][CHUNK];           // weight chunks in stream order; the neighbour encoder's 9 stay pinned during its passes
     uint8_t xbuf[2][TILE_M * 32 * 2];      // per stream: the 128 x 32 bf16 first-layer input, K-chunk-major core matrices
     float bias[N_BIAS];
     float xchg[TILE_M][MAX_ACT];           // head partial sums of the upper column half
-    uint64_t full[STAGES], empty[STAGES], acc_full[2], epi_done[2], x_ready, res_full;
+    float4 headw[FF];                      // head weights of outputs 0..3, transposed (outputs 4..7 are read through L1)
+    uint64_t full[STAGES], empty[STAGES], acc_full[2], epi_done[2], x_ready, mean_ready;
     uint32_t tmem_base;
 };
+
+static_assert(sizeof(Smem) <= 232448, "shared-memory map exceeds the 227 KB a block can opt into");
 
 // element (row, k) of an x tile: K-chunk (8 elements, 16 B) major, then 8-row groups of 128 B: LBO = 2048, SBO = 128
 __device__ __forceinline__ uint32_t xoff(int row, int kchunk) { return (uint32_t)(kchunk * 2048 + (row >> 3) * 128 + (row & 7) * 16); }
 
 __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a)
 {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (t == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.epi_done[s], EPI_WARPS); }
         mbar_init(&sm.x_ready, EPI_WARPS);
-        mbar_init(&sm.res_full, 1);
+        mbar_init(&sm.mean_ready, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -217,125 +277,167 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
     const int S = a.S, W = a.W, V = a.V, A = a.A;
     const int n_tiles = (a.n + TILE_M - 1) / TILE_M;
     // phase bookkeeping, advanced identically by every role: items issued per stream, tiles, ring chunks
-    uint32_t n_item[2] = { 0u, 0u }, n_tile = 0u, n_chunk = 0u;
+    uint32_t n_it0 = 0u, n_it1 = 0u, n_tile = 0u, n_chunk = 0u;
+#define N_ITEM(s) ((s) ? n_it1 : n_it0)
+#define N_ITEM_INC(s) do { if (s) n_it1 += 1; else n_it0 += 1; } while (0)
+    // every role runs its own loop over the two towers and meets the others at one block-wide barrier per tower (TOWER_SYNC): all chunks
+    // consumed and all accumulators read, so the resident weights, the biases and the head weights may be replaced
+#define TOWER_SYNC() do { tc_fence_before(); __syncthreads(); tc_fence_after(); } while (0)
 
-    for (int tower = 0; tower < 2; ++tower) {
-        const uint8_t *img = a.wimg[tower];
-        const TowerParams *P = a.params[tower];
-        if (warp < EPI_WARPS)
-            for (int i = t; i < N_BIAS; i += EPI_THREADS) sm.bias[i] = P->bias[i];
-        if (warp == 9 && lane == 0 && V > 0) {                          // resident neighbour-encoder weights of this tower
-            mbar_expect_tx(&sm.res_full, RES_BYTES);
-            for (int i = 0; i < RES_BYTES / CHUNK; ++i) bulk_load(sm.wres + i * CHUNK, img + (size_t)i * CHUNK, CHUNK, &sm.res_full);
-        }
-        __syncthreads();
-
+    if (warp >= EPI_WARPS) {
+        // the producer / issuer warpgroup gives its registers to the epilogue warps (which hold 128 running sums per thread)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         if (warp == 9) {
-            // =========================== WEIGHT PRODUCER ===========================
-            if (lane == 0) {
-                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                    const uint8_t *src = img + RES_BYTES;
-                    for (int i = 0; i < 42; ++i) {
-                        const uint32_t bytes = i < 2 ? CHUNK1 : CHUNK;
-                        const uint32_t slot = n_chunk % STAGES;
-                        mbar_wait(&sm.empty[slot], ((n_chunk / STAGES) & 1u) ^ 1u);      // the MMAs that read this slot have completed
-                        mbar_expect_tx(&sm.full[slot], bytes);
-                        bulk_load(sm.ring[slot], src, bytes, &sm.full[slot]);
-                        src += bytes;
-                        n_chunk += 1;
+            for (int tower = 0; tower < 2; ++tower) {
+                // the whole tower image, in consumption order, once per tile: [neighbour encoder (9 chunks, skipped without neighbours) |
+                // self L1 | self L2 x 8 | feed-forward x 32]
+                if (lane == 0) {
+                    const uint8_t *img = a.wimg[tower] + (V > 0 ? 0 : RES_BYTES);
+                    const int n_loads = (V > 0 ? RES_CHUNKS : 0) + 41;
+                    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                        for (int i = 0; i < n_loads; ++i) {
+                            const uint32_t slot = n_chunk % STAGES;
+                            mbar_wait(&sm.empty[slot], ((n_chunk / STAGES) & 1u) ^ 1u);      // the MMAs that read this slot have completed
+                            mbar_expect_tx(&sm.full[slot], CHUNK);
+                            bulk_load(sm.ring[slot], img + (size_t)i * CHUNK, CHUNK, &sm.full[slot]);
+                            n_chunk += 1;
+                        }
                     }
                 }
+                __syncwarp();
+                TOWER_SYNC();
             }
-            __syncwarp();
         } else if (warp == 8) {
-            // =========================== MMA ISSUER ===========================
-            if (lane == 0) {
-                const uint32_t wres = smem_u32(sm.wres), xb0 = smem_u32(sm.xbuf[0]), xb1 = smem_u32(sm.xbuf[1]);
-                auto wait_prev = [&](int s) {                            // the epilogue of the stream's previous item has drained its accumulator
-                    if (n_item[s] > 0) { mbar_wait(&sm.epi_done[s], (n_item[s] - 1u) & 1u); tc_fence_after(); }
-                };
-                auto ring_take = [&]() -> uint32_t {                     // next streamed chunk has landed
-                    const uint32_t slot = n_chunk % STAGES;
-                    mbar_wait(&sm.full[slot], (n_chunk / STAGES) & 1u);
-                    tc_fence_after();
-                    return slot;
-                };
-                auto ring_release = [&](uint32_t slot) { tc_commit(&sm.empty[slot]); n_chunk += 1; };
-                if (V > 0) mbar_wait(&sm.res_full, (uint32_t)tower & 1u);
-                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                    mbar_wait(&sm.x_ready, n_tile & 1u);
-                    n_tile += 1;
-                    tc_fence_after();
-                    // ---- neighbour passes, two at a time on the two streams
-                    for (int j0 = 0; j0 < V; j0 += 2) {
-                        const int nact = (V - j0) < 2 ? (V - j0) : 2;
-                        for (int it = 0; it < 4; ++it)
-                            for (int s = 0; s < nact; ++s) {
-                                const uint32_t acc = tmem + (s ? ACC1 : ACC0);
-                                const int h = it & 1;
-                                wait_prev(s);
-                                if (it < 2) {                            // layer 1: A = the stream's x tile (shared memory), K = 32
-                                    const uint32_t xa = s ? xb1 : xb0, wb = wres + (uint32_t)h * CHUNK1;
-                                    for (int k = 0; k < 2; ++k)
-                                        mma_ss(acc, smem_desc(xa + (uint32_t)k * 4096u, 2048u, 128u), smem_desc(wb + (uint32_t)k * 256u, 128u, 512u), IDESC, k != 0);
-                                } else {                                 // layer 2: A = the stream's hidden activations (tensor memory), K = 256
-                                    const uint32_t r1 = tmem + (s ? R11 : R10);
-                                    for (int c = 0; c < 4; ++c) {
-                                        const uint32_t wb = wres + 2u * CHUNK1 + (uint32_t)(h * 4 + c) * CHUNK;
-                                        for (int k = 0; k < 4; ++k)
-                                            mma_ts(acc, r1 + (uint32_t)(c * 32 + k * 8), smem_desc(wb + (uint32_t)k * 256u, 128u, 1024u), IDESC, (c | k) != 0);
+            for (int tower = 0; tower < 2; ++tower) {
+                // =========================== MMA ISSUER ===========================
+                if (lane == 0) {
+                    const uint32_t ring0 = smem_u32(sm.ring[0]), xb0 = smem_u32(sm.xbuf[0]), xb1 = smem_u32(sm.xbuf[1]);
+                    bool tr = false;
+                    int tm = 256;
+                    auto wait_prev = [&](int s) {                            // the epilogue of the stream's previous item has drained its accumulator
+                        if (N_ITEM(s) > 0) { mbar_wait(&sm.epi_done[s], (N_ITEM(s) - 1u) & 1u); tc_fence_after(); }
+                        if (tr) a.trace[tm++] = clock64();
+                    };
+                    auto ring_take = [&]() -> uint32_t {                     // next streamed chunk has landed
+                        const uint32_t slot = n_chunk % STAGES;
+                        mbar_wait_fast(&sm.full[slot], (n_chunk / STAGES) & 1u);
+                        tc_fence_after();
+                        return slot;
+                    };
+                    auto ring_release = [&](uint32_t slot) { tc_commit(&sm.empty[slot]); n_chunk += 1; };
+                    // grouped form: take 4 chunks one by one, release them with 4 commits back to back (a commit between two MMA groups costs
+                    // the tensor pipe ~180 clk; grouped, that is paid once per 16 MMAs)
+                    uint32_t held[4];
+                    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                        mbar_wait(&sm.x_ready, n_tile & 1u);
+                        n_tile += 1;
+                        tc_fence_after();
+                        tr = a.trace != nullptr && tower == 0 && blockIdx.x == 0 && tile == (int)gridDim.x;
+                        // ---- the neighbour encoder's 9 chunks have landed; they stay in their slots until the last neighbour MMA has been issued
+                        const uint32_t nbr0 = n_chunk;
+                        if (V > 0) {
+                            for (uint32_t i = 0; i < (uint32_t)RES_CHUNKS; ++i) mbar_wait(&sm.full[(nbr0 + i) % STAGES], ((nbr0 + i) / STAGES) & 1u);
+                            tc_fence_after();
+                            n_chunk += RES_CHUNKS;
+                        }
+                        uint32_t nbr_w[RES_CHUNKS];                           // shared-memory addresses of the pinned chunks
+#pragma unroll
+                        for (uint32_t i = 0; i < (uint32_t)RES_CHUNKS; ++i) nbr_w[i] = ring0 + ((nbr0 + i) % STAGES) * (uint32_t)CHUNK;
+                        // ---- neighbour passes, two at a time on the two streams
+                        for (int j0 = 0; j0 < V; j0 += 2) {
+                            const int nact = (V - j0) < 2 ? (V - j0) : 2;
+                            for (int it = 0; it < 4; ++it)
+                                for (int s = 0; s < nact; ++s) {
+                                    const uint32_t acc = tmem + (s ? ACC1 : ACC0);
+                                    const int h = it & 1;
+                                    wait_prev(s);
+                                    if (it < 2) {                            // layer 1: A = the stream's x tile (shared memory), K = 32
+                                        issue_l1_ss(acc, s ? xb1 : xb0, nbr_w[0] + (uint32_t)h * CHUNK1);
+                                    } else {                                 // layer 2: A = the stream's hidden activations (tensor memory), K = 256
+                                        const uint32_t r1 = tmem + (s ? R11 : R10);
+                                        const uint32_t *w = nbr_w + 1 + h * 4;
+                                        issue_chunk_ts<true>(acc, r1, w[0]);
+                                        issue_chunk_ts<false>(acc, r1 + 32u, w[1]);
+                                        issue_chunk_ts<false>(acc, r1 + 64u, w[2]);
+                                        issue_chunk_ts<false>(acc, r1 + 96u, w[3]);
                                     }
+                                    tc_commit(&sm.acc_full[s]);
+                                    N_ITEM_INC(s);
+                                    if (tr) a.trace[tm++] = clock64();
                                 }
+                        }
+                        if (V > 0)
+                            for (uint32_t i = 0; i < (uint32_t)RES_CHUNKS; ++i) tc_commit(&sm.empty[(nbr0 + i) % STAGES]);      // free once those MMAs complete
+                        // ---- self encoder layer 1: halves on the two accumulators, A = x tile of stream 0 (its neighbour chunk meets zero weights)
+                        {
+                            const uint32_t slot = ring_take();
+                            for (int s = 0; s < 2; ++s) {
+                                wait_prev(s);
+                                issue_l1_ss(tmem + (s ? ACC1 : ACC0), xb0, ring0 + slot * (uint32_t)CHUNK + (uint32_t)s * CHUNK1);
                                 tc_commit(&sm.acc_full[s]);
-                                n_item[s] += 1;
+                                N_ITEM_INC(s);
+                                if (tr) a.trace[tm++] = clock64();
                             }
-                    }
-                    // ---- self encoder layer 1: halves on the two accumulators, A = x tile of stream 0 (its neighbour chunk meets zero weights)
-                    for (int s = 0; s < 2; ++s) {
-                        wait_prev(s);
-                        const uint32_t slot = ring_take();
-                        const uint32_t wb = smem_u32(sm.ring[slot]);
-                        for (int k = 0; k < 2; ++k)
-                            mma_ss(tmem + (s ? ACC1 : ACC0), smem_desc(xb0 + (uint32_t)k * 4096u, 2048u, 128u), smem_desc(wb + (uint32_t)k * 256u, 128u, 512u), IDESC, k != 0);
-                        ring_release(slot);
-                        tc_commit(&sm.acc_full[s]);
-                        n_item[s] += 1;
-                    }
-                    // ---- self encoder layer 2: A = R10 (both layer-1 epilogues must have written it)
-                    wait_prev(0);
-                    wait_prev(1);
-                    for (int s = 0; s < 2; ++s) {
-                        for (int c = 0; c < 4; ++c) {
-                            const uint32_t slot = ring_take();
-                            const uint32_t wb = smem_u32(sm.ring[slot]);
-                            for (int k = 0; k < 4; ++k)
-                                mma_ts(tmem + (s ? ACC1 : ACC0), tmem + R10 + (uint32_t)(c * 32 + k * 8), smem_desc(wb + (uint32_t)k * 256u, 128u, 1024u), IDESC, (c | k) != 0);
                             ring_release(slot);
                         }
-                        tc_commit(&sm.acc_full[s]);
-                        n_item[s] += 1;
-                    }
-                    // ---- feed-forward: four quarters of 128 outputs, A = [R10 (self encoder) | R11 (neighbour mean)], K = 512
-                    wait_prev(0);
-                    wait_prev(1);
-                    for (int qtr = 0; qtr < 4; ++qtr) {
-                        const int s = qtr & 1;
-                        wait_prev(s);
-                        for (int c = 0; c < 8; ++c) {
-                            const uint32_t slot = ring_take();
-                            const uint32_t wb = smem_u32(sm.ring[slot]);
-                            const uint32_t acol = tmem + (c < 4 ? R10 + (uint32_t)c * 32u : R11 + (uint32_t)(c - 4) * 32u);
-                            for (int k = 0; k < 4; ++k)
-                                mma_ts(tmem + (s ? ACC1 : ACC0), acol + (uint32_t)k * 8u, smem_desc(wb + (uint32_t)k * 256u, 128u, 1024u), IDESC, (c | k) != 0);
-                            ring_release(slot);
+                        // ---- self encoder layer 2: A = R11 (hidden, written by both layer-1 epilogues), output goes to R10 -- no in-place hazard,
+                        //      so the epilogue of half 0 runs under the MMA of half 1
+                        wait_prev(0);
+                        wait_prev(1);
+                        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const uint32_t slot = ring_take();
+                                if (c == 0) issue_chunk_ts<true>(tmem + (s ? ACC1 : ACC0), tmem + R11, ring0 + slot * (uint32_t)CHUNK);
+                                else issue_chunk_ts<false>(tmem + (s ? ACC1 : ACC0), tmem + R11 + (uint32_t)c * 32u, ring0 + slot * (uint32_t)CHUNK);
+                                held[c] = slot;
+                                n_chunk += 1;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) tc_commit(&sm.empty[held[c]]);
+                            tc_commit(&sm.acc_full[s]);
+                            N_ITEM_INC(s);
+                            if (tr) a.trace[tm++] = clock64();
                         }
-                        tc_commit(&sm.acc_full[s]);
-                        n_item[s] += 1;
+                        // ---- feed-forward: four quarters of 128 outputs, K = 512: chunks 0-3 read R10 (self encoder), chunks 4-7 R11 (neighbour
+                        //      mean, written by the epilogue warps while the first half of quarter 0 runs)
+                        for (int qtr = 0; qtr < 4; ++qtr) {
+                            const int s = qtr & 1;
+                            wait_prev(s);
+                            if (qtr == 0) wait_prev(1);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const uint32_t slot = ring_take();
+                                const uint32_t acol = tmem + (c < 4 ? R10 + (uint32_t)c * 32u : R11 + (uint32_t)(c - 4) * 32u);
+                                if (c == 4 && qtr == 0) { mbar_wait(&sm.mean_ready, (n_tile - 1u) & 1u); tc_fence_after(); }
+                                if (c == 0) issue_chunk_ts<true>(tmem + (s ? ACC1 : ACC0), acol, ring0 + slot * (uint32_t)CHUNK);
+                                else issue_chunk_ts<false>(tmem + (s ? ACC1 : ACC0), acol, ring0 + slot * (uint32_t)CHUNK);
+                                held[c & 3] = slot;
+                                n_chunk += 1;
+                                if ((c & 3) == 3) {
+#pragma unroll
+                                    for (int r = 0; r < 4; ++r) tc_commit(&sm.empty[held[r]]);
+                                }
+                            }
+                            tc_commit(&sm.acc_full[s]);
+                            N_ITEM_INC(s);
+                            if (tr) a.trace[tm++] = clock64();
+                        }
                     }
                 }
+                __syncwarp();
+                TOWER_SYNC();
             }
-            __syncwarp();
         } else {
+            for (int tower = 0; tower < 2; ++tower) TOWER_SYNC();
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        for (int tower = 0; tower < 2; ++tower) {
+            const TowerParams *P = a.params[tower];
+            for (int i = t; i < N_BIAS; i += EPI_THREADS) sm.bias[i] = P->bias[i];
+            for (int i = t; i < FF; i += EPI_THREADS) sm.headw[i] = *reinterpret_cast<const float4 *>(P->head_wt + (size_t)i * MAX_ACT);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             // =========================== EPILOGUE WARPS ===========================
             const int row_l = 32 * (warp & 3) + lane, q = warp >> 2;     // this thread: one row, one half (64) of an accumulator's 128 columns
             const uint32_t lane_addr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -344,27 +446,34 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
 #pragma unroll
             for (int i = 0; i < 128; ++i) nsum[i] = 0.f;
 
-            auto wait_acc = [&](int s) { mbar_wait(&sm.acc_full[s], n_item[s] & 1u); tc_fence_after(); };
+            bool tr = false;                                             // this thread records the traced tile (qp_debug_trace)
+            int te = 0;
+            auto wait_acc = [&](int s) {
+                mbar_wait(&sm.acc_full[s], N_ITEM(s) & 1u);
+                tc_fence_after();
+                if (tr) a.trace[te++] = clock64();
+            };
             auto item_done = [&](int s) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.epi_done[s]);
-                n_item[s] += 1;
+                N_ITEM_INC(s);
+                if (tr) a.trace[te++] = clock64();
             };
             // accumulator -> + bias -> tanh -> packed bf16 -> activation region `dst` (columns of layer half h, this thread's 64)
             auto epi_to_tmem = [&](uint32_t acc, int bias0, int h, uint32_t dst) {
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    uint32_t v[32], u[16];
-                    tmem_ld32(lane_addr + acc + (uint32_t)(q * 64 + b * 32), v);
-                    const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + bias0 + h * 128 + q * 64 + b * 32);
+                for (int b = 0; b < 4; ++b) {                            // 16 columns at a time (register budget: the 128 running sums stay live)
+                    uint32_t v[16], u[8];
+                    tmem_ld16(lane_addr + acc + (uint32_t)(q * 64 + b * 16), v);
+                    const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + bias0 + h * 128 + q * 64 + b * 16);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         const float4 bb = bp[i];
                         u[2 * i] = pack_bf16(tanh_fast(__uint_as_float(v[4 * i]) + bb.x), tanh_fast(__uint_as_float(v[4 * i + 1]) + bb.y));
                         u[2 * i + 1] = pack_bf16(tanh_fast(__uint_as_float(v[4 * i + 2]) + bb.z), tanh_fast(__uint_as_float(v[4 * i + 3]) + bb.w));
                     }
-                    tmem_st16(lane_addr + dst + (uint32_t)(h * 64 + q * 32 + b * 16), u);
+                    tmem_st8(lane_addr + dst + (uint32_t)(h * 64 + q * 32 + b * 8), u);
                 }
                 tmem_st_wait();
             };
@@ -372,6 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int row = tile * TILE_M + row_l;
                 const bool live = row < a.n;
+                tr = a.trace != nullptr && t == 0 && tower == 0 && blockIdx.x == 0 && tile == (int)gridDim.x;
                 const float *orow = a.obs + (size_t)(live ? row : 0) * a.stride;
                 // the 16-byte neighbour chunk (K 24..31) of neighbour j
                 auto nbr_chunk = [&](int j) -> uint4 {
@@ -419,14 +529,14 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                             wait_acc(s);
                             const float kp = (s == 0) ? keep : 1.f;
 #pragma unroll
-                            for (int b = 0; b < 2; ++b) {
-                                uint32_t v[32];
-                                tmem_ld32(lane_addr + (s ? ACC1 : ACC0) + (uint32_t)(q * 64 + b * 32), v);
-                                const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + B_NBR2 + h * 128 + q * 64 + b * 32);
+                            for (int b = 0; b < 4; ++b) {                // 16 columns at a time: the 128 running sums leave few registers
+                                uint32_t v[16];
+                                tmem_ld16(lane_addr + (s ? ACC1 : ACC0) + (uint32_t)(q * 64 + b * 16), v);
+                                const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + B_NBR2 + h * 128 + q * 64 + b * 16);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
+                                for (int i = 0; i < 4; ++i) {
                                     const float4 bb = bp[i];
-                                    float *ns = nsum + h * 64 + b * 32 + 4 * i;
+                                    float *ns = nsum + h * 64 + b * 16 + 4 * i;
                                     ns[0] = fmaf(ns[0], kp, tanh_fast(__uint_as_float(v[4 * i]) + bb.x));
                                     ns[1] = fmaf(ns[1], kp, tanh_fast(__uint_as_float(v[4 * i + 1]) + bb.y));
                                     ns[2] = fmaf(ns[2], kp, tanh_fast(__uint_as_float(v[4 * i + 2]) + bb.z));
@@ -436,7 +546,12 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                             item_done(s);
                         }
                 }
-                // ---- neighbour mean -> R11 (no neighbours: zeros, like an absent encoder half); R11's last reader has completed
+                // ---- self encoder layer 1 (halves on the two accumulators) -> hidden in R11 (stream 1's last MMAs have completed)
+                for (int s = 0; s < 2; ++s) { wait_acc(s); epi_to_tmem(s ? ACC1 : ACC0, B_SELF1, s, R11); item_done(s); }
+                // ---- self encoder layer 2 -> R10
+                for (int s = 0; s < 2; ++s) { wait_acc(s); epi_to_tmem(s ? ACC1 : ACC0, B_SELF2, s, R10); item_done(s); }
+                // ---- neighbour mean -> R11 (no neighbours: zeros, like an absent encoder half).  Both layer-2 MMAs, R11's last readers,
+                //      have completed (their accumulators were waited for above); the feed-forward reads R11 from its 5th K chunk on
                 {
                     const float inv = V > 0 ? 1.0f / (float)V : 0.f;
 #pragma unroll
@@ -449,13 +564,10 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                             tmem_st16(lane_addr + R11 + (uint32_t)(h * 64 + q * 32 + b * 16), u);
                         }
                     tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.mean_ready);
                 }
-                // ---- self encoder layer 1 (halves on the two accumulators) -> hidden in R10
-                for (int s = 0; s < 2; ++s) { wait_acc(s); epi_to_tmem(s ? ACC1 : ACC0, B_SELF1, s, R10); item_done(s); }
-                // ---- self encoder layer 2 -> R10 in place: both halves' MMAs must have read R10 before it is overwritten
-                wait_acc(0);
-                wait_acc(1);
-                for (int s = 0; s < 2; ++s) { epi_to_tmem(s ? ACC1 : ACC0, B_SELF2, s, R10); item_done(s); }
                 // ---- feed-forward quarters with the head folded in
                 float head[MAX_ACT];
 #pragma unroll
@@ -469,7 +581,6 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                         tmem_ld32(lane_addr + (s ? ACC1 : ACC0) + (uint32_t)(q * 64 + b * 32), v);
                         const int c0 = qtr * 128 + q * 64 + b * 32;
                         const float4 *bp = reinterpret_cast<const float4 *>(sm.bias + B_FF + c0);
-                        const float4 *hp = reinterpret_cast<const float4 *>(P->head_wt + (size_t)c0 * MAX_ACT);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const float4 bb = bp[i];
@@ -477,11 +588,14 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                                                  tanh_fast(__uint_as_float(v[4 * i + 2]) + bb.z), tanh_fast(__uint_as_float(v[4 * i + 3]) + bb.w) };
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float4 w0 = __ldg(hp + (4 * i + e) * 2);
+                                const float4 w0 = sm.headw[c0 + 4 * i + e];
                                 head[0] = fmaf(y[e], w0.x, head[0]); head[1] = fmaf(y[e], w0.y, head[1]);
                                 head[2] = fmaf(y[e], w0.z, head[2]); head[3] = fmaf(y[e], w0.w, head[3]);
-                                if (n_out > 4) {
-                                    const float4 w1 = __ldg(hp + (4 * i + e) * 2 + 1);
+                            }
+                            if (n_out > 4) {                             // wide action spaces: outputs 4..7 straight from L1
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 w1 = __ldg(reinterpret_cast<const float4 *>(P->head_wt + (size_t)(c0 + 4 * i + e) * MAX_ACT) + 1);
                                     head[4] = fmaf(y[e], w1.x, head[4]); head[5] = fmaf(y[e], w1.y, head[5]);
                                     head[6] = fmaf(y[e], w1.z, head[6]); head[7] = fmaf(y[e], w1.w, head[7]);
                                 }
@@ -506,12 +620,12 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                         }
                 }
             }
+            TOWER_SYNC();
         }
-        // tower done: every chunk consumed, every accumulator read; the resident weights and biases may be replaced
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
     }
+#undef N_ITEM
+#undef N_ITEM_INC
+#undef TOWER_SYNC
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -551,6 +665,8 @@ struct qp_policy {
     uint8_t *wimg[2];
     TowerParams *params[2];
     long long launches;
+    long long *trace;
+    int max_grid;           // tuning knob QP_MAX_GRID (0 = one block per SM)
     std::string err;
 };
 
@@ -582,7 +698,8 @@ int qp_create(const qp_config *cfg, int device, qp_policy **out)
     cudaGetDevice(&prev);
     cudaSetDevice(device);
     qp_policy *p = new qp_policy();
-    p->cfg = *cfg; p->device = device; p->launches = 0;
+    p->cfg = *cfg; p->device = device; p->launches = 0; p->trace = nullptr; p->max_grid = 0;
+    if (const char *g = getenv("QP_MAX_GRID")) p->max_grid = atoi(g);
     p->wimg[0] = p->wimg[1] = nullptr; p->params[0] = p->params[1] = nullptr;
     cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t r = cudaSuccess;
@@ -592,7 +709,7 @@ int qp_create(const qp_config *cfg, int device, qp_policy **out)
         if (r == cudaSuccess) r = cudaMalloc(&p->params[t], sizeof(TowerParams));
         if (r == cudaSuccess) r = cudaMemset(p->params[t], 0, sizeof(TowerParams));
     }
-    if (r == cudaSuccess) r = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     cudaSetDevice(prev);
     if (r != cudaSuccess) {
         for (int t = 0; t < 2; ++t) { cudaFree(p->wimg[t]); cudaFree(p->params[t]); }
@@ -612,6 +729,10 @@ int qp_destroy(qp_policy *p)
 }
 
 int64_t qp_launch_count(const qp_policy *p) { return p ? p->launches : 0; }
+
+/* profiling aid, not part of quadpolicy.h: `buf` = 512 int64 on the device (or null to switch off); the next forwards write clock64
+ * stamps of block 0's second tile (actor tower): [0, 256) epilogue warp 0 (accumulator ready / item done), [256, 512) the MMA issuer */
+int qp_debug_trace(qp_policy *p, long long *buf) { if (!p) return QP_ERR_NULL; p->trace = buf; return QP_OK; }
 
 int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *stream)
 {
@@ -663,10 +784,11 @@ int qp_forward(qp_policy *p, const float *obs, int n, int obs_stride, float *mea
     Args a;
     a.obs = obs; a.n = n; a.stride = obs_stride; a.S = p->cfg.self_dim; a.W = p->cfg.nbr_dim; a.V = p->cfg.num_nbr; a.A = p->cfg.act_dim;
     for (int t = 0; t < 2; ++t) { a.wimg[t] = p->wimg[t]; a.params[t] = p->params[t]; }
-    a.mean = mean; a.value = value;
+    a.mean = mean; a.value = value; a.trace = p->trace;
     const int tiles = (n + TILE_M - 1) / TILE_M;
-    const int grid = tiles < p->sms ? tiles : p->sms;
-    policy_forward_kernel<<<grid, THREADS, sizeof(Smem) + 1024, (cudaStream_t)stream>>>(a);
+    int grid = tiles < p->sms ? tiles : p->sms;
+    if (p->max_grid > 0 && grid > p->max_grid) grid = p->max_grid;
+    policy_forward_kernel<<<grid, THREADS, sizeof(Smem), (cudaStream_t)stream>>>(a);
     p->launches += 1;
     QP_CUDA(p, cudaGetLastError());
     return QP_OK;
