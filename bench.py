@@ -424,8 +424,40 @@ def main():
             ppo_line = {"workload": "configs[4] with PPO update: 65536 envs x 8 quads in total, two-tower policy (self 18-256-256, deep-sets neighbours, "
                                     "512-512), rollout of 8 steps + 1 epoch of 65536-row minibatches",
                         "rollout_value": samples / roll_s, "loop_value": samples / (roll_s + upd_s), "unit": "drone-steps/s",
-                        "rollout_s": roll_s, "update_s": upd_s, "policy_path": getattr(algo, "policy_path", "torch"),
+                        "rollout_s": roll_s, "update_s": upd_s,
+                        "policy_path": ("rollout forward + GAE: hand-written sm_100a kernels (qp::policy_forward_kernel, tcgen05 / TMEM; qp::gae_kernel); "
+                                        "update: torch autograd, bf16 autocast") if algo.fused is not None else "torch (bf16 autocast)",
                         "simulator_launches_per_env_step": 1}
+            if algo.fused is not None:
+                # the rollout's dense forward alone, device-timed: fused tcgen05 kernel vs the torch module it replaces (same weights, same rows)
+                def ev_ms(fn, reps):
+                    for _ in range(2):
+                        fn()
+                    torch.cuda.synchronize()
+                    ts = []
+                    for _ in range(reps):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                        ts.append(e0.elapsed_time(e1))
+                    return sorted(ts)[len(ts) // 2]
+
+                def eager():
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                        return algo.policy.action_net(algo.policy.actor(algo.obs)), algo.policy.value(algo.obs)
+
+                fp = algo.fused
+                rows = algo.obs.shape[0]
+                flop_row = 4.0 * (fp.S * 256 + 65536 + fp.V * ((fp.S + fp.W) * 256 + 65536) + 262144 + 256 * (fp.A + 1))
+                ms_f, ms_t = ev_ms(lambda: fp.forward(algo.obs), 10), ev_ms(eager, 3)
+                try:
+                    tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+                except Exception:
+                    tf_peak = None
+                ppo_line["policy_forward"] = {
+                    "kernel": "qp::policy_forward_kernel", "rows": rows, "flop_per_row": flop_row, "ms_fused": ms_f, "ms_torch_bf16_autocast": ms_t,
+                    "tflops": flop_row * rows / ms_f * 1e-9, "bound": "tensor", "peak_tflops": tf_peak,
+                    "frac": (flop_row * rows / ms_f * 1e-9 / tf_peak) if tf_peak else None,
+                    "peak_source": "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)", "speedup_vs_torch": ms_t / ms_f}
             psim.close()
             del algo, psim
         except Exception as ex:      # the PPO loop is a secondary key: never lose the bench line over it

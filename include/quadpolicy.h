@@ -7,6 +7,8 @@
  *   qp_create / qp_destroy   ActorCriticPolicyCustomSeparateWeights.__init__ / _build   swarm_rl/models/ActorCriticPolicyCustom.py:284-411
  *                            QuadMultiEncoder.__init__ (one per tower)                  swarm_rl/models/quad_multi_model.py:250-331
  *   qp_set_weights           the state_dict of one tower (nn.Linear weights [out, in], biases)
+ *   qp_gae                   stable_baselines3 RolloutBuffer.compute_returns_and_advantage as driven by PPO.collect_rollouts
+ *                            (swarm_rl/sb_train.py:54-99 -> model.learn): one launch over the device-resident rollout
  *   qp_forward               ActorCriticPolicyCustom.forward / predict_values: action mean of the actor tower and value of the
  *                            critic tower for a batch of observations           ActorCriticPolicyCustom.py:430-480,
  *                            QuadMultiEncoder.forward                           quad_multi_model.py:333-354,
@@ -36,8 +38,8 @@ typedef enum { QP_OK = 0, QP_ERR_NULL = -1, QP_ERR_BAD_CONFIG = -2, QP_ERR_CUDA 
 
 typedef struct {
     int32_t api_version; /* QP_API_VERSION */
-    int32_t self_dim;    /* S: 18 / 19 / 24 (quad_utils.py:30-38) */
-    int32_t nbr_dim;     /* W: 6 for pos_vel (quad_utils.py:40-58); S + W <= 32 */
+    int32_t self_dim;    /* S: 18 / 19 / 24 (quad_utils.py:30-38); S <= 24 */
+    int32_t nbr_dim;     /* W: 6 for pos_vel (quad_utils.py:40-58); W <= 8 */
     int32_t num_nbr;     /* V: neighbour rows in the observation, 0 = no neighbour encoder */
     int32_t hidden;      /* rnn_size: 256 (the only width built) */
     int32_t act_dim;     /* A <= 8 */
@@ -67,6 +69,11 @@ int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *str
 /* obs: [n, obs_stride] fp32 (self block first, then V neighbour rows of W values, as Appendix B of SURVEY.md);
  * mean: [n, A]; value: [n].  One kernel launch, nothing touches the host. */
 int qp_forward(qp_policy *p, const float *obs, int n, int obs_stride, float *mean, float *value, void *stream);
+
+/* GAE over a rollout held on the device: rewards / values [T, n] fp32, dones [T, n] bytes (dones[t] = the transition produced by step t
+ * ended its episode), last_values [n] = V(s_T); writes advantages and returns [T, n].  One launch; no handle needed. */
+int qp_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, int T, int n, float gamma, float lam,
+           float *advantages, float *returns, void *stream);
 
 #ifdef __cplusplus
 }

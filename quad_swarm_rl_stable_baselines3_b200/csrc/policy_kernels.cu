@@ -655,6 +655,26 @@ __global__ void pack_head_kernel(const float *w, int n_out, float *wt)
     wt[idx] = o < n_out ? w[(size_t)o * FF + c] : 0.f;
 }
 
+// ---- generalised advantage estimation over a rollout (SB3 RolloutBuffer.compute_returns_and_advantage, buffers.py: the recursion
+// last = delta_t + gamma * lambda * nonterminal_t * last, delta_t = r_t + gamma * V_{t+1} * nonterminal_t - V_t, backwards in time).
+// One thread per agent row, [T, n] arrays row-major: every step's loads and stores are coalesced across the warp.
+__global__ void gae_kernel(const float *rew, const float *val, const uint8_t *done, const float *last_val, int T, int n, float gamma, float lam,
+                           float *adv, float *ret)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float next_v = last_val[i], last = 0.f;
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t k = (size_t)t * n + i;
+        const float nonterminal = done[k] ? 0.f : 1.f, v = val[k];
+        const float delta = rew[k] + gamma * next_v * nonterminal - v;
+        last = delta + gamma * lam * nonterminal * last;
+        adv[k] = last;
+        ret[k] = last + v;
+        next_v = v;
+    }
+}
+
 }  // namespace qp
 
 using namespace qp;
@@ -774,6 +794,17 @@ int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *str
     QP_CUDA(p, cudaMemsetAsync(P->head_b, 0, sizeof(P->head_b), s));
     QP_CUDA(p, cudaMemcpyAsync(P->head_b, w->head_b, (size_t)n_out * sizeof(float), dd, s));
     QP_CUDA(p, cudaGetLastError());
+    return QP_OK;
+}
+
+int qp_gae(const float *rewards, const float *values, const uint8_t *dones, const float *last_values, int T, int n, float gamma, float lam,
+           float *advantages, float *returns, void *stream)
+{
+    if (!rewards || !values || !dones || !last_values || !advantages || !returns) return qp_fail(nullptr, QP_ERR_NULL, "qp_gae: null argument");
+    if (T < 1 || n < 1) return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_gae: bad T / n");
+    gae_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, T, n, gamma, lam, advantages, returns);
+    cudaError_t r = cudaGetLastError();
+    if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_gae: ") + cudaGetErrorString(r));
     return QP_OK;
 }
 

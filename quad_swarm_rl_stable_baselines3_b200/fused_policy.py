@@ -27,13 +27,30 @@ def supported(policy) -> bool:
     """The architecture the kernel is built for: deep-sets ('mean_embed') or no neighbour encoder, no obstacle encoder, hidden 256."""
     enc = policy.actor
     return (enc.kind in ("mean_embed", "none") and enc.O == 0 and enc.self_encoder[0].out_features == 256
-            and enc.S + enc.W <= 32 and policy.action_net.out_features <= 8 and (enc.kind == "none" or enc.neighbor[0].out_features == 256))
+            and enc.S <= 24 and enc.W <= 8 and policy.action_net.out_features <= 8 and (enc.kind == "none" or enc.neighbor[0].out_features == 256))
+
+
+def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_values: torch.Tensor, gamma: float, lam: float):
+    """`ppo.compute_gae` in one CUDA launch (`qp_gae`): rewards / values [T, n] float32, dones [T, n] bool, last_values [n]."""
+    if rewards.device.type != "cuda":
+        raise RuntimeError("fused_policy.gae runs on CUDA tensors only (no CPU path)")
+    T, n = rewards.shape
+    rewards, values, last_values = rewards.contiguous(), values.contiguous(), last_values.contiguous().float()
+    d8 = dones.contiguous().view(torch.uint8)
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    lib = _capi.lib()
+    with torch.cuda.device(rewards.device):
+        rc = lib.qp_gae(rewards.data_ptr(), values.data_ptr(), d8.data_ptr(), last_values.data_ptr(), T, n, gamma, lam, adv.data_ptr(), ret.data_ptr(),
+                        C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"qp_gae failed ({rc}): {lib.qp_last_error(None).decode()}")
+    return adv, ret
 
 
 class FusedPolicy:
     def __init__(self, policy, device):
         if not supported(policy):
-            raise ValueError("the fused policy kernel is built for hidden 256, deep-sets / no neighbour encoder, no obstacle encoder")
+            raise ValueError("the fused policy kernel is built for hidden 256, deep-sets / no neighbour encoder, no obstacle encoder, S <= 24, W <= 8")
         self.policy = policy
         self.device = torch.device(device)
         if self.device.type != "cuda":

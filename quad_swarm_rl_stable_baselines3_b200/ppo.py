@@ -9,9 +9,11 @@ The policy mirrors the reference's `ActorCriticPolicyCustomSeparateWeights` (swa
 with a `QuadMultiEncoder` per tower (swarm_rl/models/quad_multi_model.py:250-354): self-observation MLP, neighbour encoder
 ('mlp' or deep-sets 'mean_embed'), optional obstacle MLP, tanh feed-forward to 2*rnn_size; separate actor and critic weights;
 state-independent log-std diagonal Gaussian (log_std_init 0, no squashing), xavier-uniform initialisation.  The dense layers
-are plain PyTorch (cuBLAS): nothing here is a hand-written kernel, and nothing of SB3's arithmetic is pinned by a reference
-test (SB3 is not installed in the build image) -- "parity unpinned" for this file; the GAE recursion is tested against a
-numpy restatement of SB3's `RolloutBuffer.compute_returns_and_advantage`.
+of the torch module are plain PyTorch (cuBLAS) and are what the update differentiates; at rollout time the forward runs on the
+hand-written tcgen05 kernel (`fused_policy.py`, csrc/policy_kernels.cu: both towers and heads in one launch, activations in
+tensor memory; parity against this module in tests/test_gpu_policy.py) and GAE on `qp_gae` (one launch).  Nothing of SB3's
+arithmetic is pinned by a reference test (SB3 is not installed in the build image) -- "parity unpinned" for the update; the
+GAE recursion is tested against a numpy restatement of SB3's `RolloutBuffer.compute_returns_and_advantage`.
 
 Multi-GPU: one process per GPU, each with its own env shard (sharding.py); the only collectives are the gradient all-reduce
 per minibatch (one flat NCCL buffer) and the episode-stat all-reduce per rollout.
@@ -142,6 +144,7 @@ class PPOConfig:
     neighbor_hidden: int = 256
     neighbor_encoder: str = "mean_embed"
     autocast_bf16: bool = False     # bf16 autocast for the dense layers (tensor cores); the simulator stays fp32
+    fused_rollout: bool = True      # rollout-time forward on the tcgen05 kernel (fused_policy.py) when the architecture is the one it is built for
 
 
 class DevicePPO:
@@ -166,6 +169,11 @@ class DevicePPO:
         self._flat = None
         self.obs = sim.reset().clone()
         self.total_agent_steps = 0
+        self.fused = None
+        if self.p.fused_rollout and self.device.type == "cuda":
+            from . import fused_policy
+            if fused_policy.supported(self.policy):
+                self.fused = fused_policy.FusedPolicy(self.policy, self.device)
 
     def _sync(self):
         if self.device.type == "cuda":
@@ -180,16 +188,24 @@ class DevicePPO:
         p = self.p
         t0 = time.perf_counter()
         for t in range(p.n_steps):
-            with self._autocast():
-                a, logp, v = self.policy.act(self.obs)
+            if self.fused is not None:
+                a, logp, v = self.fused.act(self.obs)                    # one tcgen05 kernel: both towers, heads included
+            else:
+                with self._autocast():
+                    a, logp, v = self.policy.act(self.obs)
             self.obs_buf[t].copy_(self.obs)
             self.act_buf[t].copy_(a); self.logp_buf[t].copy_(logp.float()); self.val_buf[t].copy_(v.float())
             obs, rew, done = self.sim.step(a.float().contiguous())       # the env clips the action itself (RawControl.step)
             self.rew_buf[t].copy_(rew); self.done_buf[t].copy_(done)
             self.obs.copy_(obs)                                          # sim.obs aliases a buffer that the next step overwrites
-        with self._autocast():
-            last_v = self.policy.value(self.obs).float()
-        self.adv, self.ret = compute_gae(self.rew_buf, self.val_buf, self.done_buf, last_v, p.gamma, p.gae_lambda)
+        if self.fused is not None:
+            from . import fused_policy
+            last_v = self.fused.forward(self.obs)[1]
+            self.adv, self.ret = fused_policy.gae(self.rew_buf, self.val_buf, self.done_buf, last_v, p.gamma, p.gae_lambda)   # one launch
+        else:
+            with self._autocast():
+                last_v = self.policy.value(self.obs).float()
+            self.adv, self.ret = compute_gae(self.rew_buf, self.val_buf, self.done_buf, last_v, p.gamma, p.gae_lambda)
         self._sync()
         n = self.obs.shape[0]
         self.total_agent_steps += n * p.n_steps * self.world
@@ -219,7 +235,7 @@ class DevicePPO:
         total = T * n
         obs = self.obs_buf.view(total, -1); act = self.act_buf.view(total, -1)
         logp_old = self.logp_buf.view(total); adv = self.adv.reshape(total); ret = self.ret.reshape(total)
-        stats = dict(pg=0.0, vf=0.0, ent=0.0, kl=0.0, clip_frac=0.0)
+        acc = torch.zeros(5, device=self.device)                    # pg, vf, ent, kl, clip_frac: summed on the device, read once
         nb = 0
         for _ in range(p.n_epochs):
             perm = torch.randperm(total, device=self.device)
@@ -241,11 +257,13 @@ class DevicePPO:
                 nn.utils.clip_grad_norm_(self.policy.parameters(), p.max_grad_norm)
                 self.opt.step()
                 with torch.no_grad():
-                    stats["pg"] += float(pg); stats["vf"] += float(vf); stats["ent"] += float(ent.mean())
-                    stats["kl"] += float((logp_old[idx] - logp).mean()); stats["clip_frac"] += float(((ratio - 1).abs() > p.clip_range).float().mean())
+                    acc += torch.stack([pg.detach(), vf.detach(), ent.mean(), (logp_old[idx] - logp).mean(),
+                                        ((ratio - 1).abs() > p.clip_range).float().mean()])
                 nb += 1
+        if self.fused is not None:
+            self.fused.sync()                                          # re-pack the updated weights for the next rollout
         self._sync()
-        out = {k: v / max(nb, 1) for k, v in stats.items()}
+        out = dict(zip(("pg", "vf", "ent", "kl", "clip_frac"), (acc / max(nb, 1)).tolist()))
         out["update_s"] = time.perf_counter() - t0
         out["minibatches"] = nb
         return out

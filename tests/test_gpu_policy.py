@@ -134,3 +134,40 @@ def test_weight_resync_and_act():
     a, logp, v = fp.act(obs)
     d = torch.distributions.Normal(m1, pol.log_std.detach().exp().expand_as(m1))
     assert torch.allclose(logp, d.log_prob(a).sum(-1), atol=1e-4) and torch.equal(v, v1)
+
+
+def test_gae_kernel_matches_the_recursion():
+    """`qp_gae` against `ppo.compute_gae` (itself pinned against a numpy restatement of SB3's recursion in tests/test_ppo_cpu.py)."""
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200.fused_policy import gae
+    from quad_swarm_rl_stable_baselines3_b200.ppo import compute_gae
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    for T, n in ((1, 5), (7, 1000), (128, 4096 + 3)):
+        rew, val = torch.randn(T, n, device=dev), torch.randn(T, n, device=dev)
+        done = torch.rand(T, n, device=dev) < 0.05
+        last = torch.randn(n, device=dev)
+        a0, r0 = compute_gae(rew, val, done, last, 0.99, 0.95)
+        a1, r1 = gae(rew, val, done, last, 0.99, 0.95)
+        assert float((a0 - a1).abs().max()) <= 2e-5 * max(1.0, float(a0.abs().max())), (T, n)
+        assert float((r0 - r1).abs().max()) <= 2e-5 * max(1.0, float(r0.abs().max())), (T, n)
+
+
+def test_device_ppo_uses_the_fused_rollout():
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200.ppo import DevicePPO, PPOConfig
+    from quad_swarm_rl_stable_baselines3_b200.sim import QuadSwarmSim
+    cfg = QuadSimConfig(num_envs=256, num_agents=8, ep_time=0.3, seed=1)
+    sim = QuadSwarmSim(cfg, device="cuda:0")
+    sim.want_terminal_obs = False
+    ppo = DevicePPO(sim, cfg, PPOConfig(n_steps=8, batch_size=4096, n_epochs=1))
+    assert ppo.fused is not None
+    l0 = ppo.fused.launch_count
+    hist = ppo.learn(2)
+    assert ppo.fused.launch_count - l0 == 2 * (8 + 1)               # one launch per env step + the bootstrap value
+    assert all(torch.isfinite(torch.tensor([r[k] for k in ("pg", "vf", "ent", "kl")])).all() for r in hist)
+    obs = torch.randn(512, 54, device="cuda:0")
+    m, _ = ppo.fused.forward(obs)                                  # the packed weights follow the optimiser
+    with torch.no_grad():
+        r = ppo.policy.action_net(ppo.policy.actor(obs))
+    assert float((m - r).abs().max()) <= TOL_FP32_MAX
