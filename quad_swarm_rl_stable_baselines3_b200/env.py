@@ -153,7 +153,7 @@ class QuadrotorEnvMulti:
         self._pending: Optional[np.ndarray] = None      # fork: first observation of the episode the kernel already started
         self._cache = None
         self._rew_info = None
-        if hasattr(sim, "enable_reward_info") and not self.is_fork:
+        if hasattr(sim, "enable_reward_info"):                       # fork mode: column 0 carries goal_dist (QS_RI_RAW_POS)
             self._rew_info = sim.enable_reward_info()
 
     # ---- state views -----------------------------------------------------------------------------------------------
@@ -201,9 +201,16 @@ class QuadrotorEnvMulti:
         infos: List[dict] = [{} for _ in range(K)]
         if self._rew_info is not None:
             rows = self.sim.reward_info_host()
-            rc = self._rew_coeff()
-            for i in range(K):
-                infos[i]["rewards"] = reward_info_dict(rows[i], rc, self.cfg.use_obstacles)
+            if self.is_fork:
+                # the fork's step returns {'rewards': dict(), 'goal_dist': |pos - goal|} per agent (quadrotor_single_rewards.py:457),
+                # read by swarm_rl/sb_eval.py:28; the kernel evaluates it before the worker's auto-reset, as the reference does
+                for i in range(K):
+                    infos[i]["rewards"] = {}
+                    infos[i]["goal_dist"] = float(rows[i][0])
+            else:
+                rc = self._rew_coeff()
+                for i in range(K):
+                    infos[i]["rewards"] = reward_info_dict(rows[i], rc, self.cfg.use_obstacles)
         if done and hasattr(self.sim, "episode_records_host"):
             self.sim.episode_records_host(self._erec, self._arec)
             for i in range(K):

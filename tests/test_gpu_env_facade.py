@@ -107,6 +107,11 @@ def test_facade_on_gpu_runs_an_episode():
     assert info == {"success": False}
     for t in range(20):
         obs, rew, dones, infos = fenv.step(rs.uniform(-1, 1, (4, 2)))
+        # quadrotor_single_rewards.py:457: every agent's info carries 'goal_dist' (what swarm_rl/sb_eval.py:28 averages) and an empty 'rewards'
+        assert all(i["rewards"] == {} and 0.0 < i["goal_dist"] < 30.0 for i in infos)
+        if not dones[0]:
+            gd = [np.linalg.norm(e.dynamics.pos - e.goal) for e in fenv.envs]
+            np.testing.assert_allclose([i["goal_dist"] for i in infos], gd, atol=0.02)    # the evader moves <= 5 mm per sub-step
         if dones[0]:
             obs2, info = fenv.reset()
             assert set(info) == {"success"} and not np.array_equal(obs, obs2)
