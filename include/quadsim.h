@@ -71,7 +71,8 @@ enum { QS_SCENARIO_STATIC_SAME_GOAL = 0,      /* scenarios/static_same_goal.py *
        QS_SCENARIO_MIX = 10,                  /* scenarios/mix.py without obstacles: one of the 9 (K = 1: 5) modes per episode */
        QS_SCENARIO_EP_LISSAJOUS3D = 11,       /* scenarios/ep_lissajous3D.py: common goal integrating a Lissajous velocity */
        QS_SCENARIO_EP_RAND_BEZIER = 12,       /* scenarios/ep_rand_bezier.py: common goal along random quadratic Bezier arcs */
-       QS_SCENARIO_SWARM_VS_SWARM = 13 };     /* scenarios/swarm_vs_swarm.py: two half-swarms exchanging formation centres */
+       QS_SCENARIO_SWARM_VS_SWARM = 13,       /* scenarios/swarm_vs_swarm.py: two half-swarms exchanging formation centres */
+       QS_SCENARIO_RUN_AWAY = 14 };           /* scenarios/run_away.py: every second drones 0 and 1 take over the goals of two random others (K >= 2) */
 
 /* per-env state of the formation scenarios (the reference's QuadrotorScenario object, scenarios/base.py:9-35), as a row of
  * QS_SC_COUNT floats in qs_state_view.scenario.  Integers are stored as exactly representable floats. */

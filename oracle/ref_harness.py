@@ -174,8 +174,9 @@ class Tape:
         # legacy np.random.randint(low, high): one taped uniform, low + floor(u * (high - low)) on the truncated bounds
         if high is None:
             low, high = 0, low
-        assert size is None
         low, high = int(low), int(high)
+        if size is not None:                                     # run_away.py:20: size=2 -> one taped uniform per element, in order
+            return np.array([low + int(np.floor(self.rand() * (high - low))) for _ in range(int(np.prod(size)))]).reshape(size)
         return low + int(np.floor(self.rand() * (high - low)))
 
     def choice(self, a, size=None, replace=True, p=None):

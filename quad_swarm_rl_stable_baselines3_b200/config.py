@@ -18,9 +18,9 @@ QS_MAX_OBSTACLES = 64
 
 SCENARIOS = {"static_same_goal": 0, "o_mix": 1, "o_random": 2, "o_static_same_goal": 3, "dynamic_repulsive": 4,
              "static_diff_goal": 5, "dynamic_same_goal": 6, "dynamic_diff_goal": 7, "swap_goals": 8, "dynamic_formations": 9,
-             "mix": 10, "ep_lissajous3D": 11, "ep_rand_bezier": 12, "swarm_vs_swarm": 13}
+             "mix": 10, "ep_lissajous3D": 11, "ep_rand_bezier": 12, "swarm_vs_swarm": 13, "run_away": 14}
 FORMATION_SCENARIOS = ("static_same_goal", "static_diff_goal", "dynamic_same_goal", "dynamic_diff_goal", "swap_goals",
-                       "dynamic_formations", "mix", "ep_lissajous3D", "ep_rand_bezier", "swarm_vs_swarm")
+                       "dynamic_formations", "mix", "ep_lissajous3D", "ep_rand_bezier", "swarm_vs_swarm", "run_away")
 QS_SC_COUNT = 24       # floats per env of formation-scenario state (include/quadsim.h QS_SC_*)
 SCENARIO_NAMES = {v: k for k, v in SCENARIOS.items()}
 # qs_episode_records layout (include/quadsim.h QS_ER_*)
@@ -271,6 +271,8 @@ class QuadSimConfig:
             raise ValueError("swap_goals needs num_agents >= 3 on the device")
         if mode == "swarm_vs_swarm" and K < 2:
             raise ValueError("swarm_vs_swarm needs num_agents >= 2")             # scenarios/utils.py:10
+        if mode == "run_away" and K < 2:
+            raise ValueError("run_away needs num_agents >= 2")                   # run_away.py:20,23-24: randint(1, K), envs[1]
         if mode == "mix" and K == 2:
             raise ValueError("mix needs num_agents == 1 or >= 3 on the device (it contains swap_goals)")
         return SCENARIOS[mode]

@@ -294,11 +294,12 @@ static int validate(const qs_config *c, std::string &why)
         if (cells - c->num_obstacles < c->num_agents) { why = "not enough free cells for the drones"; return 0; }
     } else {
         const int sc = c->scenario, K = c->num_agents;
-        const bool formation = sc == QS_SCENARIO_STATIC_SAME_GOAL || (sc >= QS_SCENARIO_STATIC_DIFF_GOAL && sc <= QS_SCENARIO_SWARM_VS_SWARM);
+        const bool formation = sc == QS_SCENARIO_STATIC_SAME_GOAL || (sc >= QS_SCENARIO_STATIC_DIFF_GOAL && sc <= QS_SCENARIO_RUN_AWAY);
         if (!formation) { why = "obstacle scenario without use_obstacles"; return 0; }
         // a sphere of n < 3 drones still has 3 goal rows (scenarios/utils.py:77-80): scenarios permuting stored rows need rows == drones
         if (sc == QS_SCENARIO_SWAP_GOALS && K < 3) { why = "swap_goals needs num_agents >= 3"; return 0; }
         if (sc == QS_SCENARIO_SWARM_VS_SWARM && K < 2) { why = "swarm_vs_swarm needs num_agents >= 2"; return 0; }
+        if (sc == QS_SCENARIO_RUN_AWAY && K < 2) { why = "run_away needs num_agents >= 2"; return 0; }
         if (sc == QS_SCENARIO_MIX && K == 2) { why = "mix needs num_agents == 1 or >= 3"; return 0; }
     }
     if (!(c->mass > 0) || !(c->inertia[0] > 0) || !(c->inertia[1] > 0) || !(c->inertia[2] > 0)) { why = "bad mass / inertia"; return 0; }

@@ -19,7 +19,7 @@ enum { QF_CIRCLE_H = 0, QF_CIRCLE_XZ, QF_CIRCLE_YZ, QF_SPHERE, QF_GRID_H, QF_GRI
 __device__ __forceinline__ void scen_params(int scen, int &nform, float &low, float &high)
 {
     nform = 1; low = 0.f; high = 0.f;
-    if (scen == QS_SCENARIO_STATIC_DIFF_GOAL || scen == QS_SCENARIO_DYNAMIC_DIFF_GOAL || scen == QS_SCENARIO_SWARM_VS_SWARM) { nform = 8; low = 0.25f; high = 0.5f; }
+    if (scen == QS_SCENARIO_STATIC_DIFF_GOAL || scen == QS_SCENARIO_DYNAMIC_DIFF_GOAL || scen == QS_SCENARIO_SWARM_VS_SWARM || scen == QS_SCENARIO_RUN_AWAY) { nform = 8; low = 0.25f; high = 0.5f; }
     else if (scen == QS_SCENARIO_SWAP_GOALS) { nform = 8; low = 0.4f; high = 0.8f; }
     else if (scen == QS_SCENARIO_DYNAMIC_FORMATIONS) { nform = 8; low = 0.f; high = 1.0f; }
 }
@@ -258,6 +258,16 @@ static __device__ __noinline__ float3 scenario_event(const DevConst &c, const Rn
         const float4 o = stage[2 * (base + perm[d < K ? d : 0])];
         goal[0] = o.x; goal[1] = o.y; goal[2] = o.z;
         __syncwarp(gmask);
+    } else if (scen == QS_SCENARIO_RUN_AWAY) {                          // run_away.py:18-25: goals[0] <- goals[g0], goals[1] <- goals[g1], g in [1, K)
+        rng_u4(g, SITE_SCENARIO, 0xFF, 10, 0, u0);
+        const int g0 = min(1 + (int)floorf(u0[0] * (float)(K - 1)), K - 1), g1 = min(1 + (int)floorf(u0[1] * (float)(K - 1)), K - 1);
+        stage[2 * lane] = make_float4(goal[0], goal[1], goal[2], 0.f);
+        __syncwarp(gmask);
+        if (d < 2) {                                                    // g1 >= 1: the second copy never reads the row the first one wrote
+            const float4 o = stage[2 * (base + (d == 0 ? g0 : g1))];
+            goal[0] = o.x; goal[1] = o.y; goal[2] = o.z;
+        }
+        __syncwarp(gmask);
     } else if (scen == QS_SCENARIO_SWARM_VS_SWARM) {                    // swarm_vs_swarm.py:67-90
 #pragma unroll
         for (int a = 0; a < 3; ++a) { const float t = aux9[a]; aux9[a] = aux9[3 + a]; aux9[3 + a] = t; }
@@ -338,7 +348,7 @@ __device__ __forceinline__ void formation_scenario_step(const DevConst &c, const
             goal[0] = w0 * b3.x + w1 * b3.w + w2 * b4.z; goal[1] = w0 * b3.y + w1 * b4.x + w2 * b4.w; goal[2] = w0 * b3.z + w1 * b4.y + w2 * b5.x;
         }
     } else {                                                            // timer scenarios: goals change when tick % control_step_for_sec == 0
-        const int ctl = (int)rs[2].y;
+        const int ctl = (scen == QS_SCENARIO_RUN_AWAY) ? (int)c.control_freq : (int)rs[2].y;   // run_away.py:16: a local of step(), every second
         if (ctl > 0 && tick % ctl == 0 && tick > 0) {
             const float3 ng = scenario_event(c, g, scen, d, leader, gmask, lane, base, row, stage, make_float3(goal[0], goal[1], goal[2]));
             goal[0] = ng.x; goal[1] = ng.y; goal[2] = ng.z;

@@ -66,6 +66,7 @@ SCENARIO_TRACES = {
     "scen_dyn_same_k3": dict(env=dict(num_agents=3, quads_mode="dynamic_same_goal", ep_time=6.3, **_SC), steps=680, act="hover"),
     "scen_dyn_diff_k4": dict(env=dict(num_agents=4, quads_mode="dynamic_diff_goal", ep_time=6.3, **_SC), steps=680, act="hover"),
     "scen_swap_k3": dict(env=dict(num_agents=3, quads_mode="swap_goals", ep_time=6.3, **_SC), steps=680, act="hover"),
+    "scen_runaway_k5": dict(env=dict(num_agents=5, quads_mode="run_away", ep_time=4.3, **_SC), steps=900, act="hover"),
     "scen_swarm_k6": dict(env=dict(num_agents=6, quads_mode="swarm_vs_swarm", ep_time=6.3, **_SC), steps=680, act="hover"),
     # halves of 2 drones: a sphere of fewer than 3 drones still yields 3 goal rows (scenarios/utils.py:77-80)
     "scen_swarm_k4": dict(env=dict(num_agents=4, quads_mode="swarm_vs_swarm", ep_time=0.08, **_SC), steps=260, act="hover"),

@@ -88,7 +88,10 @@ def test_config_derivations():
     with pytest.raises(ValueError):
         QuadSimConfig(num_agents=4, neighbor_visible_num=6).to_c()
     with pytest.raises(ValueError):
-        QuadSimConfig(quads_mode="run_away").to_c()                  # not a scenario the device runs
+        QuadSimConfig(quads_mode="o_swap_goals").to_c()              # not a scenario the device runs (nor the reference: DESIGN.md 9 f2)
+    with pytest.raises(ValueError):
+        QuadSimConfig(quads_mode="run_away", num_agents=1, neighbor_visible_num=0).to_c()     # run_away.py:20: randint(1, 1)
+    assert QuadSimConfig(quads_mode="run_away").to_c().scenario == 14
     with pytest.raises(AssertionError):
         QuadSimConfig(rew_coeff=dict(typo=1.0)).to_c()
     cc = c.to_c()

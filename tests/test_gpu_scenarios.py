@@ -24,6 +24,8 @@ SCENARIO_CONFIGS = {
     "dyn_diff_k9": (dict(num_envs=24, num_agents=9, quads_mode="dynamic_diff_goal", ep_time=0.3), 70, True),
     "swap_k3": (dict(num_envs=40, num_agents=3, quads_mode="swap_goals", neighbor_visible_num=1, ep_time=0.4), 90, True),
     "swap_k8": (dict(num_envs=32, num_agents=8, quads_mode="swap_goals", ep_time=0.4), 90, True),
+    "runaway_k5": (dict(num_envs=40, num_agents=5, quads_mode="run_away", neighbor_visible_num=2, ep_time=1.2), 140, False),
+    "runaway_k2": (dict(num_envs=24, num_agents=2, quads_mode="run_away", neighbor_visible_num=1, ep_time=1.2), 130, False),
     "swarm_k6": (dict(num_envs=32, num_agents=6, quads_mode="swarm_vs_swarm", neighbor_visible_num=2, ep_time=0.4), 90, True),
     "swarm_k4": (dict(num_envs=32, num_agents=4, quads_mode="swarm_vs_swarm", neighbor_visible_num=2, ep_time=0.3), 70, True),
     "swarm_k7": (dict(num_envs=24, num_agents=7, quads_mode="swarm_vs_swarm", ep_time=0.3), 70, True),

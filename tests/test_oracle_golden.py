@@ -106,9 +106,9 @@ TRACE_NAMES = ["cfg2_k8", "smallroom_k8", "crowd_k16", "cfg3_obst_k8", "cfg4_k32
 # reference scenario object's own state per step (QS_SC_* row)
 SCENARIO_TRACE_NAMES = ["scen_static_diff_k8", "scen_static_diff_k12", "scen_dyn_same_k3", "scen_dyn_diff_k4", "scen_swap_k3",
                         "scen_swarm_k6", "scen_swarm_k4", "scen_dynform_k5", "scen_lissajous_k3", "scen_bezier_k3",
-                        "scen_mix_k4", "scen_mix_k1"]
+                        "scen_mix_k4", "scen_mix_k1", "scen_runaway_k5"]
 SCENARIO_IDS = {"static_same_goal": 0, "static_diff_goal": 5, "dynamic_same_goal": 6, "dynamic_diff_goal": 7, "swap_goals": 8,
-                "dynamic_formations": 9, "ep_lissajous3D": 11, "ep_rand_bezier": 12, "swarm_vs_swarm": 13}
+                "dynamic_formations": 9, "ep_lissajous3D": 11, "ep_rand_bezier": 12, "swarm_vs_swarm": 13, "run_away": 14}
 
 
 def load_trace(golden_dir, name):
