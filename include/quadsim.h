@@ -99,7 +99,9 @@ enum { QS_OBS_XYZ_VXYZ_R_OMEGA = 0, QS_OBS_XYZ_VXYZ_R_OMEGA_FLOOR = 1, QS_OBS_XY
        /* fork 2-D representations (get_state.py:7-103), QS_MODE_FORK only */
        QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_ANGLE_ANGLEDOT = 3,   /* 6 floats, get_state.py:37-69 */
        QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_SANGLE_ANGLEDOT = 4,  /* 7 floats, get_state.py:71-103 */
-       QS_OBS_AW_AWDOT_DIST_DISTDOT_ANGLE_ANGLEDOT = 5 };       /* 6 floats, get_state.py:7-35 */
+       QS_OBS_AW_AWDOT_DIST_DISTDOT_ANGLE_ANGLEDOT = 5,         /* 6 floats, get_state.py:7-35 */
+       QS_OBS_CDIST_CDISTDOT_NDIST_DISTDOT_NSANGLE_ANGLEDOT = 6 }; /* 7 floats, get_state.py:190-224: distance and bearing of the goal as
+                                                                     the camera model measures them (pixel noise, best of n cameras) */
 
 /* neighbor_obs_type (quad_utils.py:40-58) */
 enum { QS_NEIGHBOR_NONE = 0, QS_NEIGHBOR_POS_VEL = 1,

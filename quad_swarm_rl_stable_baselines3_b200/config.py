@@ -70,10 +70,10 @@ def episode_extra_stats(env_rec, agent_rec, num_agents: int, use_obstacles: bool
 ENV_MODES = {"upstream": 0, "fork": 1}
 OBS_REPR = {"xyz_vxyz_R_omega": 0, "xyz_vxyz_R_omega_floor": 1, "xyz_vxyz_R_omega_wall": 2,
             "cdist_cdistdot_dist_distdot_angle_angledot": 3, "cdist_cdistdot_dist_distdot_sangle_angledot": 4,
-            "aw_awdot_dist_distdot_angle_angledot": 5}
+            "aw_awdot_dist_distdot_angle_angledot": 5, "cdist_cdistdot_ndist_distdot_nsangle_angledot": 6}
 OBS_REPR_DIM = {"xyz_vxyz_R_omega": 18, "xyz_vxyz_R_omega_floor": 19, "xyz_vxyz_R_omega_wall": 24,       # quad_utils.py:30-38
                 "cdist_cdistdot_dist_distdot_angle_angledot": 6, "cdist_cdistdot_dist_distdot_sangle_angledot": 7,
-                "aw_awdot_dist_distdot_angle_angledot": 6}
+                "aw_awdot_dist_distdot_angle_angledot": 6, "cdist_cdistdot_ndist_distdot_nsangle_angledot": 7}
 FORK_OBS_REPR = {k for k, v in OBS_REPR.items() if v >= 3}
 NEIGHBOR_OBS = {"none": 0, "pos_vel": 1, "dist_angle": 2, "dist_sangle": 3, "dist_angle_heading": 4,
                 "dist_sangle_sheading": 5, "ndist_nsangle": 6}

@@ -133,7 +133,9 @@ __device__ __forceinline__ void fork_controller(const DevConst &c, const ForkCon
 }
 
 // state_{cdist_cdistdot,aw_awdot}_dist_distdot_{angle,sangle}_angledot, get_state.py:7-103
-__device__ __forceinline__ void fork_self_obs(const DevConst &c, const Rng &g, int site, int drone, const Drone &q, float angle,
+__device__ __forceinline__ void camera_measure(const ForkConst &f, float rx, float ry, float global_angle, float n1, float n2, float &dist, float &angle_rel);
+
+__device__ __forceinline__ void fork_self_obs(const DevConst &c, const ForkConst &f, const Rng &g, int site, int drone, const Drone &q, float angle,
                                               float ang_vel, float *o)
 {
     float p0 = q.p[0], p1 = q.p[1], v0 = q.v[0], v1 = q.v[1];
@@ -155,7 +157,15 @@ __device__ __forceinline__ void fork_self_obs(const DevConst &c, const Rng &g, i
     else { o[0] = cdist; o[1] = cdistdot; }
     o[2] = rel_dist; o[3] = dot_rel;
     if (c.obs_repr == QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_SANGLE_ANGLEDOT) { float s, cc; sincosf(rel_angle, &s, &cc); o[4] = cc; o[5] = s; o[6] = adot; }
-    else { o[4] = rel_angle; o[5] = adot; }
+    else if (c.obs_repr == QS_OBS_CDIST_CDISTDOT_NDIST_DISTDOT_NSANGLE_ANGLEDOT) {
+        // get_state.py:190-224: the goal as the camera model sees it from the (noisy) own position -- distance clipped to 0..10, cos / sin of
+        // the measured bearing; the sign of angledot still comes from the exact relative angle.  Own noise stream: aux 0xF0 + site.
+        const float4 n = rng_n4v(g, SITE_CAMERA, drone, 0xF0 + site, 0);
+        float nd, na, s, cc;
+        camera_measure(f, rx, ry, angle, n.x, n.y, nd, na);
+        sincosf(na, &s, &cc);
+        o[2] = clampf(nd, 0.f, 10.f); o[4] = cc; o[5] = s; o[6] = adot;
+    } else { o[4] = rel_angle; o[5] = adot; }
 }
 
 // simulate_camera_measurement_vect (quadrotor_multi_rewards.py:278-324): the two tangent rays from the camera to a disc of
@@ -445,7 +455,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
             any_done = any_cap || timeout || bad_now;
             // ---- self observation of the last executed sub-step (goal = evader before scenario.step)
             if (valid && (any_done || sub == f.substeps - 1)) {
-                fork_self_obs(c, g, SITE_SENSOR, d, q, angle, ang_vel, orow);
+                fork_self_obs(c, f, g, SITE_SENSOR, d, q, angle, ang_vel, orow);
                 // infos[i]['goal_dist'] of the last executed sub-step (quadrotor_single_rewards.py:457): 3-D distance to self.goal
                 if (__builtin_expect(P.rew_info != nullptr, 0))
                     P.rew_info[2 * gi] = make_float4(norm3f(q.p[0] - q.goal[0], q.p[1] - q.goal[1], q.p[2] - q.goal[2]), 0.f, 0.f, 0.f);
@@ -547,7 +557,7 @@ __global__ void __launch_bounds__(128, 2) fork_step_kernel(const __grid_constant
         q.flags = 0; q.colmask = 0u;
         tick = 0;
         fflags = FF_PLACED;
-        if (valid) fork_self_obs(c, g, SITE_SENSOR_RESET, d, q, angle, ang_vel, orow);
+        if (valid) fork_self_obs(c, f, g, SITE_SENSOR_RESET, d, q, angle, ang_vel, orow);
         fork_neighbor_obs<KG>(c, f, g, d, lane, gmask, valid, q, angle, hsnap, orow + c.S, stage);   // self.heading is NOT refreshed by reset()
     }
     // ---- write back
@@ -624,7 +634,7 @@ __global__ void __launch_bounds__(128, 2) fork_reset_kernel(const __grid_constan
     if (valid) {
         store_drone(P, gi, q, true);
         F.plane[FP_HEADING][gi] = make_float4(angle, ang_vel, hsnap, 0.f);
-        fork_self_obs(c, g, SITE_SENSOR_RESET, d, q, angle, ang_vel, orow);
+        fork_self_obs(c, f, g, SITE_SENSOR_RESET, d, q, angle, ang_vel, orow);
     }
     if (sel && d == 0) {
         int *pe = P.ecnt + env * EC_COUNT;

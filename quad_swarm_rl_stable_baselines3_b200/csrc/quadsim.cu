@@ -185,7 +185,7 @@ static void fill_const(const qs_config &c, DevConst &d)
     d.ep_len = c.ep_len; d.sim_steps = c.sim_steps; d.svd_period = c.svd_period;
     d.obst_L = c.obst_area_len; d.obst_W = c.obst_area_wid; d.M = c.num_obstacles;
     if (c.env_mode == QS_MODE_FORK) {
-        d.S = c.obs_repr == QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_SANGLE_ANGLEDOT ? 7 : 6;
+        d.S = (c.obs_repr == QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_SANGLE_ANGLEDOT || c.obs_repr == QS_OBS_CDIST_CDISTDOT_NDIST_DISTDOT_NSANGLE_ANGLEDOT) ? 7 : 6;
         int W = 0;
         switch (c.neighbor_obs_type) {
             case QS_NEIGHBOR_DIST_ANGLE: W = 2; break;
@@ -267,7 +267,7 @@ static int validate(const qs_config *c, std::string &why)
         if (c->num_envs < 1) { why = "num_envs < 1"; return 0; }
         if (c->num_agents < 1 || c->num_agents > QS_MAX_AGENTS) { why = "num_agents out of [1, 32]"; return 0; }
         if (c->scenario != QS_SCENARIO_DYNAMIC_REPULSIVE) { why = "fork mode supports quads_mode dynamic_repulsive only"; return 0; }
-        if (c->obs_repr < QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_ANGLE_ANGLEDOT || c->obs_repr > QS_OBS_AW_AWDOT_DIST_DISTDOT_ANGLE_ANGLEDOT) { why = "fork mode needs a fork obs_repr"; return 0; }
+        if (c->obs_repr < QS_OBS_CDIST_CDISTDOT_DIST_DISTDOT_ANGLE_ANGLEDOT || c->obs_repr > QS_OBS_CDIST_CDISTDOT_NDIST_DISTDOT_NSANGLE_ANGLEDOT) { why = "fork mode needs a fork obs_repr"; return 0; }
         if (c->neighbor_obs_type != QS_NEIGHBOR_NONE && (c->neighbor_obs_type < QS_NEIGHBOR_DIST_ANGLE || c->neighbor_obs_type > QS_NEIGHBOR_NDIST_NSANGLE)) { why = "fork mode needs a fork neighbor_obs_type"; return 0; }
         if (c->neighbor_obs_type == QS_NEIGHBOR_NDIST_NSANGLE && (c->fork.cam_num < 1 || !(c->fork.cam_focal_length > 0) || !(c->fork.cam_target_size > 0))) { why = "bad camera parameters"; return 0; }
         if (c->neighbor_visible_num < 0 || c->neighbor_visible_num > c->num_agents - 1) { why = "neighbor_visible_num out of range"; return 0; }

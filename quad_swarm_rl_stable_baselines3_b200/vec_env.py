@@ -74,6 +74,7 @@ def make_spaces(cfg: QuadSimConfig):
         "omega": ([-wmax] * 3, [wmax] * 3), "floor": ([0.0], [H]), "wall": ([0.0] * 6, [5.0] * 6),
         "cdist": ([0.0], [L / 2]), "cdistdot": ([-vmax], [vmax]), "dist": ([-L / 2], [L / 2]), "distdot": ([-vmax], [vmax]),
         "angle": ([-math.pi], [math.pi]), "sangle": ([-1.0] * 2, [1.0] * 2), "angledot": ([-wmax], [wmax]),
+        "ndist": ([-L / 2], [L / 2]), "nsangle": ([-1.0] * 2, [1.0] * 2),
         "aw": ([-math.pi], [math.pi]), "awdot": ([-wmax], [wmax]),
         "rxyz": ([-v for v in room], room), "rvxyz": ([-2 * vmax] * 3, [2 * vmax] * 3), "octmap": ([-10.0] * 9, [10.0] * 9),
     }

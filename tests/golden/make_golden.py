@@ -274,6 +274,10 @@ FORK_TRACES = {
     # camera model + ranking (2 nearest of 5): the ranking pass draws its own pixel noise
     "fork_k6_cam_v2": dict(env=dict(num_agents=6, episode_duration=0.8, initial_capture_radius=2.2, pixel_noise_cam=1.0,
                                     n_cameras=4, neighbor_obs_type="ndist_nsangle", neighbor_visible_num=2), steps=30, radius={}),
+    # the noisy self representation (get_state.py:190-224; commented out in sb_train.py:123 but a valid cfg.obs_repr), pixel noise on
+    "fork_k3_nself": dict(salt=5, env=dict(num_agents=3, episode_duration=0.8, initial_capture_radius=2.3, pixel_noise_cam=0.7,
+                                   obs_repr="cdist_cdistdot_ndist_distdot_nsangle_angledot", neighbor_obs_type="ndist_nsangle"),
+                          steps=40, radius={}),
     # relative-heading neighbour types
     "fork_k4_heading": dict(env=dict(num_agents=4, episode_duration=0.8, initial_capture_radius=2.4,
                                      neighbor_obs_type="dist_angle_heading"), steps=40, radius={}),

@@ -33,6 +33,8 @@ FORK_CONFIGS = {
                         obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot"),
     "fork_k6_cam_v2": dict(num_envs=12, num_agents=6, ep_time=0.4, capture_radius=2.2, neighbor_obs_type="ndist_nsangle",
                            neighbor_visible_num=2, camera=dict(cam_pixel_noise=1.0, cam_num=4)),
+    "fork_k3_nself": dict(num_envs=20, num_agents=3, ep_time=0.4, capture_radius=2.3, neighbor_obs_type="ndist_nsangle",
+                          obs_repr="cdist_cdistdot_ndist_distdot_nsangle_angledot", camera=dict(cam_pixel_noise=0.7)),
     "fork_k4_heading": dict(num_envs=16, num_agents=4, ep_time=0.4, capture_radius=2.4, neighbor_obs_type="dist_angle_heading"),
     "fork_k5_sheading_v3": dict(num_envs=10, num_agents=5, ep_time=0.4, capture_radius=2.2, neighbor_obs_type="dist_sangle_sheading",
                                 neighbor_visible_num=3, obs_repr="cdist_cdistdot_dist_distdot_sangle_angledot"),

@@ -233,7 +233,7 @@ def test_env_trace(golden_dir, name):
 # ------------------------------------------------------------------------------------------------------------------
 # fork mode (quadrotor_multi_rewards.py: PID pre-controller, 8 control steps per call, capture task)
 # ------------------------------------------------------------------------------------------------------------------
-FORK_TRACE_NAMES = ["fork_k4", "fork_k1", "fork_k8_sangle", "fork_k4_cam", "fork_k6_cam_v2", "fork_k4_heading", "fork_k5_sheading_v3"]
+FORK_TRACE_NAMES = ["fork_k4", "fork_k1", "fork_k8_sangle", "fork_k4_cam", "fork_k6_cam_v2", "fork_k4_heading", "fork_k5_sheading_v3", "fork_k3_nself"]
 
 
 def fork_cfg_from_kwargs(kw):
