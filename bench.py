@@ -447,7 +447,7 @@ def main():
 
                 fp = algo.fused
                 rows = algo.obs.shape[0]
-                flop_row = 4.0 * (fp.S * 256 + 65536 + fp.V * ((fp.S + fp.W) * 256 + 65536) + 262144 + 256 * (fp.A + 1))
+                flop_row = 4.0 * (fp.S * 256 + 65536 + fp.V * (fp.W * 256 + 65536) + 262144 + 256 * (fp.A + 1))
                 ms_f, ms_t = ev_ms(lambda: fp.forward(algo.obs), 10), ev_ms(eager, 3)
                 try:
                     tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
@@ -474,6 +474,14 @@ def main():
             threads = os.cpu_count() or 1
             v, sample = cpu_port_throughput(ENVS_CFG2, AGENTS, 12.0, threads)
             cpu = {"value": v, "unit": "drone-steps/s", "cores": threads, "kind": "port", "sample": sample}
+            try:      # the Python reference cannot travel to this box: its per-core rate relative to the port was measured where it exists
+                rv = json.load(open(os.path.join(ROOT, "profiles", "r2_reference_vs_port.json")))
+                k = next(k for k in rv if k.startswith("cfg2"))
+                cpu["python_reference"] = {"port_over_reference_per_core": rv[k]["port_over_reference"],
+                                           "reference_drone_steps_per_s_per_core": rv[k]["reference_drone_steps_per_s_per_core"],
+                                           "source": "profiles/r2_reference_vs_port.json (build container, numba JIT on, 1 core; profiles/tools/ref_vs_port.py)"}
+            except Exception:
+                pass
         line = {
             "metric": "drone-steps/sec", "value": value, "unit": "drone-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -14,7 +14,7 @@
  *                            QuadMultiEncoder.forward                           quad_multi_model.py:333-354,
  *                            QuadNeighborhoodEncoderDeepsets.forward            quad_multi_model.py:16-41
  *
- * Architecture built: self encoder S -> 256 -> 256, deep-sets neighbour encoder (S + W) -> 256 -> 256 averaged over V neighbours,
+ * Architecture built: self encoder S -> 256 -> 256, deep-sets neighbour encoder ('mean_embed') W -> 256 -> 256 averaged over V neighbours,
  * feed-forward 512 -> 512, all tanh; heads 512 -> A (actor) and 512 -> 1 (critic).  bf16 operands, fp32 accumulation
  * (tcgen05 tensor cores); biases, heads and outputs fp32.  Sampling and log-probabilities stay with the caller (state-independent
  * log-std diagonal Gaussian, ActorCriticPolicyCustom.py:312).
@@ -49,7 +49,7 @@ typedef struct {
 typedef struct {
     const float *self_w1, *self_b1; /* [256, S], [256] */
     const float *self_w2, *self_b2; /* [256, 256], [256] */
-    const float *nbr_w1, *nbr_b1;   /* [256, S + W], [256]   (ignored when num_nbr == 0) */
+    const float *nbr_w1, *nbr_b1;   /* [256, W], [256]   (ignored when num_nbr == 0) */
     const float *nbr_w2, *nbr_b2;   /* [256, 256], [256] */
     const float *ff_w, *ff_b;       /* [512, 512], [512]; input = [self encoder | neighbour encoder] */
     const float *head_w, *head_b;   /* actor: [A, 512], [A]; critic: [1, 512], [1] */

@@ -23,7 +23,7 @@ pol = QuadActorCritic(cfg).to(dev)
 fp = FusedPolicy(pol, dev)
 obs = torch.randn(rows, 54, device=dev)
 S, W, V, A = fp.S, fp.W, fp.V, fp.A
-flop_row = 2 * 2 * (S * 256 + 256 * 256 + V * ((S + W) * 256 + 256 * 256) + 512 * 512 + 512 * (A + 1) / 2)
+flop_row = 2 * 2 * (S * 256 + 256 * 256 + V * (W * 256 + 256 * 256) + 512 * 512 + 512 * (A + 1) / 2)
 
 
 def timed(fn):
@@ -53,7 +53,7 @@ def eager_bf16():
 
 
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-out = {"rows": rows, "flop_per_row": flop_row, "policy": f"2 towers x (self {S}-256-256, deep-sets {S + W}-256-256 x {V}, ff 512-512, heads {A}/1)"}
+out = {"rows": rows, "flop_per_row": flop_row, "policy": f"2 towers x (self {S}-256-256, deep-sets {W}-256-256 x {V}, ff 512-512, heads {A}/1)"}
 for name, fn in (("fused_tcgen05", lambda: fp.forward(obs)), ("torch_bf16_autocast", eager_bf16), ("torch_fp32", eager_fp32)):
     med, best = timed(fn)
     out[name] = {"ms_median": med, "ms_min": best, "rows_per_s": rows / med * 1e3, "tflops": flop_row * rows / med * 1e-9,

@@ -3,7 +3,7 @@
 // What it replaces: the per-step forward of the reference's `ActorCriticPolicyCustomSeparateWeights`
 // (swarm_rl/models/ActorCriticPolicyCustom.py:284-556) with one `QuadMultiEncoder` per tower
 // (swarm_rl/models/quad_multi_model.py:250-354): self-observation MLP S -> 256 -> 256 (tanh), deep-sets neighbour encoder
-// phi([self, nbr_j]) = (S + W) -> 256 -> 256 (tanh) averaged over the V visible neighbours (quad_multi_model.py:16-41), feed-forward
+// phi(nbr_j) = W -> 256 -> 256 (tanh) averaged over the V visible neighbours (quad_multi_model.py:23-41), feed-forward
 // 512 -> 512 (tanh), then the action-mean head (512 -> A) of the actor tower and the value head (512 -> 1) of the critic tower.
 // This is the one dense contraction of the system: ~3.06 MFLOP per drone row, 1.6 TFLOP per 65536 x 8 step.
 //
@@ -23,8 +23,9 @@
 //   both 2048 clk per 128 x 256 layer, the MMA 2048 clk as well), not by their sum.  Feed-forward: four N = 128 quarters ping-pong
 //   between the two accumulators; A = [self-encoder output | neighbour mean] in the two activation regions.
 //   Weight images are pre-packed on the device (qp_set_weights) into the canonical no-swizzle K-major core-matrix layout (8 rows x 16
-//   bytes), in the order the kernel consumes them.  The first layers' K is laid out [self (24) | neighbour (8)], so the self part of
-//   the observation tile is written once per tile and each neighbour pass rewrites one 16-byte chunk per row.
+//   bytes), in the order the kernel consumes them.  The first layers share one 128 x 32 observation tile per stream, K laid out
+//   [self (24) | neighbour (8)]: the self encoder's image has zeros in the neighbour slots and the neighbour encoder's in the self slots,
+//   so the self part is written once per tile and each neighbour pass rewrites one 16-byte chunk per row.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -759,7 +760,7 @@ int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *str
     if (!p || !w) return qp_fail(p, QP_ERR_NULL, "qp_set_weights: null argument");
     if (tower < 0 || tower > 1) return qp_fail(p, QP_ERR_BAD_CONFIG, "qp_set_weights: tower must be 0 (actor) or 1 (critic)");
     cudaStream_t s = (cudaStream_t)stream;
-    const int S = p->cfg.self_dim, SW = p->cfg.self_dim + p->cfg.nbr_dim;
+    const int S = p->cfg.self_dim;
     const int n_out = tower == 0 ? p->cfg.act_dim : 1;
     uint8_t *img = p->wimg[tower];
     // one (N = 128) x kc image
@@ -768,7 +769,8 @@ int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *str
     };
     // resident block: neighbour L1 halves, neighbour L2 (half, K chunk)
     if (p->cfg.num_nbr > 0) {
-        for (int h = 0; h < 2; ++h) pack(w->nbr_w1, H, SW, NH * h, 0, 32, SELF_PAD, S, img + (size_t)h * CHUNK1);
+        // phi reads the neighbour row alone: its W inputs sit in K slots 24..31 (the x tile's neighbour chunk), the self slots meet zeros
+        for (int h = 0; h < 2; ++h) pack(w->nbr_w1, H, p->cfg.nbr_dim, NH * h, 0, 32, SELF_PAD, 0, img + (size_t)h * CHUNK1);
         for (int h = 0; h < 2; ++h)
             for (int c = 0; c < 4; ++c) pack(w->nbr_w2, H, H, NH * h, 64 * c, 64, 0, 0, img + 2 * CHUNK1 + (size_t)(h * 4 + c) * CHUNK);
     }

@@ -28,6 +28,7 @@ def supported(policy) -> bool:
     enc = policy.actor
     return (enc.kind in ("mean_embed", "none") and enc.O == 0 and enc.self_encoder[0].out_features == 256
             and enc.S <= 24 and enc.W <= 8 and policy.action_net.out_features <= 8 and (enc.kind == "none" or enc.neighbor[0].out_features == 256))
+    # 'attention' (the fork's default, quad_multi_model.py:42-102) and 'mlp' stay on the torch path
 
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_values: torch.Tensor, gamma: float, lam: float):

@@ -53,11 +53,16 @@ class QuadEncoder(nn.Module):
         if self.kind == "mlp":                       # QuadNeighborhoodEncoderMlp (:104-122)
             self.neighbor = _mlp([self.W * self.V, neighbor_hidden, neighbor_hidden, neighbor_hidden])
             out += neighbor_hidden
-        elif self.kind == "mean_embed":              # QuadNeighborhoodEncoderDeepsets (:16-41): phi([self, nbr]) averaged over neighbours
-            self.neighbor = _mlp([self.S + self.W, neighbor_hidden, neighbor_hidden])
+        elif self.kind == "mean_embed":              # QuadNeighborhoodEncoderDeepsets (:23-41): phi(nbr_j) -- the neighbour row alone -- averaged
+            self.neighbor = _mlp([self.W, neighbor_hidden, neighbor_hidden])
+            out += neighbor_hidden
+        elif self.kind == "attention":               # QuadNeighborhoodEncoderAttention (:42-102), the fork's default (global_cfg.py:71)
+            self.neighbor = _mlp([self.S + self.W, neighbor_hidden, neighbor_hidden])                       # e_i = phi([self, nbr_i])
+            self.neighbor_value = _mlp([neighbor_hidden, neighbor_hidden, neighbor_hidden])                 # h_i
+            self.attention = nn.Sequential(*_mlp([2 * neighbor_hidden, neighbor_hidden, neighbor_hidden]), nn.Linear(neighbor_hidden, 1))   # alpha_i
             out += neighbor_hidden
         elif self.kind != "none":
-            raise NotImplementedError(f"neighbor_encoder {neighbor_encoder!r} (available: mlp, mean_embed)")
+            raise NotImplementedError(f"neighbor_encoder {neighbor_encoder!r} (available: mlp, mean_embed, attention)")
         if self.O:
             self.obstacle = _mlp([self.O, hidden, hidden])
             out += hidden
@@ -70,9 +75,19 @@ class QuadEncoder(nn.Module):
         if self.kind == "mlp":
             parts.append(self.neighbor(obs[:, self.S:self.S + self.W * self.V]))
         elif self.kind == "mean_embed":
-            nb = obs[:, self.S:self.S + self.W * self.V].reshape(-1, self.V, self.W)
-            x = torch.cat([s.unsqueeze(1).expand(-1, self.V, -1), nb], dim=2)
-            parts.append(self.neighbor(x.reshape(-1, self.S + self.W)).reshape(-1, self.V, self.neighbor[-2].out_features).mean(dim=1))
+            nb = obs[:, self.S:self.S + self.W * self.V].reshape(-1, self.W)
+            parts.append(self.neighbor(nb).reshape(-1, self.V, self.neighbor[-2].out_features).mean(dim=1))
+        elif self.kind == "attention":
+            # Quirk replicated (quad_multi_model.py:79-96): the neighbour rows are flattened batch-major ([b0 n0, b0 n1, ...]) but the self
+            # observation and the mean embedding are tiled with .repeat(V, 1) ([b0, b1, ..., b0, b1, ...]), so for batch sizes > 1 row
+            # b*V + j is paired with the self observation of batch element (b*V + j) mod n.  Exact only for n == 1; kept as the reference has it.
+            n, H = s.shape[0], self.neighbor[-2].out_features
+            nb = obs[:, self.S:self.S + self.W * self.V].reshape(-1, self.W)
+            e = self.neighbor(torch.cat([s.repeat(self.V, 1), nb], dim=1))                     # e_i
+            h = self.neighbor_value(e)                                                          # h_i
+            em = e.reshape(n, -1, H).mean(dim=1)                                                # e_m
+            alpha = torch.softmax(self.attention(torch.cat([e, em.repeat(self.V, 1)], dim=1)).view(n, -1), dim=1).view(-1, 1)
+            parts.append((alpha * h).view(n, -1, H).sum(dim=1))
         if self.O:
             parts.append(self.obstacle(obs[:, self.S + self.W * self.V:]))
         return self.feed_forward(torch.cat(parts, dim=1))

@@ -42,8 +42,7 @@ def emulated_forward(pol, obs):
             nb = obs[:, enc.S:enc.S + enc.W * enc.V].reshape(-1, enc.V, enc.W)
             acc = 0
             for j in range(enc.V):
-                x = torch.cat([s, nb[:, j]], dim=1)
-                acc = acc + torch.tanh(lin(enc.neighbor[2], torch.tanh(lin(enc.neighbor[0], x))))
+                acc = acc + torch.tanh(lin(enc.neighbor[2], torch.tanh(lin(enc.neighbor[0], nb[:, j]))))
             m = acc * (1.0 / enc.V)
         else:
             m = torch.zeros_like(h)

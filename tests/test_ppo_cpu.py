@@ -110,3 +110,40 @@ def test_two_rank_gradient_allreduce_keeps_replicas_identical(tmp_path):
     torch.testing.assert_close(a["w1"], b["w1"], rtol=0, atol=1e-6)   # averaged gradients -> replicas stay in lock-step
     assert a["hist"][-1]["agent_steps"] == 2 * 2 * (2 * 2) * 6 and all(np.isfinite(r["pg"]) for r in a["hist"])
     assert a["hist"][-1]["episodes"] == b["hist"][-1]["episodes"]      # episode stats were reduced over both ranks
+
+
+# ---- the encoder against the reference's own module ---------------------------------------------------------------------
+# tests/golden/policy_encoder.npz (tests/golden/make_policy_golden.py): weights, observations and outputs of the unmodified
+# swarm_rl/models/quad_multi_model.py:QuadMultiEncoder for every neighbour encoder type.  Parameter-name map reference -> ours.
+_REF_TO_OURS = {
+    "self_encoder.": "self_encoder.", "feed_forward.": "feed_forward.", "obstacle_encoder.": "obstacle.",
+    "neighbor_encoder.embedding_mlp.": "neighbor.", "neighbor_encoder.neighbor_mlp.": "neighbor.",
+    "neighbor_encoder.neighbor_value_mlp.": "neighbor_value.", "neighbor_encoder.attention_mlp.": "attention.",
+}
+_ENCODER_CASES = {
+    "mean_embed_k8": (dict(num_agents=8), "mean_embed"),
+    "attention_k8": (dict(num_agents=8), "attention"),
+    "mlp_k8": (dict(num_agents=8), "mlp"),
+    "mean_embed_obst": (dict(num_agents=8, quads_mode="mix", use_obstacles=True, obs_repr="xyz_vxyz_R_omega_floor", neighbor_visible_num=2), "mean_embed"),
+    "no_neighbours": (dict(num_agents=1, neighbor_obs_type="none", neighbor_visible_num=0), "mean_embed"),
+}
+
+
+@pytest.mark.parametrize("name", list(_ENCODER_CASES))
+def test_encoder_matches_the_reference_module(name, golden_dir):
+    import os
+    from quad_swarm_rl_stable_baselines3_b200.ppo import QuadEncoder
+    g = np.load(os.path.join(golden_dir, "policy_encoder.npz"))
+    kw, kind = _ENCODER_CASES[name]
+    enc = QuadEncoder(QuadSimConfig(num_envs=2, **kw), hidden=64, neighbor_hidden=48, neighbor_encoder=kind)
+    sd = {}
+    for key in g.files:
+        if not key.startswith(name + "/w/"):
+            continue
+        ref = key[len(name) + 3:]
+        pre = next(p for p in _REF_TO_OURS if ref.startswith(p))
+        sd[_REF_TO_OURS[pre] + ref[len(pre):]] = torch.from_numpy(g[key])
+    enc.load_state_dict(sd, strict=True)                          # every parameter of ours has a counterpart in the reference, and vice versa
+    with torch.no_grad():
+        y = enc(torch.from_numpy(g[name + "/obs"]))
+    np.testing.assert_allclose(y.numpy(), g[name + "/out"], rtol=0, atol=2e-6)
