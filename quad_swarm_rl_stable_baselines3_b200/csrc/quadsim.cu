@@ -449,7 +449,10 @@ int qs_create(const qs_config *cfg, int device, qs_env **out)
         e->hot_cnt[b3] = (int *)(b + o_hot[b3]); e->hot_list[b3] = e->hot_cnt[b3] + 64; e->hot_flag[b3] = e->hot_list[b3] + e->hot_cap;
     }
     e->hot_phase = 0;
-    e->hot = !e->fork;
+    // reset-first scheduling pays where a reset is expensive (obstacle map generation, formation scenarios): cfg3 101.5 -> 98.8 us, mix
+    // 108.7 -> 105.4 us; with the cheap static_same_goal reset it costs 1 % (cfg2 77.4 -> 78.0 us) and with 32-lane groups 5 % (cfg4
+    // 109.4 -> 114.6 us: one env per warp, the listed tiles are 4x as many) -- profiles/README.md round 2.  Compiled out there (HOT_OK).
+    e->hot = !e->fork && (e->feat & 5) != 0 && e->KG < 32;
     if (const char *hv = getenv("QS_HOT")) e->hot = e->hot && atoi(hv) != 0;   // tuning knob: 0 = plain block order
     if (e->fork) {
         for (int p = 0; p < FP_COUNT; ++p) e->fp.plane[p] = (float4 *)(b + fplane_off[p]);

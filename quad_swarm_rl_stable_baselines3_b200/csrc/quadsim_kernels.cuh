@@ -1242,7 +1242,8 @@ __global__ void __launch_bounds__(QS_STEP_MAXTHREADS, QS_STEP_MINBLOCKS) step_ke
 #ifndef QS_HOT_MODE
 #define QS_HOT_MODE 1           // 0: reset-first scheduling compiled out
 #endif
-    const bool HOT = QS_HOT_MODE && !PERSIST && QS_EARLY_RNG && P.hot_flag_cur != nullptr;   // warp-uniform (the flag travels with the early-draw scalars)
+    constexpr bool HOT_OK = QS_HOT_MODE && !PERSIST && QS_EARLY_RNG && (FEAT & 5) != 0 && KG < 32;     // same rule as qs_create's e->hot
+    const bool HOT = HOT_OK && P.hot_flag_cur != nullptr;   // warp-uniform (the flag travels with the early-draw scalars)
     bool hot_role = false;
     if (HOT) {
         if (blockIdx.x == 0 && threadIdx.x == 0) *P.hot_cnt_clear = 0;  // the buffer the previous step consumed: the next step produces into it
