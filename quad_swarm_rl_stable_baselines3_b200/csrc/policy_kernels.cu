@@ -44,6 +44,7 @@ constexpr int TILE_M = 128;
 constexpr int NH = 128;                     // N of one MMA group (half an encoder layer, a quarter of the feed-forward)
 constexpr int CHUNK = 16 * 1024;            // one (N = 128) x (K = 64) bf16 weight image
 constexpr int CHUNK1 = 8 * 1024;            // one (N = 128) x (K = 32) image (first layers)
+constexpr int STAGGER_CLK = 0;                // start offset between neighbouring blocks (tuning knob QP_STAGGER; measured: no gain, see below)
 constexpr int STAGES = 12;                  // ring slots of one 16 KB chunk: 9 hold the neighbour encoder during its passes, all 12 stream otherwise
 constexpr int MAX_ACT = 8;
 constexpr int SELF_PAD = 24, NBR_PAD = 8;   // K layout of the first layers: [self | neighbour]
@@ -66,6 +67,7 @@ struct Args {
     const uint8_t *wimg[2];                 // per tower: [resident block | streamed block]
     const TowerParams *params[2];
     float *mean, *value;                    // [n, A], [n]
+    int stagger;                            // clocks between the start of neighbouring blocks (0 = off)
     long long *trace;                       // debug (qp_debug_trace): clock64 stamps of block 0's second tile, tower 0; null = off
 };
 
@@ -119,6 +121,18 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint3
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- tcgen05 ---------------------------------------------------------------------------------------------------------
+// exactly one lane of a converged warp (the compiler then moves MMA operands to uniform registers without a waterfall loop)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
@@ -147,6 +161,7 @@ __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_
 }
 // K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 B contiguous); LBO = distance between the two K-halves of one MMA,
 // SBO = distance between 8-row groups (cute/atom/mma_traits_sm100.hpp, "LayoutType::INTERLEAVE ((8,n),2):((1,SBO),LBO)")
+__device__ __forceinline__ void commit_one(uint64_t *bar) { if (elect_one()) tc_commit(bar); __syncwarp(); }
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
 {
     uint64_t d = 0;
@@ -174,17 +189,23 @@ template <bool FIRST>
 __device__ __noinline__ void issue_chunk_ts(uint32_t acc, uint32_t a_col, uint32_t w_addr)
 {
     const uint64_t bd = DESC_W64 | (uint64_t)(w_addr >> 4);
-    mma_ts(acc, a_col, bd, IDESC, FIRST ? 0u : 1u);
-    mma_ts(acc, a_col + 8u, bd + 16u, IDESC, 1u);
-    mma_ts(acc, a_col + 16u, bd + 32u, IDESC, 1u);
-    mma_ts(acc, a_col + 24u, bd + 48u, IDESC, 1u);
+    if (elect_one()) {
+        mma_ts(acc, a_col, bd, IDESC, FIRST ? 0u : 1u);
+        mma_ts(acc, a_col + 8u, bd + 16u, IDESC, 1u);
+        mma_ts(acc, a_col + 16u, bd + 32u, IDESC, 1u);
+        mma_ts(acc, a_col + 24u, bd + 48u, IDESC, 1u);
+    }
+    __syncwarp();
 }
 // first layers: the 128 x 32 x tile (shared memory) against an (N = 128) x (K = 32) image
 __device__ __noinline__ void issue_l1_ss(uint32_t acc, uint32_t x_addr, uint32_t w_addr)
 {
     const uint64_t ad = DESC_X | (uint64_t)(x_addr >> 4), bd = DESC_W32 | (uint64_t)(w_addr >> 4);
-    mma_ss(acc, ad, bd, IDESC, 0u);
-    mma_ss(acc, ad + 256u, bd + 16u, IDESC, 1u);           // next K-half of the x tile: 2 chunks of 2048 B
+    if (elect_one()) {
+        mma_ss(acc, ad, bd, IDESC, 0u);
+        mma_ss(acc, ad + 256u, bd + 16u, IDESC, 1u);       // next K-half of the x tile: 2 chunks of 2048 B
+    }
+    __syncwarp();
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
 {
@@ -274,6 +295,13 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    // Optional start offset between blocks (off).  The feed-forward phase streams 512 KB per tile and runs at ~42 B/clk per SM (97 clk per MMA
+    // instead of 64); de-phasing the blocks does not change that (QP_STAGGER = 7000 / 14000 / 28000: 2.00 / 2.10 / 2.48 ms vs 1.93 ms) and a
+    // one-block grid streams at the same rate -- it is the per-SM L2 -> shared-memory rate, not contention.
+    if (a.stagger > 0 && gridDim.x > 4 && (blockIdx.x & 3) != 0) {
+        const long long until = clock64() + (long long)(blockIdx.x & 3) * a.stagger;
+        while (clock64() < until) __nanosleep(256);
+    }
     constexpr uint32_t ACC0 = 0, ACC1 = 128, R10 = 256, R11 = 384;      // TMEM columns: stream accumulators, stream activation regions
     const int S = a.S, W = a.W, V = a.V, A = a.A;
     const int n_tiles = (a.n + TILE_M - 1) / TILE_M;
@@ -311,13 +339,13 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
         } else if (warp == 8) {
             for (int tower = 0; tower < 2; ++tower) {
                 // =========================== MMA ISSUER ===========================
-                if (lane == 0) {
+                {                                                            // the whole warp runs the role (uniform control flow and addresses); one elected lane issues
                     const uint32_t ring0 = smem_u32(sm.ring[0]), xb0 = smem_u32(sm.xbuf[0]), xb1 = smem_u32(sm.xbuf[1]);
                     bool tr = false;
                     int tm = 256;
                     auto wait_prev = [&](int s) {                            // the epilogue of the stream's previous item has drained its accumulator
                         if (N_ITEM(s) > 0) { mbar_wait(&sm.epi_done[s], (N_ITEM(s) - 1u) & 1u); tc_fence_after(); }
-                        if (tr) a.trace[tm++] = clock64();
+                        if (tr) { if (lane == 0) a.trace[tm] = clock64(); tm += 1; }
                     };
                     auto ring_take = [&]() -> uint32_t {                     // next streamed chunk has landed
                         const uint32_t slot = n_chunk % STAGES;
@@ -325,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                         tc_fence_after();
                         return slot;
                     };
-                    auto ring_release = [&](uint32_t slot) { tc_commit(&sm.empty[slot]); n_chunk += 1; };
+                    auto ring_release = [&](uint32_t slot) { commit_one(&sm.empty[slot]); n_chunk += 1; };
                     // grouped form: take 4 chunks one by one, release them with 4 commits back to back (a commit between two MMA groups costs
                     // the tensor pipe ~180 clk; grouped, that is paid once per 16 MMAs)
                     uint32_t held[4];
@@ -362,22 +390,22 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                                         issue_chunk_ts<false>(acc, r1 + 64u, w[2]);
                                         issue_chunk_ts<false>(acc, r1 + 96u, w[3]);
                                     }
-                                    tc_commit(&sm.acc_full[s]);
+                                    commit_one(&sm.acc_full[s]);
                                     N_ITEM_INC(s);
-                                    if (tr) a.trace[tm++] = clock64();
+                                    if (tr) { if (lane == 0) a.trace[tm] = clock64(); tm += 1; }
                                 }
                         }
                         if (V > 0)
-                            for (uint32_t i = 0; i < (uint32_t)RES_CHUNKS; ++i) tc_commit(&sm.empty[(nbr0 + i) % STAGES]);      // free once those MMAs complete
+                            for (uint32_t i = 0; i < (uint32_t)RES_CHUNKS; ++i) commit_one(&sm.empty[(nbr0 + i) % STAGES]);      // free once those MMAs complete
                         // ---- self encoder layer 1: halves on the two accumulators, A = x tile of stream 0 (its neighbour chunk meets zero weights)
                         {
                             const uint32_t slot = ring_take();
                             for (int s = 0; s < 2; ++s) {
                                 wait_prev(s);
                                 issue_l1_ss(tmem + (s ? ACC1 : ACC0), xb0, ring0 + slot * (uint32_t)CHUNK + (uint32_t)s * CHUNK1);
-                                tc_commit(&sm.acc_full[s]);
+                                commit_one(&sm.acc_full[s]);
                                 N_ITEM_INC(s);
-                                if (tr) a.trace[tm++] = clock64();
+                                if (tr) { if (lane == 0) a.trace[tm] = clock64(); tm += 1; }
                             }
                             ring_release(slot);
                         }
@@ -395,10 +423,10 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                                 n_chunk += 1;
                             }
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) tc_commit(&sm.empty[held[c]]);
-                            tc_commit(&sm.acc_full[s]);
+                            for (int c = 0; c < 4; ++c) commit_one(&sm.empty[held[c]]);
+                            commit_one(&sm.acc_full[s]);
                             N_ITEM_INC(s);
-                            if (tr) a.trace[tm++] = clock64();
+                            if (tr) { if (lane == 0) a.trace[tm] = clock64(); tm += 1; }
                         }
                         // ---- feed-forward: four quarters of 128 outputs, K = 512: chunks 0-3 read R10 (self encoder), chunks 4-7 R11 (neighbour
                         //      mean, written by the epilogue warps while the first half of quarter 0 runs)
@@ -417,12 +445,12 @@ __global__ void __launch_bounds__(THREADS, 1) policy_forward_kernel(const Args a
                                 n_chunk += 1;
                                 if ((c & 3) == 3) {
 #pragma unroll
-                                    for (int r = 0; r < 4; ++r) tc_commit(&sm.empty[held[r]]);
+                                    for (int r = 0; r < 4; ++r) commit_one(&sm.empty[held[r]]);
                                 }
                             }
-                            tc_commit(&sm.acc_full[s]);
+                            commit_one(&sm.acc_full[s]);
                             N_ITEM_INC(s);
-                            if (tr) a.trace[tm++] = clock64();
+                            if (tr) { if (lane == 0) a.trace[tm] = clock64(); tm += 1; }
                         }
                     }
                 }
@@ -688,6 +716,7 @@ struct qp_policy {
     long long launches;
     long long *trace;
     int max_grid;           // tuning knob QP_MAX_GRID (0 = one block per SM)
+    int stagger;            // tuning knob QP_STAGGER (clocks; default STAGGER_CLK)
     std::string err;
 };
 
@@ -721,6 +750,8 @@ int qp_create(const qp_config *cfg, int device, qp_policy **out)
     qp_policy *p = new qp_policy();
     p->cfg = *cfg; p->device = device; p->launches = 0; p->trace = nullptr; p->max_grid = 0;
     if (const char *g = getenv("QP_MAX_GRID")) p->max_grid = atoi(g);
+    p->stagger = STAGGER_CLK;
+    if (const char *g = getenv("QP_STAGGER")) p->stagger = atoi(g);
     p->wimg[0] = p->wimg[1] = nullptr; p->params[0] = p->params[1] = nullptr;
     cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
     cudaError_t r = cudaSuccess;
@@ -818,6 +849,7 @@ int qp_forward(qp_policy *p, const float *obs, int n, int obs_stride, float *mea
     a.obs = obs; a.n = n; a.stride = obs_stride; a.S = p->cfg.self_dim; a.W = p->cfg.nbr_dim; a.V = p->cfg.num_nbr; a.A = p->cfg.act_dim;
     for (int t = 0; t < 2; ++t) { a.wimg[t] = p->wimg[t]; a.params[t] = p->params[t]; }
     a.mean = mean; a.value = value; a.trace = p->trace;
+    a.stagger = (n >= 8 * p->sms * TILE_M) ? p->stagger : 0;            // only worth it when every block has several tiles
     const int tiles = (n + TILE_M - 1) / TILE_M;
     int grid = tiles < p->sms ? tiles : p->sms;
     if (p->max_grid > 0 && grid > p->max_grid) grid = p->max_grid;
