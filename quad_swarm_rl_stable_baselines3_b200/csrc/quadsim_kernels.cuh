@@ -262,8 +262,10 @@ __device__ __forceinline__ float norm3f(float a, float b, float c) { return sqrt
 // unit vector (c, s) with angle atan2(y, x); atan2(0,0) = 0 -> (1, 0)
 __device__ __forceinline__ void unit_dir(float x, float y, float &c, float &s)
 {
-    float h = sqrtf(x * x + y * y);
-    if (h > 0.0f) { c = x / h; s = y / h; } else { c = 1.0f; s = 0.0f; }
+    // one reciprocal square root instead of a square root and two divisions: in steady state most drones of a random-action rollout sit on
+    // the floor and take this path twice per sub-step (3 % of the step's instructions with the divisions, profiles/README.md round 2)
+    const float hh = x * x + y * y;
+    if (hh > 0.0f) { const float inv = rsqrtf(hh); c = x * inv; s = y * inv; } else { c = 1.0f; s = 0.0f; }
 }
 __device__ __forceinline__ void set_yaw(float *R, float c, float s)
 {
@@ -386,7 +388,7 @@ __device__ __forceinline__ void dynamics_substep(const DevConst &c, const Rng &g
             unit_dir(q.R[0] + 1e-6f, q.R[3], cy, sy);
             set_yaw(q.R, cy, sy);
             float fr = c.mu * (c.mass * 9.81f - fz);
-            if (norm3f(q.v[0], q.v[1], q.v[2]) < 1e-6f) {
+            if (q.v[0] * q.v[0] + q.v[1] * q.v[1] + q.v[2] * q.v[2] < 1e-12f) {      // |v| < 1e-6 (:601)
                 float fm = sqrtf(fx * fx + fy * fy);
                 float fn = fmaxf(fm - fr, 0.0f);
                 if (fn == 0.0f) { fx = 0.f; fy = 0.f; }
