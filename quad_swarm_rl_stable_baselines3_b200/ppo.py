@@ -111,7 +111,8 @@ class QuadActorCritic(nn.Module):
 
     def dist(self, obs):
         mean = self.action_net(self.actor(obs))
-        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean))
+        # validate_args=False: the argument check reads a device boolean on the host (a sync per call, and illegal under graph capture)
+        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean), validate_args=False)
 
     def value(self, obs):
         return self.value_net(self.critic(obs)).squeeze(-1)
@@ -160,6 +161,7 @@ class PPOConfig:
     neighbor_encoder: str = "mean_embed"
     autocast_bf16: bool = False     # bf16 autocast for the dense layers (tensor cores); the simulator stays fp32
     fused_rollout: bool = True      # rollout-time forward on the tcgen05 kernel (fused_policy.py) when the architecture is the one it is built for
+
 
 
 class DevicePPO:
@@ -243,7 +245,26 @@ class DevicePPO:
             q.grad.copy_(self._flat[off:off + q.numel()].view_as(q.grad)); off += q.numel()
 
     # ---- PPO update: minibatches gathered on the device ------------------------------------------------------------
+    def _minibatch_loss(self, obs_mb, act_mb, logp_old_mb, adv_mb, ret_mb, acc):
+        """Clipped-surrogate PPO loss of one minibatch (SB3 PPO.train); adds the five diagnostics to `acc` on the device."""
+        p = self.p
+        if p.normalize_advantage and adv_mb.numel() > 1:
+            adv_mb = (adv_mb - adv_mb.mean()) / (adv_mb.std() + 1e-8)
+        with self._autocast():
+            logp, ent, v = self.policy.evaluate(obs_mb, act_mb)
+        logp, ent, v = logp.float(), ent.float(), v.float()
+        ratio = (logp - logp_old_mb).exp()
+        pg = -torch.min(adv_mb * ratio, adv_mb * ratio.clamp(1 - p.clip_range, 1 + p.clip_range)).mean()
+        vf = torch.nn.functional.mse_loss(v, ret_mb)
+        loss = pg + p.vf_coef * vf - p.ent_coef * ent.mean()
+        with torch.no_grad():
+            acc += torch.stack([pg.detach(), vf.detach(), ent.mean(), (logp_old_mb - logp).mean(), ((ratio - 1).abs() > p.clip_range).float().mean()])
+        return loss
+
     def update(self) -> Dict[str, float]:
+        """PPO.train of SB3: n_epochs passes over the rollout in shuffled minibatches.  Measured on the device (round 2): capturing the
+        minibatch step in CUDA graphs buys 4 % (0.365 -> 0.349 s per 4.2 M samples) -- the step is bound by its ~5.5 ms of GPU work per
+        65536 rows (tanh / cast / reduction kernels around small-K GEMMs), not by launches -- so the plain eager step ships."""
         p = self.p
         t0 = time.perf_counter()
         T, n = self.rew_buf.shape
@@ -256,24 +277,12 @@ class DevicePPO:
             perm = torch.randperm(total, device=self.device)
             for s in range(0, total, p.batch_size):
                 idx = perm[s:s + p.batch_size]
-                a_mb = adv[idx]
-                if p.normalize_advantage and a_mb.numel() > 1:
-                    a_mb = (a_mb - a_mb.mean()) / (a_mb.std() + 1e-8)
-                with self._autocast():
-                    logp, ent, v = self.policy.evaluate(obs[idx], act[idx])
-                logp, ent, v = logp.float(), ent.float(), v.float()
-                ratio = (logp - logp_old[idx]).exp()
-                pg = -torch.min(a_mb * ratio, a_mb * ratio.clamp(1 - p.clip_range, 1 + p.clip_range)).mean()
-                vf = torch.nn.functional.mse_loss(v, ret[idx])
-                loss = pg + p.vf_coef * vf - p.ent_coef * ent.mean()
+                loss = self._minibatch_loss(obs[idx], act[idx], logp_old[idx], adv[idx], ret[idx], acc)
                 self.opt.zero_grad(set_to_none=False)
                 loss.backward()
                 self._allreduce_grads()
                 nn.utils.clip_grad_norm_(self.policy.parameters(), p.max_grad_norm)
                 self.opt.step()
-                with torch.no_grad():
-                    acc += torch.stack([pg.detach(), vf.detach(), ent.mean(), (logp_old[idx] - logp).mean(),
-                                        ((ratio - 1).abs() > p.clip_range).float().mean()])
                 nb += 1
         if self.fused is not None:
             self.fused.sync()                                          # re-pack the updated weights for the next rollout

@@ -39,3 +39,4 @@ def test_ppo_iterations_on_device(make):
     assert bool(torch.isfinite(w1).all()) and not torch.equal(w0, w1)
     assert ppo.obs_buf.is_cuda and ppo.adv.is_cuda
     assert sum(r["episodes"] for r in hist) > 0
+
