@@ -170,3 +170,36 @@ def test_device_ppo_uses_the_fused_rollout():
     with torch.no_grad():
         r = ppo.policy.action_net(ppo.policy.actor(obs))
     assert float((m - r).abs().max()) <= TOL_FP32_MAX
+
+
+def test_two_policies_and_argument_checks():
+    """Two handles alive at once (a training policy and an evaluation copy, as sb_train.py keeps them), interleaved forwards; the C-ABI
+    rejects bad shapes with a message instead of launching."""
+    import ctypes as C
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200 import _capi
+    from quad_swarm_rl_stable_baselines3_b200.fused_policy import FusedPolicy
+    from quad_swarm_rl_stable_baselines3_b200.ppo import QuadActorCritic
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    pa = QuadActorCritic(QuadSimConfig(num_envs=8, num_agents=8)).to(dev)
+    pb = QuadActorCritic(QuadSimConfig.fork_default(num_envs=8)).to(dev)
+    fa, fb = FusedPolicy(pa, dev), FusedPolicy(pb, dev)
+    oa, ob = torch.randn(3000, 54, device=dev), torch.randn(700, pb.actor.S + pb.actor.W * pb.actor.V, device=dev)
+    for _ in range(3):
+        ma, _ = fa.forward(oa)
+        mb, vb = fb.forward(ob)
+    with torch.no_grad():
+        assert float((ma - pa.action_net(pa.actor(oa))).abs().max()) <= TOL_FP32_MAX
+        assert float((mb - pb.action_net(pb.actor(ob))).abs().max()) <= TOL_FP32_MAX
+        assert float((vb - pb.value(ob)).abs().max()) <= TOL_FP32_MAX
+    lib = _capi.lib()
+    mean, value = torch.empty(10, 4, device=dev), torch.empty(10, device=dev)
+    s = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    assert lib.qp_forward(fa._h, oa.data_ptr(), 10, 40, mean.data_ptr(), value.data_ptr(), s) == -2      # stride shorter than S + V*W
+    assert b"obs_stride" in lib.qp_last_error(fa._h)
+    assert lib.qp_forward(fa._h, None, 10, 54, mean.data_ptr(), value.data_ptr(), s) == -1
+    assert lib.qp_forward(fa._h, oa.data_ptr(), 0, 54, mean.data_ptr(), value.data_ptr(), s) == -2
+    with pytest.raises(ValueError):
+        fa.forward(oa.double())
+    fa.close(); fb.close()
