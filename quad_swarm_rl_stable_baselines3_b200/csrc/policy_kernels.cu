@@ -704,6 +704,129 @@ __global__ void gae_kernel(const float *rew, const float *val, const uint8_t *do
     }
 }
 
+// ---- fused bias + tanh of a dense layer and its backward (the PPO update's elementwise work around the cuBLAS GEMMs) -------------------
+// forward:  y = tanh(z + b)            z, y [n, h] (bf16 under autocast, else fp32), b [h] fp32
+// backward: gz = gy * (1 - y^2),  gb[c] += sum_rows gz[., c]   -- one pass instead of tanh_backward + a separate column reduction
+// (eager autograd: 27 % of the update's device time, profiles/r2_ppo_update_kernels.md).  Block = h / 2 threads, one column pair per thread,
+// grid-stride over rows: every row is one contiguous, coalesced segment.
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+    static __device__ __forceinline__ float2 ld(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+    static __device__ __forceinline__ void st(float *p, float2 v) { *reinterpret_cast<float2 *>(p) = v; }
+};
+template <> struct Pair<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat16 *p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p)); }
+    static __device__ __forceinline__ void st(__nv_bfloat16 *p, float2 v) { *reinterpret_cast<__nv_bfloat162 *>(p) = __float22bfloat162_rn(v); }
+};
+template <typename T>
+__global__ void bias_tanh_kernel(const T *z, const float *b, int n, int h, T *y)
+{
+    const int c = 2 * threadIdx.x;
+    if (c >= h) return;
+    const float b0 = b[c], b1 = b[c + 1];
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const float2 v = Pair<T>::ld(z + (size_t)r * h + c);
+        Pair<T>::st(y + (size_t)r * h + c, make_float2(tanhf(v.x + b0), tanhf(v.y + b1)));
+    }
+}
+template <typename T>
+__global__ void bias_tanh_bwd_kernel(const T *gy, const T *y, int n, int h, T *gz, float *gb)
+{
+    const int c = 2 * threadIdx.x;
+    if (c >= h) return;
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const float2 g = Pair<T>::ld(gy + (size_t)r * h + c), t = Pair<T>::ld(y + (size_t)r * h + c);
+        const float2 o = make_float2(g.x * (1.f - t.x * t.x), g.y * (1.f - t.y * t.y));
+        Pair<T>::st(gz + (size_t)r * h + c, o);
+        a0 += o.x; a1 += o.y;
+    }
+    atomicAdd(gb + c, a0);
+    atomicAdd(gb + c + 1, a1);
+}
+
+// 16-byte form (h % 8 == 0): a thread owns 8 adjacent columns, the block's threads form (h / 8 column groups) x (RL row lanes); two rows per
+// lane are in flight per trip.  Column sums: registers -> shared memory across the row lanes -> one atomicAdd per column and block.
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void ld(const float *p, float *v)
+    {
+        const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void st(float *p, const float *v)
+    {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16 *p, float *v)
+    {
+        const uint4 u = *reinterpret_cast<const uint4 *>(p);
+        const uint32_t w[4] = { u.x, u.y, u.z, u.w };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+    }
+    static __device__ __forceinline__ void st(__nv_bfloat16 *p, const float *v)
+    {
+        uint4 u;
+        u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(p) = u;
+    }
+};
+template <typename T>
+__global__ void __launch_bounds__(256) bias_tanh_v8_kernel(const T *z, const float *b, int n, int h, int RL, T *y)
+{
+    const int G = h >> 3, cg = threadIdx.x % G, rl = threadIdx.x / G;
+    float bb[8];
+    Vec8<float>::ld(b + 8 * cg, bb);
+    for (int r = blockIdx.x * RL + rl; r < n; r += gridDim.x * RL) {
+        float v[8];
+        Vec8<T>::ld(z + (size_t)r * h + 8 * cg, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i] + bb[i]);
+        Vec8<T>::st(y + (size_t)r * h + 8 * cg, v);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) bias_tanh_bwd_v8_kernel(const T *gy, const T *y, int n, int h, int RL, T *gz, float *gb)
+{
+    __shared__ float red[256 * 8];
+    const int G = h >> 3, cg = threadIdx.x % G, rl = threadIdx.x / G;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int stride = gridDim.x * RL;
+    int r = blockIdx.x * RL + rl;
+    for (; r + stride < n; r += 2 * stride) {                           // two rows in flight
+        float g0[8], t0[8], g1[8], t1[8];
+        Vec8<T>::ld(gy + (size_t)r * h + 8 * cg, g0); Vec8<T>::ld(y + (size_t)r * h + 8 * cg, t0);
+        Vec8<T>::ld(gy + (size_t)(r + stride) * h + 8 * cg, g1); Vec8<T>::ld(y + (size_t)(r + stride) * h + 8 * cg, t1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { g0[i] *= 1.f - t0[i] * t0[i]; g1[i] *= 1.f - t1[i] * t1[i]; acc[i] += g0[i] + g1[i]; }
+        Vec8<T>::st(gz + (size_t)r * h + 8 * cg, g0); Vec8<T>::st(gz + (size_t)(r + stride) * h + 8 * cg, g1);
+    }
+    if (r < n) {
+        float g0[8], t0[8];
+        Vec8<T>::ld(gy + (size_t)r * h + 8 * cg, g0); Vec8<T>::ld(y + (size_t)r * h + 8 * cg, t0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { g0[i] *= 1.f - t0[i] * t0[i]; acc[i] += g0[i]; }
+        Vec8<T>::st(gz + (size_t)r * h + 8 * cg, g0);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+    __syncthreads();
+    if (rl == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float sum = 0.f;
+            for (int k = 0; k < RL; ++k) sum += red[(k * G + cg) * 8 + i];
+            atomicAdd(gb + 8 * cg + i, sum);
+        }
+    }
+}
+
 }  // namespace qp
 
 using namespace qp;
@@ -838,6 +961,52 @@ int qp_gae(const float *rewards, const float *values, const uint8_t *dones, cons
     gae_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, T, n, gamma, lam, advantages, returns);
     cudaError_t r = cudaGetLastError();
     if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_gae: ") + cudaGetErrorString(r));
+    return QP_OK;
+}
+
+static int bias_tanh_grid(int n)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int g = sms * 8;
+    return n < g ? n : g;
+}
+
+int qp_bias_tanh(const void *z, const float *bias, int n, int h, int is_bf16, void *y, void *stream)
+{
+    if (!z || !bias || !y) return qp_fail(nullptr, QP_ERR_NULL, "qp_bias_tanh: null argument");
+    if (n < 1 || h < 2 || (h & 1) || h > 2048) return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_bias_tanh: h must be even and <= 2048, n >= 1");
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((h & 7) == 0 && (((size_t)z | (size_t)y | (size_t)bias) & 15) == 0) {
+        const int G = h / 8, RL = G >= 256 ? 1 : 256 / G, rows = (n + RL - 1) / RL, grid = bias_tanh_grid(rows);
+        if (is_bf16) bias_tanh_v8_kernel<<<grid, G * RL, 0, s>>>((const __nv_bfloat16 *)z, bias, n, h, RL, (__nv_bfloat16 *)y);
+        else bias_tanh_v8_kernel<<<grid, G * RL, 0, s>>>((const float *)z, bias, n, h, RL, (float *)y);
+    } else if (is_bf16) bias_tanh_kernel<<<bias_tanh_grid(n), h / 2, 0, s>>>((const __nv_bfloat16 *)z, bias, n, h, (__nv_bfloat16 *)y);
+    else bias_tanh_kernel<<<bias_tanh_grid(n), h / 2, 0, s>>>((const float *)z, bias, n, h, (float *)y);
+    cudaError_t r = cudaGetLastError();
+    if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_bias_tanh: ") + cudaGetErrorString(r));
+    return QP_OK;
+}
+
+int qp_bias_tanh_backward(const void *grad_y, const void *y, int n, int h, int is_bf16, void *grad_z, float *grad_bias, void *stream)
+{
+    if (!grad_y || !y || !grad_z || !grad_bias) return qp_fail(nullptr, QP_ERR_NULL, "qp_bias_tanh_backward: null argument");
+    if (n < 1 || h < 2 || (h & 1) || h > 2048) return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_bias_tanh_backward: h must be even and <= 2048, n >= 1");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t r = cudaMemsetAsync(grad_bias, 0, (size_t)h * sizeof(float), s);
+    if (r == cudaSuccess) {
+        if ((h & 7) == 0 && (((size_t)grad_y | (size_t)y | (size_t)grad_z) & 15) == 0) {
+            const int G = h / 8, RL = G >= 256 ? 1 : 256 / G, rows = (n + RL - 1) / RL;
+            int grid = bias_tanh_grid(rows);
+            if (grid > 592) grid = 592;                                 // 4 blocks per SM: fewer, longer blocks = fewer atomics per column
+            if (is_bf16) bias_tanh_bwd_v8_kernel<<<grid, G * RL, 0, s>>>((const __nv_bfloat16 *)grad_y, (const __nv_bfloat16 *)y, n, h, RL, (__nv_bfloat16 *)grad_z, grad_bias);
+            else bias_tanh_bwd_v8_kernel<<<grid, G * RL, 0, s>>>((const float *)grad_y, (const float *)y, n, h, RL, (float *)grad_z, grad_bias);
+        } else if (is_bf16) bias_tanh_bwd_kernel<<<bias_tanh_grid(n), h / 2, 0, s>>>((const __nv_bfloat16 *)grad_y, (const __nv_bfloat16 *)y, n, h, (__nv_bfloat16 *)grad_z, grad_bias);
+        else bias_tanh_bwd_kernel<<<bias_tanh_grid(n), h / 2, 0, s>>>((const float *)grad_y, (const float *)y, n, h, (float *)grad_z, grad_bias);
+        r = cudaGetLastError();
+    }
+    if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_bias_tanh_backward: ") + cudaGetErrorString(r));
     return QP_OK;
 }
 

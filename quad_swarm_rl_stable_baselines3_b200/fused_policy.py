@@ -48,6 +48,41 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, last_v
     return adv, ret
 
 
+def _bt_check(t: torch.Tensor):
+    if t.device.type != "cuda" or t.dtype not in (torch.float32, torch.bfloat16) or t.dim() != 2 or not t.is_contiguous():
+        raise ValueError("bias_tanh works on contiguous 2-D float32 / bfloat16 CUDA tensors")
+
+
+def bias_tanh(z: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """y = tanh(z + bias) in one launch (`qp_bias_tanh`); z [n, h] float32 / bfloat16, bias [h]."""
+    _bt_check(z)
+    b = bias.detach().to(device=z.device, dtype=torch.float32).contiguous()
+    y = torch.empty_like(z)
+    lib = _capi.lib()
+    with torch.cuda.device(z.device):
+        rc = lib.qp_bias_tanh(z.data_ptr(), b.data_ptr(), z.shape[0], z.shape[1], int(z.dtype == torch.bfloat16), y.data_ptr(),
+                              C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"qp_bias_tanh failed ({rc}): {lib.qp_last_error(None).decode()}")
+    return y
+
+
+def bias_tanh_backward(grad_y: torch.Tensor, y: torch.Tensor):
+    """(grad_z, grad_bias) of `bias_tanh` in one pass (`qp_bias_tanh_backward`); grad_bias is float32 [h]."""
+    _bt_check(y)
+    if grad_y.dtype != y.dtype or not grad_y.is_contiguous():
+        grad_y = grad_y.to(y.dtype).contiguous()
+    gz = torch.empty_like(y)
+    gb = torch.empty(y.shape[1], dtype=torch.float32, device=y.device)
+    lib = _capi.lib()
+    with torch.cuda.device(y.device):
+        rc = lib.qp_bias_tanh_backward(grad_y.data_ptr(), y.data_ptr(), y.shape[0], y.shape[1], int(y.dtype == torch.bfloat16), gz.data_ptr(),
+                                       gb.data_ptr(), C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"qp_bias_tanh_backward failed ({rc}): {lib.qp_last_error(None).decode()}")
+    return gz, gb
+
+
 class FusedPolicy:
     def __init__(self, policy, device):
         if not supported(policy):

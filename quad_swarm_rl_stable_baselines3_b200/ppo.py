@@ -31,11 +31,55 @@ import torch.nn as nn
 from .config import NEIGHBOR_OBS_DIM, OBS_REPR_DIM, QuadSimConfig
 
 
+class _BiasTanh(torch.autograd.Function):
+    """tanh(z + b) with a fused backward (`qp_bias_tanh[_backward]`): the bias gradient is reduced in the same pass that applies 1 - y^2."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, z, b):
+        from . import fused_policy
+        y = fused_policy.bias_tanh(z, b)
+        ctx.save_for_backward(y)
+        ctx.bias_dtype = b.dtype
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        from . import fused_policy
+        (y,) = ctx.saved_tensors
+        gz, gb = fused_policy.bias_tanh_backward(gy, y)
+        return gz, gb.to(ctx.bias_dtype)
+
+
+class TanhMLP(nn.Sequential):
+    """nn.Sequential of Linear / Tanh modules (same parameter names).  On CUDA, when gradients are recorded, every (Linear, Tanh) pair runs
+    as a bias-free GEMM (cuBLAS) followed by the fused bias + tanh kernel; everywhere else it is the plain Sequential."""
+    fused = True
+
+    def forward(self, x):
+        if not (self.fused and x.is_cuda and torch.is_grad_enabled() and x.dtype in (torch.float32, torch.bfloat16)):
+            return super().forward(x)
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.Tanh) and m.out_features % 2 == 0 and m.bias is not None:
+                z = torch.nn.functional.linear(x, m.weight)
+                lead = z.shape[:-1]
+                x = _BiasTanh.apply(z.reshape(-1, z.shape[-1]).contiguous(), m.bias).reshape(*lead, z.shape[-1])
+                i += 2
+            else:
+                x = m(x)
+                i += 1
+        return x
+
+
 def _mlp(sizes, act=nn.Tanh):
     layers = []
     for a, b in zip(sizes[:-1], sizes[1:]):
         layers += [nn.Linear(a, b), act()]
-    return nn.Sequential(*layers)
+    return TanhMLP(*layers)
 
 
 class QuadEncoder(nn.Module):
@@ -59,14 +103,14 @@ class QuadEncoder(nn.Module):
         elif self.kind == "attention":               # QuadNeighborhoodEncoderAttention (:42-102), the fork's default (global_cfg.py:71)
             self.neighbor = _mlp([self.S + self.W, neighbor_hidden, neighbor_hidden])                       # e_i = phi([self, nbr_i])
             self.neighbor_value = _mlp([neighbor_hidden, neighbor_hidden, neighbor_hidden])                 # h_i
-            self.attention = nn.Sequential(*_mlp([2 * neighbor_hidden, neighbor_hidden, neighbor_hidden]), nn.Linear(neighbor_hidden, 1))   # alpha_i
+            self.attention = TanhMLP(*_mlp([2 * neighbor_hidden, neighbor_hidden, neighbor_hidden]), nn.Linear(neighbor_hidden, 1))   # alpha_i
             out += neighbor_hidden
         elif self.kind != "none":
             raise NotImplementedError(f"neighbor_encoder {neighbor_encoder!r} (available: mlp, mean_embed, attention)")
         if self.O:
             self.obstacle = _mlp([self.O, hidden, hidden])
             out += hidden
-        self.feed_forward = nn.Sequential(nn.Linear(out, 2 * hidden), nn.Tanh())
+        self.feed_forward = TanhMLP(nn.Linear(out, 2 * hidden), nn.Tanh())
         self.out_size = 2 * hidden
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:

@@ -40,3 +40,40 @@ def test_ppo_iterations_on_device(make):
     assert ppo.obs_buf.is_cuda and ppo.adv.is_cuda
     assert sum(r["episodes"] for r in hist) > 0
 
+
+
+@pytest.mark.parametrize("dtype_name", ["float32", "bfloat16"])
+def test_fused_bias_tanh_layer_matches_autograd(dtype_name):
+    """`TanhMLP` on CUDA (bias-free GEMM + `qp_bias_tanh` / `qp_bias_tanh_backward`) against the plain nn.Sequential it subclasses:
+    outputs, input gradient, weight and bias gradients, with and without bf16 autocast."""
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200.ppo import TanhMLP, _mlp
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    bf16 = dtype_name == "bfloat16"
+    for sizes, n in (([24, 256, 256], 3001), ([6, 48, 48, 48], 517), ([512, 512], 1024)):
+        a = _mlp(sizes).to(dev)
+        assert isinstance(a, TanhMLP)
+        b = torch.nn.Sequential(*[type(m)(m.in_features, m.out_features) if isinstance(m, torch.nn.Linear) else type(m)() for m in a]).to(dev)
+        b.load_state_dict(a.state_dict())
+        with torch.no_grad():
+            for m in a:
+                if isinstance(m, torch.nn.Linear):
+                    m.bias.uniform_(-0.5, 0.5)
+            b.load_state_dict(a.state_dict())
+        x = torch.randn(n, sizes[0], device=dev)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        g = torch.randn(n, sizes[-1], device=dev)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            ya, yb = a(xa), b(xb)
+        (ya.float() * g).sum().backward()
+        (yb.float() * g).sum().backward()
+        tol = 3e-2 if bf16 else 2e-5
+        scale = lambda t: max(1.0, float(t.abs().max()))
+        assert float((ya.float() - yb.float()).abs().max()) <= tol
+        assert float((xa.grad - xb.grad).abs().max()) <= tol * scale(xb.grad)
+        for (na, pa), (nb, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert float((pa.grad - pb.grad).abs().max()) <= tol * scale(pb.grad), (sizes, na)
+    a.fused = False                                                 # the switch gives the plain Sequential back
+    with torch.no_grad():
+        assert torch.equal(a(x), b(x))
