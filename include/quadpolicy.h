@@ -81,6 +81,12 @@ int qp_gae(const float *rewards, const float *values, const uint8_t *dones, cons
 int qp_bias_tanh(const void *z, const float *bias, int n, int h, int is_bf16, void *y, void *stream);
 int qp_bias_tanh_backward(const void *grad_y, const void *y, int n, int h, int is_bf16, void *grad_z, float *grad_bias, void *stream);
 
+/* Tail of the deep-sets neighbour encoder (QuadNeighborhoodEncoderDeepsets.forward, quad_multi_model.py:35-40): y = tanh(z + bias) on [n * V, h]
+ * and mean [n, h] = the average of each group of V consecutive rows, in one pass; the backward takes grad_mean [n, h] and writes
+ * grad_z [n * V, h] = grad_mean[group] / V * (1 - y^2) and grad_bias.  h a multiple of 8, pointers 16-byte aligned. */
+int qp_bias_tanh_mean(const void *z, const float *bias, int n, int V, int h, int is_bf16, void *y, void *mean, void *stream);
+int qp_bias_tanh_mean_backward(const void *grad_mean, const void *y, int n, int V, int h, int is_bf16, void *grad_z, float *grad_bias, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

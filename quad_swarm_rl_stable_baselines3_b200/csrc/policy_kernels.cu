@@ -827,6 +827,72 @@ __global__ void __launch_bounds__(256) bias_tanh_bwd_v8_kernel(const T *gy, cons
     }
 }
 
+// deep-sets tail (quad_multi_model.py:35-40): y = tanh(z + b) on [n * V, h] rows and m = mean over the V rows of each group, in one pass; the
+// backward takes the gradient of m ([n, h]) and produces grad_z = gm[group] / V * (1 - y^2) and the bias gradient without ever materialising the
+// expanded gradient (eager autograd: a [n * V, h] division kernel + tanh_backward + a column reduction).  Thread = (group, 8 columns).
+template <typename T>
+__global__ void __launch_bounds__(256) bias_tanh_mean_kernel(const T *z, const float *b, int n, int V, int h, int RL, T *y, T *m)
+{
+    const int G = h >> 3, cg = threadIdx.x % G, rl = threadIdx.x / G;
+    float bb[8];
+    Vec8<float>::ld(b + 8 * cg, bb);
+    const float inv = 1.0f / (float)V;
+    for (int g = blockIdx.x * RL + rl; g < n; g += gridDim.x * RL) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int j = 0; j < V; ++j) {
+            const size_t off = ((size_t)g * V + j) * h + 8 * cg;
+            float v[8];
+            Vec8<T>::ld(z + off, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i] + bb[i]);
+            Vec8<T>::st(y + off, v);
+            Vec8<T>::ld(y + off, v);                                    // the mean is taken over the values as stored (bf16-rounded), like torch's
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= inv;
+        Vec8<T>::st(m + (size_t)g * h + 8 * cg, acc);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) bias_tanh_mean_bwd_kernel(const T *gm, const T *y, int n, int V, int h, int RL, T *gz, float *gb)
+{
+    __shared__ float red[256 * 8];
+    const int G = h >> 3, cg = threadIdx.x % G, rl = threadIdx.x / G;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const float inv = 1.0f / (float)V;
+    for (int g = blockIdx.x * RL + rl; g < n; g += gridDim.x * RL) {
+        float gv[8];
+        Vec8<T>::ld(gm + (size_t)g * h + 8 * cg, gv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gv[i] *= inv;
+        for (int j = 0; j < V; ++j) {
+            const size_t off = ((size_t)g * V + j) * h + 8 * cg;
+            float t[8], o[8];
+            Vec8<T>::ld(y + off, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { o[i] = gv[i] * (1.f - t[i] * t[i]); acc[i] += o[i]; }
+            Vec8<T>::st(gz + off, o);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+    __syncthreads();
+    if (rl == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float sum = 0.f;
+            for (int k = 0; k < RL; ++k) sum += red[(k * G + cg) * 8 + i];
+            atomicAdd(gb + 8 * cg + i, sum);
+        }
+    }
+}
+
 }  // namespace qp
 
 using namespace qp;
@@ -1007,6 +1073,39 @@ int qp_bias_tanh_backward(const void *grad_y, const void *y, int n, int h, int i
         r = cudaGetLastError();
     }
     if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_bias_tanh_backward: ") + cudaGetErrorString(r));
+    return QP_OK;
+}
+
+int qp_bias_tanh_mean(const void *z, const float *bias, int n, int V, int h, int is_bf16, void *y, void *mean, void *stream)
+{
+    if (!z || !bias || !y || !mean) return qp_fail(nullptr, QP_ERR_NULL, "qp_bias_tanh_mean: null argument");
+    if (n < 1 || V < 1 || h < 8 || (h & 7) || h > 2048 || ((((size_t)z | (size_t)y | (size_t)mean | (size_t)bias) & 15) != 0))
+        return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_bias_tanh_mean: h must be a multiple of 8 (<= 2048), pointers 16-byte aligned");
+    const int G = h / 8, RL = G >= 256 ? 1 : 256 / G, grid = bias_tanh_grid((n + RL - 1) / RL);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (is_bf16) bias_tanh_mean_kernel<<<grid, G * RL, 0, s>>>((const __nv_bfloat16 *)z, bias, n, V, h, RL, (__nv_bfloat16 *)y, (__nv_bfloat16 *)mean);
+    else bias_tanh_mean_kernel<<<grid, G * RL, 0, s>>>((const float *)z, bias, n, V, h, RL, (float *)y, (float *)mean);
+    cudaError_t r = cudaGetLastError();
+    if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_bias_tanh_mean: ") + cudaGetErrorString(r));
+    return QP_OK;
+}
+
+int qp_bias_tanh_mean_backward(const void *grad_mean, const void *y, int n, int V, int h, int is_bf16, void *grad_z, float *grad_bias, void *stream)
+{
+    if (!grad_mean || !y || !grad_z || !grad_bias) return qp_fail(nullptr, QP_ERR_NULL, "qp_bias_tanh_mean_backward: null argument");
+    if (n < 1 || V < 1 || h < 8 || (h & 7) || h > 2048 || ((((size_t)grad_mean | (size_t)y | (size_t)grad_z) & 15) != 0))
+        return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_bias_tanh_mean_backward: h must be a multiple of 8 (<= 2048), pointers 16-byte aligned");
+    const int G = h / 8, RL = G >= 256 ? 1 : 256 / G;
+    int grid = bias_tanh_grid((n + RL - 1) / RL);
+    if (grid > 592) grid = 592;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t r = cudaMemsetAsync(grad_bias, 0, (size_t)h * sizeof(float), s);
+    if (r == cudaSuccess) {
+        if (is_bf16) bias_tanh_mean_bwd_kernel<<<grid, G * RL, 0, s>>>((const __nv_bfloat16 *)grad_mean, (const __nv_bfloat16 *)y, n, V, h, RL, (__nv_bfloat16 *)grad_z, grad_bias);
+        else bias_tanh_mean_bwd_kernel<<<grid, G * RL, 0, s>>>((const float *)grad_mean, (const float *)y, n, V, h, RL, (float *)grad_z, grad_bias);
+        r = cudaGetLastError();
+    }
+    if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_bias_tanh_mean_backward: ") + cudaGetErrorString(r));
     return QP_OK;
 }
 

@@ -83,6 +83,36 @@ def bias_tanh_backward(grad_y: torch.Tensor, y: torch.Tensor):
     return gz, gb
 
 
+def bias_tanh_mean(z: torch.Tensor, bias: torch.Tensor, V: int):
+    """(y, mean): y = tanh(z + bias) on [n * V, h], mean [n, h] over each group of V rows (`qp_bias_tanh_mean`)."""
+    _bt_check(z)
+    n = z.shape[0] // V
+    b = bias.detach().to(device=z.device, dtype=torch.float32).contiguous()
+    y, m = torch.empty_like(z), torch.empty((n, z.shape[1]), dtype=z.dtype, device=z.device)
+    lib = _capi.lib()
+    with torch.cuda.device(z.device):
+        rc = lib.qp_bias_tanh_mean(z.data_ptr(), b.data_ptr(), n, V, z.shape[1], int(z.dtype == torch.bfloat16), y.data_ptr(), m.data_ptr(),
+                                   C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"qp_bias_tanh_mean failed ({rc}): {lib.qp_last_error(None).decode()}")
+    return y, m
+
+
+def bias_tanh_mean_backward(grad_mean: torch.Tensor, y: torch.Tensor, V: int):
+    _bt_check(y)
+    if grad_mean.dtype != y.dtype or not grad_mean.is_contiguous():
+        grad_mean = grad_mean.to(y.dtype).contiguous()
+    gz = torch.empty_like(y)
+    gb = torch.empty(y.shape[1], dtype=torch.float32, device=y.device)
+    lib = _capi.lib()
+    with torch.cuda.device(y.device):
+        rc = lib.qp_bias_tanh_mean_backward(grad_mean.data_ptr(), y.data_ptr(), y.shape[0] // V, V, y.shape[1], int(y.dtype == torch.bfloat16),
+                                            gz.data_ptr(), gb.data_ptr(), C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"qp_bias_tanh_mean_backward failed ({rc}): {lib.qp_last_error(None).decode()}")
+    return gz, gb
+
+
 class FusedPolicy:
     def __init__(self, policy, device):
         if not supported(policy):

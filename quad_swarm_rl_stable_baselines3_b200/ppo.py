@@ -52,6 +52,27 @@ class _BiasTanh(torch.autograd.Function):
         return gz, gb.to(ctx.bias_dtype)
 
 
+class _BiasTanhMean(torch.autograd.Function):
+    """mean over the V rows of each group of tanh(z + b): the deep-sets tail in one pass, backward without the expanded gradient."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, z, b, V):
+        from . import fused_policy
+        y, m = fused_policy.bias_tanh_mean(z, b, V)
+        ctx.save_for_backward(y)
+        ctx.V, ctx.bias_dtype = V, b.dtype
+        return m
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gm):
+        from . import fused_policy
+        (y,) = ctx.saved_tensors
+        gz, gb = fused_policy.bias_tanh_mean_backward(gm, y, ctx.V)
+        return gz, gb.to(ctx.bias_dtype), None
+
+
 class TanhMLP(nn.Sequential):
     """nn.Sequential of Linear / Tanh modules (same parameter names).  On CUDA, when gradients are recorded, every (Linear, Tanh) pair runs
     as a bias-free GEMM (cuBLAS) followed by the fused bias + tanh kernel; everywhere else it is the plain Sequential."""
@@ -120,7 +141,14 @@ class QuadEncoder(nn.Module):
             parts.append(self.neighbor(obs[:, self.S:self.S + self.W * self.V]))
         elif self.kind == "mean_embed":
             nb = obs[:, self.S:self.S + self.W * self.V].reshape(-1, self.W)
-            parts.append(self.neighbor(nb).reshape(-1, self.V, self.neighbor[-2].out_features).mean(dim=1))
+            H = self.neighbor[-2].out_features
+            if TanhMLP.fused and nb.is_cuda and torch.is_grad_enabled() and H % 8 == 0 and len(self.neighbor) == 4:
+                # training on CUDA: layer 1 through the fused bias + tanh, layer 2 + the mean over neighbours in one pass (no [n * V, H] mean / division)
+                h1 = self.neighbor[:2](nb)
+                z2 = torch.nn.functional.linear(h1, self.neighbor[2].weight)
+                parts.append(_BiasTanhMean.apply(z2.contiguous(), self.neighbor[2].bias, self.V))
+            else:
+                parts.append(self.neighbor(nb).reshape(-1, self.V, H).mean(dim=1))
         elif self.kind == "attention":
             # Quirk replicated (quad_multi_model.py:79-96): the neighbour rows are flattened batch-major ([b0 n0, b0 n1, ...]) but the self
             # observation and the mean embedding are tiled with .repeat(V, 1) ([b0, b1, ..., b0, b1, ...]), so for batch sizes > 1 row

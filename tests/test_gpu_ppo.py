@@ -77,3 +77,38 @@ def test_fused_bias_tanh_layer_matches_autograd(dtype_name):
     a.fused = False                                                 # the switch gives the plain Sequential back
     with torch.no_grad():
         assert torch.equal(a(x), b(x))
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_fused_encoder_training_path_matches_plain_autograd(autocast):
+    """The whole tower on CUDA with gradients (TanhMLP pairs + the fused layer-2 / neighbour-mean tail, `qp_bias_tanh_mean[_backward]`) against the
+    same module with the fused path switched off: output and every parameter gradient."""
+    import torch
+    from quad_swarm_rl_stable_baselines3_b200.ppo import QuadEncoder, TanhMLP
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    for kw, hidden, nh in ((dict(num_agents=8), 256, 256), (dict(num_agents=5, neighbor_visible_num=3), 64, 48)):
+        enc = QuadEncoder(QuadSimConfig(num_envs=2, **kw), hidden=hidden, neighbor_hidden=nh, neighbor_encoder="mean_embed").to(dev)
+        with torch.no_grad():
+            for m in enc.modules():
+                if isinstance(m, torch.nn.Linear):
+                    m.bias.uniform_(-0.4, 0.4)
+        D = enc.S + enc.W * enc.V
+        obs = torch.randn(1500 + 7, D, device=dev)
+        g = torch.randn(obs.shape[0], enc.out_size, device=dev)
+        res = []
+        for fused in (True, False):
+            TanhMLP.fused = fused
+            try:
+                enc.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    y = enc(obs)
+                (y.float() * g).sum().backward()
+                res.append((y.detach().float().clone(), {n: p.grad.clone() for n, p in enc.named_parameters()}))
+            finally:
+                TanhMLP.fused = True
+        tol = 4e-2 if autocast else 3e-5
+        assert float((res[0][0] - res[1][0]).abs().max()) <= tol
+        for n in res[0][1]:
+            ref = res[1][1][n]
+            assert float((res[0][1][n] - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max())), (kw, n)
