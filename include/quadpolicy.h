@@ -9,6 +9,7 @@
  *   qp_set_weights           the state_dict of one tower (nn.Linear weights [out, in], biases)
  *   qp_gae                   stable_baselines3 RolloutBuffer.compute_returns_and_advantage as driven by PPO.collect_rollouts
  *                            (swarm_rl/sb_train.py:54-99 -> model.learn): one launch over the device-resident rollout
+ *   qp_bias_tanh[_mean][_backward]   the elementwise half of the dense tanh layers under autograd in the PPO update (evaluate_actions)
  *   qp_forward               ActorCriticPolicyCustom.forward / predict_values: action mean of the actor tower and value of the
  *                            critic tower for a batch of observations           ActorCriticPolicyCustom.py:430-480,
  *                            QuadMultiEncoder.forward                           quad_multi_model.py:333-354,
