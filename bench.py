@@ -426,7 +426,8 @@ def main():
                         "rollout_value": samples / roll_s, "loop_value": samples / (roll_s + upd_s), "unit": "drone-steps/s",
                         "rollout_s": roll_s, "update_s": upd_s,
                         "policy_path": ("rollout forward + GAE: hand-written sm_100a kernels (qp::policy_forward_kernel, tcgen05 / TMEM; qp::gae_kernel); "
-                                        "update: torch autograd, bf16 autocast") if algo.fused is not None else "torch (bf16 autocast)",
+                                        "update: torch autograd + cuBLAS under bf16 autocast with the elementwise work on qp::bias_tanh* kernels") if algo.fused is not None
+                                       else "torch (bf16 autocast)",
                         "simulator_launches_per_env_step": 1}
             if algo.fused is not None:
                 # the rollout's dense forward alone, device-timed: fused tcgen05 kernel vs the torch module it replaces (same weights, same rows)
