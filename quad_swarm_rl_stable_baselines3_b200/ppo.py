@@ -301,20 +301,21 @@ class DevicePPO:
         return {"rollout_s": time.perf_counter() - t0, "mean_reward": float(self.rew_buf.mean()),
                 "done_frac": float(self.done_buf.float().mean())}
 
+    def _flatten_grads(self):
+        """Every parameter's .grad becomes a view into one flat buffer (once): the gradient all-reduce is then ONE NCCL call on that buffer
+        with no gather / scatter copies around it, and zero_grad(set_to_none=False) is one memset-like pass."""
+        params = [q for q in self.policy.parameters() if q.requires_grad]
+        self._flat = torch.zeros(sum(q.numel() for q in params), device=self.device, dtype=params[0].dtype)
+        off = 0
+        for q in params:
+            q.grad = self._flat[off:off + q.numel()].view_as(q)
+            off += q.numel()
+
     def _allreduce_grads(self):
         if self.world == 1:
             return
-        params = [q for q in self.policy.parameters() if q.grad is not None]
-        if self._flat is None:
-            self._flat = torch.empty(sum(q.numel() for q in params), device=self.device)
-        off = 0
-        for q in params:
-            self._flat[off:off + q.numel()].copy_(q.grad.reshape(-1)); off += q.numel()
         torch.distributed.all_reduce(self._flat)                  # NCCL over NVLink: the gradient all-reduce
         self._flat.div_(self.world)
-        off = 0
-        for q in params:
-            q.grad.copy_(self._flat[off:off + q.numel()].view_as(q.grad)); off += q.numel()
 
     # ---- PPO update: minibatches gathered on the device ------------------------------------------------------------
     def _minibatch_loss(self, obs_mb, act_mb, logp_old_mb, adv_mb, ret_mb, acc):
@@ -350,10 +351,13 @@ class DevicePPO:
             for s in range(0, total, p.batch_size):
                 idx = perm[s:s + p.batch_size]
                 loss = self._minibatch_loss(obs[idx], act[idx], logp_old[idx], adv[idx], ret[idx], acc)
-                self.opt.zero_grad(set_to_none=False)
+                if self._flat is None:
+                    self._flatten_grads()
+                self._flat.zero_()                                     # = opt.zero_grad(set_to_none=False) on the flat views
                 loss.backward()
                 self._allreduce_grads()
-                nn.utils.clip_grad_norm_(self.policy.parameters(), p.max_grad_norm)
+                # nn.utils.clip_grad_norm_ on the flat buffer: total 2-norm, scale by min(1, max_norm / (norm + 1e-6))
+                self._flat.mul_((p.max_grad_norm / (self._flat.norm() + 1e-6)).clamp(max=1.0))
                 self.opt.step()
                 nb += 1
         if self.fused is not None:
