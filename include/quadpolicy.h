@@ -82,6 +82,13 @@ int qp_gae(const float *rewards, const float *values, const uint8_t *dones, cons
 int qp_bias_tanh(const void *z, const float *bias, int n, int h, int is_bf16, void *y, void *stream);
 int qp_bias_tanh_backward(const void *grad_y, const void *y, int n, int h, int is_bf16, void *grad_z, float *grad_bias, void *stream);
 
+/* Backward of a FIRST tanh layer with at most 8 inputs (the deep-sets phi, 6 -> 256 over n * V rows) whose input needs no gradient: grad_bias [h] and
+ * grad_weight [h, in_dim] (nn.Linear layout) from one pass over grad_y and y; grad_z is never written.  x: fp32 [n, in_dim] row-major; `workspace`:
+ * device scratch of qp_bias_tanh_backward_first_workspace(h, in_dim) bytes (per-block partial sums, no atomics). */
+size_t qp_bias_tanh_backward_first_workspace(int h, int in_dim);
+int qp_bias_tanh_backward_first(const void *grad_y, const void *y, const float *x, int n, int h, int in_dim, int is_bf16, void *workspace,
+                                float *grad_bias, float *grad_weight, void *stream);
+
 /* Tail of the deep-sets neighbour encoder (QuadNeighborhoodEncoderDeepsets.forward, quad_multi_model.py:35-40): y = tanh(z + bias) on [n * V, h]
  * and mean [n, h] = the average of each group of V consecutive rows, in one pass; the backward takes grad_mean [n, h] and writes
  * grad_z [n * V, h] = grad_mean[group] / V * (1 - y^2) and grad_bias.  h a multiple of 8, pointers 16-byte aligned. */

@@ -25,7 +25,7 @@ EXPORTS = ("qs_config_size", "qs_stats_size", "qs_api_version", "qs_last_error",
            "qs_reset_host", "qs_step_host", "qs_get_state", "qs_set_state", "qs_set_param", "qs_episode_stats",
            "qs_episode_records", "qs_episode_records_host", "qs_set_reward_info")
 # every symbol include/quadpolicy.h declares (fused policy forward, csrc/policy_kernels.cu)
-POLICY_EXPORTS = ("qp_config_size", "qp_last_error", "qp_create", "qp_destroy", "qp_launch_count", "qp_set_weights", "qp_forward", "qp_gae", "qp_bias_tanh", "qp_bias_tanh_backward", "qp_bias_tanh_mean", "qp_bias_tanh_mean_backward")
+POLICY_EXPORTS = ("qp_config_size", "qp_last_error", "qp_create", "qp_destroy", "qp_launch_count", "qp_set_weights", "qp_forward", "qp_gae", "qp_bias_tanh", "qp_bias_tanh_backward", "qp_bias_tanh_mean", "qp_bias_tanh_mean_backward", "qp_bias_tanh_backward_first", "qp_bias_tanh_backward_first_workspace")
 
 
 KG_VALUES = (1, 2, 4, 8, 16, 32)
@@ -119,6 +119,9 @@ def lib():
     L.qp_gae.argtypes = [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, vp, vp, vp]
     L.qp_bias_tanh.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.qp_bias_tanh_backward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    L.qp_bias_tanh_backward_first.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.qp_bias_tanh_backward_first_workspace.argtypes = [i32, i32]
+    L.qp_bias_tanh_backward_first_workspace.restype = C.c_size_t
     L.qp_bias_tanh_mean.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
     L.qp_bias_tanh_mean_backward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
     if L.qs_config_size() != C.sizeof(QsConfigC) or L.qs_stats_size() != C.sizeof(QsStatsC):

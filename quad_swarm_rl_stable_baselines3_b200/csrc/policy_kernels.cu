@@ -827,6 +827,80 @@ __global__ void __launch_bounds__(256) bias_tanh_bwd_v8_kernel(const T *gy, cons
     }
 }
 
+// backward of a FIRST dense tanh layer with few inputs (the deep-sets phi: 6 -> 256 over n * V rows): the input needs no gradient, so grad_z is
+// never written; the pass produces grad_bias [h] and grad_weight [h, IN] = grad_z^T x directly (cuBLAS runs this 256 x 6 output, K = 393216
+// reduction on an sm80 kernel without split-K: 185 us; here it rides on the one read of grad_y and y).  x is fp32 [rows, IN], IN <= 8.  Two rows per
+// thread in flight; every block writes its partial sums to `part[block][(IN + 1) * h]` (no atomics), a second small kernel adds the blocks up.
+template <typename T, int IN>
+__global__ void __launch_bounds__(256) bias_tanh_bwd_w_kernel(const T *gy, const T *y, const float *x, int n, int h, int RL, float *part)
+{
+    __shared__ float red[256 * 8];
+    const int G = h >> 3, cg = threadIdx.x % G, rl = threadIdx.x / G;
+    float ab[8], aw[8][IN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ab[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < IN; ++k) aw[i][k] = 0.f;
+    }
+    const int stride = gridDim.x * RL;
+    int r = blockIdx.x * RL + rl;
+    for (; r + stride < n; r += 2 * stride) {
+        float g0[8], t0[8], g1[8], t1[8], x0[IN], x1[IN];
+        Vec8<T>::ld(gy + (size_t)r * h + 8 * cg, g0); Vec8<T>::ld(y + (size_t)r * h + 8 * cg, t0);
+        Vec8<T>::ld(gy + (size_t)(r + stride) * h + 8 * cg, g1); Vec8<T>::ld(y + (size_t)(r + stride) * h + 8 * cg, t1);
+#pragma unroll
+        for (int k = 0; k < IN; ++k) { x0[k] = __ldg(x + (size_t)r * IN + k); x1[k] = __ldg(x + (size_t)(r + stride) * IN + k); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float o0 = g0[i] * (1.f - t0[i] * t0[i]), o1 = g1[i] * (1.f - t1[i] * t1[i]);
+            ab[i] += o0 + o1;
+#pragma unroll
+            for (int k = 0; k < IN; ++k) aw[i][k] = fmaf(o1, x1[k], fmaf(o0, x0[k], aw[i][k]));
+        }
+    }
+    if (r < n) {
+        float g0[8], t0[8], x0[IN];
+        Vec8<T>::ld(gy + (size_t)r * h + 8 * cg, g0); Vec8<T>::ld(y + (size_t)r * h + 8 * cg, t0);
+#pragma unroll
+        for (int k = 0; k < IN; ++k) x0[k] = __ldg(x + (size_t)r * IN + k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float o0 = g0[i] * (1.f - t0[i] * t0[i]);
+            ab[i] += o0;
+#pragma unroll
+            for (int k = 0; k < IN; ++k) aw[i][k] = fmaf(o0, x0[k], aw[i][k]);
+        }
+    }
+    float *mine = part + (size_t)blockIdx.x * (size_t)(IN + 1) * h;      // [k][column], k = IN: the bias
+#pragma unroll
+    for (int k = 0; k <= IN; ++k) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = (k < IN) ? aw[i][k < IN ? k : 0] : ab[i];
+        __syncthreads();
+        if (rl == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float sum = 0.f;
+                for (int q = 0; q < RL; ++q) sum += red[(q * G + cg) * 8 + i];
+                mine[(size_t)k * h + 8 * cg + i] = sum;
+            }
+        }
+    }
+}
+// part [blocks][(in + 1) * h] -> gw [h, in] (nn.Linear layout), gb [h]
+__global__ void bias_tanh_bwd_w_reduce_kernel(const float *part, int blocks, int h, int in_dim, float *gb, float *gw)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, total = (in_dim + 1) * h;
+    if (e >= total) return;
+    float sum = 0.f;
+    for (int b = 0; b < blocks; ++b) sum += part[(size_t)b * total + e];
+    const int k = e / h, c = e - k * h;
+    if (k < in_dim) gw[(size_t)c * in_dim + k] = sum;
+    else gb[c] = sum;
+}
+
 // deep-sets tail (quad_multi_model.py:35-40): y = tanh(z + b) on [n * V, h] rows and m = mean over the V rows of each group, in one pass; the
 // backward takes the gradient of m ([n, h]) and produces grad_z = gm[group] / V * (1 - y^2) and the bias gradient without ever materialising the
 // expanded gradient (eager autograd: a [n * V, h] division kernel + tanh_backward + a column reduction).  Thread = (group, 8 columns).
@@ -896,6 +970,21 @@ __global__ void __launch_bounds__(256) bias_tanh_mean_bwd_kernel(const T *gm, co
 }  // namespace qp
 
 using namespace qp;
+
+template <typename T>
+static void launch_bwd_w(int in_dim, int grid, int threads, cudaStream_t s, const T *gy, const T *y, const float *x, int n, int h, int RL, float *part)
+{
+    switch (in_dim) {
+    case 1: bias_tanh_bwd_w_kernel<T, 1><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    case 2: bias_tanh_bwd_w_kernel<T, 2><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    case 3: bias_tanh_bwd_w_kernel<T, 3><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    case 4: bias_tanh_bwd_w_kernel<T, 4><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    case 5: bias_tanh_bwd_w_kernel<T, 5><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    case 6: bias_tanh_bwd_w_kernel<T, 6><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    case 7: bias_tanh_bwd_w_kernel<T, 7><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    default: bias_tanh_bwd_w_kernel<T, 8><<<grid, threads, 0, s>>>(gy, y, x, n, h, RL, part); break;
+    }
+}
 
 struct qp_policy {
     qp_config cfg;
@@ -1073,6 +1162,28 @@ int qp_bias_tanh_backward(const void *grad_y, const void *y, int n, int h, int i
         r = cudaGetLastError();
     }
     if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_bias_tanh_backward: ") + cudaGetErrorString(r));
+    return QP_OK;
+}
+
+size_t qp_bias_tanh_backward_first_workspace(int h, int in_dim) { return (size_t)592 * (size_t)(in_dim + 1) * (size_t)h * sizeof(float); }
+
+int qp_bias_tanh_backward_first(const void *grad_y, const void *y, const float *x, int n, int h, int in_dim, int is_bf16, void *workspace,
+                                float *grad_bias, float *grad_weight, void *stream)
+{
+    if (!grad_y || !y || !x || !workspace || !grad_bias || !grad_weight) return qp_fail(nullptr, QP_ERR_NULL, "qp_bias_tanh_backward_first: null argument");
+    if (n < 1 || h < 8 || (h & 7) || h > 2048 || in_dim < 1 || in_dim > 8 || ((((size_t)grad_y | (size_t)y) & 15) != 0))
+        return qp_fail(nullptr, QP_ERR_BAD_CONFIG, "qp_bias_tanh_backward_first: h a multiple of 8 (<= 2048), 1 <= in_dim <= 8, pointers 16-byte aligned");
+    const int G = h / 8, RL = G >= 256 ? 1 : 256 / G;
+    int grid = bias_tanh_grid((n + RL - 1) / RL);
+    if (grid > 592) grid = 592;
+    cudaStream_t s = (cudaStream_t)stream;
+    float *part = (float *)workspace;
+    if (is_bf16) launch_bwd_w<__nv_bfloat16>(in_dim, grid, G * RL, s, (const __nv_bfloat16 *)grad_y, (const __nv_bfloat16 *)y, x, n, h, RL, part);
+    else launch_bwd_w<float>(in_dim, grid, G * RL, s, (const float *)grad_y, (const float *)y, x, n, h, RL, part);
+    const int total = (in_dim + 1) * h;
+    bias_tanh_bwd_w_reduce_kernel<<<(total + 127) / 128, 128, 0, s>>>(part, grid, h, in_dim, grad_bias, grad_weight);
+    cudaError_t r = cudaGetLastError();
+    if (r != cudaSuccess) return qp_fail(nullptr, QP_ERR_CUDA, std::string("qp_bias_tanh_backward_first: ") + cudaGetErrorString(r));
     return QP_OK;
 }
 

@@ -83,6 +83,30 @@ def bias_tanh_backward(grad_y: torch.Tensor, y: torch.Tensor):
     return gz, gb
 
 
+_first_ws = {}
+
+
+def bias_tanh_backward_first(grad_y: torch.Tensor, y: torch.Tensor, x: torch.Tensor):
+    """(grad_weight [h, in], grad_bias [h]) of a first tanh layer with in <= 8 inputs (`qp_bias_tanh_backward_first`); x float32 [n, in]."""
+    _bt_check(y)
+    if grad_y.dtype != y.dtype or not grad_y.is_contiguous():
+        grad_y = grad_y.to(y.dtype).contiguous()
+    x = x.detach().to(torch.float32).contiguous()
+    lib = _capi.lib()
+    key = (y.device, y.shape[1], x.shape[1])
+    if key not in _first_ws:
+        _first_ws[key] = torch.empty(int(lib.qp_bias_tanh_backward_first_workspace(y.shape[1], x.shape[1])) // 4, dtype=torch.float32, device=y.device)
+    gb = torch.empty(y.shape[1], dtype=torch.float32, device=y.device)
+    gw = torch.empty((y.shape[1], x.shape[1]), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        rc = lib.qp_bias_tanh_backward_first(grad_y.data_ptr(), y.data_ptr(), x.data_ptr(), y.shape[0], y.shape[1], x.shape[1],
+                                             int(y.dtype == torch.bfloat16), _first_ws[key].data_ptr(), gb.data_ptr(), gw.data_ptr(),
+                                             C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"qp_bias_tanh_backward_first failed ({rc}): {lib.qp_last_error(None).decode()}")
+    return gw, gb
+
+
 def bias_tanh_mean(z: torch.Tensor, bias: torch.Tensor, V: int):
     """(y, mean): y = tanh(z + bias) on [n * V, h], mean [n, h] over each group of V rows (`qp_bias_tanh_mean`)."""
     _bt_check(z)

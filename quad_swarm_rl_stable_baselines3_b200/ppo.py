@@ -52,6 +52,28 @@ class _BiasTanh(torch.autograd.Function):
         return gz, gb.to(ctx.bias_dtype)
 
 
+class _FirstBiasTanh(torch.autograd.Function):
+    """tanh(z + b) of a first layer with few inputs, z = x @ w^T computed outside without autograd: the backward returns the weight and bias
+    gradients from one pass over (grad_y, y, x) and no grad_z at all (`qp_bias_tanh_backward_first`).  x must not need a gradient."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, z, x, w, b):
+        from . import fused_policy
+        y = fused_policy.bias_tanh(z, b)
+        ctx.save_for_backward(y, x)
+        ctx.dtypes = (w.dtype, b.dtype)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        from . import fused_policy
+        y, x = ctx.saved_tensors
+        gw, gb = fused_policy.bias_tanh_backward_first(gy, y, x)
+        return None, None, gw.to(ctx.dtypes[0]), gb.to(ctx.dtypes[1])
+
+
 class _BiasTanhMean(torch.autograd.Function):
     """mean over the V rows of each group of tanh(z + b): the deep-sets tail in one pass, backward without the expanded gradient."""
 
@@ -86,9 +108,14 @@ class TanhMLP(nn.Sequential):
         while i < len(mods):
             m = mods[i]
             if isinstance(m, nn.Linear) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.Tanh) and m.out_features % 2 == 0 and m.bias is not None:
-                z = torch.nn.functional.linear(x, m.weight)
-                lead = z.shape[:-1]
-                x = _BiasTanh.apply(z.reshape(-1, z.shape[-1]).contiguous(), m.bias).reshape(*lead, z.shape[-1])
+                if i == 0 and m.in_features <= 8 and m.out_features % 8 == 0 and x.dim() == 2 and not x.requires_grad:
+                    with torch.no_grad():                                # first layer on raw observations: no input gradient, dW fused into the backward
+                        z = torch.nn.functional.linear(x, m.weight)
+                    x = _FirstBiasTanh.apply(z.contiguous(), x, m.weight, m.bias)
+                else:
+                    z = torch.nn.functional.linear(x, m.weight)
+                    lead = z.shape[:-1]
+                    x = _BiasTanh.apply(z.reshape(-1, z.shape[-1]).contiguous(), m.bias).reshape(*lead, z.shape[-1])
                 i += 2
             else:
                 x = m(x)
