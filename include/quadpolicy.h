@@ -64,7 +64,8 @@ int qp_create(const qp_config *cfg, int device, qp_policy **out);
 int qp_destroy(qp_policy *p);
 int64_t qp_launch_count(const qp_policy *p);
 
-/* (re)pack one tower's weights into the kernel's bf16 tile images; tower 0 = actor, 1 = critic.  Asynchronous on `stream`. */
+/* (re)pack one tower's weights into the kernel's bf16 tile images; tower 0 = actor, 1 = critic.  Asynchronous on `stream`: the source arrays must
+ * stay valid (and unchanged) until the stream has passed this call; a later qp_forward on the same stream sees the new weights. */
 int qp_set_weights(qp_policy *p, int tower, const qp_tower_weights *w, void *stream);
 
 /* obs: [n, obs_stride] fp32 (self block first, then V neighbour rows of W values, as Appendix B of SURVEY.md);
